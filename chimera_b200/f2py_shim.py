@@ -1,0 +1,482 @@
+"""f2py-compatible front end for a C-ABI backend of CHIMERA's `fimera` extension module.
+
+The reference driver does ``import chimera.moduls.fimera as chimera`` (reference
+moduls/chimera_main.py:20, solvers.py:23, species.py:22) and calls the Fortran subroutines of
+f90/*.f90 through f2py.  This module reproduces that Python-visible interface -- names, argument
+order, hidden dimension arguments, return conventions -- on top of any shared
+library that exports ``<prefix>_<name>`` entry points with the signatures declared in
+``include/chimera_b200.h``.  It is instantiated twice:
+
+  * ``chimera_b200.fimera``  -> libchimera_b200.so (CUDA, prefix ``chimera``)   [the product]
+  * ``oracle.fimera``        -> liboracle.so       (CPU,  prefix ``oracle``)    [test checker]
+
+f2py semantics reproduced here
+  * ``intent(in,out)`` arguments are returned; the same object is returned (modified in place)
+    when it already is a Fortran-contiguous array of the right dtype, otherwise a converted copy
+    (the driver always rebinds: ``self.Data[k] = chimera.f(self.Data[k], ...)``);
+  * ``intent(out)`` arguments are freshly allocated numpy-owned arrays (the driver ``resize``s
+    them, species.py:394) and multiple outputs come back as a tuple in dummy-argument order;
+  * ``intent(hide)`` dimensions are derived from shapes exactly as f2py derives them and
+    mismatches raise ``<module>.error``.
+"""
+from __future__ import annotations
+
+import ctypes
+import types
+
+import numpy as np
+
+_F8 = np.dtype("float64")
+_C16 = np.dtype("complex128")
+_I4 = np.dtype("int32")
+_I8 = np.dtype("int64")
+_I1 = np.dtype("int8")
+
+_i64 = ctypes.c_longlong
+_dbl = ctypes.c_double
+_int = ctypes.c_int
+
+
+class FimeraError(Exception):
+    """Counterpart of f2py's ``fimera.error``."""
+
+
+def _ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _check(a: np.ndarray, name: str, shape):
+    if a.ndim != len(shape):
+        raise FimeraError("%s: rank %d array expected, got rank %d" % (name, len(shape), a.ndim))
+    for i, (got, want) in enumerate(zip(a.shape, shape)):
+        if want is not None and got != want:
+            raise FimeraError(
+                "%s: shape mismatch in dimension %d: expected %d, got %d (shape %s)"
+                % (name, i, want, got, a.shape)
+            )
+
+
+def _in(a, dtype, name, shape):
+    """intent(in): any array-like; cast/copy to a Fortran-contiguous array of `dtype`."""
+    b = np.asarray(a)
+    if b.dtype != dtype or not b.flags.f_contiguous or not b.flags.aligned:
+        b = np.asfortranarray(b, dtype=dtype)
+    _check(b, name, shape)
+    return b
+
+
+def _inout(a, dtype, name, shape):
+    """intent(in,out): reuse the caller's buffer when f2py would, else a converted copy."""
+    b = a if isinstance(a, np.ndarray) else np.asarray(a)
+    if b.dtype != dtype or not b.flags.f_contiguous or not b.flags.aligned or not b.flags.writeable:
+        b = np.array(b, dtype=dtype, order="F")
+    _check(b, name, shape)
+    return b
+
+
+def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> types.ModuleType:
+    """Create a module object exposing the `fimera` API on top of `lib`."""
+
+    mod = types.ModuleType(modname)
+    mod.error = FimeraError
+    mod.__doc__ = "fimera-compatible API backed by %s_* entry points of %s" % (prefix, getattr(lib, "_name", lib))
+    mod._lib = lib
+    mod._prefix = prefix
+
+    last_error = getattr(lib, prefix + "_last_error", None)
+    if last_error is not None:
+        last_error.restype = ctypes.c_char_p
+
+    def call(name, *args):
+        fn = getattr(lib, "%s_%s" % (prefix, name))
+        fn.restype = ctypes.c_int
+        conv = []
+        for x in args:
+            conv.append(_ptr(x) if isinstance(x, np.ndarray) else x)
+        rc = fn(*conv)
+        if rc != 0:
+            msg = last_error().decode() if last_error is not None else ""
+            raise FimeraError("%s_%s failed with status %d %s" % (prefix, name, rc, msg))
+
+    def export(f):
+        setattr(mod, f.__name__, f)
+        return f
+
+    # ------------------------------------------------------------------ particle_tools.f90
+    @export
+    def push_velocs(momenta, fld, dt):
+        momenta = _inout(momenta, _F8, "momenta", (3, None))
+        n = momenta.shape[1]
+        fld = _in(fld, _F8, "fld", (6, n))
+        call("push_velocs", momenta, fld, _dbl(dt), _i64(n))
+        return momenta
+
+    @export
+    def push_coords(coord, momenta, coord_cntr, dt):
+        coord = _inout(coord, _F8, "coord", (3, None))
+        n = coord.shape[1]
+        momenta = _in(momenta, _F8, "momenta", (3, n))
+        coord_cntr = _inout(coord_cntr, _F8, "coord_cntr", (3, n))
+        call("push_coords", coord, momenta, coord_cntr, _dbl(dt), _i64(n))
+        return coord, coord_cntr
+
+    @export
+    def genparts(coord, xgrid, rgrid, randpacko, packx, packr, packo):
+        coord = _inout(coord, _F8, "coord", (4, None))
+        n = coord.shape[1]
+        xgrid = _in(xgrid, _F8, "xgrid", (None,))
+        rgrid = _in(rgrid, _F8, "rgrid", (None,))
+        nx, nr = xgrid.shape[0], rgrid.shape[0]
+        randpacko = _in(randpacko, _F8, "randpacko", (nx, nr))
+        packx = _in(packx, _F8, "packx", (None,))
+        ppc = packx.shape[0]
+        packr = _in(packr, _F8, "packr", (ppc,))
+        packo = _in(packo, _C16, "packo", (ppc,))
+        indpart = _int(0)
+        call("genparts", coord, ctypes.byref(indpart), xgrid, rgrid, randpacko, packx, packr, packo,
+             _i64(n), _i64(nx), _i64(nr), _i64(ppc))
+        return coord, indpart.value
+
+    @export
+    def sortpartsout(coord, lims):
+        coord = _in(coord, _F8, "coord", (3, None))
+        n = coord.shape[1]
+        lims = _in(lims, _F8, "lims", (4,))
+        idx = np.zeros((n,), dtype=_I4)
+        num = _int(0)
+        call("sortpartsout", idx, ctypes.byref(num), coord, lims, _i64(n))
+        return idx, num.value
+
+    @export
+    def sortoutghosts(coord):
+        coord = _in(coord, _F8, "coord", (None,))
+        n = coord.shape[0]
+        idx = np.zeros((n,), dtype=_I4)
+        num = _int(0)
+        call("sortoutghosts", idx, ctypes.byref(num), coord, _i64(n))
+        return idx, num.value
+
+    @export
+    def chunk_coords_boundaries(coord, lims, xgrid, nchnk):
+        coord = _in(coord, _F8, "coord", (3, None))
+        n = coord.shape[1]
+        lims = _in(lims, _F8, "lims", (4,))
+        xgrid = _in(xgrid, _F8, "xgrid", (None,))
+        nchnk = int(nchnk)
+        chunked = np.zeros((n,), dtype=_I1)
+        ind = np.zeros((nchnk + 1,), dtype=_I4)
+        goout = _int(0)
+        call("chunk_coords_boundaries", chunked, ind, ctypes.byref(goout), coord, lims, xgrid,
+             _int(nchnk), _i64(n), _i64(xgrid.shape[0]))
+        return chunked, ind, goout.value
+
+    @export
+    def align_data_vec(dat, chunked_indx):
+        dat = _inout(dat, _F8, "dat", (3, None))
+        idx = _in(chunked_indx, _I8, "chunked_indx", (None,))
+        if idx.shape[0] > dat.shape[1]:
+            raise FimeraError("align_data_vec: more indices than particles")
+        call("align_data_vec", dat, idx, _i64(idx.shape[0]), _i64(dat.shape[1]))
+        return dat
+
+    @export
+    def align_data_scl(dat, chunked_indx):
+        dat = _inout(dat, _F8, "dat", (None,))
+        idx = _in(chunked_indx, _I8, "chunked_indx", (None,))
+        if idx.shape[0] > dat.shape[0]:
+            raise FimeraError("align_data_scl: more indices than particles")
+        call("align_data_scl", dat, idx, _i64(idx.shape[0]), _i64(dat.shape[0]))
+        return dat
+
+    # ------------------------------------------------------------------ grid_deps*.f90
+    def _env_modes(nm, name):
+        if nm % 2 != 1:
+            raise FimeraError("%s: envelope grids need an odd number of mode slots, got %d" % (name, nm))
+
+    def _dep(name, env, curr, chnk):
+        def f(*args):
+            args = list(args)
+            coord = _in(args.pop(0), _F8, "coord", (3, None))
+            n = coord.shape[1]
+            momenta = _in(args.pop(0), _F8, "momenta", (3, n)) if curr else None
+            wghts = _in(args.pop(0), _F8, "wghts", (n,))
+            tail = (None, None, None, 3) if curr else (None, None, None)
+            grid = _inout(args.pop(0), _C16, "curr" if curr else "dens", tail)
+            nxn, nrn, nm = grid.shape[:3]
+            if env:
+                _env_modes(nm, name)
+            if chnk:
+                ind = _in(args.pop(0), _I4, "indinchunk", (None,))
+                guards = int(args.pop(0))
+            leftx = float(args.pop(0))
+            rgrid = _in(args.pop(0), _F8, "rgrid", (nrn,))
+            dx_inv = float(args.pop(0))
+            dr_inv = float(args.pop(0))
+            kx0 = float(args.pop(0)) if env else None
+            if args:
+                raise TypeError("%s: too many arguments" % name)
+            cargs = [coord] + ([momenta] if curr else []) + [wghts, grid]
+            if chnk:
+                cargs += [ind, _int(guards)]
+            cargs += [_dbl(leftx), rgrid, _dbl(dx_inv), _dbl(dr_inv)]
+            if env:
+                cargs += [_dbl(kx0)]
+            cargs += [_i64(n), _i64(nxn), _i64(nrn), _i64(nm)]
+            if chnk:
+                cargs += [_i64(ind.shape[0] - 1)]
+            call(name, *cargs)
+            return grid
+
+        f.__name__ = name
+        return f
+
+    for _env in (0, 1):
+        for _chnk in (0, 1):
+            for _curr in (0, 1):
+                _n = ("dep_curr" if _curr else "dep_dens") + ("_env" if _env else "") + ("_chnk" if _chnk else "")
+                setattr(mod, _n, _dep(_n, _env, _curr, _chnk))
+
+    def _proj(name, env):
+        def f(coord, wghts, fld, fld_tot, leftx, rgrid, dx_inv, dr_inv, *rest):
+            coord = _in(coord, _F8, "coord", (3, None))
+            n = coord.shape[1]
+            wghts = _in(wghts, _F8, "wghts", (n,))
+            fld = _in(fld, _C16, "fld", (None, None, None, 6))
+            nxn, nrn, nm = fld.shape[:3]
+            if env:
+                _env_modes(nm, name)
+            fld_tot = _inout(fld_tot, _F8, "fld_tot", (6, n))
+            rgrid = _in(rgrid, _F8, "rgrid", (nrn,))
+            cargs = [coord, wghts, fld, fld_tot, _dbl(leftx), rgrid, _dbl(dx_inv), _dbl(dr_inv)]
+            if env:
+                (kx0,) = rest
+                cargs.append(_dbl(kx0))
+            elif rest:
+                raise TypeError("%s: too many arguments" % name)
+            cargs += [_i64(n), _i64(nxn), _i64(nrn), _i64(nm)]
+            call(name, *cargs)
+            return fld_tot
+
+        f.__name__ = name
+        return f
+
+    mod.proj_fld = _proj("proj_fld", 0)
+    mod.proj_fld_env = _proj("proj_fld_env", 1)
+
+    def _ebcorr(name, env):
+        def f(eb_spc):
+            eb = _inout(eb_spc, _C16, "eb_spc", (None, None, None, 6))
+            if env:
+                _env_modes(eb.shape[2], name)
+            call(name, eb, _i64(eb.shape[0]), _i64(eb.shape[1]), _i64(eb.shape[2]))
+            return eb
+
+        f.__name__ = name
+        return f
+
+    mod.eb_correction = _ebcorr("eb_correction", 0)
+    mod.eb_correction_env = _ebcorr("eb_correction_env", 1)
+
+    # ------------------------------------------------------------------ fb_io.f90
+    def _fb_in(name, ncomp):
+        tail = (3,) if ncomp == 3 else ()
+
+        def f(out_fb, inp, leftx, kx, in_):
+            out_fb = _inout(out_fb, _C16, "vec_fb", (None, None, None) + tail)
+            nkx, nkr, nm = out_fb.shape[:3]
+            inp = _in(inp, _C16, "vec", (nkx, None, nm) + tail)
+            nrn = inp.shape[1]
+            kx = _in(kx, _F8, "kx", (nkx,))
+            in_ = _in(in_, _F8, "in", (nrn - 1, nkr, nm))
+            call(name, out_fb, inp, _dbl(leftx), kx, in_, _i64(nkx), _i64(nrn), _i64(nm), _i64(nkr))
+            return out_fb
+
+        f.__name__ = name
+        return f
+
+    mod.fb_vec_in = _fb_in("fb_vec_in", 3)
+    mod.fb_scl_in = _fb_in("fb_scl_in", 1)
+
+    def _fb_out(name, ncomp):
+        tail = (3,) if ncomp == 3 else ()
+
+        def f(inp_fb, leftx, kx, out):
+            inp_fb = _in(inp_fb, _C16, "vec_fb", (None, None, None) + tail)
+            nkx, nkr, nm = inp_fb.shape[:3]
+            kx = _in(kx, _F8, "kx", (nkx,))
+            out = _in(out, _F8, "out", (nkr, None, nm))
+            nrn = out.shape[1] + 1
+            res = np.zeros((nkx, nrn, nm) + tail, dtype=_C16, order="F")
+            call(name, res, inp_fb, _dbl(leftx), kx, out, _i64(nkx), _i64(nrn), _i64(nm), _i64(nkr))
+            return res
+
+        f.__name__ = name
+        return f
+
+    mod.fb_vec_out = _fb_out("fb_vec_out", 3)
+    mod.fb_scl_out = _fb_out("fb_scl_out", 1)
+
+    @export
+    def fb_eb_out(eb_spc, e_fb, b_fb, leftx, kx, out):
+        eb_spc = _inout(eb_spc, _C16, "eb_spc", (None, None, None, 6))
+        nkx, nrn, nm = eb_spc.shape[:3]
+        e_fb = _in(e_fb, _C16, "e_fb", (nkx, None, nm, 6))
+        nkr = e_fb.shape[1]
+        b_fb = _in(b_fb, _C16, "b_fb", (nkx, nkr, nm, 3))
+        kx = _in(kx, _F8, "kx", (nkx,))
+        out = _in(out, _F8, "out", (nkr, nrn - 1, nm))
+        call("fb_eb_out", eb_spc, e_fb, b_fb, _dbl(leftx), kx, out, _i64(nkx), _i64(nrn), _i64(nm), _i64(nkr))
+        return eb_spc
+
+    @export
+    def fb_filtr(vec, leftx, kx, filtr, modefilt):
+        vec = _inout(vec, _C16, "vec", (None, None, None, 3))
+        nkx, nkr, nm = vec.shape[:3]
+        kx = _in(kx, _F8, "kx", (nkx,))
+        filtr = _in(filtr, _F8, "filtr", (None,))
+        call("fb_filtr", vec, _dbl(leftx), kx, filtr, _int(int(modefilt)), _i64(nkx), _i64(nkr), _i64(nm),
+             _i64(filtr.shape[0]))
+        return vec
+
+    # ------------------------------------------------------------------ fb_math*.f90
+    def _nd(nm, env):
+        """number of mode slots the D matrices must have (f2py: 2+nko / 3+2*nko)"""
+        return nm + 2 if env else nm + 1
+
+    def _fb_diff(name, env, in_comp, out_comp):
+        def f(out_loc, inp, dps2s, dms2s, kx):
+            otail = (3,) if out_comp == 3 else ()
+            itail = (3,) if in_comp == 3 else ()
+            out_loc = _inout(out_loc, _C16, "vec_fb_loc", (None, None, None) + otail)
+            nkx, nkr_loc, nm = out_loc.shape[:3]
+            if env:
+                _env_modes(nm, name)
+            inp = _in(inp, _C16, "vec_fb", (nkx, None, nm) + itail)
+            nkr = inp.shape[1]
+            dps2s = _in(dps2s, _F8, "dps2s", (nkr, nkr_loc, _nd(nm, env)))
+            dms2s = _in(dms2s, _F8, "dms2s", (nkr, nkr_loc, _nd(nm, env)))
+            kx = _in(kx, _F8, "kx", (nkx,))
+            call(name, out_loc, inp, dps2s, dms2s, kx, _i64(nkx), _i64(nkr), _i64(nm), _i64(nkr_loc))
+            return out_loc
+
+        f.__name__ = name
+        return f
+
+    for _env, _sfx in ((0, ""), (1, "_env")):
+        setattr(mod, "fb_rot" + _sfx, _fb_diff("fb_rot" + _sfx, _env, 3, 3))
+        setattr(mod, "fb_grad" + _sfx, _fb_diff("fb_grad" + _sfx, _env, 1, 3))
+        setattr(mod, "fb_div" + _sfx, _fb_diff("fb_div" + _sfx, _env, 3, 1))
+
+    def _graddiv(name, env):
+        def f(vec_fb, dps2s, dms2s, kx):
+            vec_fb = _inout(vec_fb, _C16, "vec_fb", (None, None, None, 3))
+            nkx, nkr, nm = vec_fb.shape[:3]
+            if env:
+                _env_modes(nm, name)
+            dps2s = _in(dps2s, _F8, "dps2s", (nkr, None, _nd(nm, env)))
+            nkr_loc = dps2s.shape[1]
+            dms2s = _in(dms2s, _F8, "dms2s", (nkr, nkr_loc, _nd(nm, env)))
+            kx = _in(kx, _F8, "kx", (nkx,))
+            call(name, vec_fb, dps2s, dms2s, kx, _i64(nkx), _i64(nkr), _i64(nm), _i64(nkr_loc))
+            return vec_fb
+
+        f.__name__ = name
+        return f
+
+    mod.fb_graddiv = _graddiv("fb_graddiv", 0)
+    mod.fb_graddiv_env = _graddiv("fb_graddiv_env", 1)
+
+    # ------------------------------------------------------------------ maxwell_solvers.f90
+    def _spec3(a, name, tail):
+        a = _inout(a, _C16, name, (None, None, None) + tail)
+        return a, a.shape[0], a.shape[1], a.shape[2]
+
+    @export
+    def maxwell_push_with_spchrg(eg_fb, j_fb, grad_rho_n_fb, grad_rho_np1_fb, c1, c2):
+        eg, nkx, nkr, nm = _spec3(eg_fb, "eg_fb", (6,))
+        s3 = (nkx, nkr, nm, 3)
+        j = _in(j_fb, _C16, "j_fb", s3)
+        gn = _in(grad_rho_n_fb, _C16, "grad_rho_n_fb", s3)
+        gp = _in(grad_rho_np1_fb, _C16, "grad_rho_np1_fb", s3)
+        c1 = _in(c1, _F8, "c1", (nkx, nkr, nm, 5))
+        c2 = _in(c2, _F8, "c2", (nkx, nkr, nm, 5))
+        call("maxwell_push_with_spchrg", eg, j, gn, gp, c1, c2, _i64(nkx), _i64(nkr), _i64(nm))
+        return eg
+
+    @export
+    def maxwell_push_wo_spchrg(eg_fb, j_fb, c1, c2):
+        eg, nkx, nkr, nm = _spec3(eg_fb, "eg_fb", (6,))
+        j = _in(j_fb, _C16, "j_fb", (nkx, nkr, nm, 3))
+        c1 = _in(c1, _C16, "c1", (nkx, nkr, nm, 3))  # real tables are cast, maxwell_solvers.f90:67
+        c2 = _in(c2, _C16, "c2", (nkx, nkr, nm, 3))
+        call("maxwell_push_wo_spchrg", eg, j, c1, c2, _i64(nkx), _i64(nkr), _i64(nm))
+        return eg
+
+    @export
+    def maxwell_init_push(eg_fb, j_fb, grad_rho_n_fb, c1, c2):
+        eg, nkx, nkr, nm = _spec3(eg_fb, "eg_fb", (6,))
+        j = _in(j_fb, _C16, "j_fb", (nkx, nkr, nm, 3))
+        gn = _in(grad_rho_n_fb, _C16, "grad_rho_n_fb", (nkx, nkr, nm, 3))
+        c1 = _in(c1, _C16, "c1", (nkx, nkr, nm, 2))
+        c2 = _in(c2, _C16, "c2", (nkx, nkr, nm, 2))
+        call("maxwell_init_push", eg, j, gn, c1, c2, _i64(nkx), _i64(nkr), _i64(nm))
+        return eg
+
+    @export
+    def poiss_corr(j_fb, grad_div_j_fb, grad_rho_n_fb, grad_rho_np1_fb, dt_inv, w2_inv):
+        j, nkx, nkr, nm = _spec3(j_fb, "j_fb", (3,))
+        s3 = (nkx, nkr, nm, 3)
+        gdj = _in(grad_div_j_fb, _C16, "grad_div_j_fb", s3)
+        gn = _in(grad_rho_n_fb, _C16, "grad_rho_n_fb", s3)
+        gp = _in(grad_rho_np1_fb, _C16, "grad_rho_np1_fb", s3)
+        w2 = _in(w2_inv, _F8, "w2_inv", (nkx, nkr, nm))
+        call("poiss_corr", j, gdj, gn, gp, _dbl(dt_inv), w2, _i64(nkx), _i64(nkr), _i64(nm))
+        return j
+
+    @export
+    def poiss_corr_stat(j_fb, grad_div_j_fb, grad_rho_n_fb, dt, w2_inv):
+        j, nkx, nkr, nm = _spec3(j_fb, "j_fb", (3,))
+        s3 = (nkx, nkr, nm, 3)
+        gdj = _in(grad_div_j_fb, _C16, "grad_div_j_fb", s3)
+        gn = _in(grad_rho_n_fb, _C16, "grad_rho_n_fb", s3)
+        dtc = _in(dt, _C16, "dt", (nkx,))
+        w2 = _in(w2_inv, _F8, "w2_inv", (nkx, nkr, nm))
+        call("poiss_corr_stat", j, gdj, gn, dtc, w2, _i64(nkx), _i64(nkr), _i64(nm))
+        return j
+
+    @export
+    def field_drift(eg_fb, kx, beta0, dt):
+        eg, nkx, nkr, nm = _spec3(eg_fb, "eg_fb", (6,))
+        kx = _in(kx, _F8, "kx", (nkx,))
+        call("field_drift", eg, kx, _dbl(beta0), _dbl(dt), _i64(nkx), _i64(nkr), _i64(nm))
+        return eg
+
+    def _elem(name, ncomp, adtype, a_has_comp):
+        tail = (3,) if ncomp == 3 else ()
+
+        def f(x_fb, a):
+            x, nkx, nkr, nm = _spec3(x_fb, "vec_fb", tail)
+            a = _in(a, adtype, "a", (nkx, nkr, nm) + (tail if a_has_comp else ()))
+            call(name, x, a, _i64(nkx), _i64(nkr), _i64(nm))
+            return x
+
+        f.__name__ = name
+        return f
+
+    mod.omp_mult_vec = _elem("omp_mult_vec", 3, _F8, False)
+    mod.omp_mult_scl = _elem("omp_mult_scl", 1, _F8, False)
+    mod.omp_add_vec = _elem("omp_add_vec", 3, _C16, True)
+    mod.omp_add_scl = _elem("omp_add_scl", 1, _C16, True)
+
+    # ------------------------------------------------------------------ devices.f90 (NEXT-1)
+    @export
+    def undul_analytic(coord, fld, t, params):
+        coord = _in(coord, _F8, "coord", (3, None))
+        n = coord.shape[1]
+        fld = _inout(fld, _F8, "fld", (6, n))
+        params = _in(params, _F8, "params", (4,))
+        call("undul_analytic", coord, fld, _dbl(t), params, _i64(n))
+        return fld
+
+    mod.API_NAMES = sorted(k for k, v in vars(mod).items() if callable(v) and not k.startswith("_") and k != "error")
+    return mod

@@ -1,0 +1,39 @@
+"""`fimera`-compatible module backed by the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE: the checker for the CUDA path, never the product.  Usage::
+
+    from oracle import fimera as ofimera          # strict IEEE build
+    from oracle.fimera import load; fast = load(fast=True)   # -O3 -ffast-math speed baseline
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+from chimera_b200.f2py_shim import build_module
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(force=False):
+    """Compile liboracle.so / liboracle_fast.so from chimera_oracle.cpp (g++, OpenMP)."""
+    src = os.path.join(_HERE, "chimera_oracle.cpp")
+    libs = [os.path.join(_HERE, n) for n in ("liboracle.so", "liboracle_fast.so")]
+    stale = force or any((not os.path.exists(l)) or os.path.getmtime(l) < os.path.getmtime(src) for l in libs)
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "all"])
+
+
+def load(fast=False):
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        build()
+    lib = ctypes.CDLL(path)
+    return build_module(lib, "oracle", "oracle_fimera_fast" if fast else "oracle_fimera")
+
+
+_mod = load(fast=False)
+_mod.load = load
+_mod.build = build
+sys.modules[__name__] = _mod
