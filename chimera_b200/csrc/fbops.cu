@@ -1,0 +1,341 @@
+// fbops.cu -- see fbops.cuh.  Reference: f90/fb_io.f90, f90/fb_math.f90, f90/fb_math_env.f90.
+#include "fbops.cuh"
+
+namespace chb {
+
+// ------------------------------------------------------------------------------------------
+static size_t round_mb(size_t b) { return (b + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1); }
+
+int Scratch::reserve(size_t bytes) {
+  for (auto& b : blocks)
+    if (b.cap - b.used >= bytes + 256) return 0;
+  Block nb{nullptr, round_mb(bytes + 256), 0};
+  CHB_CUDA(cudaMalloc((void**)&nb.p, nb.cap));
+  blocks.push_back(nb);
+  return 0;
+}
+void* Scratch::take(size_t bytes) {
+  for (int pass = 0; pass < 2; ++pass) {
+    if (!blocks.empty()) {
+      Block& b = blocks.back();
+      const size_t a = (b.used + 255) & ~size_t(255);
+      if (a + bytes <= b.cap) {
+        b.used = a + bytes;
+        size_t tot = 0;
+        for (auto& q : blocks) tot += q.used;
+        if (tot > high) high = tot;
+        return b.p + a;
+      }
+    }
+    if (pass == 0) {
+      size_t want = bytes + 256;
+      if (want < (size_t(32) << 20)) want = size_t(32) << 20;
+      Block nb{nullptr, round_mb(want), 0};
+      if (cudaMalloc((void**)&nb.p, nb.cap) != cudaSuccess) {
+        set_error("scratch: cudaMalloc of %zu bytes failed", nb.cap);
+        return nullptr;
+      }
+      blocks.push_back(nb);
+    }
+  }
+  return nullptr;
+}
+void Scratch::reset() {
+  if (blocks.size() > 1) {  // coalesce so the next round fits in one block
+    size_t tot = 0;
+    for (auto& b : blocks) { tot += b.cap; cudaFree(b.p); }
+    blocks.clear();
+    Block nb{nullptr, round_mb(tot), 0};
+    if (cudaMalloc((void**)&nb.p, nb.cap) == cudaSuccess) blocks.push_back(nb);
+  }
+  for (auto& b : blocks) b.used = 0;
+}
+void Scratch::destroy() {
+  for (auto& b : blocks) cudaFree(b.p);
+  blocks.clear();
+}
+
+int FFTCache::exec(cudaStream_t st, cd* data, i64 n, i64 batch, int dir) {
+  if (n <= 0 || batch <= 0) return 0;
+  auto key = std::make_pair(n, batch);
+  auto it = plans.find(key);
+  if (it == plans.end()) {
+    cufftHandle h;
+    int nn[1] = {(int)n};
+    cufftResult r = cufftPlanMany(&h, 1, nn, nullptr, 1, (int)n, nullptr, 1, (int)n, CUFFT_Z2Z, (int)batch);
+    if (r != CUFFT_SUCCESS) { set_error("cufftPlanMany(n=%lld,batch=%lld) failed: %d", n, batch, (int)r); return 7; }
+    it = plans.emplace(key, h).first;
+  }
+  cufftResult r = cufftSetStream(it->second, st);
+  if (r == CUFFT_SUCCESS) r = cufftExecZ2Z(it->second, (cufftDoubleComplex*)data, (cufftDoubleComplex*)data, dir);
+  if (r != CUFFT_SUCCESS) { set_error("cufftExecZ2Z failed: %d", (int)r); return 7; }
+  return 0;
+}
+void FFTCache::destroy() {
+  for (auto& kv : plans) cufftDestroy(kv.second);
+  plans.clear();
+}
+
+size_t packed_ops_bytes(i64 K, i64 N, int nslots) { return (size_t)gemm_packed_size(K, N) * sizeof(double) * nslots; }
+
+int pack_ops(cudaStream_t st, PackedOps& out, double* dst, const double* op, i64 K, i64 N, int nslots) {
+  if (nslots > (int)(sizeof(out.slot) / sizeof(out.slot[0]))) { set_error("too many operator slots"); return 8; }
+  out.K = K; out.N = N; out.nslots = nslots;
+  const i64 sz = gemm_packed_size(K, N);
+  for (int s = 0; s < nslots; ++s) {
+    CHB_TRY(launch_gemm_pack_b(st, dst + sz * s, op + K * N * s, K, N, K));
+    out.slot[s] = dst + sz * s;
+  }
+  return 0;
+}
+
+namespace {
+struct Batcher {
+  cudaStream_t st;
+  i64 M, N, K, lda, ldc;
+  GemmBatch b;
+  int rc = 0;
+  Batcher(cudaStream_t s, i64 M_, i64 N_, i64 K_, i64 lda_, i64 ldc_) : st(s), M(M_), N(N_), K(K_), lda(lda_), ldc(ldc_) { b.count = 0; }
+  void add(const cd* A, const double* Bp, cd* C, double alpha, double beta) {
+    if (rc) return;
+    if (b.count == kGemmMaxBatch) flush();
+    b.p[b.count++] = GemmProblem{(const double*)A, Bp, (double*)C, alpha, beta};
+  }
+  int flush() {
+    if (!rc && b.count) rc = launch_gemm(st, b, M, N, K, lda, ldc);
+    b.count = 0;
+    return rc;
+  }
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+int fb_in_dev(FBCtx& c, cd* out_fb, const cd* in, double leftX, const double* kx, const PackedOps& In,
+              const double* fact, i64 nkx, i64 nrn, i64 nm, i64 nkr, int ncomp) {
+  const i64 nr = nrn - 1;
+  Batcher gb(c.st, 2 * nkx, nkr, nr, 2 * nkx, 2 * nkx);
+  for (int l = 0; l < ncomp; ++l)
+    for (i64 m = 0; m < nm; ++m)
+      gb.add(in + nkx * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nkx * nkr * (m + nm * l), 1.0, 0.0);
+  CHB_TRY(gb.flush());
+  CHB_TRY(c.fft->exec(c.st, out_fb, nkx, nkr * nm * ncomp, CUFFT_FORWARD));
+  CHB_TRY(launch_rowscale_phase(c.st, out_fb, kx, leftX, -1.0, 1.0, fact, nkx, nkr * nm * ncomp, nkr * nm));
+  return 0;
+}
+
+int fb_out_dev(FBCtx& c, cd* out, const cd* const* srcs, int nsrc, int ncomp_each, double leftX, const double* kx,
+               const PackedOps& Out, i64 nkx, i64 nrn, i64 nm, i64 nkr) {
+  const i64 nr = nrn - 1;
+  const int ncomp = nsrc * ncomp_each;
+  CHB_CUDA(cudaMemsetAsync(out, 0, sizeof(cd) * nkx * nrn * nm * ncomp, c.st));
+  Batcher gb(c.st, 2 * nkx, nr, nkr, 2 * nkx, 2 * nkx);
+  for (int j = 0; j < nsrc; ++j)
+    for (int l = 0; l < ncomp_each; ++l)
+      for (i64 m = 0; m < nm; ++m)
+        gb.add(srcs[j] + nkx * nkr * (m + nm * l), Out.slot[m],
+               out + nkx * (1 + nrn * (m + nm * (l + ncomp_each * j))), 1.0, 0.0);
+  CHB_TRY(gb.flush());
+  CHB_TRY(launch_rowscale_phase(c.st, out, kx, leftX, +1.0, 1.0, nullptr, nkx, nrn * nm * ncomp, 1));
+  CHB_TRY(c.fft->exec(c.st, out, nkx, nrn * nm * ncomp, CUFFT_INVERSE));
+  return 0;
+}
+
+int fb_filtr_dev(FBCtx& c, cd* vec, double leftX, const double* kx, const double* filtr, int modefilt, i64 nkx,
+                 i64 nkr, i64 nm, i64 nxfilt) {
+  const i64 ncols = nkr * nm * 3;
+  CHB_TRY(launch_rowscale_phase(c.st, vec, kx, leftX, +1.0, 1.0, nullptr, nkx, ncols, 1));
+  CHB_TRY(c.fft->exec(c.st, vec, nkx, ncols, CUFFT_INVERSE));
+  CHB_TRY(launch_window(c.st, vec, filtr, modefilt, nkx, ncols, nxfilt));
+  CHB_TRY(c.fft->exec(c.st, vec, nkx, ncols, CUFFT_FORWARD));
+  // shiftX_inv = 1 / (nkx * shiftX) = conj(shiftX) / nkx
+  CHB_TRY(launch_rowscale_phase(c.st, vec, kx, leftX, -1.0, 1.0 / (double)nkx, nullptr, nkx, ncols, 1));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Modes {
+  int env;
+  i64 nm, nko, lo, hi;
+  explicit Modes(const FBMathDims& d) : env(d.env), nm(d.nm) {
+    nko = env ? (nm - 1) / 2 : nm - 1;
+    lo = env ? -nko : 0;
+    hi = nko;
+  }
+  i64 vslot(i64 mode) const { return mode - lo; }
+  i64 dslot(i64 mode) const { return env ? mode + nko + 1 : mode; }
+};
+const Unit U1{1, 0}, Um1{-1, 0}, Ui{0, 1}, U0{0, 0};
+
+// copy the leading nkr_loc columns of a (nkx, nkr) plane through i*kx: dst(:, 0:nkr_loc) (+)= sign*i*kx*src
+int ikx_plane(cudaStream_t st, cd* dst, const cd* src, const double* kx, double sign, int acc, const FBMathDims& d) {
+  return launch_ikx(st, dst, src, kx, sign, acc, d.nkx, d.nkr_loc);
+}
+
+// S[mode - slo] = [i kx v1[mode]] + Dm(mode).T1[mode-1] + Dp(mode).T2[mode+1],  T1 = i v3 - v2, T2 = i v3 + v2
+// (fb_div fb_math.f90:151-199, fb_div_env fb_math_env.f90:63-104, first halves of fb_graddiv[_env])
+int div_like(FBCtx& c, cd* S, i64 slo, i64 shi, const cd* vec, const PackedOps& Dp, const PackedOps& Dm,
+             const double* kx, const FBMathDims& d) {
+  const Modes mo(d);
+  const i64 Pv = d.nkx * d.nkr, Ps = d.nkx * d.nkr_loc;
+  const cd* v1 = vec;
+  const cd* v2 = vec + Pv * d.nm;
+  const cd* v3 = vec + Pv * d.nm * 2;
+  cd* T1 = c.scr->take_n<cd>(Pv * d.nm);
+  cd* T2 = c.scr->take_n<cd>(Pv * d.nm);
+  cd* T1ext = nullptr;
+  if (!T1 || !T2) return 6;
+  CHB_TRY(launch_combine(c.st, T1, v3, Ui, v2, Um1, 0, d.nkx, d.nkr * d.nm));
+  CHB_TRY(launch_combine(c.st, T2, v3, Ui, v2, U1, 0, d.nkx, d.nkr * d.nm));
+  if (!d.env && mo.nko > 0) {  // Q7: with nko = 0 the missing mode 1 is taken as zero
+    T1ext = c.scr->take_n<cd>(Pv);
+    if (!T1ext) return 6;
+    CHB_TRY(launch_combine(c.st, T1ext, v3 + Pv * mo.vslot(1), Ui, v2 + Pv * mo.vslot(1), Um1, 1, d.nkx, d.nkr));
+  }
+  for (i64 mode = slo; mode <= shi; ++mode) {
+    cd* o = S + Ps * (mode - slo);
+    if (mode >= mo.lo && mode <= mo.hi) CHB_TRY(ikx_plane(c.st, o, v1 + Pv * mo.vslot(mode), kx, +1.0, 0, d));
+    else CHB_CUDA(cudaMemsetAsync(o, 0, sizeof(cd) * Ps, c.st));
+  }
+  Batcher gm(c.st, 2 * d.nkx, d.nkr_loc, d.nkr, 2 * d.nkx, 2 * d.nkx);
+  for (i64 mode = slo; mode <= shi; ++mode) {
+    const cd* src = nullptr;
+    if (!d.env) src = (mode > 0) ? T1 + Pv * mo.vslot(mode - 1) : T1ext;
+    else if (mode > -mo.nko) src = T1 + Pv * mo.vslot(mode - 1);
+    if (src) gm.add(src, Dm.slot[mo.dslot(mode)], S + Ps * (mode - slo), 1.0, 1.0);
+  }
+  CHB_TRY(gm.flush());
+  Batcher gp(c.st, 2 * d.nkx, d.nkr_loc, d.nkr, 2 * d.nkx, 2 * d.nkx);
+  for (i64 mode = slo; mode <= shi; ++mode)
+    if (mode < mo.nko) gp.add(T2 + Pv * mo.vslot(mode + 1), Dp.slot[mo.dslot(mode)], S + Ps * (mode - slo), 1.0, 1.0);
+  CHB_TRY(gp.flush());
+  return 0;
+}
+
+// out(:,:,mode,1) = i kx S[mode];  G1 = Dm(mode).S[mode-1],  G2 = Dp(mode).S[mode+1];
+// out(..,2) = -G1 + G2 ;  out(..,3) = i G1 + i G2
+// (fb_grad fb_math.f90:96-149, fb_grad_env fb_math_env.f90:18-61, second halves of fb_graddiv[_env])
+int grad_like(FBCtx& c, cd* out, const cd* S, i64 slo, i64 shi, const PackedOps& Dp, const PackedOps& Dm,
+              const double* kx, const FBMathDims& d, bool always_both) {
+  const Modes mo(d);
+  const i64 Pin = d.nkx * d.nkr, Ps = d.nkx * d.nkr_loc;
+  auto Sp = [&](i64 mode) { return S + Pin * (mode - slo); };
+  (void)shi;
+  cd* G1 = c.scr->take_n<cd>(Ps * d.nm);
+  cd* G2 = c.scr->take_n<cd>(Ps * d.nm);
+  if (!G1 || !G2) return 6;
+  CHB_CUDA(cudaMemsetAsync(G1, 0, sizeof(cd) * Ps * d.nm, c.st));
+  CHB_CUDA(cudaMemsetAsync(G2, 0, sizeof(cd) * Ps * d.nm, c.st));
+  cd* Sext = nullptr;
+  if (!d.env && mo.nko > 0) {
+    Sext = c.scr->take_n<cd>(Pin);
+    if (!Sext) return 6;
+    CHB_TRY(launch_combine(c.st, Sext, Sp(1), U1, nullptr, U0, 1, d.nkx, d.nkr));
+  }
+  for (i64 mode = mo.lo; mode <= mo.hi; ++mode)
+    CHB_TRY(ikx_plane(c.st, out + Ps * mo.vslot(mode), Sp(mode), kx, +1.0, 0, d));
+  Batcher gb(c.st, 2 * d.nkx, d.nkr_loc, d.nkr, 2 * d.nkx, 2 * d.nkx);
+  for (i64 mode = mo.lo; mode <= mo.hi; ++mode) {
+    const cd* lower = nullptr;
+    if (!d.env) lower = (mode > 0) ? Sp(mode - 1) : Sext;
+    else if (always_both || mode > -mo.nko) lower = Sp(mode - 1);
+    if (lower) gb.add(lower, Dm.slot[mo.dslot(mode)], G1 + Ps * mo.vslot(mode), 1.0, 0.0);
+    if (always_both || mode < mo.nko)
+      gb.add(Sp(mode + 1), Dp.slot[mo.dslot(mode)], G2 + Ps * mo.vslot(mode), 1.0, 0.0);
+  }
+  CHB_TRY(gb.flush());
+  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm, G1, Um1, G2, U1, 0, Ps * d.nm));
+  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm * 2, G1, Ui, G2, Ui, 0, Ps * d.nm));
+  return 0;
+}
+}  // namespace
+
+size_t fb_math_scratch_bytes(const FBMathDims& d) {
+  const size_t P = (size_t)d.nkx * (size_t)(d.nkr > d.nkr_loc ? d.nkr : d.nkr_loc) * sizeof(cd);
+  return (6 * (size_t)d.nm + 12) * (P + 256);
+}
+
+int fb_grad_dev(FBCtx& c, cd* out, const cd* scl, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
+                const FBMathDims& d) {
+  const Modes mo(d);
+  return grad_like(c, out, scl, mo.lo, mo.hi, Dp, Dm, kx, d, false);
+}
+
+int fb_div_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
+               const FBMathDims& d) {
+  const Modes mo(d);
+  return div_like(c, out, mo.lo, mo.hi, vec, Dp, Dm, kx, d);
+}
+
+// fb_graddiv (fb_math.f90:201-293) / fb_graddiv_env (fb_math_env.f90:164-233), in place
+int fb_graddiv_dev(FBCtx& c, cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx, const FBMathDims& d) {
+  if (d.nkr != d.nkr_loc) { set_error("fb_graddiv needs nkr == nkr_loc"); return 9; }
+  const Modes mo(d);
+  const i64 slo = d.env ? mo.lo - 1 : 0, shi = mo.hi + 1;
+  cd* S = c.scr->take_n<cd>(d.nkx * d.nkr_loc * (shi - slo + 1));
+  if (!S) return 6;
+  CHB_TRY(div_like(c, S, slo, shi, vec, Dp, Dm, kx, d));
+  CHB_TRY(grad_like(c, vec, S, slo, shi, Dp, Dm, kx, d, true));
+  return 0;
+}
+
+// fb_rot (fb_math.f90:18-94) / fb_rot_env (fb_math_env.f90:106-162)
+//   out1 = -Dp.(i v2 - v3)[m+1] - Dm.(i v2 + v3)[m-1]        (env: the Dm term is dropped, Q5)
+//   out2 = -i kx v3 + i GP + i GM ;  out3 = +i kx v2 - GP + GM ;  GP = Dp.v1[m+1], GM = Dm.v1[m-1]
+int fb_rot_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
+               const FBMathDims& d) {
+  const Modes mo(d);
+  const i64 Pv = d.nkx * d.nkr, Ps = d.nkx * d.nkr_loc;
+  const cd* v1 = vec;
+  const cd* v2 = vec + Pv * d.nm;
+  const cd* v3 = vec + Pv * d.nm * 2;
+  cd* R1 = c.scr->take_n<cd>(Pv * d.nm);
+  cd* R2 = c.scr->take_n<cd>(Pv * d.nm);
+  cd* GP = c.scr->take_n<cd>(Ps * d.nm);
+  cd* GM = c.scr->take_n<cd>(Ps * d.nm);
+  if (!R1 || !R2 || !GP || !GM) return 6;
+  CHB_TRY(launch_combine(c.st, R1, v2, Ui, v3, Um1, 0, d.nkx, d.nkr * d.nm));
+  if (!d.env) CHB_TRY(launch_combine(c.st, R2, v2, Ui, v3, U1, 0, d.nkx, d.nkr * d.nm));
+  cd *R2ext = nullptr, *V1ext = nullptr;
+  if (!d.env && mo.nko > 0) {
+    R2ext = c.scr->take_n<cd>(Pv);
+    V1ext = c.scr->take_n<cd>(Pv);
+    if (!R2ext || !V1ext) return 6;
+    CHB_TRY(launch_combine(c.st, R2ext, v2 + Pv * mo.vslot(1), Ui, v3 + Pv * mo.vslot(1), U1, 1, d.nkx, d.nkr));
+    CHB_TRY(launch_combine(c.st, V1ext, v1 + Pv * mo.vslot(1), U1, nullptr, U0, 1, d.nkx, d.nkr));
+  }
+  CHB_CUDA(cudaMemsetAsync(out, 0, sizeof(cd) * Ps * d.nm, c.st));  // component 1
+  CHB_CUDA(cudaMemsetAsync(GP, 0, sizeof(cd) * Ps * d.nm, c.st));
+  CHB_CUDA(cudaMemsetAsync(GM, 0, sizeof(cd) * Ps * d.nm, c.st));
+  Batcher g1(c.st, 2 * d.nkx, d.nkr_loc, d.nkr, 2 * d.nkx, 2 * d.nkx);
+  for (i64 mode = mo.lo; mode <= mo.hi; ++mode) {
+    const i64 s = mo.vslot(mode);
+    if (mode < mo.nko) {
+      g1.add(R1 + Pv * mo.vslot(mode + 1), Dp.slot[mo.dslot(mode)], out + Ps * s, -1.0, 0.0);
+      g1.add(v1 + Pv * mo.vslot(mode + 1), Dp.slot[mo.dslot(mode)], GP + Ps * s, 1.0, 0.0);
+    }
+    const cd* l1 = nullptr;
+    if (!d.env) l1 = (mode > 0) ? v1 + Pv * mo.vslot(mode - 1) : V1ext;
+    else if (mode > -mo.nko) l1 = v1 + Pv * mo.vslot(mode - 1);
+    if (l1) g1.add(l1, Dm.slot[mo.dslot(mode)], GM + Ps * s, 1.0, 0.0);
+  }
+  CHB_TRY(g1.flush());
+  if (!d.env) {  // second term of component 1 accumulates on top of the first => separate launch
+    Batcher g2(c.st, 2 * d.nkx, d.nkr_loc, d.nkr, 2 * d.nkx, 2 * d.nkx);
+    for (i64 mode = mo.lo; mode <= mo.hi; ++mode) {
+      const cd* l2 = (mode > 0) ? R2 + Pv * mo.vslot(mode - 1) : R2ext;
+      if (l2) g2.add(l2, Dm.slot[mo.dslot(mode)], out + Ps * mo.vslot(mode), -1.0, 1.0);
+    }
+    CHB_TRY(g2.flush());
+  }
+  for (i64 mode = mo.lo; mode <= mo.hi; ++mode) {
+    const i64 s = mo.vslot(mode);
+    CHB_TRY(ikx_plane(c.st, out + Ps * (s + d.nm), v3 + Pv * s, kx, -1.0, 0, d));
+    CHB_TRY(ikx_plane(c.st, out + Ps * (s + d.nm * 2), v2 + Pv * s, kx, +1.0, 0, d));
+  }
+  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm, GP, Ui, GM, Ui, 1, Ps * d.nm));
+  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm * 2, GP, Um1, GM, U1, 1, Ps * d.nm));
+  return 0;
+}
+
+}  // namespace chb

@@ -1,0 +1,77 @@
+// fbops.cuh -- composite Fourier-Bessel operations on device pointers: DHT+FFT transforms
+// (fb_io.f90) and spectral vector calculus (fb_math*.f90) assembled from the DMMA GEMM, cuFFT
+// and the elementwise kernels.  Shared by the C-ABI host layer and the resident engine.
+#pragma once
+#include <cufft.h>
+#include <map>
+#include <vector>
+#include <utility>
+#include "kernels.cuh"
+
+namespace chb {
+
+// bump allocator over device memory for per-call temporaries.  take() never fails for lack of
+// reserved space: it adds a block when the current one is exhausted; reset() (call it between
+// top-level operations, after the stream has been synchronised or the temporaries are dead)
+// coalesces the blocks into one, so a steady-state loop performs no cudaMalloc at all.
+struct Scratch {
+  struct Block { char* p; size_t cap, used; };
+  std::vector<Block> blocks;
+  size_t high = 0;
+  int reserve(size_t bytes);            // make sure one block of at least `bytes` exists
+  void* take(size_t bytes);             // 256-byte aligned; nullptr only if cudaMalloc fails
+  template <typename T> T* take_n(i64 n) { return (T*)take(sizeof(T) * (size_t)(n > 0 ? n : 1)); }
+  void reset();
+  void destroy();
+};
+
+struct FFTCache {
+  std::map<std::pair<i64, i64>, cufftHandle> plans;
+  int exec(cudaStream_t st, cd* data, i64 n, i64 batch, int dir);  // in place, dir = CUFFT_FORWARD / CUFFT_INVERSE
+  void destroy();
+};
+
+// operator stack packed for the GEMM: one packed B per mode slot
+struct PackedOps {
+  const double* slot[2 * kMaxModes + 4];
+  i64 K = 0, N = 0;
+  int nslots = 0;
+};
+// bytes needed to pack an operator stack (K, N, nslots)
+size_t packed_ops_bytes(i64 K, i64 N, int nslots);
+// pack a device-resident operator stack op(K, N, nslots) (Fortran order) into `dst`
+int pack_ops(cudaStream_t st, PackedOps& out, double* dst, const double* op, i64 K, i64 N, int nslots);
+
+struct FBCtx {
+  cudaStream_t st;
+  Scratch* scr;
+  FFTCache* fft;
+};
+
+// forward DHT + x-FFT + phase (fb_vec_in / fb_scl_in, fb_io.f90:18-98); fact (optional, (nkx,nkr,nm))
+// is fused into the phase pass (the driver's omp_mult_vec(J_fb, DepFact), solvers.py:419)
+int fb_in_dev(FBCtx& c, cd* out_fb, const cd* in, double leftX, const double* kx, const PackedOps& In,
+              const double* fact, i64 nkx, i64 nrn, i64 nm, i64 nkr, int ncomp);
+// backward DHT + phase + inverse x-FFT (fb_vec_out / fb_scl_out / fb_eb_out, fb_io.f90:100-228)
+// srcs[j] is the spectral source of output component block j (ncomp_each comps each)
+int fb_out_dev(FBCtx& c, cd* out, const cd* const* srcs, int nsrc, int ncomp_each, double leftX, const double* kx,
+               const PackedOps& Out, i64 nkx, i64 nrn, i64 nm, i64 nkr);
+// absorbing-layer window (fb_filtr, fb_io.f90:230-308)
+int fb_filtr_dev(FBCtx& c, cd* vec, double leftX, const double* kx, const double* filtr, int modefilt, i64 nkx,
+                 i64 nkr, i64 nm, i64 nxfilt);
+
+struct FBMathDims {
+  i64 nkx, nkr, nm, nkr_loc;
+  int env;
+};
+int fb_grad_dev(FBCtx& c, cd* out, const cd* scl, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
+                const FBMathDims& d);
+int fb_div_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
+               const FBMathDims& d);
+int fb_rot_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
+               const FBMathDims& d);
+int fb_graddiv_dev(FBCtx& c, cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx, const FBMathDims& d);
+// scratch bytes an fb_* call may take (upper bound), for reserve()
+size_t fb_math_scratch_bytes(const FBMathDims& d);
+
+}  // namespace chb

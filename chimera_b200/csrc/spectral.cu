@@ -1,0 +1,331 @@
+// spectral.cu -- bandwidth-bound elementwise kernels of the Fourier-Bessel PSATD field update.
+//
+// Replaces reference f90/maxwell_solvers.f90 (PSATD advance, Poisson correction, field drift,
+// omp_* helpers), the phase/normalisation passes of f90/fb_io.f90, eb_correction[_env] of
+// f90/grid_deps*.f90 and the linear combinations around the mode-coupling contractions of
+// f90/fb_math*.f90.  All arrays are complex128 (double2) in Fortran order with x fastest, so a
+// thread block walks contiguous x and every access is a coalesced 128-bit load/store.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace chb {
+
+namespace {
+constexpr int TPB = 256;
+__device__ __forceinline__ cd ldg(const cd* p) { return __ldg(p); }
+__device__ __forceinline__ cd unit_mul(Unit u, cd a) {  // (re + i im) * a with re,im in {-1,0,1}
+  return make_double2(u.re * a.x - u.im * a.y, u.re * a.y + u.im * a.x);
+}
+}  // namespace
+
+// a(:,col) *= scale * exp(i*sign*kx*leftX) [* fact(:, col % fact_cols)]      (fb_io.f90:40,52 / :121,129)
+__global__ void __launch_bounds__(TPB) rowscale_phase_k(cd* __restrict__ a, const double* __restrict__ kx,
+                                                        double leftX, double sign, double scale,
+                                                        const double* __restrict__ fact, i64 nkx, i64 ncols,
+                                                        i64 fact_cols, i64 cols_per_block) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nkx) return;
+  double sn, cs;
+  sincos(leftX * __ldg(kx + i), &sn, &cs);
+  const cd ph = cmake(scale * cs, scale * sign * sn);
+  const i64 c0 = (i64)blockIdx.y * cols_per_block;
+  const i64 c1 = (c0 + cols_per_block < ncols) ? c0 + cols_per_block : ncols;
+  for (i64 c = c0; c < c1; ++c) {
+    cd v = cmul(a[i + nkx * c], ph);
+    if (fact) v = cscale(__ldg(fact + i + nkx * (c % fact_cols)), v);
+    a[i + nkx * c] = v;
+  }
+}
+
+int launch_rowscale_phase(cudaStream_t st, cd* a, const double* kx, double leftX, double sign, double scale,
+                          const double* fact, i64 nkx, i64 ncols, i64 fact_cols) {
+  if (nkx <= 0 || ncols <= 0) return 0;
+  const i64 cpb = 16;
+  dim3 grid(grid_for(nkx, TPB), (unsigned)((ncols + cpb - 1) / cpb));
+  rowscale_phase_k<<<grid, TPB, 0, st>>>(a, kx, leftX, sign, scale, fact, nkx, ncols, fact_cols ? fact_cols : 1, cpb);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// a(:,col) *= s(:)   complex row scale
+__global__ void __launch_bounds__(TPB) rowscale_cplx_k(cd* __restrict__ a, const cd* __restrict__ s, i64 nkx, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  a[e] = cmul(a[e], ldg(s + e % nkx));
+}
+int launch_rowscale_cplx(cudaStream_t st, cd* a, const cd* s, i64 nkx, i64 ncols) {
+  const i64 n = nkx * ncols;
+  if (n <= 0) return 0;
+  rowscale_cplx_k<<<grid_for(n, TPB), TPB, 0, st>>>(a, s, nkx, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// eb_correction (grid_deps.f90:219-266) / eb_correction_env (grid_deps_env.f90:240-283):
+// normalise by 1/2pi (m=0, real) or 1/pi, then fill the ghost row from row 1 (copy or negate).
+__global__ void __launch_bounds__(TPB) eb_correction_k(cd* __restrict__ eb, i64 nxn, i64 nrn, i64 nm, int env) {
+  const i64 ix = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ix >= nxn) return;
+  const i64 q = blockIdx.y;  // plane = slot + nm*l
+  const int slot = (int)(q % nm);
+  const double pi_inv = 1.0 / 3.14159265358979323846;
+  const double f = (!env && slot == 0) ? 0.5 * pi_inv : pi_inv;
+  const bool negate = env ? (nm > 1) : (slot > 0);  // Q6
+  cd* pl = eb + nxn * nrn * q;
+  for (i64 ir = 1; ir < nrn; ++ir) {
+    cd v = cscale(f, pl[ix + nxn * ir]);
+    pl[ix + nxn * ir] = v;
+    if (ir == 1) pl[ix] = negate ? cneg(v) : v;
+  }
+}
+int launch_eb_correction(cudaStream_t st, cd* eb, i64 nxn, i64 nrn, i64 nm, int env) {
+  if (nxn <= 0) return 0;
+  dim3 grid(grid_for(nxn, TPB), (unsigned)(nm * 6));
+  eb_correction_k<<<grid, TPB, 0, st>>>(eb, nxn, nrn, nm, env);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// PSATD advance (maxwell_solvers.f90:18-96).  NCOEF = 5 with real tables (space charge),
+// NCOEF = 3 with real or complex tables.  One thread per spectral point, 3 components each:
+// the coefficient tables are read once and reused for the three components.
+template <int NCOEF, typename CT>
+__global__ void __launch_bounds__(TPB) maxwell_push_k(cd* __restrict__ EG, const cd* __restrict__ J,
+                                                      const cd* __restrict__ gn, const cd* __restrict__ gp,
+                                                      const CT* __restrict__ C1, const CT* __restrict__ C2, i64 P) {
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  CT c1[NCOEF], c2[NCOEF];
+#pragma unroll
+  for (int k = 0; k < NCOEF; ++k) { c1[k] = __ldg(C1 + p + P * k); c2[k] = __ldg(C2 + p + P * k); }
+  auto mul = [](CT c, cd v) -> cd {
+    if constexpr (sizeof(CT) == sizeof(double)) return cscale(*(const double*)&c, v);
+    else return cmul(*(const cd*)&c, v);
+  };
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const cd e = EG[p + P * l], g = EG[p + P * (l + 3)], j = ldg(J + p + P * l);
+    cd en = cadd(cadd(mul(c1[0], e), mul(c1[1], g)), mul(c1[2], j));
+    cd gw = cadd(cadd(mul(c2[0], e), mul(c2[1], g)), mul(c2[2], j));
+    if constexpr (NCOEF == 5) {
+      const cd a = ldg(gn + p + P * l), b = ldg(gp + p + P * l);
+      en = cadd(cadd(en, mul(c1[3], a)), mul(c1[4], b));
+      gw = cadd(cadd(gw, mul(c2[3], a)), mul(c2[4], b));
+    }
+    EG[p + P * (l + 3)] = gw;
+    EG[p + P * l] = en;
+  }
+}
+int launch_maxwell_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const cd* gp, const void* C1,
+                        const void* C2, int ncoef, int coef_complex, i64 P) {
+  if (P <= 0) return 0;
+  const unsigned nb = grid_for(P, TPB);
+  if (ncoef == 5 && !coef_complex)
+    maxwell_push_k<5, double><<<nb, TPB, 0, st>>>(EG, J, gn, gp, (const double*)C1, (const double*)C2, P);
+  else if (ncoef == 3 && !coef_complex)
+    maxwell_push_k<3, double><<<nb, TPB, 0, st>>>(EG, J, nullptr, nullptr, (const double*)C1, (const double*)C2, P);
+  else if (ncoef == 3 && coef_complex)
+    maxwell_push_k<3, cd><<<nb, TPB, 0, st>>>(EG, J, nullptr, nullptr, (const cd*)C1, (const cd*)C2, P);
+  else { set_error("maxwell_push: unsupported coefficient layout"); return 5; }
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// maxwell_solvers.f90:98-129
+__global__ void __launch_bounds__(TPB) maxwell_init_push_k(cd* __restrict__ EG, const cd* __restrict__ J,
+                                                           const cd* __restrict__ gn, const cd* __restrict__ C1,
+                                                           const cd* __restrict__ C2, i64 P) {
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const cd c10 = ldg(C1 + p), c11 = ldg(C1 + p + P), c20 = ldg(C2 + p), c21 = ldg(C2 + p + P);
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const cd j = ldg(J + p + P * l), a = ldg(gn + p + P * l);
+    EG[p + P * l] = cadd(cadd(EG[p + P * l], cmul(c10, j)), cmul(c11, a));
+    EG[p + P * (l + 3)] = cadd(cadd(EG[p + P * (l + 3)], cmul(c20, j)), cmul(c21, a));
+  }
+}
+int launch_maxwell_init_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const cd* C1, const cd* C2, i64 P) {
+  if (P <= 0) return 0;
+  maxwell_init_push_k<<<grid_for(P, TPB), TPB, 0, st>>>(EG, J, gn, C1, C2, P);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// maxwell_solvers.f90:131-164
+__global__ void __launch_bounds__(TPB) poiss_corr_k(cd* __restrict__ J, const cd* __restrict__ gdj,
+                                                    const cd* __restrict__ gn, const cd* __restrict__ gp,
+                                                    double dt_inv, const double* __restrict__ w2inv, i64 P) {
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double wi = __ldg(w2inv + p);
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const i64 e = p + P * l;
+    const cd d = cscale(dt_inv, csub(ldg(gp + e), ldg(gn + e)));
+    J[e] = cadd(J[e], cscale(wi, cadd(ldg(gdj + e), d)));
+  }
+}
+int launch_poiss_corr(cudaStream_t st, cd* J, const cd* gdj, const cd* gn, const cd* gp, double dt_inv,
+                      const double* w2inv, i64 P) {
+  if (P <= 0) return 0;
+  poiss_corr_k<<<grid_for(P, TPB), TPB, 0, st>>>(J, gdj, gn, gp, dt_inv, w2inv, P);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// maxwell_solvers.f90:166-197
+__global__ void __launch_bounds__(TPB) poiss_corr_stat_k(cd* __restrict__ J, const cd* __restrict__ gdj,
+                                                         const cd* __restrict__ gn, const cd* __restrict__ DT,
+                                                         const double* __restrict__ w2inv, i64 nkx, i64 P) {
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double wi = __ldg(w2inv + p);
+  const cd dt = ldg(DT + p % nkx);
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const i64 e = p + P * l;
+    J[e] = cadd(J[e], cscale(wi, cadd(ldg(gdj + e), cmul(dt, ldg(gn + e)))));
+  }
+}
+int launch_poiss_corr_stat(cudaStream_t st, cd* J, const cd* gdj, const cd* gn, const cd* DT, const double* w2inv,
+                           i64 nkx, i64 P) {
+  if (P <= 0) return 0;
+  poiss_corr_stat_k<<<grid_for(P, TPB), TPB, 0, st>>>(J, gdj, gn, DT, w2inv, nkx, P);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// maxwell_solvers.f90:199-226 : EG *= exp(-i dt/2 beta0 kx)
+__global__ void __launch_bounds__(TPB) field_drift_k(cd* __restrict__ EG, const double* __restrict__ kx, double fac,
+                                                     i64 nkx, i64 ncols, i64 cols_per_block) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nkx) return;
+  double sn, cs;
+  sincos(fac * __ldg(kx + i), &sn, &cs);
+  const cd ph = cmake(cs, sn);
+  const i64 c0 = (i64)blockIdx.y * cols_per_block;
+  const i64 c1 = (c0 + cols_per_block < ncols) ? c0 + cols_per_block : ncols;
+  for (i64 c = c0; c < c1; ++c) EG[i + nkx * c] = cmul(EG[i + nkx * c], ph);
+}
+int launch_field_drift(cudaStream_t st, cd* EG, const double* kx, double beta0, double dt, i64 nkx, i64 ncols) {
+  if (nkx <= 0 || ncols <= 0) return 0;
+  const i64 cpb = 16;
+  dim3 grid(grid_for(nkx, TPB), (unsigned)((ncols + cpb - 1) / cpb));
+  field_drift_k<<<grid, TPB, 0, st>>>(EG, kx, -0.5 * dt * beta0, nkx, ncols, cpb);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// omp_mult_vec / omp_mult_scl (maxwell_solvers.f90:228-272): v(:,:,:,l) *= A  (real A shared by comps)
+__global__ void __launch_bounds__(TPB) mult_real_k(cd* __restrict__ v, const double* __restrict__ A, i64 P, int ncomp) {
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double a = __ldg(A + p);
+  for (int l = 0; l < ncomp; ++l) v[p + P * l] = cscale(a, v[p + P * l]);
+}
+int launch_mult_real(cudaStream_t st, cd* v, const double* A, i64 P, int ncomp) {
+  if (P <= 0) return 0;
+  mult_real_k<<<grid_for(P, TPB), TPB, 0, st>>>(v, A, P, ncomp);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// omp_add_vec / omp_add_scl (maxwell_solvers.f90:274-318)
+__global__ void __launch_bounds__(TPB) add_k(cd* __restrict__ v, const cd* __restrict__ A, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) v[e] = cadd(v[e], ldg(A + e));
+}
+int launch_add(cudaStream_t st, cd* v, const cd* A, i64 n) {
+  if (n <= 0) return 0;
+  add_k<<<grid_for(n, TPB), TPB, 0, st>>>(v, A, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// x-space window of fb_filtr (fb_io.f90:257-303), applied between the two FFTs
+__global__ void __launch_bounds__(TPB) window_k(cd* __restrict__ a, const double* __restrict__ filtr, int modefilt,
+                                                i64 nkx, i64 nxfilt, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const i64 i = e % nkx;
+  double f = 1.0;
+  if ((modefilt == 0 || modefilt == 2) && i < nxfilt) f *= __ldg(filtr + i);
+  if ((modefilt == 1 || modefilt == 2) && i >= nkx - nxfilt) f *= __ldg(filtr + (nkx - 1 - i));
+  if (f != 1.0) a[e] = cscale(f, a[e]);
+}
+int launch_window(cudaStream_t st, cd* a, const double* filtr, int modefilt, i64 nkx, i64 ncols, i64 nxfilt) {
+  const i64 n = nkx * ncols;
+  if (n <= 0) return 0;
+  window_k<<<grid_for(n, TPB), TPB, 0, st>>>(a, filtr, modefilt, nkx, nxfilt, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// out = ca*a + cb*b (b may be null); mirror != 0 applies the real solver's m=0 coupling source
+//   ext(i) = -conj(src((nkx - i) mod nkx))      (fb_math.f90:35-36)
+// to both inputs *before* the unit factors.
+__global__ void __launch_bounds__(TPB) combine_k(cd* __restrict__ out, const cd* __restrict__ a, Unit ca,
+                                                 const cd* __restrict__ b, Unit cb, int mirror, i64 nkx, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  i64 src = e;
+  if (mirror) {
+    const i64 i = e % nkx;
+    src = e - i + (i == 0 ? 0 : nkx - i);
+  }
+  cd va = ldg(a + src);
+  if (mirror) va = cmake(-va.x, va.y);
+  cd r = unit_mul(ca, va);
+  if (b) {
+    cd vb = ldg(b + src);
+    if (mirror) vb = cmake(-vb.x, vb.y);
+    r = cadd(r, unit_mul(cb, vb));
+  }
+  out[e] = r;
+}
+int launch_combine(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, Unit cb, int mirror, i64 nkx,
+                   i64 ncols) {
+  const i64 n = nkx * ncols;
+  if (n <= 0) return 0;
+  combine_k<<<grid_for(n, TPB), TPB, 0, st>>>(out, a, ca, b, cb, mirror, nkx, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(TPB) axpby_k(cd* __restrict__ out, const cd* __restrict__ a, Unit ca,
+                                               const cd* __restrict__ b, Unit cb, int acc, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  cd r = unit_mul(ca, ldg(a + e));
+  if (b) r = cadd(r, unit_mul(cb, ldg(b + e)));
+  if (acc) r = cadd(r, out[e]);
+  out[e] = r;
+}
+int launch_axpby(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, Unit cb, int acc, i64 n) {
+  if (n <= 0) return 0;
+  axpby_k<<<grid_for(n, TPB), TPB, 0, st>>>(out, a, ca, b, cb, acc, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// out (+)= sign * i * kx * a
+__global__ void __launch_bounds__(TPB) ikx_k(cd* __restrict__ out, const cd* __restrict__ a,
+                                             const double* __restrict__ kx, double sign, int acc, i64 nkx, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double k = sign * __ldg(kx + e % nkx);
+  const cd v = ldg(a + e);
+  cd r = cmake(-k * v.y, k * v.x);
+  if (acc) r = cadd(r, out[e]);
+  out[e] = r;
+}
+int launch_ikx(cudaStream_t st, cd* out, const cd* a, const double* kx, double sign, int acc, i64 nkx, i64 ncols) {
+  const i64 n = nkx * ncols;
+  if (n <= 0) return 0;
+  ikx_k<<<grid_for(n, TPB), TPB, 0, st>>>(out, a, kx, sign, acc, nkx, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace chb
