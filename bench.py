@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Benchmark of the PIC-cycle hot path (BASELINE.json metric: particle-steps/s, full PIC cycle).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA engine
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] the reference's algorithm on the
+                                                                       host cores (oracle port: the
+                                                                       Fortran cannot be built here)
+Under torchrun (N > 1) one rank per GPU: particles are sharded (weak scaling: the per-GPU particle
+count is fixed), the deposited grids are all-reduced over NCCL.  One JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/s full PIC cycle"
+UNIT = "particle-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ppc", type=int, default=48, choices=[16, 48],
+                    help="macro-particles per cell: 48 = 1.0e8 particles (the '~1e8' BASELINE.json names), 16 = 3.4e7")
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--nr", type=int, default=512)
+    ap.add_argument("--modes", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-nx", type=int, default=256)
+    return ap.parse_args()
+
+
+CELL = {16: (2, 2, 4), 48: (4, 3, 4)}
+
+
+def workload_name(a):
+    return ("LWFA synthetic Nz=%d Nr=%d %d azimuthal modes, %d ppc (%.2e macro-particles per GPU), real PSATD solver "
+            "with SpaceCharge + 3 Poisson iterations, Xchunked=(16,10), dt=dx" % (a.nx, a.nr, a.modes, a.ppc, n_particles(a)))
+
+
+def n_particles(a):
+    return (a.nx - 1 - 24) * (a.nr - 8) * a.ppc
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        time.sleep(0.15)
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dgemm_peak_tflops(torch, n=8192, reps=5):
+    """cuBLAS DGEMM n^3: the FP64-tensor denominator (MEASURED_PEAKS.json has no FP64 figure)."""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+# algorithmic HBM bytes per particle of the particle phases of the engine
+ALG_BYTES = {
+    "push_coords": 96.0,   # R x,p  W x,x_half
+    "deposit_J": 56.0,     # R x_half,p,w   (+ grid RW, added below)
+    "deposit_rho": 32.0,   # R x,w
+    "gather_push": 80.0,   # fused proj_fld + push_velocs: R x,w,p  W p  (the per-particle EB never hits HBM)
+}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_problem(a, torch, rank, world, group):
+    from chimera_b200 import synthetic
+    from chimera_b200.engine import Engine
+    from chimera_b200.solver_setup import SolverSetup
+    import chimera_b200.fimera as gfim
+
+    S = SolverSetup(synthetic.lwfa_solver_config(nx=a.nx, nr=a.nr, modes=a.modes))
+    eng = Engine(S, group=group)
+    eng.use_stream(torch.cuda.current_stream().cuda_stream)
+    x, p, w = synthetic.plasma_fixed_cell(S.Args, cell=CELL[a.ppc], seed=20260101 + rank, xp=torch)
+    n = x.shape[0]
+    torch.cuda.synchronize()
+    eng.add_species_device(x.data_ptr(), p.data_ptr(), w.data_ptr(), n)
+    del x, p, w
+    torch.cuda.empty_cache()
+    # still ions coincide with the electrons at t=0: BckGrndRho = - rho_e(0)  (chimera_main.py:220 dep_bg)
+    eng.run("sort", 0.0)
+    eng.run("deposit_rho", 0.0)
+    if world > 1:
+        torch.distributed.all_reduce(eng.device_tensor("Rho"), group=eng._group)
+    bg = eng.device_tensor("BckGrndRho")
+    bg.copy_(-eng.device_tensor("Rho"))
+    eng.upload("EG_fb", synthetic.laser_seed(S, gfim))
+    eng.make_halfstep(px0=(0.0,))
+    eng.sync()
+    return S, eng, n
+
+
+def run_ours(a):
+    import torch
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = True
+    from chimera_b200 import _lib
+
+    lib = _lib.load()
+    lib.chimera_set_device(local)
+    S, eng, n_local = build_problem(a, torch, rank, world, group)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    eng.step(a.warmup)
+    barrier()
+    eng.profile(True)
+    eng.timings(reset=True)
+    lib.chimera_gemm_profile(1)
+    l0 = _lib.kernel_launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    eng.step(a.steps)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.finish() if sampler else None
+    launches = _lib.kernel_launches() - l0
+    phases = eng.timings(reset=True)
+    eng.profile(False)
+    g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    lib.chimera_gemm_profile_read(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n), 1)
+    lib.chimera_gemm_profile(0)
+    n_now = eng.count(0)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_total = float(t.item())
+        cnt = torch.tensor([float(n_local)], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(cnt)
+        n_total = int(cnt.item())
+    else:
+        n_total = n_local
+    ms_step = ms_total / a.steps
+    value = n_total / (ms_step * 1e-3)
+
+    out = None
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        fp64_peak = dgemm_peak_tflops(torch)
+        c = eng.cfg
+        grid_pts = c.nx * c.nrn * c.nm
+        stages = {}
+        for name, (ms, calls) in phases.items():
+            per = ms / calls
+            ent = {"ms_per_call": per, "share": ms / ms_total}
+            if name in ALG_BYTES:
+                by = ALG_BYTES[name] * n_local
+                if name == "deposit_J":
+                    by += 2 * 48.0 * grid_pts
+                if name == "deposit_rho":
+                    by += 2 * 16.0 * grid_pts
+                ent.update(bound="hbm", alg_bytes=by, achieved_gbs=by / (per * 1e-3) / 1e9,
+                           frac=by / (per * 1e-3) / 1e9 / hbm_peak)
+            stages[name] = ent
+        gemm = {"ms_per_launch": g_ms.value / max(g_n.value, 1), "launches_per_step": g_n.value / a.steps,
+                "share": g_ms.value / ms_total, "tflops": g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value else 0.0}
+        # dominant kernel by share of the timed region: the DMMA contraction or one particle kernel
+        cand = {k: v["share"] for k, v in stages.items() if "bound" in v}
+        top = max(cand, key=cand.get) if cand else None
+        if top is None or gemm["share"] >= cand[top]:
+            roof = {"kernel": "gemm_dmma_k (DHT + mode-coupling contractions)", "bound": "tensor",
+                    "achieved": gemm["tflops"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm["tflops"] / fp64_peak,
+                    "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor; MEASURED_PEAKS.json has no FP64 figure)",
+                    "share_of_step": gemm["share"]}
+        else:
+            s = stages[top]
+            roof = {"kernel": top, "bound": "hbm", "achieved": s["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": s["frac"], "traffic": None, "peak_source": hbm_src, "share_of_step": s["share"]}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "particles_total": n_total, "particles_after": n_now,
+                       "parallelism": "particles sharded x%d, grids all-reduced (NCCL), spectral solve replicated" % world,
+                       "l2": "inputs larger than L2 (particle arrays %.1f GB, grids %.2f GB)"
+                             % (n_local * 80 / 1e9, grid_pts * 16 * 10 / 1e9)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": stages, "gemm": gemm,
+            "fp64_peak_tflops": fp64_peak,
+        }
+    # ---- end to end through the reference-facing drop-in (host buffers, copies inside the timed region)
+    if rank == 0 and not a.no_e2e:
+        out["e2e"] = run_e2e(a, torch, S, eng, n_local, world)
+    if rank == 0 and not a.no_cpu and world == 1:
+        out["cpu_baseline"] = cpu_baseline(a)
+    eng.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+def pinned_like(torch, arr):
+    t = torch.from_numpy(np.ascontiguousarray(arr.T if arr.ndim == 2 else arr)).pin_memory()
+    v = t.numpy()
+    return (v.T if arr.ndim == 2 else v), t
+
+
+def run_e2e(a, torch, S, eng, n_local, world):
+    """One make_step through chimera_b200.fimera -- the f2py-compatible C ABI with HOST buffers -- in the
+    reference's call sequence (tests/pic_ref.RefRun == chimera_main.py:82-92): every call copies its
+    arguments host->device and its results device->host inside the timed region."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import chimera_b200.fimera as gfim
+    from pic_ref import RefRun, RefSpecies
+
+    x, xh, p, w = eng.particles(0)
+    keep = []
+    xs, t0 = pinned_like(torch, x); keep.append(t0)
+    ps, t1 = pinned_like(torch, p); keep.append(t1)
+    sp = RefSpecies.__new__(RefSpecies)
+    sp.coords, sp.momenta, sp.weights = xs, ps, w
+    sp.coords_halfstep, t2 = pinned_like(torch, xh); keep.append(t2)
+    sp.push_fact, sp.still, sp.device, sp.chunks = -2 * np.pi, False, None, eng.chunks(0)
+    sp.EB = np.zeros((6, 0), order="F")
+    run = RefRun(gfim, S, [sp], sort_every=0)
+    run.Bck = eng.download("BckGrndRho")
+    run.EG_fb = eng.download("EG_fb")
+    run.g_nxt = eng.download("gradRho_fb_nxt")
+    from chimera_b200 import _lib
+
+    lib = _lib.load()
+    run.make_step()  # warm-up (scratch growth, cuFFT plans)
+    torch.cuda.synchronize()
+    lib.chimera_host_traffic(None, None, 1)
+    t = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        run.make_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t) / a.e2e_steps
+    n = sp.coords.shape[1]
+    h2d, d2h = ctypes.c_longlong(), ctypes.c_longlong()
+    lib.chimera_host_traffic(ctypes.byref(h2d), ctypes.byref(d2h), 1)  # counted by the library per copied buffer
+    return {"value": n * world / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": a.e2e_steps,
+            "h2d_bytes_per_step": int(h2d.value // a.e2e_steps), "d2h_bytes_per_step": int(d2h.value // a.e2e_steps),
+            "path": "chimera_b200.fimera (f2py-compatible C ABI, host buffers) driven by the reference's make_step call sequence"}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_step_model(a, steps, warmup):
+    """Time the reference's algorithm (oracle port, -O3 -ffast-math -fopenmp as the reference Makefile:14)
+    on the host cores on a bounded sample of the workload and scale linearly to the full one:
+      particle kernels on `cpu_particles` of the particles (cost linear in the particle count),
+      spectral update on `cpu_nx` of the Nx kx-rows (every spectral kernel is row-independent;
+      the x-FFT's log factor is ignored, which favours the CPU)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    from oracle.fimera import load
+    from chimera_b200 import synthetic
+    from chimera_b200.solver_setup import SolverSetup
+    from pic_ref import RefRun, RefSpecies
+
+    fast = load(fast=True)
+    cores = int(fast._lib.oracle_num_threads())
+    nx_s = min(a.cpu_nx, a.nx)
+    S = SolverSetup(synthetic.lwfa_solver_config(nx=nx_s, nr=a.nr, modes=a.modes, chunks=cores if nx_s % (2 * cores) == 0 else 16))
+    x, p, w = synthetic.plasma_fixed_cell(S.Args, cell=CELL[a.ppc], xp=np)  # the whole sample grid: every chunk thread busy
+    n_s = x.shape[1]
+    run = RefRun(fast, S, [RefSpecies(x, p, w)])
+    run.EG_fb[:] = synthetic.laser_seed(S, fast, x0=S.Args["Xgrid"][nx_s // 2])
+    run.make_halfstep()
+    f = fast
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        s = run.sp[0]
+        run.istep += 1
+        s.coords, s.coords_halfstep = f.push_coords(s.coords, s.momenta, s.coords_halfstep, S.Args["dt"])
+        run.J[:] = 0.0
+        run.J = run._dep("curr", run.J, s, s.coords_halfstep)
+        run.Rho[:] = 0.0
+        run.Rho = run._dep("dens", run.Rho, s, s.coords)
+        t1 = time.perf_counter()
+        aa = S.Args
+        run.J_fb = f.omp_mult_vec(f.fb_vec_in(run.J_fb, run.J, aa["leftX"], *aa["FBCurrIn"]), aa["DepFact"])
+        run.g_prv[:] = run.g_nxt
+        run.Rho_fb = f.omp_mult_scl(f.fb_scl_in(run.Rho_fb, run.Rho, aa["leftX"], *aa["FBCurrIn"]), aa["DepFact"])
+        run.g_nxt = f.fb_grad(run.g_nxt, run.Rho_fb, *aa["FBDiff"])
+        run.update_fields()
+        rot = f.fb_rot(run.B_fb, run.EG_fb[:, :, :, 3:], *aa["FBDiff"])
+        run.B_fb = f.omp_mult_vec(rot, aa["PoissFact"])
+        run.EB = f.eb_correction(f.fb_eb_out(run.EB, run.EG_fb, run.B_fb, aa["leftX"], *aa["FBout"]))
+        t2 = time.perf_counter()
+        s.EB = np.zeros((6, n_s), order="F")
+        s.EB = f.proj_fld(s.coords, s.weights, run.EB, s.EB, aa["leftX"], *aa["DepProj"])
+        s.momenta = f.push_velocs(s.momenta, s.EB, s.push_fact * aa["dt"])
+        t3 = time.perf_counter()
+        if it >= warmup:
+            times.append(((t1 - t0) + (t3 - t2), t2 - t1))
+    tp = float(np.median([t[0] for t in times]))
+    ts = float(np.median([t[1] for t in times]))
+    n_full = n_particles(a)
+    t_full = tp * n_full / n_s + ts * a.nx / nx_s
+    return {
+        "value": n_full / t_full, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": "%d of %d particles (particle kernels, scaled linearly) and %d of %d kx rows (spectral update, scaled linearly); "
+                  "g++ -O3 -ffast-math -fopenmp build of oracle/chimera_oracle.cpp, OMP threads=%d; gfortran/FFTW3 absent so the "
+                  "Fortran itself cannot be built" % (n_s, n_full, nx_s, a.nx, cores),
+        "particle_s_per_step_full": tp * n_full / n_s, "spectral_s_per_step_full": ts * a.nx / nx_s,
+        "ms_per_step_full": t_full * 1e3,
+    }
+
+
+def cpu_baseline(a):
+    return cpu_step_model(a, steps=3, warmup=1)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    r = cpu_step_model(a, steps=a.steps, warmup=a.warmup)
+    world = int(os.environ.get("WORLD_SIZE", a.gpus))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": r["ms_per_step_full"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": r, "gpu_launches": 0,
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

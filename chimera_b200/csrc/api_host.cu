@@ -19,7 +19,8 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-long long g_launches = 0;  // bumped by the host layer per kernel-launching helper call (approximate count)
+long long g_h2d_bytes = 0, g_d2h_bytes = 0;  // host<->device traffic of the host-buffer API
+long long g_launches = 0;  // kernels launched by this library (bumped by CHB_LAUNCH_CHECK)
 
 // process-wide context of the host-buffer API
 struct HostCtx {
@@ -59,6 +60,7 @@ struct Call {
   template <typename T> T* dev(i64 n) { return c.scr.take_n<T>(n); }
   template <typename T> T* up(const T* h, i64 n) {
     T* d = dev<T>(n);
+    if (n > 0) g_h2d_bytes += (long long)(sizeof(T) * (size_t)n);
     if (d && n > 0 && cudaMemcpyAsync(d, h, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, c.st) != cudaSuccess) {
       set_error("H2D copy failed");
       return nullptr;
@@ -67,6 +69,7 @@ struct Call {
   }
   template <typename T> int down(T* h, const T* d, i64 n) {
     if (n > 0) CHB_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, c.st));
+    if (n > 0) g_d2h_bytes += (long long)(sizeof(T) * (size_t)n);
     return 0;
   }
   int sync() {
@@ -112,7 +115,6 @@ static int deposit_host(int env, int curr, const double* coord, const double* mo
   GridGeom g = make_geom(Rgrid, d_r, leftX, dx_inv, dr_inv, kx0, nxn, nrn, nm);
   CHB_TRY(launch_deposit_direct(call.c.st, env, curr, aos((const double*)d_x, 3), aos((const double*)d_p, 3), d_w, d_g,
                                 g, ch, np, true));
-  g_launches += 2;
   CHB_TRY(call.down(grid, (double*)d_g, 2 * ng));
   return call.sync();
 }
@@ -129,7 +131,6 @@ static int gather_host(int env, const double* coord, const double* wghts, const 
   double* d_r = call.up(Rgrid, nrn); NEED(d_r);
   GridGeom g = make_geom(Rgrid, d_r, leftX, dx_inv, dr_inv, kx0, nxn, nrn, nm);
   CHB_TRY(launch_gather(call.c.st, env, aos((const double*)d_x, 3), d_w, d_f, aos(d_o, 6), g, np));
-  g_launches += 1;
   CHB_TRY(call.down(Fld_tot, d_o, 6 * np));
   return call.sync();
 }
@@ -147,7 +148,6 @@ static int fb_in_host(double* out_fb, const double* in, double leftX, const doub
   CHB_TRY(pack_ops(call.c.st, P, d_pk, d_op, nr, nkr, (int)nm));
   FBCtx fb = call.fb();
   CHB_TRY(fb_in_dev(fb, d_out, d_in, leftX, d_kx, P, nullptr, nkx, nrn, nm, nkr, ncomp));
-  g_launches += nm + 3;
   CHB_TRY(call.down(out_fb, (double*)d_out, 2 * nkx * nkr * nm * ncomp));
   return call.sync();
 }
@@ -169,7 +169,6 @@ static int fb_out_host(double* out, const double* src0, const double* src1, int 
   CHB_TRY(pack_ops(call.c.st, P, d_pk, d_op, nkr, nr, (int)nm));
   FBCtx fb = call.fb();
   CHB_TRY(fb_out_dev(fb, d_out, srcs, nsrc, ncomp_each, leftX, d_kx, P, nkx, nrn, nm, nkr));
-  g_launches += nm + 4;
   CHB_TRY(call.down(out, (double*)d_out, 2 * nkx * nrn * nm * ncomp_each * nsrc));
   return call.sync();
 }
@@ -201,7 +200,6 @@ static int fb_math_host(FBMathOp op, int env, double* out, const double* in, con
     case OP_DIV: CHB_TRY(fb_div_dev(fb, d_out, d_in, PP, PM, d_kx, d)); break;
     case OP_GRADDIV: CHB_TRY(fb_graddiv_dev(fb, d_in, PP, PM, d_kx, d)); break;
   }
-  g_launches += 2 * nd + 12;
   CHB_TRY(call.down(out, (double*)d_out, 2 * nkx * nkr_loc * nm * out_comp));
   return call.sync();
 }
@@ -216,7 +214,6 @@ static int compact_host(Call& call, const int* d_flag, int* h_idx, int* h_num, i
   void* d_tmp = call.c.scr.take(tmp_bytes + 16); NEED(d_tmp);
   CHB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flag, d_pos, (int)np, call.c.st));
   CHB_TRY(launch_compact_index(call.c.st, d_flag, d_pos, d_idx, np));
-  g_launches += 3;
   int last_pos = 0, last_flag = 0;
   if (np > 0) {
     CHB_CUDA(cudaMemcpyAsync(&last_pos, d_pos + np - 1, sizeof(int), cudaMemcpyDeviceToHost, call.c.st));
@@ -260,6 +257,17 @@ __global__ void __launch_bounds__(256) genparts_scatter_k(double* __restrict__ c
   for (int c = 0; c < 4; ++c) coord[4 * j + c] = cand[4 * e + c];
 }
 
+// pseudo-random fill in [-1,1) for the microbenchmark (zeros would under-state the power draw)
+__global__ void __launch_bounds__(256) fill_pattern_k(double* __restrict__ a, i64 n, unsigned long long seed) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  unsigned long long z = seed + (unsigned long long)e * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  a[e] = (double)(long long)(z >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+}
+
 }  // namespace chb
 
 using namespace chb;
@@ -282,6 +290,12 @@ int chimera_sync(void) {
   return 0;
 }
 int chimera_kernel_launches(chb_i64* n) { *n = g_launches; return 0; }
+int chimera_host_traffic(chb_i64* h2d, chb_i64* d2h, int reset) {
+  if (h2d) *h2d = g_h2d_bytes;
+  if (d2h) *d2h = g_d2h_bytes;
+  if (reset) g_h2d_bytes = g_d2h_bytes = 0;
+  return 0;
+}
 
 // ------------------------------------------------------------------ particle_tools.f90
 int chimera_push_velocs(double* momenta, const double* Fld, double dt, chb_i64 np) {
@@ -289,7 +303,6 @@ int chimera_push_velocs(double* momenta, const double* Fld, double dt, chb_i64 n
   double* d_p = call.up(momenta, 3 * np); NEED(d_p);
   double* d_f = call.up(Fld, 6 * np); NEED(d_f);
   CHB_TRY(launch_push_velocs(call.c.st, aos(d_p, 3), aos((const double*)d_f, 6), dt, np));
-  g_launches += 1;
   CHB_TRY(call.down(momenta, d_p, 3 * np));
   return call.sync();
 }
@@ -300,7 +313,6 @@ int chimera_push_coords(double* coord, const double* momenta, double* coord_cntr
   double* d_p = call.up(momenta, 3 * np); NEED(d_p);
   double* d_c = call.dev<double>(3 * np); NEED(d_c);
   CHB_TRY(launch_push_coords(call.c.st, aos(d_x, 3), aos((const double*)d_p, 3), aos(d_c, 3), dt, np));
-  g_launches += 1;
   CHB_TRY(call.down(coord, d_x, 3 * np));
   CHB_TRY(call.down(coord_cntr, d_c, 3 * np));
   return call.sync();
@@ -333,7 +345,6 @@ int chimera_genparts(double* coord, int* indPart, const double* Xgrid, const dou
     CHB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flag, d_pos, (int)ncand, call.c.st));
     genparts_scatter_k<<<grid_for(ncand, 256), 256, 0, call.c.st>>>(d_coord, d_cand, d_flag, d_pos, ncand, np);
     CHB_LAUNCH_CHECK();
-    g_launches += 3;
     int lp = 0, lf = 0;
     CHB_CUDA(cudaMemcpyAsync(&lp, d_pos + ncand - 1, sizeof(int), cudaMemcpyDeviceToHost, call.c.st));
     CHB_CUDA(cudaMemcpyAsync(&lf, d_flag + ncand - 1, sizeof(int), cudaMemcpyDeviceToHost, call.c.st));
@@ -377,7 +388,6 @@ int chimera_chunk_coords_boundaries(int8_t* chunked_indx, int* IndInChnk, int* G
   CHB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (nchnk + 1), call.c.st));
   CHB_TRY(launch_chunk_bin(call.c.st, aos((const double*)d_x, 3), d_id, d_cnt, d_cnt + nchnk, Xgrid[0], inv, lims,
                            nchnk, np));
-  g_launches += 1;
   std::vector<int> cnt(nchnk + 1, 0);
   CHB_TRY(call.down(chunked_indx, d_id, np));
   CHB_TRY(call.down(cnt.data(), d_cnt, nchnk + 1));
@@ -395,7 +405,6 @@ static int align_host(double* dat, const chb_i64* idx, i64 np, i64 np0, int ncom
   i64* d_idx = call.up((const i64*)idx, np); NEED(d_idx);
   double* d_dst = call.dev<double>(ncomp * np); NEED(d_dst);
   CHB_TRY(launch_permute(call.c.st, aos(d_dst, ncomp), aos((const double*)d_src, ncomp), d_idx, ncomp, np));
-  g_launches += 1;
   CHB_TRY(call.down(dat, d_dst, ncomp * np));
   return call.sync();
 }
@@ -457,7 +466,6 @@ static int ebcorr_host(double* eb, i64 nxn, i64 nrn, i64 nm, int env) {
   const i64 n = nxn * nrn * nm * 6;
   cd* d = (cd*)call.up(eb, 2 * n); NEED(d);
   CHB_TRY(launch_eb_correction(call.c.st, d, nxn, nrn, nm, env));
-  g_launches += 1;
   CHB_TRY(call.down(eb, (double*)d, 2 * n));
   return call.sync();
 }
@@ -496,7 +504,6 @@ int chimera_fb_filtr(double* vec, double leftX, const double* kx, const double* 
   double* d_f = call.up(filtr, nxfilt); NEED(d_f);
   FBCtx fb = call.fb();
   CHB_TRY(fb_filtr_dev(fb, d, leftX, d_kx, d_f, modefilt, nkx, nkr, nm, nxfilt));
-  g_launches += 5;
   CHB_TRY(call.down(vec, (double*)d, 2 * n));
   return call.sync();
 }
@@ -534,7 +541,6 @@ int chimera_maxwell_push_with_spchrg(double* EG, const double* j, const double* 
   double* d_c1 = call.up(C1, P * 5); NEED(d_c1);
   double* d_c2 = call.up(C2, P * 5); NEED(d_c2);
   CHB_TRY(launch_maxwell_push(call.c.st, d_eg, d_j, d_gn, d_gp, d_c1, d_c2, 5, 0, P));
-  g_launches += 1;
   CHB_TRY(call.down(EG, (double*)d_eg, 2 * P * 6));
   return call.sync();
 }
@@ -547,7 +553,6 @@ int chimera_maxwell_push_wo_spchrg(double* EG, const double* j, const double* C1
   double* d_c1 = call.up(C1, 2 * P * 3); NEED(d_c1);
   double* d_c2 = call.up(C2, 2 * P * 3); NEED(d_c2);
   CHB_TRY(launch_maxwell_push(call.c.st, d_eg, d_j, nullptr, nullptr, d_c1, d_c2, 3, 1, P));
-  g_launches += 1;
   CHB_TRY(call.down(EG, (double*)d_eg, 2 * P * 6));
   return call.sync();
 }
@@ -561,7 +566,6 @@ int chimera_maxwell_init_push(double* EG, const double* j, const double* gn, con
   cd* d_c1 = (cd*)call.up(C1, 2 * P * 2); NEED(d_c1);
   cd* d_c2 = (cd*)call.up(C2, 2 * P * 2); NEED(d_c2);
   CHB_TRY(launch_maxwell_init_push(call.c.st, d_eg, d_j, d_gn, d_c1, d_c2, P));
-  g_launches += 1;
   CHB_TRY(call.down(EG, (double*)d_eg, 2 * P * 6));
   return call.sync();
 }
@@ -575,7 +579,6 @@ int chimera_poiss_corr(double* j, const double* gdj, const double* gn, const dou
   cd* d_gp = (cd*)call.up(gp, 2 * P * 3); NEED(d_gp);
   double* d_w = call.up(w2_inv, P); NEED(d_w);
   CHB_TRY(launch_poiss_corr(call.c.st, d_j, d_gd, d_gn, d_gp, dt_inv, d_w, P));
-  g_launches += 1;
   CHB_TRY(call.down(j, (double*)d_j, 2 * P * 3));
   return call.sync();
 }
@@ -589,7 +592,6 @@ int chimera_poiss_corr_stat(double* j, const double* gdj, const double* gn, cons
   cd* d_dt = (cd*)call.up(DT, 2 * nkx); NEED(d_dt);
   double* d_w = call.up(w2_inv, P); NEED(d_w);
   CHB_TRY(launch_poiss_corr_stat(call.c.st, d_j, d_gd, d_gn, d_dt, d_w, nkx, P));
-  g_launches += 1;
   CHB_TRY(call.down(j, (double*)d_j, 2 * P * 3));
   return call.sync();
 }
@@ -599,7 +601,6 @@ int chimera_field_drift(double* EG, const double* kx, double beta0, double dt, c
   cd* d = (cd*)call.up(EG, 2 * n); NEED(d);
   double* d_kx = call.up(kx, nkx); NEED(d_kx);
   CHB_TRY(launch_field_drift(call.c.st, d, d_kx, beta0, dt, nkx, nkr * nm * 6));
-  g_launches += 1;
   CHB_TRY(call.down(EG, (double*)d, 2 * n));
   return call.sync();
 }
@@ -608,7 +609,6 @@ static int mult_host(double* v, const double* A, i64 P, int ncomp) {
   cd* d = (cd*)call.up(v, 2 * P * ncomp); NEED(d);
   double* d_a = call.up(A, P); NEED(d_a);
   CHB_TRY(launch_mult_real(call.c.st, d, d_a, P, ncomp));
-  g_launches += 1;
   CHB_TRY(call.down(v, (double*)d, 2 * P * ncomp));
   return call.sync();
 }
@@ -617,7 +617,6 @@ static int add_host(double* v, const double* A, i64 n) {
   cd* d = (cd*)call.up(v, 2 * n); NEED(d);
   cd* d_a = (cd*)call.up(A, 2 * n); NEED(d_a);
   CHB_TRY(launch_add(call.c.st, d, d_a, n));
-  g_launches += 1;
   CHB_TRY(call.down(v, (double*)d, 2 * n));
   return call.sync();
 }
@@ -634,9 +633,14 @@ int chimera_undul_analytic(const double* coord, double* Fld, double t, const dou
   double* d_f = call.up(Fld, 6 * np); NEED(d_f);
   UndulParams u{1, params[0], params[1], params[2], params[3]};
   CHB_TRY(launch_undul(call.c.st, aos((const double*)d_x, 3), aos(d_f, 6), u, np));
-  g_launches += 1;
   CHB_TRY(call.down(Fld, d_f, 6 * np));
   return call.sync();
+}
+
+int chimera_gemm_profile(int on) { gemm_profile_enable(on); return 0; }
+int chimera_gemm_profile_read(double* ms, double* flops, chb_i64* launches, int reset) {
+  gemm_profile_read(ms, flops, launches, reset);
+  return 0;
 }
 
 // ------------------------------------------------------------------ GEMM microbenchmark
@@ -648,8 +652,10 @@ int chimera_bench_gemm(chb_i64 nkx, chb_i64 K, chb_i64 N, int batch, int iters, 
   double* C = call.dev<double>(M * N * batch); NEED(C);
   double* B = call.dev<double>(K * N); NEED(B);
   double* Bp = call.dev<double>(gemm_packed_size(K, N)); NEED(Bp);
-  CHB_CUDA(cudaMemsetAsync(A, 0, sizeof(double) * M * K * batch, call.c.st));
-  CHB_CUDA(cudaMemsetAsync(B, 0, sizeof(double) * K * N, call.c.st));
+  fill_pattern_k<<<grid_for(M * K * batch, 256), 256, 0, call.c.st>>>(A, M * K * batch, 0x9E3779B97F4A7C15ull);
+  CHB_LAUNCH_CHECK();
+  fill_pattern_k<<<grid_for(K * N, 256), 256, 0, call.c.st>>>(B, K * N, 0xD1B54A32D192ED03ull);
+  CHB_LAUNCH_CHECK();
   CHB_TRY(launch_gemm_pack_b(call.c.st, Bp, B, K, N, K));
   GemmBatch gb;
   gb.count = batch;
@@ -665,7 +671,6 @@ int chimera_bench_gemm(chb_i64 nkx, chb_i64 K, chb_i64 N, int batch, int iters, 
   float t = 0;
   CHB_CUDA(cudaEventElapsedTime(&t, e0, e1));
   *ms = (double)t / iters;
-  g_launches += iters + 3;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return 0;

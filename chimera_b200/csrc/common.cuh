@@ -30,7 +30,13 @@ const char* get_error();
     if (_rc != 0) return _rc;    \
   } while (0)
 
-#define CHB_LAUNCH_CHECK() CHB_CUDA(cudaGetLastError())
+// every kernel launch of this library is followed by CHB_LAUNCH_CHECK(): it doubles as the launch counter
+extern long long g_launches;
+#define CHB_LAUNCH_CHECK()        \
+  do {                            \
+    ++chb::g_launches;            \
+    CHB_CUDA(cudaGetLastError()); \
+  } while (0)
 
 // ---- complex helpers on double2 (x = re, y = im)
 typedef double2 cd;

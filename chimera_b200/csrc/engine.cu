@@ -1,0 +1,705 @@
+// engine.cu -- device-resident PIC engine: particles (structure of arrays), grids, spectral state
+// and operator tables live in HBM; one call runs the reference's step sequence on the device.
+//
+// Stage order and semantics follow the reference's Python driver, which stays the specification:
+//   make_step      moduls/chimera_main.py:82-92      make_halfstep   :61-80
+//   dep_curr/dep_dens/dep_bg  :153-248                project_fields  :130-151
+//   fb_curr_in/fb_dens_in/FBGradDens/poiss_corr/maxwell_solver/G2B_FBRot/fb_fld_out
+//                  moduls/solvers.py:407,422,517,301,281,536,450
+//   chunk_and_damp moduls/species.py:351-398 (re-binning; here a device radix sort by
+//                  (x-chunk, r-cell, x-cell) which refines the reference's chunk order)
+#include <cub/device/device_radix_sort.cuh>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/chimera_b200.h"
+#include "fbops.cuh"
+
+namespace chb {
+
+struct NamedArray {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Species {
+  double *x = nullptr, *xh = nullptr, *p = nullptr, *w = nullptr;       // SoA, component stride = cap
+  double *x2 = nullptr, *xh2 = nullptr, *p2 = nullptr, *w2 = nullptr;   // permutation targets
+  i64 np = 0, cap = 0;
+  double push_fact = 0.0;
+  int still = 0;
+  int* d_ind = nullptr;          // IndInChunk(0:nchnk); the last entry is the number of particles kept
+  std::vector<int> h_ind;
+};
+
+}  // namespace chb
+
+using namespace chb;
+
+struct chimera_engine {
+  chimera_engine_config cfg;
+  cudaStream_t st = nullptr;
+  bool own_stream = false;
+  Scratch scr;
+  FFTCache fft;
+  std::map<std::string, NamedArray> arr;
+  std::vector<Species> sp;
+  PackedOps pInCurr, pOut, pDp, pDm;
+  double* packed = nullptr;
+  bool ops_dirty = true;
+  // sort scratch
+  unsigned *key_a = nullptr, *key_b = nullptr;
+  int *idx_a = nullptr, *idx_b = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  i64 sort_cap = 0;
+  // profiling
+  int profile = 0;
+  double ms[CHB_NPHASES];
+  long long calls[CHB_NPHASES];
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+  std::vector<cudaEvent_t> ev_pool;
+
+  cd* A(const char* n) { return (cd*)arr[n].p; }
+  double* D(const char* n) { return (double*)arr[n].p; }
+};
+
+namespace chb {
+
+// ------------------------------------------------------------------------------------------
+// layout conversion between the reference's (ncomp, np) Fortran arrays and the engine's SoA
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) aos_to_soa_k(double* __restrict__ dst, const double* __restrict__ src, int ncomp,
+                                                    i64 cap, i64 np) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= np * ncomp) return;
+  const i64 ip = e / ncomp;
+  const int c = (int)(e - ip * ncomp);
+  dst[c * cap + ip] = src[e];
+}
+__global__ void __launch_bounds__(256) soa_to_aos_k(double* __restrict__ dst, const double* __restrict__ src, int ncomp,
+                                                    i64 cap, i64 np) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= np * ncomp) return;
+  const i64 ip = e / ncomp;
+  const int c = (int)(e - ip * ncomp);
+  dst[e] = src[c * cap + ip];
+}
+
+// ------------------------------------------------------------------------------------------
+// re-binning keys: (x-chunk as particle_tools.f90:183, r-cell, x-cell); kdrop = leaves the domain
+// ------------------------------------------------------------------------------------------
+struct BinSpec {
+  double x0, chunk_inv;       // Xgrid(0), 1 / chunk length
+  double l0, l1, l2, l3;      // SimDom
+  double leftX, dx_inv, r0, dr_inv;
+  int nchnk;
+  i64 nx, nrc;                // x cells used for the minor key, r cells
+  unsigned kdrop;             // key of a particle that leaves the domain (sorts last)
+};
+
+__global__ void __launch_bounds__(256) bin_keys_k(const double* __restrict__ x, i64 cap, unsigned* __restrict__ key,
+                                                  int* __restrict__ idx, BinSpec b, i64 np) {
+  const i64 ip = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  const double xp = x[ip], yp = x[cap + ip], zp = x[2 * cap + ip];
+  const double r2 = yp * yp + zp * zp;
+  unsigned k = b.kdrop;
+  if (xp >= b.l0 && xp <= b.l1 && r2 >= b.l2 && r2 <= b.l3) {
+    i64 c = (i64)floor((xp - b.x0) * b.chunk_inv);
+    c = c < 0 ? 0 : (c > b.nchnk - 1 ? b.nchnk - 1 : c);
+    i64 ix = (i64)floor((xp - b.leftX) * b.dx_inv);
+    ix = ix < 0 ? 0 : (ix > b.nx - 1 ? b.nx - 1 : ix);
+    i64 ir = (i64)floor((sqrt(r2) - b.r0) * b.dr_inv);
+    ir = ir < 0 ? 0 : (ir > b.nrc - 1 ? b.nrc - 1 : ir);
+    k = (unsigned)((c * b.nrc + ir) * b.nx + ix);
+  }
+  key[ip] = k;
+  idx[ip] = (int)ip;
+}
+
+// IndInChunk(c) = first sorted position whose key belongs to chunk >= c; IndInChunk(nchnk) = particles
+// kept (dropped particles carry the key nchnk*per_chunk and sort last)
+__global__ void chunk_bounds_k(const unsigned* __restrict__ key, int* __restrict__ ind, int nchnk, i64 per_chunk,
+                               i64 np) {
+  const int c = threadIdx.x;
+  if (c > nchnk) return;
+  const unsigned long long target = (unsigned long long)c * (unsigned long long)per_chunk;
+  i64 lo = 0, hi = np;
+  while (lo < hi) {
+    const i64 mid = (lo + hi) >> 1;
+    if ((unsigned long long)key[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  ind[c] = (int)lo;
+}
+
+__global__ void __launch_bounds__(256) permute_soa_k(double* __restrict__ dx, double* __restrict__ dxh,
+                                                     double* __restrict__ dp, double* __restrict__ dw,
+                                                     const double* __restrict__ sx, const double* __restrict__ sxh,
+                                                     const double* __restrict__ sp, const double* __restrict__ sw,
+                                                     const int* __restrict__ idx, i64 cap, i64 np) {
+  const i64 ip = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  const i64 j = idx[ip];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    dx[c * cap + ip] = sx[c * cap + j];
+    dxh[c * cap + ip] = sxh[c * cap + j];
+    dp[c * cap + ip] = sp[c * cap + j];
+  }
+  dw[ip] = sw[j];
+}
+
+__global__ void __launch_bounds__(256) add_cd_k(cd* __restrict__ a, const cd* __restrict__ b, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) a[e] = cadd(a[e], b[e]);
+}
+
+}  // namespace chb
+
+// ==========================================================================================
+namespace {
+
+#define ENG_CHECK(e) \
+  if (!(e)) { set_error("null engine handle"); return 2; }
+
+int alloc_named(chimera_engine* e, const char* name, size_t bytes, bool zero = true) {
+  NamedArray a;
+  a.bytes = bytes;
+  CHB_CUDA(cudaMalloc(&a.p, bytes ? bytes : 16));
+  if (zero) CHB_CUDA(cudaMemsetAsync(a.p, 0, bytes ? bytes : 16, e->st));
+  e->arr[name] = a;
+  return 0;
+}
+
+GridGeom geom(chimera_engine* e) {
+  const auto& c = e->cfg;
+  GridGeom g;
+  g.leftX = c.leftX; g.dx_inv = 1.0 / c.dx; g.dr_inv = 1.0 / c.dr; g.kx0 = c.kx0;
+  g.r0 = -0.5 * c.dr;  // overwritten from the uploaded Rgrid in ensure_ops
+  g.rmax = 0.0;
+  g.Rgrid = e->D("Rgrid");
+  g.nxn = c.nx; g.nrn = c.nrn; g.nm = c.nm;
+  return g;
+}
+
+struct EngineHost {  // host copies of the few table entries the launch code needs
+  double r0 = 0, rmax = 0;
+};
+std::map<chimera_engine*, EngineHost> g_host;
+
+int ensure_ops(chimera_engine* e) {
+  if (!e->ops_dirty) return 0;
+  const auto& c = e->cfg;
+  const i64 nr = c.nrn - 1;
+  const int nd = (int)(c.env ? c.nm + 2 : c.nm + 1);
+  const size_t b_in = packed_ops_bytes(nr, c.nkr, (int)c.nm), b_out = packed_ops_bytes(c.nkr, nr, (int)c.nm);
+  const size_t b_d = packed_ops_bytes(c.nkr, c.nkr, nd);
+  if (!e->packed) CHB_CUDA(cudaMalloc((void**)&e->packed, b_in + b_out + 2 * b_d));
+  double* q = e->packed;
+  CHB_TRY(pack_ops(e->st, e->pInCurr, q, e->D("InCurr"), nr, c.nkr, (int)c.nm)); q += b_in / sizeof(double);
+  CHB_TRY(pack_ops(e->st, e->pOut, q, e->D("Out"), c.nkr, nr, (int)c.nm)); q += b_out / sizeof(double);
+  CHB_TRY(pack_ops(e->st, e->pDp, q, e->D("DpS2S"), c.nkr, c.nkr, nd)); q += b_d / sizeof(double);
+  CHB_TRY(pack_ops(e->st, e->pDm, q, e->D("DmS2S"), c.nkr, c.nkr, nd));
+  double ends[2];
+  CHB_CUDA(cudaMemcpyAsync(&ends[0], e->D("Rgrid"), sizeof(double), cudaMemcpyDeviceToHost, e->st));
+  CHB_CUDA(cudaMemcpyAsync(&ends[1], e->D("Rgrid") + (c.nrn - 1), sizeof(double), cudaMemcpyDeviceToHost, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  g_host[e].r0 = ends[0];
+  g_host[e].rmax = ends[1];
+  e->ops_dirty = false;
+  return 0;
+}
+
+GridGeom geom_ready(chimera_engine* e) {
+  GridGeom g = geom(e);
+  g.r0 = g_host[e].r0;
+  g.rmax = g_host[e].rmax;
+  return g;
+}
+
+FBCtx fbctx(chimera_engine* e) { return FBCtx{e->st, &e->scr, &e->fft}; }
+FBMathDims mdims(chimera_engine* e) { return FBMathDims{e->cfg.nx, e->cfg.nkr, e->cfg.nm, e->cfg.nkr, e->cfg.env}; }
+
+ChunkSpec chunkspec(chimera_engine* e, const Species& s) {
+  if (!e->cfg.chunked) return ChunkSpec{0, nullptr, 1, 0, e->cfg.nx};
+  return ChunkSpec{1, s.d_ind, e->cfg.nchnk, e->cfg.guards, e->cfg.nx / e->cfg.nchnk};
+}
+
+// ---- phases ----------------------------------------------------------------------------------
+int ph_push_coords(chimera_engine* e) {
+  for (auto& s : e->sp) {
+    if (s.still || s.np == 0) continue;
+    CHB_TRY(launch_push_coords(e->st, soa(s.x, s.cap), soa((const double*)s.p, s.cap), soa(s.xh, s.cap), e->cfg.dt, s.np));
+  }
+  return 0;
+}
+
+int ensure_sort_scratch(chimera_engine* e, i64 n) {
+  if (n <= e->sort_cap) return 0;
+  if (e->key_a) { cudaFree(e->key_a); cudaFree(e->key_b); cudaFree(e->idx_a); cudaFree(e->idx_b); cudaFree(e->cub_tmp); }
+  CHB_CUDA(cudaMalloc((void**)&e->key_a, sizeof(unsigned) * n));
+  CHB_CUDA(cudaMalloc((void**)&e->key_b, sizeof(unsigned) * n));
+  CHB_CUDA(cudaMalloc((void**)&e->idx_a, sizeof(int) * n));
+  CHB_CUDA(cudaMalloc((void**)&e->idx_b, sizeof(int) * n));
+  size_t tb = 0;
+  CHB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, e->key_a, e->key_b, e->idx_a, e->idx_b, (int)n, 0, 32, e->st));
+  CHB_CUDA(cudaMalloc(&e->cub_tmp, tb + 16));
+  e->cub_tmp_bytes = tb;
+  e->sort_cap = n;
+  return 0;
+}
+
+int ph_sort(chimera_engine* e, int on_halfstep) {
+  const auto& c = e->cfg;
+  const int nchnk = c.chunked ? c.nchnk : 1;
+  for (auto& s : e->sp) {
+    if (s.np == 0) continue;
+    if (s.np > 0x7FFFFFF0LL) { set_error("re-binning supports up to 2^31 particles per GPU"); return 2; }
+    CHB_TRY(ensure_sort_scratch(e, s.np));
+    BinSpec b;
+    const i64 cs = c.nx / nchnk;  // nodes per chunk
+    b.x0 = c.leftX;
+    (void)cs;
+    b.chunk_inv = 1.0 / c.chunk_len;
+    b.l0 = c.leftX; b.l1 = c.rightX; b.l2 = 0.0; b.l3 = c.rcull2;
+    b.leftX = c.leftX; b.dx_inv = 1.0 / c.dx; b.r0 = g_host[e].r0; b.dr_inv = 1.0 / c.dr;
+    b.nchnk = nchnk; b.nx = c.nx; b.nrc = c.nrn - 1;
+    const unsigned long long kmax = (unsigned long long)nchnk * b.nrc * b.nx;
+    if (kmax >= 0xFFFFFFFFull) { set_error("re-binning key does not fit 32 bits"); return 2; }
+    b.kdrop = (unsigned)kmax;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < kmax + 1) ++bits;
+    const double* src = on_halfstep ? s.xh : s.x;
+    bin_keys_k<<<grid_for(s.np, 256), 256, 0, e->st>>>(src, s.cap, e->key_a, e->idx_a, b, s.np);
+    CHB_LAUNCH_CHECK();
+    size_t tb = e->cub_tmp_bytes;
+    CHB_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp, tb, e->key_a, e->key_b, e->idx_a, e->idx_b, (int)s.np, 0, bits, e->st));
+    chunk_bounds_k<<<1, 256, 0, e->st>>>(e->key_b, s.d_ind, nchnk, (i64)b.nrc * b.nx, s.np);
+    CHB_LAUNCH_CHECK();
+    permute_soa_k<<<grid_for(s.np, 256), 256, 0, e->st>>>(s.x2, s.xh2, s.p2, s.w2, s.x, s.xh, s.p, s.w, e->idx_b, s.cap, s.np);
+    CHB_LAUNCH_CHECK();
+    std::swap(s.x, s.x2); std::swap(s.xh, s.xh2); std::swap(s.p, s.p2); std::swap(s.w, s.w2);
+    s.h_ind.assign(nchnk + 1, 0);
+    CHB_CUDA(cudaMemcpyAsync(s.h_ind.data(), s.d_ind, sizeof(int) * (nchnk + 1), cudaMemcpyDeviceToHost, e->st));
+    CHB_CUDA(cudaStreamSynchronize(e->st));
+    s.np = s.h_ind[nchnk];
+  }
+  return 0;
+}
+
+int deposit_species(chimera_engine* e, int curr, cd* grid, bool still_only, bool use_half) {
+  GridGeom g = geom_ready(e);
+  for (auto& s : e->sp) {
+    if (s.np == 0) continue;
+    if (still_only != (s.still != 0)) continue;
+    const double* xs = use_half ? s.xh : s.x;
+    CHB_TRY(launch_deposit_direct(e->st, e->cfg.env, curr, soa(xs, s.cap), soa((const double*)s.p, s.cap), s.w, grid, g,
+                                  chunkspec(e, s), s.np, false));
+  }
+  return 0;
+}
+
+int ph_deposit_j(chimera_engine* e) {
+  const auto& c = e->cfg;
+  const i64 n = c.nx * c.nrn * c.nm * 3;
+  CHB_CUDA(cudaMemsetAsync(e->A("J"), 0, sizeof(cd) * n, e->st));
+  CHB_TRY(deposit_species(e, 1, e->A("J"), false, true));
+  return launch_ghost_fold(e->st, e->A("J"), c.nx, c.nrn, c.nm * 3);
+}
+
+int ph_deposit_rho(chimera_engine* e, int from_bg) {
+  const auto& c = e->cfg;
+  const i64 n = c.nx * c.nrn * c.nm;
+  if (from_bg) CHB_CUDA(cudaMemcpyAsync(e->A("Rho"), e->A("BckGrndRho"), sizeof(cd) * n, cudaMemcpyDeviceToDevice, e->st));
+  else CHB_CUDA(cudaMemsetAsync(e->A("Rho"), 0, sizeof(cd) * n, e->st));
+  CHB_TRY(deposit_species(e, 0, e->A("Rho"), false, false));
+  return launch_ghost_fold(e->st, e->A("Rho"), c.nx, c.nrn, c.nm);
+}
+
+int ph_deposit_bg(chimera_engine* e) {
+  const auto& c = e->cfg;
+  const i64 n = c.nx * c.nrn * c.nm;
+  CHB_CUDA(cudaMemsetAsync(e->A("BckGrndRho"), 0, sizeof(cd) * n, e->st));
+  CHB_TRY(deposit_species(e, 0, e->A("BckGrndRho"), true, false));
+  return launch_ghost_fold(e->st, e->A("BckGrndRho"), c.nx, c.nrn, c.nm);
+}
+
+int ph_add_bg(chimera_engine* e) {
+  const auto& c = e->cfg;
+  const i64 n = c.nx * c.nrn * c.nm;
+  add_cd_k<<<grid_for(n, 256), 256, 0, e->st>>>(e->A("Rho"), e->A("BckGrndRho"), n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+int ph_fb_in_j(chimera_engine* e) {
+  const auto& c = e->cfg;
+  FBCtx fb = fbctx(e);
+  return fb_in_dev(fb, e->A("J_fb"), e->A("J"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"), c.nx, c.nrn, c.nm,
+                   c.nkr, 3);
+}
+
+int ph_fb_in_rho(chimera_engine* e) {
+  const auto& c = e->cfg;
+  FBCtx fb = fbctx(e);
+  std::swap(e->arr["gradRho_fb_prv"], e->arr["gradRho_fb_nxt"]);  // gradRho_fb_prv[:] = gradRho_fb_nxt
+  CHB_TRY(fb_in_dev(fb, e->A("Rho_fb"), e->A("Rho"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"), c.nx, c.nrn,
+                    c.nm, c.nkr, 1));
+  return fb_grad_dev(fb, e->A("gradRho_fb_nxt"), e->A("Rho_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e));
+}
+
+int ph_poisson(chimera_engine* e) {
+  const auto& c = e->cfg;
+  const i64 P = c.nx * c.nkr * c.nm;
+  FBCtx fb = fbctx(e);
+  for (int it = 0; it < c.poisson_iters; ++it) {
+    CHB_CUDA(cudaMemcpyAsync(e->A("vec_fb"), e->A("J_fb"), sizeof(cd) * P * 3, cudaMemcpyDeviceToDevice, e->st));
+    CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
+    if (c.space_charge) {
+      CHB_TRY(launch_poiss_corr(e->st, e->A("J_fb"), e->A("vec_fb"), e->A("gradRho_fb_prv"), e->A("gradRho_fb_nxt"),
+                                1.0 / c.dt, e->D("PoissFact"), P));
+    } else {
+      CHB_TRY(launch_mult_real(e->st, e->A("vec_fb"), e->D("PoissFact"), P, 3));
+      CHB_TRY(launch_add(e->st, e->A("J_fb"), e->A("vec_fb"), P * 3));
+    }
+  }
+  return 0;
+}
+
+int ph_maxwell(chimera_engine* e) {
+  const auto& c = e->cfg;
+  const i64 P = c.nx * c.nkr * c.nm;
+  if (c.space_charge)
+    return launch_maxwell_push(e->st, e->A("EG_fb"), e->A("J_fb"), e->A("gradRho_fb_prv"), e->A("gradRho_fb_nxt"),
+                               e->arr["PSATD_E"].p, e->arr["PSATD_G"].p, 5, 0, P);
+  return launch_maxwell_push(e->st, e->A("EG_fb"), e->A("J_fb"), nullptr, nullptr, e->arr["PSATD_E"].p, e->arr["PSATD_G"].p,
+                             3, c.coef_complex, P);
+}
+
+int ph_init_push(chimera_engine* e) {
+  const auto& c = e->cfg;
+  const i64 P = c.nx * c.nkr * c.nm;
+  return launch_maxwell_init_push(e->st, e->A("EG_fb"), e->A("J_fb"), e->A("gradRho_fb_nxt"), e->A("CPSATD1"),
+                                  e->A("CPSATD2"), P);
+}
+
+int ph_fields_out(chimera_engine* e) {
+  const auto& c = e->cfg;
+  const i64 P = c.nx * c.nkr * c.nm;
+  FBCtx fb = fbctx(e);
+  CHB_TRY(fb_rot_dev(fb, e->A("B_fb"), e->A("EG_fb") + P * 3, e->pDp, e->pDm, e->D("kx"), mdims(e)));
+  CHB_TRY(launch_mult_real(e->st, e->A("B_fb"), e->D("PoissFact"), P, 3));
+  const cd* srcs[2] = {e->A("EG_fb"), e->A("B_fb")};
+  CHB_TRY(fb_out_dev(fb, e->A("EB"), srcs, 2, 3, c.leftX, e->D("kx_base"), e->pOut, c.nx, c.nrn, c.nm, c.nkr));
+  return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
+}
+
+int ph_gather_push(chimera_engine* e, double dt_frac) {
+  const auto& c = e->cfg;
+  GridGeom g = geom_ready(e);
+  UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
+  for (auto& s : e->sp) {
+    if (s.still || s.np == 0) continue;
+    CHB_TRY(launch_gather_push(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
+                               s.push_fact * c.dt * dt_frac, und, s.np));
+  }
+  return 0;
+}
+
+cudaEvent_t get_event(chimera_engine* e) {
+  if (!e->ev_pool.empty()) { cudaEvent_t v = e->ev_pool.back(); e->ev_pool.pop_back(); return v; }
+  cudaEvent_t v;
+  cudaEventCreate(&v);
+  return v;
+}
+
+int collect_timings(chimera_engine* e) {
+  if (e->pending.empty()) return 0;
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  for (auto& pe : e->pending) {
+    float t = 0;
+    cudaEventElapsedTime(&t, pe.second.first, pe.second.second);
+    e->ms[pe.first] += t;
+    e->calls[pe.first] += 1;
+    e->ev_pool.push_back(pe.second.first);
+    e->ev_pool.push_back(pe.second.second);
+  }
+  e->pending.clear();
+  return 0;
+}
+
+int run_phase(chimera_engine* e, int phase, double arg) {
+  CHB_TRY(ensure_ops(e));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (e->profile) {
+    e0 = get_event(e); e1 = get_event(e);
+    cudaEventRecord(e0, e->st);
+  }
+  int rc = 0;
+  switch (phase) {
+    case CHB_PUSH_COORDS: rc = ph_push_coords(e); break;
+    case CHB_SORT: rc = ph_sort(e, arg != 0.0); break;
+    case CHB_DEPOSIT_J: rc = ph_deposit_j(e); break;
+    case CHB_DEPOSIT_RHO: rc = ph_deposit_rho(e, arg != 0.0); break;
+    case CHB_DEPOSIT_BG: rc = ph_deposit_bg(e); break;
+    case CHB_FB_IN_J: rc = ph_fb_in_j(e); break;
+    case CHB_FB_IN_RHO: rc = ph_fb_in_rho(e); break;
+    case CHB_POISSON: rc = ph_poisson(e); break;
+    case CHB_MAXWELL: rc = ph_maxwell(e); break;
+    case CHB_INIT_PUSH: rc = ph_init_push(e); break;
+    case CHB_FIELDS_OUT: rc = ph_fields_out(e); break;
+    case CHB_GATHER_PUSH: rc = ph_gather_push(e, arg); break;
+    case CHB_ADD_BG: rc = ph_add_bg(e); break;
+    default: set_error("unknown engine phase %d", phase); rc = 2;
+  }
+  if (e->profile) {
+    cudaEventRecord(e1, e->st);
+    e->pending.push_back({phase, {e0, e1}});
+    if (e->pending.size() > 4096) collect_timings(e);
+  }
+  // temporaries of this phase are dead once the stream reaches this point; later phases on the same
+  // stream may reuse them
+  e->scr.reset();
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out) {
+  if (!cfg || !out) { set_error("engine_create: null argument"); return 2; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: libchimera_b200 has no CPU fallback");
+    return 1;
+  }
+  const auto& c = *cfg;
+  if (c.nx < 2 || c.nrn < 2 || c.nkr < 1 || c.nm < 1 || c.nm > 2 * kMaxModes) { set_error("engine_create: bad grid shape"); return 2; }
+  if (c.env && (c.nm % 2) != 1) { set_error("engine_create: envelope solver needs an odd number of mode slots"); return 2; }
+  if (c.chunked && (c.nchnk < 1 || c.nchnk > 127 || c.nx % c.nchnk)) { set_error("engine_create: bad chunking"); return 2; }
+  chimera_engine* e = new chimera_engine();
+  e->cfg = c;
+  for (int i = 0; i < CHB_NPHASES; ++i) { e->ms[i] = 0; e->calls[i] = 0; }
+  CHB_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  e->own_stream = true;
+  const size_t Pg = (size_t)c.nx * c.nrn * c.nm, Pf = (size_t)c.nx * c.nkr * c.nm, C = sizeof(cd);
+  const i64 nr = c.nrn - 1;
+  const int nd = (int)(c.env ? c.nm + 2 : c.nm + 1);
+  const int ncoef = c.space_charge ? 5 : 3;
+  struct { const char* n; size_t b; } spec[] = {
+      {"J", Pg * 3 * C}, {"Rho", Pg * C}, {"BckGrndRho", Pg * C}, {"EB", Pg * 6 * C},
+      {"EG_fb", Pf * 6 * C}, {"J_fb", Pf * 3 * C}, {"B_fb", Pf * 3 * C}, {"Rho_fb", Pf * C},
+      {"gradRho_fb_prv", Pf * 3 * C}, {"gradRho_fb_nxt", Pf * 3 * C}, {"vec_fb", Pf * 3 * C},
+      {"InCurr", sizeof(double) * nr * c.nkr * c.nm}, {"Out", sizeof(double) * nr * c.nkr * c.nm},
+      {"DpS2S", sizeof(double) * c.nkr * c.nkr * nd}, {"DmS2S", sizeof(double) * c.nkr * c.nkr * nd},
+      {"kx", sizeof(double) * c.nx}, {"kx_base", sizeof(double) * c.nx},
+      {"DepFact", sizeof(double) * Pf}, {"PoissFact", sizeof(double) * Pf},
+      {"PSATD_E", (c.coef_complex ? C : sizeof(double)) * Pf * ncoef},
+      {"PSATD_G", (c.coef_complex ? C : sizeof(double)) * Pf * ncoef},
+      {"CPSATD1", Pf * 2 * C}, {"CPSATD2", Pf * 2 * C}, {"Rgrid", sizeof(double) * c.nrn}};
+  for (auto& s : spec) {
+    int rc = alloc_named(e, s.n, s.b);
+    if (rc) { chimera_engine_destroy(e); return rc; }
+  }
+  *out = e;
+  return 0;
+}
+
+int chimera_engine_destroy(chimera_engine* e) {
+  if (!e) return 0;
+  cudaStreamSynchronize(e->st);
+  for (auto& kv : e->arr) cudaFree(kv.second.p);
+  for (auto& s : e->sp) {
+    cudaFree(s.x); cudaFree(s.xh); cudaFree(s.p); cudaFree(s.w);
+    cudaFree(s.x2); cudaFree(s.xh2); cudaFree(s.p2); cudaFree(s.w2); cudaFree(s.d_ind);
+  }
+  cudaFree(e->packed);
+  cudaFree(e->key_a); cudaFree(e->key_b); cudaFree(e->idx_a); cudaFree(e->idx_b); cudaFree(e->cub_tmp);
+  e->scr.destroy();
+  e->fft.destroy();
+  for (auto& pe : e->pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
+  for (auto v : e->ev_pool) cudaEventDestroy(v);
+  if (e->own_stream) cudaStreamDestroy(e->st);
+  g_host.erase(e);
+  delete e;
+  return 0;
+}
+
+static int find_array(chimera_engine* e, const char* name, NamedArray** a) {
+  auto it = e->arr.find(name ? name : "");
+  if (it == e->arr.end()) { set_error("engine has no array named '%s'", name ? name : "(null)"); return 2; }
+  *a = &it->second;
+  return 0;
+}
+
+int chimera_engine_upload(chimera_engine* e, const char* name, const void* src, chb_i64 nbytes) {
+  ENG_CHECK(e);
+  NamedArray* a;
+  CHB_TRY(find_array(e, name, &a));
+  if ((size_t)nbytes != a->bytes) { set_error("upload '%s': %lld bytes given, %zu expected", name, nbytes, a->bytes); return 2; }
+  CHB_CUDA(cudaMemcpyAsync(a->p, src, a->bytes, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  const std::string n(name);
+  if (n == "InCurr" || n == "Out" || n == "DpS2S" || n == "DmS2S" || n == "Rgrid") e->ops_dirty = true;
+  return 0;
+}
+
+int chimera_engine_download(chimera_engine* e, const char* name, void* dst, chb_i64 nbytes) {
+  ENG_CHECK(e);
+  NamedArray* a;
+  CHB_TRY(find_array(e, name, &a));
+  if ((size_t)nbytes != a->bytes) { set_error("download '%s': %lld bytes given, %zu expected", name, nbytes, a->bytes); return 2; }
+  CHB_CUDA(cudaMemcpyAsync(dst, a->p, a->bytes, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int chimera_engine_array(chimera_engine* e, const char* name, void** dev_ptr, chb_i64* nbytes) {
+  ENG_CHECK(e);
+  NamedArray* a;
+  CHB_TRY(find_array(e, name, &a));
+  *dev_ptr = a->p;
+  *nbytes = (chb_i64)a->bytes;
+  return 0;
+}
+
+int chimera_engine_add_species(chimera_engine* e, const double* coords, const double* coords_half, const double* momenta,
+                               const double* weights, chb_i64 np, double push_fact, int still, chb_i64 capacity,
+                               int* id) {
+  ENG_CHECK(e);
+  if (np < 0) { set_error("add_species: np < 0"); return 2; }
+  Species s;
+  s.np = np;
+  s.cap = capacity > np ? capacity : np;
+  if (s.cap < 1) s.cap = 1;
+  s.cap = (s.cap + 31) & ~31LL;  // keep every component row 256-byte aligned
+  s.push_fact = push_fact;
+  s.still = still;
+  const size_t b3 = sizeof(double) * 3 * s.cap, b1 = sizeof(double) * s.cap;
+  CHB_CUDA(cudaMalloc((void**)&s.x, b3)); CHB_CUDA(cudaMalloc((void**)&s.xh, b3)); CHB_CUDA(cudaMalloc((void**)&s.p, b3));
+  CHB_CUDA(cudaMalloc((void**)&s.w, b1));
+  CHB_CUDA(cudaMalloc((void**)&s.x2, b3)); CHB_CUDA(cudaMalloc((void**)&s.xh2, b3)); CHB_CUDA(cudaMalloc((void**)&s.p2, b3));
+  CHB_CUDA(cudaMalloc((void**)&s.w2, b1));
+  const int nchnk = e->cfg.chunked ? e->cfg.nchnk : 1;
+  CHB_CUDA(cudaMalloc((void**)&s.d_ind, sizeof(int) * (nchnk + 1)));
+  s.h_ind.assign(nchnk + 1, 0);
+  // placeholder until the first re-binning (CHB_SORT must run before a chunked deposit, as the
+  // reference's make_halfstep does, chimera_main.py:62-70)
+  for (int c2 = 1; c2 <= nchnk; ++c2) s.h_ind[c2] = (int)np;
+  CHB_CUDA(cudaMemcpyAsync(s.d_ind, s.h_ind.data(), sizeof(int) * (nchnk + 1), cudaMemcpyHostToDevice, e->st));
+  if (np > 0) {
+    // stage the (3,np) arrays through the permutation buffers, then transpose to SoA
+    const double* srcs[3] = {coords, coords_half ? coords_half : coords, momenta};
+    double* stage[3] = {s.x2, s.xh2, s.p2};
+    double* dsts[3] = {s.x, s.xh, s.p};
+    for (int k = 0; k < 3; ++k) {
+      CHB_CUDA(cudaMemcpyAsync(stage[k], srcs[k], sizeof(double) * 3 * np, cudaMemcpyDefault, e->st));
+      aos_to_soa_k<<<grid_for(3 * np, 256), 256, 0, e->st>>>(dsts[k], stage[k], 3, s.cap, np);
+      CHB_LAUNCH_CHECK();
+    }
+    CHB_CUDA(cudaMemcpyAsync(s.w, weights, sizeof(double) * np, cudaMemcpyDefault, e->st));
+  }
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  e->sp.push_back(s);
+  if (id) *id = (int)e->sp.size() - 1;
+  return 0;
+}
+
+int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np) {
+  ENG_CHECK(e);
+  if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  *np = e->sp[id].np;
+  return 0;
+}
+
+int chimera_engine_get_species(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
+                               double* weights) {
+  ENG_CHECK(e);
+  if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  Species& s = e->sp[id];
+  if (s.np == 0) return 0;
+  double* dsts[3] = {coords, coords_half, momenta};
+  const double* srcs[3] = {s.x, s.xh, s.p};
+  for (int k = 0; k < 3; ++k) {
+    if (!dsts[k]) continue;
+    soa_to_aos_k<<<grid_for(3 * s.np, 256), 256, 0, e->st>>>(s.x2, srcs[k], 3, s.cap, s.np);
+    CHB_LAUNCH_CHECK();
+    CHB_CUDA(cudaMemcpyAsync(dsts[k], s.x2, sizeof(double) * 3 * s.np, cudaMemcpyDefault, e->st));
+    CHB_CUDA(cudaStreamSynchronize(e->st));
+  }
+  if (weights) CHB_CUDA(cudaMemcpyAsync(weights, s.w, sizeof(double) * s.np, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int chimera_engine_get_chunks(chimera_engine* e, int id, int* ind) {
+  ENG_CHECK(e);
+  if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  const int nchnk = e->cfg.chunked ? e->cfg.nchnk : 1;
+  for (int c = 0; c <= nchnk; ++c) ind[c] = e->sp[id].h_ind[c];
+  return 0;
+}
+
+int chimera_engine_run(chimera_engine* e, int phase, double arg) {
+  ENG_CHECK(e);
+  return run_phase(e, phase, arg);
+}
+
+int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
+  ENG_CHECK(e);
+  const auto& c = e->cfg;
+  for (i64 k = 0; k < nsteps; ++k) {
+    const i64 istep = istep0 + k;
+    CHB_TRY(run_phase(e, CHB_PUSH_COORDS, 0));
+    if (c.sort_every > 0 && istep % c.sort_every == 0) CHB_TRY(run_phase(e, CHB_SORT, 1));
+    CHB_TRY(run_phase(e, CHB_DEPOSIT_J, 0));
+    CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
+    if (c.space_charge) {
+      CHB_TRY(run_phase(e, CHB_DEPOSIT_RHO, 1));
+      CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
+    }
+    CHB_TRY(run_phase(e, CHB_POISSON, 0));
+    CHB_TRY(run_phase(e, CHB_MAXWELL, 0));
+    CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
+    CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
+  }
+  return 0;
+}
+
+int chimera_engine_sync(chimera_engine* e) {
+  ENG_CHECK(e);
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int chimera_engine_set_stream(chimera_engine* e, void* cuda_stream) {
+  ENG_CHECK(e);
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  if (e->own_stream) cudaStreamDestroy(e->st);
+  e->st = (cudaStream_t)cuda_stream;
+  e->own_stream = false;
+  return 0;
+}
+
+int chimera_engine_profile(chimera_engine* e, int on) {
+  ENG_CHECK(e);
+  CHB_TRY(collect_timings(e));
+  e->profile = on;
+  return 0;
+}
+
+int chimera_engine_timings(chimera_engine* e, double* ms, chb_i64* calls, int reset) {
+  ENG_CHECK(e);
+  CHB_TRY(collect_timings(e));
+  for (int i = 0; i < CHB_NPHASES; ++i) {
+    if (ms) ms[i] = e->ms[i];
+    if (calls) calls[i] = e->calls[i];
+    if (reset) { e->ms[i] = 0; e->calls[i] = 0; }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -15,6 +15,8 @@
 //     16 x 64 tile is ONE contiguous 8 KB bulk copy and every B-fragment read is a conflict-free
 //     LDS.64 at [tile][k4][n8][lane].
 //   * 3-stage ring; a stage is refilled right after the CTA-wide barrier that retires it.
+#include <utility>
+#include <vector>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -181,6 +183,47 @@ int launch_gemm_pack_b(cudaStream_t st, double* Bp, const double* B, i64 K, i64 
   return 0;
 }
 
+// optional per-launch timing of the contraction kernel (CUDA events on the launching stream), read by
+// bench.py for the FP64-tensor roofline of the DHT / mode-coupling GEMMs
+namespace {
+struct GemmProf {
+  int on = 0;
+  double flops = 0.0, ms = 0.0;
+  long long launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void drain() {
+    for (auto& pe : pending) {
+      cudaEventSynchronize(pe.second);
+      float t = 0;
+      cudaEventElapsedTime(&t, pe.first, pe.second);
+      ms += t;
+      pool.push_back(pe.first);
+      pool.push_back(pe.second);
+    }
+    pending.clear();
+  }
+} g_prof;
+}  // namespace
+
+void gemm_profile_enable(int on) {
+  g_prof.drain();
+  g_prof.on = on;
+}
+void gemm_profile_read(double* ms, double* flops, long long* launches, int reset) {
+  g_prof.drain();
+  if (ms) *ms = g_prof.ms;
+  if (flops) *flops = g_prof.flops;
+  if (launches) *launches = g_prof.launches;
+  if (reset) { g_prof.ms = 0; g_prof.flops = 0; g_prof.launches = 0; }
+}
+
 int launch_gemm(cudaStream_t st, const GemmBatch& batch, i64 M, i64 N, i64 K, i64 lda, i64 ldc) {
   if (batch.count <= 0 || M <= 0 || N <= 0) return 0;
   if (batch.count > kGemmMaxBatch) { set_error("gemm batch too large"); return 4; }
@@ -192,7 +235,19 @@ int launch_gemm(cudaStream_t st, const GemmBatch& batch, i64 M, i64 N, i64 K, i6
   }
   const int KT = (int)((K + BK - 1) / BK);
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)batch.count);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    e0 = g_prof.get(); e1 = g_prof.get();
+    cudaEventRecord(e0, st);
+  }
   gemm_dmma_k<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(batch, M, N, K, lda, ldc, KT);
+  if (g_prof.on) {
+    cudaEventRecord(e1, st);
+    g_prof.pending.push_back({e0, e1});
+    g_prof.flops += 2.0 * (double)M * (double)N * (double)K * batch.count;
+    g_prof.launches += 1;
+    if (g_prof.pending.size() > 2048) g_prof.drain();
+  }
   CHB_LAUNCH_CHECK();
   return 0;
 }

@@ -73,6 +73,8 @@ struct GemmBatch {
 i64 gemm_packed_size(i64 K, i64 N);  // doubles
 int launch_gemm_pack_b(cudaStream_t st, double* Bp, const double* B, i64 K, i64 N, i64 ldb);
 int launch_gemm(cudaStream_t st, const GemmBatch& batch, i64 M, i64 N, i64 K, i64 lda, i64 ldc);
+void gemm_profile_enable(int on);
+void gemm_profile_read(double* ms, double* flops, long long* launches, int reset);
 
 // ---- spectral.cu : elementwise kernels of the Fourier-Bessel PSATD update
 int launch_rowscale_phase(cudaStream_t st, cd* a, const double* kx, double leftX, double sign, double scale,

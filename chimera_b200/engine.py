@@ -1,0 +1,295 @@
+"""Device-resident PIC engine: host-side mirror of the reference's ``ChimeraRun`` step loop.
+
+The reference sequences one time step in Python (``ChimeraRun.make_step``, reference
+moduls/chimera_main.py:82-92; ``make_halfstep`` :61-80) and crosses into Fortran ~21 times per
+step with host arrays.  Here the same sequence runs inside libchimera_b200.so on arrays that stay in
+HBM (csrc/engine.cu); this module only builds the configuration from a :class:`SolverSetup`, uploads
+the operator tables once and exposes the state.
+
+Multi-GPU (one process per GPU, ``torch.distributed``): particles are sharded across ranks, every
+rank deposits into its own J / Rho grids, the grids are summed with an NCCL all-reduce over NVLink and
+every rank then advances the (replicated) spectral fields and gathers to its own particles.  There is
+no CPU fallback: without the CUDA library the import of :mod:`chimera_b200._lib` fails.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_i64 = ctypes.c_longlong
+
+PHASES = (
+    "push_coords", "sort", "deposit_J", "deposit_rho", "deposit_bg", "fb_in_J", "fb_in_rho", "poisson",
+    "maxwell", "init_push", "fields_out", "gather_push", "add_bg",
+)
+PHASE_ID = {n: i for i, n in enumerate(PHASES)}
+
+
+class EngineConfig(ctypes.Structure):
+    """Mirror of ``chimera_engine_config`` (include/chimera_b200.h)."""
+
+    _fields_ = [
+        ("env", ctypes.c_int), ("space_charge", ctypes.c_int), ("poisson_iters", ctypes.c_int),
+        ("coef_complex", ctypes.c_int), ("chunked", ctypes.c_int), ("nchnk", ctypes.c_int),
+        ("guards", ctypes.c_int), ("sort_every", ctypes.c_int), ("undulator", ctypes.c_int),
+        ("nx", _i64), ("nrn", _i64), ("nkr", _i64), ("nm", _i64),
+        ("leftX", ctypes.c_double), ("rightX", ctypes.c_double), ("dx", ctypes.c_double),
+        ("dr", ctypes.c_double), ("dt", ctypes.c_double), ("kx0", ctypes.c_double),
+        ("rcull2", ctypes.c_double), ("chunk_len", ctypes.c_double),
+        ("und_a0", ctypes.c_double), ("und_lambda", ctypes.c_double), ("und_X0", ctypes.c_double),
+        ("und_Lx", ctypes.c_double),
+    ]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _DevView:
+    """Zero-copy handle on an engine array for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, nbytes, dtype):
+        n = nbytes // np.dtype(dtype).itemsize
+        self.__cuda_array_interface__ = {
+            "shape": (n,), "typestr": np.dtype(dtype).str, "data": (ptr, False), "version": 2, "strides": None,
+        }
+
+
+class Engine:
+    """One solver + its particle species on one GPU.
+
+    Parameters
+    ----------
+    setup : SolverSetup
+        grids, operators and PSATD tables (chimera_b200.solver_setup, mirrors solvers.py:27-279)
+    chunked : bool, optional
+        use the ``*_chnk`` deposition semantics (default: the solver dict has ``Xchunked``)
+    sort_every : int, optional
+        re-binning cadence in steps (reference: ``Xchunked[1]+1``, chimera_main.py:310); 0 = never
+    poisson_iters : int, optional
+        reference default 3 (solvers.py:301); forced to 0 by the ``NoPoissonCorrection`` feature
+    undulator : dict, optional
+        ``{'a0','lambda','X0','Lx'}`` of ``undul_analytic`` (devices.f90:162)
+    group : torch.distributed process group or True, optional
+        shard particles over the ranks of the group and all-reduce the deposited grids
+    """
+
+    def __init__(self, setup, chunked=None, sort_every=None, poisson_iters=None, undulator=None, group=None):
+        self.lib = _lib.load()
+        self.setup = setup
+        a = setup.Args
+        feats = a.get("Features", ())
+        cfg = EngineConfig()
+        cfg.env = int(setup.env)
+        cfg.space_charge = int("SpaceCharge" in feats)
+        if poisson_iters is None:
+            poisson_iters = 0 if "NoPoissonCorrection" in feats else 3
+        cfg.poisson_iters = int(poisson_iters)
+        cfg.coef_complex = int(np.iscomplexobj(setup.PSATD_E))
+        if chunked is None:
+            chunked = "Xchunked" in a
+        cfg.chunked = int(bool(chunked))
+        cfg.nchnk, cfg.guards = (int(a["Xchunked"][0]), int(a["Xchunked"][1])) if chunked else (1, 0)
+        if sort_every is None:
+            sort_every = cfg.guards + 1 if chunked else 0
+        cfg.sort_every = int(sort_every)
+        cfg.nx, cfg.nrn, cfg.nkr, cfg.nm = a["Nx"], a["Nr"], a["Nkr"], a["Mtot"]
+        cfg.leftX, cfg.rightX, cfg.dx, cfg.dr, cfg.dt, cfg.kx0 = a["leftX"], a["rightX"], a["dx"], a["dr"], a["dt"], a["kx0"]
+        cfg.rcull2 = float(a["Rgrid"].max() ** 2)
+        xg = a["Xgrid"]
+        cfg.chunk_len = float(xg[a["Nx"] // cfg.nchnk] - xg[0]) if cfg.nchnk > 1 else float(xg[-1] - xg[0])
+        if undulator:
+            cfg.undulator = 1
+            cfg.und_a0, cfg.und_lambda, cfg.und_X0, cfg.und_Lx = (float(undulator[k]) for k in ("a0", "lambda", "X0", "Lx"))
+        self.cfg = cfg
+        self._h = ctypes.c_void_p()
+        self._check(self.lib.chimera_engine_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        kx_base = a["FBCurrIn"][0]
+        for name, arr in (
+            ("InCurr", a["InCurr"]), ("Out", a["Out"]), ("DpS2S", a["DpS2S"]), ("DmS2S", a["DmS2S"]),
+            ("kx", a["kx"]), ("kx_base", kx_base), ("DepFact", a["DepFact"]), ("PoissFact", a["PoissFact"]),
+            ("PSATD_E", setup.PSATD_E), ("PSATD_G", setup.PSATD_G), ("Rgrid", a["Rgrid"]),
+        ):
+            self.upload(name, arr)
+        self.nspecies = 0
+        self.istep = 0
+        self.group = group
+        self.rank, self.world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+
+            self._dist = dist
+            self._group = None if group is True else group
+            self.rank, self.world = dist.get_rank(self._group), dist.get_world_size(self._group)
+            import torch
+
+            # run on torch's current stream so that the NCCL collectives are ordered with the kernels
+            self.use_stream(torch.cuda.current_stream().cuda_stream)
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError("libchimera_b200: status %d: %s" % (rc, self.lib.chimera_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.chimera_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, name, arr):
+        arr = np.asfortranarray(arr)
+        self._check(self.lib.chimera_engine_upload(self._h, name.encode(), ctypes.c_void_p(arr.ctypes.data), _i64(arr.nbytes)))
+
+    def shape_of(self, name):
+        c = self.cfg
+        g, f = (c.nx, c.nrn, c.nm), (c.nx, c.nkr, c.nm)
+        table = {"J": g + (3,), "Rho": g, "BckGrndRho": g, "EB": g + (6,), "EG_fb": f + (6,), "J_fb": f + (3,),
+                 "B_fb": f + (3,), "Rho_fb": f, "gradRho_fb_prv": f + (3,), "gradRho_fb_nxt": f + (3,), "vec_fb": f + (3,)}
+        return table[name]
+
+    def download(self, name):
+        out = np.zeros(self.shape_of(name), dtype=complex, order="F")
+        self._check(self.lib.chimera_engine_download(self._h, name.encode(), ctypes.c_void_p(out.ctypes.data), _i64(out.nbytes)))
+        return out
+
+    def device_tensor(self, name, dtype=np.float64):
+        """torch view (no copy) of a named engine array, e.g. for ``torch.distributed.all_reduce``."""
+        import torch
+
+        ptr, nb = ctypes.c_void_p(), _i64()
+        self._check(self.lib.chimera_engine_array(self._h, name.encode(), ctypes.byref(ptr), ctypes.byref(nb)))
+        return torch.as_tensor(_DevView(ptr.value, nb.value, dtype), device="cuda")
+
+    # -- particles ---------------------------------------------------------------------------
+    def add_species(self, coords, momenta, weights, charge=-1.0, mass=1.0, still=False, coords_half=None, capacity=0):
+        """Add a species; arrays as in ``Specie.Data`` (species.py:122-126).  Returns its id."""
+        coords = np.asfortranarray(coords, dtype=float)
+        momenta = np.asfortranarray(momenta, dtype=float)
+        weights = np.asfortranarray(weights, dtype=float)
+        ch = None if coords_half is None else np.asfortranarray(coords_half, dtype=float)
+        n = coords.shape[1]
+        assert coords.shape == (3, n) and momenta.shape == (3, n) and weights.shape == (n,)
+        sid = ctypes.c_int(-1)
+        self._check(self.lib.chimera_engine_add_species(
+            self._h, ctypes.c_void_p(coords.ctypes.data), ctypes.c_void_p(ch.ctypes.data if ch is not None else None),
+            ctypes.c_void_p(momenta.ctypes.data), ctypes.c_void_p(weights.ctypes.data), _i64(n),
+            ctypes.c_double(2 * np.pi * charge / mass), int(bool(still)), _i64(capacity), ctypes.byref(sid)))
+        self.nspecies += 1
+        return sid.value
+
+    def add_species_device(self, coords_ptr, momenta_ptr, weights_ptr, n, charge=-1.0, mass=1.0, still=False):
+        """Same, from device pointers to (3,n) Fortran-ordered arrays (synthetic benchmarks)."""
+        sid = ctypes.c_int(-1)
+        self._check(self.lib.chimera_engine_add_species(
+            self._h, ctypes.c_void_p(coords_ptr), ctypes.c_void_p(None), ctypes.c_void_p(momenta_ptr),
+            ctypes.c_void_p(weights_ptr), _i64(n), ctypes.c_double(2 * np.pi * charge / mass), int(bool(still)),
+            _i64(0), ctypes.byref(sid)))
+        self.nspecies += 1
+        return sid.value
+
+    def count(self, sid=0):
+        n = _i64()
+        self._check(self.lib.chimera_engine_species_count(self._h, sid, ctypes.byref(n)))
+        return n.value
+
+    def particles(self, sid=0):
+        """(coords, coords_halfstep, momenta, weights) of a species, copied to the host."""
+        n = self.count(sid)
+        x, xh, p = (np.zeros((3, n), order="F") for _ in range(3))
+        w = np.zeros(n)
+        self._check(self.lib.chimera_engine_get_species(
+            self._h, sid, ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(xh.ctypes.data),
+            ctypes.c_void_p(p.ctypes.data), ctypes.c_void_p(w.ctypes.data)))
+        return x, xh, p, w
+
+    def chunks(self, sid=0):
+        ind = np.zeros(self.cfg.nchnk + 1, dtype=np.int32)
+        self._check(self.lib.chimera_engine_get_chunks(self._h, sid, ctypes.c_void_p(ind.ctypes.data)))
+        return ind
+
+    # -- stepping ----------------------------------------------------------------------------
+    def run(self, phase, arg=0.0):
+        self._check(self.lib.chimera_engine_run(self._h, PHASE_ID[phase], ctypes.c_double(arg)))
+
+    def sync(self):
+        self._check(self.lib.chimera_engine_sync(self._h))
+
+    def use_stream(self, cuda_stream_ptr):
+        self._check(self.lib.chimera_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def _allreduce_grids(self):
+        names = ("J", "Rho") if self.cfg.space_charge else ("J",)
+        for n in names:
+            self._dist.all_reduce(self.device_tensor(n), group=self._group)
+
+    def _deposit_and_reduce(self):
+        self.run("deposit_J")
+        if self.cfg.space_charge:
+            # the background charge enters the sum once (rank 0), chimera_main.py:189-190
+            self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
+        if self.world > 1:
+            self._allreduce_grids()
+
+    def deposit_background(self):
+        """``ChimeraRun.dep_bg`` (chimera_main.py:220-248): still species -> BckGrndRho."""
+        self.run("deposit_bg")
+        if self.world > 1:
+            self._dist.all_reduce(self.device_tensor("BckGrndRho"), group=self._group)
+
+    def make_halfstep(self, px0=(0.0,), background=False):
+        """``ChimeraRun.make_halfstep`` (chimera_main.py:61-80): bin, deposit, static field of the initial
+        momenta ``px0`` (one entry per species, ``MomentaMeans[0]``), gather, half Boris push."""
+        self.run("sort", 0.0)
+        if background:
+            self.deposit_background()
+        self._deposit_and_reduce()
+        self.run("fb_in_J")
+        if self.cfg.space_charge:
+            self.run("fb_in_rho")
+            for p in px0:  # solvers.py:333-358, one static kick per species
+                c1, c2 = self.setup.static_coeffs(p)
+                self.upload("CPSATD1", c1)
+                self.upload("CPSATD2", c2)
+                self.run("init_push")
+        self.run("fields_out")
+        self.run("gather_push", 0.5)
+
+    def step(self, nsteps=1):
+        """``nsteps`` x ``ChimeraRun.make_step`` (chimera_main.py:82-92)."""
+        if self.world == 1:
+            self._check(self.lib.chimera_engine_step(self._h, _i64(self.istep + 1), _i64(nsteps)))
+            self.istep += nsteps
+            return
+        c = self.cfg
+        for _ in range(nsteps):
+            self.istep += 1
+            self.run("push_coords")
+            if c.sort_every > 0 and self.istep % c.sort_every == 0:
+                self.run("sort", 1.0)
+            self._deposit_and_reduce()
+            self.run("fb_in_J")
+            if c.space_charge:
+                self.run("fb_in_rho")
+            self.run("poisson")
+            self.run("maxwell")
+            self.run("fields_out")
+            self.run("gather_push", 1.0)
+
+    # -- profiling ---------------------------------------------------------------------------
+    def profile(self, on=True):
+        self._check(self.lib.chimera_engine_profile(self._h, int(on)))
+
+    def timings(self, reset=True):
+        ms = (ctypes.c_double * len(PHASES))()
+        calls = (_i64 * len(PHASES))()
+        self._check(self.lib.chimera_engine_timings(self._h, ms, calls, int(reset)))
+        return {n: (ms[i], calls[i]) for i, n in enumerate(PHASES) if calls[i]}

@@ -29,6 +29,8 @@ int chimera_device_count(int* n);
 int chimera_set_device(int device);          /* default: current CUDA device */
 int chimera_sync(void);
 int chimera_kernel_launches(chb_i64* n);     /* kernels launched by this library so far */
+/* bytes copied host->device / device->host by the host-buffer entry points below since the last reset */
+int chimera_host_traffic(chb_i64* h2d, chb_i64* d2h, int reset);
 
 /* ---- f90/particle_tools.f90 ---------------------------------------------------------------- */
 /* push_velocs :18   momenta(3,np) inout, Fld(6,np) */
@@ -150,6 +152,78 @@ int chimera_undul_analytic(const double* coord, double* Fld, double t, const dou
 /* C[2nkx x N] = A[2nkx x K] . B[K x N], `batch` independent problems, `iters` timed launches;
  * returns the mean milliseconds per launch (CUDA events) in *ms. */
 int chimera_bench_gemm(chb_i64 nkx, chb_i64 K, chb_i64 N, int batch, int iters, double* ms);
+/* per-launch CUDA-event timing of the contraction kernel wherever it is launched (engine or host API):
+ * accumulated milliseconds, flop (2*M*N*K per problem) and launches since the last reset */
+int chimera_gemm_profile(int on);
+int chimera_gemm_profile_read(double* ms, double* flops, chb_i64* launches, int reset);
+
+/* ---- device-resident PIC engine ------------------------------------------------------------ */
+/* The per-function entry points above take HOST buffers and copy per call (the f2py drop-in).
+ * The engine keeps particles (structure of arrays), grids, spectral state and operator tables in
+ * HBM and runs the reference's step sequence (moduls/chimera_main.py:82-92 make_step, :61-80
+ * make_halfstep) on the device.  Stage order and per-stage semantics are those of the reference
+ * wrappers cited per phase below. */
+typedef struct chimera_engine_config {
+  int env;           /* 1: envelope solver (solver dict has KxShift, solvers.py:75)                  */
+  int space_charge;  /* 'SpaceCharge' feature: rho deposition + 5-coefficient PSATD (solvers.py:244) */
+  int poisson_iters; /* Poisson-correction iterations (solvers.py:301: 3); 0 = 'NoPoissonCorrection'  */
+  int coef_complex;  /* PSATD_E/G tables are complex128 (KxShift) instead of float64                  */
+  int chunked;       /* deposit with the *_chnk edge semantics (species dict has Xchunked)            */
+  int nchnk, guards; /* Xchunked = (nchnk, guards)                                                    */
+  int sort_every;    /* re-bin particles every this many steps (chimera_main.py:310: guards+1); 0: never */
+  int undulator;     /* add the analytic undulator device between gather and push (species.py:258)   */
+  chb_i64 nx, nrn, nkr, nm; /* x nodes, r nodes incl. ghost, radial modes, azimuthal-mode slots       */
+  double leftX, rightX, dx, dr, dt, kx0;
+  double rcull2;     /* particles with y^2+z^2 > rcull2 are removed at re-binning (SimDom[3])         */
+  double chunk_len;  /* Xgrid[Nx/nchnk]-Xgrid[0] (nchnk>1) or Xgrid[Nx-1]-Xgrid[0] (particle_tools.f90:171) */
+  double und_a0, und_lambda, und_X0, und_Lx; /* devices.f90:162 parameters                           */
+} chimera_engine_config;
+
+typedef struct chimera_engine chimera_engine;
+
+int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out);
+int chimera_engine_destroy(chimera_engine* e);
+/* named arrays: grids "J" "Rho" "BckGrndRho" "EB"; spectral "EG_fb" "J_fb" "B_fb" "Rho_fb"
+ * "gradRho_fb_prv" "gradRho_fb_nxt" "vec_fb"; tables "InCurr" "Out" "DpS2S" "DmS2S" "kx" "kx_base"
+ * "DepFact" "PoissFact" "PSATD_E" "PSATD_G" "CPSATD1" "CPSATD2" "Rgrid".  Shapes as in solvers.py:160-212;
+ * `src`/`dst` may be host or device pointers; nbytes must equal the array size. */
+int chimera_engine_upload(chimera_engine* e, const char* name, const void* src, chb_i64 nbytes);
+int chimera_engine_download(chimera_engine* e, const char* name, void* dst, chb_i64 nbytes);
+int chimera_engine_array(chimera_engine* e, const char* name, void** dev_ptr, chb_i64* nbytes);
+/* particles: (3,np) Fortran-ordered coords / coords_halfstep / momenta and weights(np), host or device;
+ * push_fact = 2 pi Charge / Mass (species.py:64); still != 0: never pushed nor deposited as current */
+int chimera_engine_add_species(chimera_engine* e, const double* coords, const double* coords_half,
+                               const double* momenta, const double* weights, chb_i64 np, double push_fact,
+                               int still, chb_i64 capacity, int* id);
+int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np);
+int chimera_engine_get_species(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
+                               double* weights);
+/* IndInChunk(0:nchnk) of the last re-binning (particle_tools.f90:155) */
+int chimera_engine_get_chunks(chimera_engine* e, int id, int* ind);
+enum chimera_engine_phase {
+  CHB_PUSH_COORDS = 0, /* species.py:300 push_coords                                              */
+  CHB_SORT = 1,        /* species.py:351 chunk_and_damp; arg: 0 bin on coords, 1 on coords_halfstep */
+  CHB_DEPOSIT_J = 2,   /* chimera_main.py:153 dep_curr (J zeroed first, ghost row folded)         */
+  CHB_DEPOSIT_RHO = 3, /* chimera_main.py:183 dep_dens; arg: 1 = start from BckGrndRho, 0 = from 0 */
+  CHB_DEPOSIT_BG = 4,  /* chimera_main.py:220 dep_bg: still species -> BckGrndRho                 */
+  CHB_FB_IN_J = 5,     /* solvers.py:407 fb_curr_in                                               */
+  CHB_FB_IN_RHO = 6,   /* chimera_main.py:110 + solvers.py:422 fb_dens_in + :517 FBGradDens       */
+  CHB_POISSON = 7,     /* solvers.py:301 poiss_corr                                               */
+  CHB_MAXWELL = 8,     /* solvers.py:281 maxwell_solver                                           */
+  CHB_INIT_PUSH = 9,   /* solvers.py:333 maxwell_solver_stat with the uploaded CPSATD1/2           */
+  CHB_FIELDS_OUT = 10, /* solvers.py:536 G2B_FBRot + :450 fb_fld_out                              */
+  CHB_GATHER_PUSH = 11,/* chimera_main.py:139 proj_fld + devices + species.py:279 push_velocs; arg: dt_frac */
+  CHB_ADD_BG = 12,     /* Rho += BckGrndRho (for ranks that deposited from zero before an all-reduce) */
+  CHB_NPHASES = 13
+};
+int chimera_engine_run(chimera_engine* e, int phase, double arg);
+/* nsteps x make_step on the engine's stream; istep0 = index of the first step (re-binning cadence) */
+int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps);
+int chimera_engine_sync(chimera_engine* e);
+int chimera_engine_set_stream(chimera_engine* e, void* cuda_stream);
+/* per-phase device time (CUDA events on the engine stream), accumulated since the last reset */
+int chimera_engine_profile(chimera_engine* e, int on);
+int chimera_engine_timings(chimera_engine* e, double* ms /* CHB_NPHASES */, chb_i64* calls /* CHB_NPHASES */, int reset);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,185 @@
+"""Reference step sequence on top of any `fimera`-compatible module (TEST INFRASTRUCTURE).
+
+A compact restatement of the reference's Python driver for the configurations the engine covers:
+``ChimeraRun.make_halfstep`` / ``make_step`` (reference moduls/chimera_main.py:61-92), the solver
+wrappers (moduls/solvers.py:281-331, 407-465, 517-553) and the species wrappers
+(moduls/species.py:246-398).  It is run on the CPU oracle (``oracle.fimera``) to produce the expected
+state for the device-resident engine, and on ``chimera_b200.fimera`` to exercise the host-buffer
+drop-in path end to end.  tools/gen_golden.py checks this restatement against the reference's own,
+unmodified driver (in the build container, where /root/reference exists).
+"""
+import numpy as np
+
+
+class RefSpecies:
+    def __init__(self, coords, momenta, weights, charge=-1.0, mass=1.0, still=False, device=None):
+        self.coords = np.asfortranarray(coords, dtype=float).copy(order="F")
+        self.coords_halfstep = self.coords.copy(order="F")
+        self.momenta = np.asfortranarray(momenta, dtype=float).copy(order="F")
+        self.weights = np.asfortranarray(weights, dtype=float).copy()
+        self.push_fact = 2 * np.pi * charge / mass  # species.py:64
+        self.still = still
+        self.device = device  # (callable, params) as in species.py:258-277
+        self.EB = np.zeros((6, 0), order="F")
+        self.chunks = None
+
+
+class RefRun:
+    def __init__(self, fim, setup, species, chunked=None, sort_every=None, poisson_iters=None, background=False):
+        self.f, self.S, self.sp = fim, setup, species
+        a = self.a = setup.Args
+        feats = a.get("Features", ())
+        self.env = setup.env
+        self.space_charge = "SpaceCharge" in feats
+        self.chunked = ("Xchunked" in a) if chunked is None else chunked
+        self.nchnk, self.guards = (a["Xchunked"] if self.chunked else (1, 0))
+        self.sort_every = (self.guards + 1 if self.chunked else 0) if sort_every is None else sort_every
+        self.npoiss = (0 if "NoPoissonCorrection" in feats else 3) if poisson_iters is None else poisson_iters
+        self.background = background
+        S = setup
+        self.J, self.Rho, self.Bck = S.zeros_sp(3), S.zeros_sp(), S.zeros_sp()
+        self.EB = S.zeros_sp(6)
+        self.EG_fb, self.J_fb, self.B_fb = S.zeros_fb(6), S.zeros_fb(3), S.zeros_fb(3)
+        self.Rho_fb, self.vec_fb = S.zeros_fb(), S.zeros_fb(3)
+        self.g_prv, self.g_nxt = S.zeros_fb(3), S.zeros_fb(3)
+        self.PE, self.PG = S.PSATD_E, S.PSATD_G
+        self.istep = 0
+
+    # ---- species.py:351-398 -------------------------------------------------------------------
+    def chunk_and_damp(self, s, position):
+        a, f = self.a, self.f
+        if s.coords.shape[1] == 0:
+            return
+        dom = np.asfortranarray([a["leftX"], a["rightX"], 0.0, a["Rgrid"].max() ** 2])
+        src = s.coords_halfstep if position == "cntr" else s.coords
+        if self.chunked:
+            ids, s.chunks, go_out = f.chunk_coords_boundaries(src, dom, a["Xgrid"], self.nchnk)
+            keep = ids.argsort(kind="stable")[go_out:]
+        else:
+            keep, n = f.sortpartsout(s.coords, dom)
+            keep = keep[:n]
+        n = keep.shape[0]
+        for k in ("coords", "coords_halfstep", "momenta"):
+            v = f.align_data_vec(getattr(s, k), keep)
+            setattr(s, k, np.asfortranarray(v[:, :n]).copy(order="F"))
+        s.weights = f.align_data_scl(s.weights, keep)[:n].copy()
+
+    # ---- chimera_main.py:153-248 ---------------------------------------------------------------
+    def _dep(self, kind, grid, s, coords):
+        a, f = self.a, self.f
+        name = "dep_" + kind + ("_env" if self.env else "") + ("_chnk" if self.chunked else "")
+        args = [coords] + ([s.momenta] if kind == "curr" else []) + [s.weights, grid]
+        if self.chunked:
+            args += [s.chunks, self.guards]
+        return getattr(f, name)(*args, a["leftX"], *a["DepProj"])
+
+    def project_current(self):
+        self.J[:] = 0.0
+        for s in self.sp:
+            if s.still or s.coords.shape[1] == 0:
+                continue
+            self.J = self._dep("curr", self.J, s, s.coords_halfstep)
+        a, f = self.a, self.f
+        self.J_fb = f.fb_vec_in(self.J_fb, self.J, a["leftX"], *a["FBCurrIn"])
+        self.J_fb = f.omp_mult_vec(self.J_fb, a["DepFact"])
+
+    def dep_bg(self):
+        self.Bck[:] = 0.0
+        for s in self.sp:
+            if s.still and s.coords.shape[1]:
+                self.Bck = self._dep("dens", self.Bck, s, s.coords)
+
+    def project_density(self):
+        if not self.space_charge:
+            return
+        a, f = self.a, self.f
+        self.g_prv[:] = self.g_nxt
+        self.Rho[:] = 0.0
+        self.Rho += self.Bck
+        for s in self.sp:
+            if s.still or s.coords.shape[1] == 0:
+                continue
+            self.Rho = self._dep("dens", self.Rho, s, s.coords)
+        self.Rho_fb = f.fb_scl_in(self.Rho_fb, self.Rho, a["leftX"], *a["FBCurrIn"])
+        self.Rho_fb = f.omp_mult_scl(self.Rho_fb, a["DepFact"])
+        grad = f.fb_grad_env if self.env else f.fb_grad
+        self.g_nxt = grad(self.g_nxt, self.Rho_fb, *a["FBDiff"])
+
+    # ---- solvers.py:281-331 --------------------------------------------------------------------
+    def update_fields(self):
+        a, f = self.a, self.f
+        graddiv = f.fb_graddiv_env if self.env else f.fb_graddiv
+        for _ in range(self.npoiss):
+            self.vec_fb[:] = self.J_fb
+            self.vec_fb = graddiv(self.vec_fb, *a["FBDiff"])
+            if self.space_charge:
+                self.J_fb = f.poiss_corr(self.J_fb, self.vec_fb, self.g_prv, self.g_nxt, a["dt_inv"], a["PoissFact"])
+            else:
+                self.vec_fb = f.omp_mult_vec(self.vec_fb, a["PoissFact"])
+                self.J_fb = f.omp_add_vec(self.J_fb, self.vec_fb)
+        if self.space_charge:
+            self.EG_fb = f.maxwell_push_with_spchrg(self.EG_fb, self.J_fb, self.g_prv, self.g_nxt, self.PE, self.PG)
+        else:
+            self.EG_fb = f.maxwell_push_wo_spchrg(self.EG_fb, self.J_fb, self.PE, self.PG)
+
+    def maxwell_solver_stat(self, px0):  # solvers.py:333-358
+        if not self.space_charge:
+            return
+        c1, c2 = self.S.static_coeffs(px0)
+        self.EG_fb = self.f.maxwell_init_push(self.EG_fb, self.J_fb, self.g_nxt, c1, c2)
+
+    # ---- chimera_main.py:130-151, solvers.py:450-465, 536-553 ------------------------------------
+    def project_fields(self):
+        a, f = self.a, self.f
+        rot = f.fb_rot_env if self.env else f.fb_rot
+        self.B_fb = rot(self.B_fb, self.EG_fb[:, :, :, 3:], *a["FBDiff"])
+        self.B_fb = f.omp_mult_vec(self.B_fb, a["PoissFact"])
+        self.EB = f.fb_eb_out(self.EB, self.EG_fb, self.B_fb, a["leftX"], *a["FBout"])
+        self.EB = (f.eb_correction_env if self.env else f.eb_correction)(self.EB)
+        proj = f.proj_fld_env if self.env else f.proj_fld
+        for s in self.sp:
+            if s.still:
+                continue
+            s.EB = np.zeros((6, s.coords.shape[1]), order="F")
+            if s.coords.shape[1] == 0:
+                continue
+            s.EB = proj(s.coords, s.weights, self.EB, s.EB, a["leftX"], *a["DepProj"])
+
+    def devices_and_push(self, dt_frac):
+        a, f = self.a, self.f
+        for s in self.sp:
+            if s.still or s.coords.shape[1] == 0:
+                continue
+            if s.device is not None:
+                fn, params = s.device
+                s.EB = fn(s.coords, s.EB, self.istep * a["dt"], np.asfortranarray(params, dtype=float))
+            s.momenta = f.push_velocs(s.momenta, s.EB, s.push_fact * a["dt"] * dt_frac)
+
+    # ---- chimera_main.py:61-92 -----------------------------------------------------------------
+    def make_halfstep(self, px0=(0.0,)):
+        for s in self.sp:
+            self.chunk_and_damp(s, "stag")
+        if self.background:
+            self.dep_bg()
+        self.project_current()
+        self.project_density()
+        for p in px0:
+            self.maxwell_solver_stat(p)
+        self.project_fields()
+        self.devices_and_push(0.5)
+
+    def make_step(self):
+        f, a = self.f, self.a
+        self.istep += 1
+        for s in self.sp:
+            if s.still or s.coords.shape[1] == 0:
+                continue
+            s.coords, s.coords_halfstep = f.push_coords(s.coords, s.momenta, s.coords_halfstep, a["dt"])
+        if self.sort_every > 0 and self.istep % self.sort_every == 0:
+            for s in self.sp:
+                self.chunk_and_damp(s, "cntr")
+        self.project_current()
+        self.project_density()
+        self.update_fields()
+        self.project_fields()
+        self.devices_and_push(1.0)

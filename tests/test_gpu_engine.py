@@ -1,0 +1,153 @@
+"""GPU parity of the device-resident engine (csrc/engine.cu) against the reference step sequence
+(tests/pic_ref.py, a restatement of ChimeraRun.make_halfstep/make_step) run on the CPU oracle.
+
+Tolerances (BASELINE.json north_star): fields and particle momenta after one step within 1e-12
+relative L2; integrated diagnostics after 100 steps within 1e-6 (atomic ordering is the only source
+of divergence)."""
+import copy
+
+import numpy as np
+import pytest
+
+from pic_ref import RefRun, RefSpecies
+from util import SETUPS, TOL, assert_close, rel_l2
+from chimera_b200.solver_setup import SolverSetup
+
+pytestmark = pytest.mark.gpu
+
+
+def plasma(S, ppc_x, ppc_r, seed, frac=(0.15, 0.85), thermal=0.05, dens=0.005):
+    """Uniform plasma slab with unique (label) weights; coordinates inside the grid."""
+    rng = np.random.default_rng(seed)
+    a = S.Args
+    nx, nr, dx, dr = a["Nx"], a["Nr"], a["dx"], a["dr"]
+    ix = np.arange(int(frac[0] * nx), int(frac[1] * nx))
+    ir = np.arange(0, int(0.8 * (nr - 1)))
+    X, R, px, pr = np.meshgrid(ix, ir, np.arange(ppc_x), np.arange(ppc_r), indexing="ij")
+    x = a["leftX"] + dx * (X + (px + 0.5) / ppc_x)
+    r = dr * (R + (pr + 0.5) / ppc_r)
+    x, r = x.ravel(), r.ravel()
+    th = 2 * np.pi * rng.random(x.size)
+    coords = np.asfortranarray(np.vstack((x, r * np.cos(th), r * np.sin(th))))
+    mom = np.asfortranarray(thermal * rng.standard_normal((3, x.size)))
+    w = -dens * dr * dx * 2 * np.pi * r / (ppc_x * ppc_r) * (1.0 + 1e-3 * rng.random(x.size))
+    return coords, mom, np.asfortranarray(w)
+
+
+def seed_fields(S, seed, amp=0.5):
+    """A smooth, band-limited initial EG_fb so that gather/push see non-trivial fields."""
+    rng = np.random.default_rng(seed)
+    nx, nkr, nm = S.shape_fb
+    eg = S.zeros_fb(6)
+    kx = np.fft.fftfreq(nx) * nx
+    env = np.exp(-(kx / (0.08 * nx)) ** 2)[:, None, None, None] * np.exp(-(np.arange(nkr) / (0.2 * nkr)) ** 2)[None, :, None, None]
+    eg[:] = amp * env * (rng.standard_normal(eg.shape) + 1j * rng.standard_normal(eg.shape))
+    return np.asfortranarray(eg)
+
+
+def match(w_ref, w_eng):
+    """permutation taking engine order to reference order via the (unique) weights"""
+    a, b = np.argsort(w_ref, kind="stable"), np.argsort(w_eng, kind="stable")
+    perm = np.empty_like(a)
+    perm[a] = b
+    assert np.array_equal(w_ref, w_eng[perm])
+    return perm
+
+
+def build_pair(ofim, name, seed, ppc=(2, 2), still_ions=False, undulator=None):
+    from chimera_b200.engine import Engine
+
+    S = SolverSetup(copy.deepcopy(SETUPS[name]))
+    x, p, w = plasma(S, ppc[0], ppc[1], seed)
+    eg0 = seed_fields(S, seed + 1)
+    dev = None
+    if undulator:
+        dev = (ofim.undul_analytic, [undulator[k] for k in ("a0", "lambda", "X0", "Lx")])
+    sp = [RefSpecies(x, p, w, device=dev)]
+    eng = Engine(S, undulator=undulator)
+    eng.add_species(x, p, w)
+    if still_ions:
+        sp.append(RefSpecies(x, 0 * p, -w, charge=1.0, mass=1886.0, still=True))
+        eng.add_species(x, 0 * p, -w, charge=1.0, mass=1886.0, still=True)
+    ref = RefRun(ofim, S, sp, background=still_ions)
+    ref.EG_fb[:] = eg0
+    eng.upload("EG_fb", eg0)
+    return S, ref, eng
+
+
+def compare_state(ref, eng, tol, names=("J", "Rho", "EG_fb", "J_fb", "EB")):
+    for n in names:
+        want = {"J": ref.J, "Rho": ref.Rho, "EG_fb": ref.EG_fb, "J_fb": ref.J_fb, "EB": ref.EB, "B_fb": ref.B_fb}[n]
+        if n == "Rho" and not ref.space_charge:
+            continue
+        assert_close(eng.download(n), want, tol, n)
+    x, xh, p, w = eng.particles(0)
+    s = ref.sp[0]
+    assert w.shape == s.weights.shape
+    perm = match(s.weights, w)
+    assert_close(p[:, perm], s.momenta, tol, "momenta")
+    assert_close(x[:, perm], s.coords, tol, "coords")
+    assert_close(xh[:, perm], s.coords_halfstep, tol, "coords_halfstep")
+
+
+@pytest.mark.parametrize("name,ions", [("real_m2", True), ("real_m3", False), ("env_m3", False), ("env_m1", False)])
+def test_engine_halfstep_and_one_step(ofim, gfim, name, ions):
+    und = dict(a0=0.3, **{"lambda": 1.3}, X0=-1.0, Lx=9.0) if name == "env_m1" else None
+    S, ref, eng = build_pair(ofim, name, 11, still_ions=ions, undulator=und)
+    ref.make_halfstep()
+    eng.make_halfstep(background=ions)
+    compare_state(ref, eng, TOL)
+    if ref.chunked:
+        assert np.array_equal(eng.chunks(0), ref.sp[0].chunks)
+    ref.make_step()
+    eng.step(1)
+    compare_state(ref, eng, TOL)
+    eng.close()
+
+
+def diagnostics(S, eg_fb, x, p, w):
+    """integrated diagnostics: total charge, field energy (diagnostics.py:109 nrg_out), a 16-bin
+    weighted energy spectrum, on-axis Ex amplitude proxy (mode-0 spectral power)"""
+    gam = np.sqrt(1 + (p ** 2).sum(0))
+    hist, _ = np.histogram(gam, bins=16, range=(1.0, 1.0 + 6 * (gam.mean() - 1.0 + 1e-3)), weights=w)
+    nrg = (np.abs(eg_fb[..., :3]) ** 2 * S.Args["EnergyFact"][..., None]).sum()
+    wake = np.abs(eg_fb[:, :, 0, 0]).sum()
+    return np.concatenate(([w.sum(), nrg, wake, (w * gam).sum()], hist))
+
+
+@pytest.mark.parametrize("name", ["real_m2", "env_m3"])
+def test_engine_100_steps_diagnostics(ofim, gfim, name):
+    S, ref, eng = build_pair(ofim, name, 21, still_ions=(name == "real_m2"))
+    ref.make_halfstep()
+    eng.make_halfstep(background=(name == "real_m2"))
+    for _ in range(100):
+        ref.make_step()
+    eng.step(100)
+    x, xh, p, w = eng.particles(0)
+    d_eng = diagnostics(S, eng.download("EG_fb"), x, p, w)
+    d_ref = diagnostics(S, ref.EG_fb, ref.sp[0].coords, ref.sp[0].momenta, ref.sp[0].weights)
+    scale = np.maximum(np.abs(d_ref), 1e-3 * np.abs(d_ref).max())
+    err = np.abs(d_eng - d_ref) / scale
+    assert err.max() < 1e-6, (err, d_eng, d_ref)
+    assert rel_l2(eng.download("EG_fb"), ref.EG_fb) < 1e-6
+    eng.close()
+
+
+def test_engine_dropin_sequence_matches(ofim, gfim):
+    """the host-buffer drop-in (chimera_b200.fimera) driven by the same step sequence"""
+    from chimera_b200.engine import Engine  # noqa: F401
+
+    S = SolverSetup(copy.deepcopy(SETUPS["real_m2"]))
+    x, p, w = plasma(S, 2, 2, 31)
+    eg0 = seed_fields(S, 32)
+    runs = []
+    for fim in (ofim, gfim):
+        r = RefRun(fim, S, [RefSpecies(x, p, w)])
+        r.EG_fb[:] = eg0
+        r.make_halfstep()
+        r.make_step()
+        runs.append(r)
+    assert_close(runs[1].EG_fb, runs[0].EG_fb, TOL, "EG_fb")
+    assert_close(runs[1].EB, runs[0].EB, TOL, "EB")
+    perm = match(runs[0].sp[0].weights, runs[1].sp[0].weights)
+    assert_close(runs[1].sp[0].momenta[:, perm], runs[0].sp[0].momenta, TOL, "momenta")
