@@ -66,9 +66,10 @@ def build_pair(ofim, name, seed, ppc=(2, 2), still_ions=False, undulator=None):
     sp = [RefSpecies(x, p, w, device=dev)]
     eng = Engine(S, undulator=undulator)
     eng.add_species(x, p, w)
-    if still_ions:
-        sp.append(RefSpecies(x, 0 * p, -w, charge=1.0, mass=1886.0, still=True))
-        eng.add_species(x, 0 * p, -w, charge=1.0, mass=1886.0, still=True)
+    if still_ions:  # an independent sample, so that the net charge density is not identically zero
+        xi, pi_, wi = plasma(S, ppc[0], ppc[1], seed + 7)
+        sp.append(RefSpecies(xi, 0 * pi_, -wi, charge=1.0, mass=1886.0, still=True))
+        eng.add_species(xi, 0 * pi_, -wi, charge=1.0, mass=1886.0, still=True)
     ref = RefRun(ofim, S, sp, background=still_ions)
     ref.EG_fb[:] = eg0
     eng.upload("EG_fb", eg0)

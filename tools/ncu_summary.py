@@ -1,0 +1,75 @@
+"""Summarise ncu artefacts brought back in gpurun_out/ into small text files under profiles/.
+
+  python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/r01_x_launches.txt
+  python tools/ncu_summary.py full gpurun_out/prof.ncu-rep profiles/r01_x_full.txt
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__average_warp_latency_per_inst_issued.ratio",
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct"]
+
+
+def short(n):
+    n = re.sub(r"\(.*", "", n)
+    n = re.sub(r"^void ", "", n)
+    n = re.sub(r"chb::|<unnamed>::", "", n)
+    return n
+
+
+def launches(src, dst):
+    rows = list(csv.reader(open(src)))
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    h = rows[hi]
+    ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+    data = [(short(r[ki]), float(r[vi].replace(",", ""))) for r in rows[hi + 1:] if len(r) > vi]
+    idx = [i for i, d in enumerate(data) if d[0].startswith("push_coords_k")]
+    out = ["ncu --metrics gpu__time_duration.sum --clock-control none: %d launches in %s" % (len(data), src)]
+    if len(idx) >= 2:
+        seg = data[idx[-2]:idx[-1]]
+        out.append("one full PIC step (between the last two push_coords_k launches): %d launches" % len(seg))
+    else:
+        seg = data
+    agg = collections.OrderedDict()
+    for n, t in seg:
+        a = agg.setdefault(n, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+    tot = sum(v[1] for v in agg.values())
+    out.append("sum of kernel durations: %.3f ms (cold-cache, serialised: compare shares)" % (tot / 1e6))
+    out.append("%-58s %6s %10s %7s" % ("kernel", "count", "ms", "share"))
+    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append("%-58s %6d %10.3f %6.1f%%" % (n[:58], c, t / 1e6, 100 * t / tot))
+    open(dst, "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
+def full(src, dst):
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units = rows[0], rows[1]
+    out = ["ncu --set full --clock-control none summary of %s" % src]
+    for r in rows[2:]:
+        out.append("== %s  (ID %s)" % (short(r[h.index("Kernel Name")]), r[h.index("ID")]))
+        for k in KEYS:
+            if k in h:
+                i = h.index(k)
+                out.append("   %-78s %s %s" % (k, r[i], units[i]))
+    open(dst, "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
