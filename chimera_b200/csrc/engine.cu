@@ -30,6 +30,9 @@ struct Species {
   int still = 0;
   int* d_ind = nullptr;          // IndInChunk(0:nchnk); the last entry is the number of particles kept
   std::vector<int> h_ind;
+  int* d_cta = nullptr;          // prefix of binned-deposit CTA counts per chunk (0:nchnk)
+  int ncta = 0;
+  i64 tile_w = 0;                // x cells per re-binning tile of the current particle order (0: unsorted)
 };
 
 }  // namespace chb
@@ -87,14 +90,17 @@ __global__ void __launch_bounds__(256) soa_to_aos_k(double* __restrict__ dst, co
 }
 
 // ------------------------------------------------------------------------------------------
-// re-binning keys: (x-chunk as particle_tools.f90:183, r-cell, x-cell); kdrop = leaves the domain
+// re-binning keys: (x-chunk as particle_tools.f90:183, x-tile, r-cell, x-cell in tile); kdrop = leaves
+// the domain.  Consecutive particles then share a cell (deposit_runs_k) and a CTA's particles sit in a
+// compact (x, r) box (gather_push_tiled_k).
 // ------------------------------------------------------------------------------------------
 struct BinSpec {
   double x0, chunk_inv;       // Xgrid(0), 1 / chunk length
   double l0, l1, l2, l3;      // SimDom
   double leftX, dx_inv, r0, dr_inv;
   int nchnk;
-  i64 nx, nrc;                // x cells used for the minor key, r cells
+  i64 nx, nrc;                // x cells, r cells
+  i64 cs, tile_w, ntile;      // x cells per chunk, per x-tile, x-tiles per chunk
   unsigned kdrop;             // key of a particle that leaves the domain (sorts last)
 };
 
@@ -112,7 +118,10 @@ __global__ void __launch_bounds__(256) bin_keys_k(const double* __restrict__ x, 
     ix = ix < 0 ? 0 : (ix > b.nx - 1 ? b.nx - 1 : ix);
     i64 ir = (i64)floor((sqrt(r2) - b.r0) * b.dr_inv);
     ir = ir < 0 ? 0 : (ir > b.nrc - 1 ? b.nrc - 1 : ir);
-    k = (unsigned)((c * b.nrc + ir) * b.nx + ix);
+    i64 lx = ix - c * b.cs;  // the chunk id follows the reference's float rule; keep the cell inside it
+    lx = lx < 0 ? 0 : (lx > b.cs - 1 ? b.cs - 1 : lx);
+    const i64 xt = lx / b.tile_w;
+    k = (unsigned)((((c * b.ntile + xt) * b.nrc + ir) * b.tile_w) + (lx - xt * b.tile_w));
   }
   key[ip] = k;
   idx[ip] = (int)ip;
@@ -226,6 +235,25 @@ ChunkSpec chunkspec(chimera_engine* e, const Species& s) {
   return ChunkSpec{1, s.d_ind, e->cfg.nchnk, e->cfg.guards, e->cfg.nx / e->cfg.nchnk};
 }
 
+// CTA -> chunk table of the binned deposit (kernels.cuh SortedSpec), rebuilt whenever IndInChunk changes
+int update_cta_table(chimera_engine* e, Species& s) {
+  const int nchnk = (int)s.h_ind.size() - 1;
+  std::vector<int> cta(nchnk + 1, 0);
+  for (int c = 0; c < nchnk; ++c) {
+    const int n = s.h_ind[c + 1] - s.h_ind[c];
+    cta[c + 1] = cta[c] + (n > 0 ? (n + kDepNPB - 1) / kDepNPB : 0);
+  }
+  s.ncta = cta[nchnk];
+  CHB_CUDA(cudaMemcpyAsync(s.d_cta, cta.data(), sizeof(int) * (nchnk + 1), cudaMemcpyHostToDevice, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+SortedSpec sortedspec(chimera_engine* e, const Species& s) {
+  const int nchnk = e->cfg.chunked ? e->cfg.nchnk : 1;
+  return SortedSpec{s.d_ind, s.d_cta, nchnk, s.ncta, e->cfg.nx / nchnk, s.tile_w};
+}
+
 // ---- phases ----------------------------------------------------------------------------------
 int ph_push_coords(chimera_engine* e) {
   for (auto& s : e->sp) {
@@ -260,12 +288,13 @@ int ph_sort(chimera_engine* e, int on_halfstep) {
     BinSpec b;
     const i64 cs = c.nx / nchnk;  // nodes per chunk
     b.x0 = c.leftX;
-    (void)cs;
     b.chunk_inv = 1.0 / c.chunk_len;
     b.l0 = c.leftX; b.l1 = c.rightX; b.l2 = 0.0; b.l3 = c.rcull2;
     b.leftX = c.leftX; b.dx_inv = 1.0 / c.dx; b.r0 = g_host[e].r0; b.dr_inv = 1.0 / c.dr;
     b.nchnk = nchnk; b.nx = c.nx; b.nrc = c.nrn - 1;
-    const unsigned long long kmax = (unsigned long long)nchnk * b.nrc * b.nx;
+    b.cs = cs; b.tile_w = cs < 32 ? cs : 32; b.ntile = (cs + b.tile_w - 1) / b.tile_w;
+    const i64 per_chunk = b.ntile * b.nrc * b.tile_w;
+    const unsigned long long kmax = (unsigned long long)nchnk * per_chunk;
     if (kmax >= 0xFFFFFFFFull) { set_error("re-binning key does not fit 32 bits"); return 2; }
     b.kdrop = (unsigned)kmax;
     int bits = 1;
@@ -275,7 +304,7 @@ int ph_sort(chimera_engine* e, int on_halfstep) {
     CHB_LAUNCH_CHECK();
     size_t tb = e->cub_tmp_bytes;
     CHB_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp, tb, e->key_a, e->key_b, e->idx_a, e->idx_b, (int)s.np, 0, bits, e->st));
-    chunk_bounds_k<<<1, 256, 0, e->st>>>(e->key_b, s.d_ind, nchnk, (i64)b.nrc * b.nx, s.np);
+    chunk_bounds_k<<<1, 256, 0, e->st>>>(e->key_b, s.d_ind, nchnk, per_chunk, s.np);
     CHB_LAUNCH_CHECK();
     permute_soa_k<<<grid_for(s.np, 256), 256, 0, e->st>>>(s.x2, s.xh2, s.p2, s.w2, s.x, s.xh, s.p, s.w, e->idx_b, s.cap, s.np);
     CHB_LAUNCH_CHECK();
@@ -284,6 +313,8 @@ int ph_sort(chimera_engine* e, int on_halfstep) {
     CHB_CUDA(cudaMemcpyAsync(s.h_ind.data(), s.d_ind, sizeof(int) * (nchnk + 1), cudaMemcpyDeviceToHost, e->st));
     CHB_CUDA(cudaStreamSynchronize(e->st));
     s.np = s.h_ind[nchnk];
+    s.tile_w = b.tile_w;
+    CHB_TRY(update_cta_table(e, s));
   }
   return 0;
 }
@@ -294,8 +325,11 @@ int deposit_species(chimera_engine* e, int curr, cd* grid, bool still_only, bool
     if (s.np == 0) continue;
     if (still_only != (s.still != 0)) continue;
     const double* xs = use_half ? s.xh : s.x;
-    CHB_TRY(launch_deposit_direct(e->st, e->cfg.env, curr, soa(xs, s.cap), soa((const double*)s.p, s.cap), s.w, grid, g,
-                                  chunkspec(e, s), s.np, false));
+    int rc = launch_deposit_binned(e->st, e->cfg.env, curr, xs, s.p, s.w, s.cap, grid, g, chunkspec(e, s), sortedspec(e, s));
+    if (rc == -1)  // mode count without a binned instantiation
+      rc = launch_deposit_runs(e->st, e->cfg.env, curr, soa(xs, s.cap), soa((const double*)s.p, s.cap), s.w, grid, g,
+                               chunkspec(e, s), s.np);
+    CHB_TRY(rc);
   }
   return 0;
 }
@@ -401,8 +435,8 @@ int ph_gather_push(chimera_engine* e, double dt_frac) {
   UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
   for (auto& s : e->sp) {
     if (s.still || s.np == 0) continue;
-    CHB_TRY(launch_gather_push(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
-                               s.push_fact * c.dt * dt_frac, und, s.np));
+    CHB_TRY(launch_gather_push_tiled(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
+                                     s.push_fact * c.dt * dt_frac, und, s.np));
   }
   return 0;
 }
@@ -514,7 +548,7 @@ int chimera_engine_destroy(chimera_engine* e) {
   for (auto& kv : e->arr) cudaFree(kv.second.p);
   for (auto& s : e->sp) {
     cudaFree(s.x); cudaFree(s.xh); cudaFree(s.p); cudaFree(s.w);
-    cudaFree(s.x2); cudaFree(s.xh2); cudaFree(s.p2); cudaFree(s.w2); cudaFree(s.d_ind);
+    cudaFree(s.x2); cudaFree(s.xh2); cudaFree(s.p2); cudaFree(s.w2); cudaFree(s.d_ind); cudaFree(s.d_cta);
   }
   cudaFree(e->packed);
   cudaFree(e->key_a); cudaFree(e->key_b); cudaFree(e->idx_a); cudaFree(e->idx_b); cudaFree(e->cub_tmp);
@@ -585,6 +619,7 @@ int chimera_engine_add_species(chimera_engine* e, const double* coords, const do
   CHB_CUDA(cudaMalloc((void**)&s.w2, b1));
   const int nchnk = e->cfg.chunked ? e->cfg.nchnk : 1;
   CHB_CUDA(cudaMalloc((void**)&s.d_ind, sizeof(int) * (nchnk + 1)));
+  CHB_CUDA(cudaMalloc((void**)&s.d_cta, sizeof(int) * (nchnk + 1)));
   s.h_ind.assign(nchnk + 1, 0);
   // placeholder until the first re-binning (CHB_SORT must run before a chunked deposit, as the
   // reference's make_halfstep does, chimera_main.py:62-70)
@@ -603,6 +638,7 @@ int chimera_engine_add_species(chimera_engine* e, const double* coords, const do
     CHB_CUDA(cudaMemcpyAsync(s.w, weights, sizeof(double) * np, cudaMemcpyDefault, e->st));
   }
   CHB_CUDA(cudaStreamSynchronize(e->st));
+  CHB_TRY(update_cta_table(e, s));
   e->sp.push_back(s);
   if (id) *id = (int)e->sp.size() - 1;
   return 0;

@@ -49,6 +49,26 @@ int launch_undul(cudaStream_t st, CPView x, PView fld, const UndulParams& und, i
 int launch_deposit_direct(cudaStream_t st, int env, int curr, CPView x, CPView mom, const double* w, cd* grid,
                           const GridGeom& g, const ChunkSpec& ch, i64 np, bool fold);
 int launch_ghost_fold(cudaStream_t st, cd* grid, i64 nxn, i64 nrn, i64 nplanes);
+// ---- particles_sorted.cu : kernels that exploit (chunk, x-tile, r-cell, x-cell)-sorted SoA particles
+// run-accumulating deposit: a thread walks `run` consecutive particles, sums the contributions of
+// those that share a cell in registers and issues one red.global.add per node value and cell run
+int launch_deposit_runs(cudaStream_t st, int env, int curr, CPView x, CPView mom, const double* w, cd* grid,
+                        const GridGeom& g, const ChunkSpec& ch, i64 np);
+// binned deposit: a CTA takes kDepNPB consecutive particles of ONE x-chunk, counting-sorts them by
+// cell in shared memory, then accumulates runs of same-cell particles in registers and issues one
+// red.global.add per node value and run.  `SortedSpec` maps CTAs to chunks.
+constexpr int kDepNPB = 1024;
+struct SortedSpec {
+  const int* ind;   // device IndInChunk(0:nchnk) (one chunk holding everything when not x-chunked)
+  const int* cta;   // device prefix of CTA counts per chunk (0:nchnk), cta[c+1]-cta[c] = ceil(n_c / kDepNPB)
+  int nchnk, ncta;
+  i64 cs, tile_w;   // x cells per chunk and per re-binning tile (0: unknown / never re-binned)
+};
+int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, const double* mom, const double* w,
+                          i64 cap, cd* grid, const GridGeom& g, const ChunkSpec& ch, const SortedSpec& sp);
+// field gather from a shared-memory tile of the EB grid + undulator + Boris push
+int launch_gather_push_tiled(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
+                             const GridGeom& g, double dt, const UndulParams& und, i64 np);
 int launch_chunk_bin(cudaStream_t st, CPView x, int8_t* chunked, int* counts, int* goout, double x0, double inv,
                      const double lims[4], int nchnk, i64 np);
 int launch_permute(cudaStream_t st, PView dst, CPView src, const i64* idx, int ncomp, i64 np);

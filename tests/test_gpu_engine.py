@@ -27,6 +27,10 @@ def plasma(S, ppc_x, ppc_r, seed, frac=(0.15, 0.85), thermal=0.05, dens=0.005):
     x = a["leftX"] + dx * (X + (px + 0.5) / ppc_x)
     r = dr * (R + (pr + 0.5) / ppc_r)
     x, r = x.ravel(), r.ravel()
+    # jitter: on a perfectly regular lattice the envelope deposit (carrier exp(-i kx0 x)) cancels almost
+    # exactly and the relative error of the tiny remainder is meaningless
+    x = x + dx * 0.4 / ppc_x * (rng.random(x.size) - 0.5)
+    r = r + dr * 0.4 / ppc_r * (rng.random(x.size) - 0.5)
     th = 2 * np.pi * rng.random(x.size)
     coords = np.asfortranarray(np.vstack((x, r * np.cos(th), r * np.sin(th))))
     mom = np.asfortranarray(thermal * rng.standard_normal((3, x.size)))
