@@ -435,8 +435,12 @@ int ph_gather_push(chimera_engine* e, double dt_frac) {
   UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
   for (auto& s : e->sp) {
     if (s.still || s.np == 0) continue;
-    CHB_TRY(launch_gather_push_tiled(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
-                                     s.push_fact * c.dt * dt_frac, und, s.np));
+    int rc = launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt * dt_frac, und,
+                                       sortedspec(e, s));
+    if (rc == -1)
+      rc = launch_gather_push_tiled(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
+                                    s.push_fact * c.dt * dt_frac, und, s.np);
+    CHB_TRY(rc);
   }
   return 0;
 }

@@ -66,6 +66,8 @@ struct SortedSpec {
 };
 int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, const double* mom, const double* w,
                           i64 cap, cd* grid, const GridGeom& g, const ChunkSpec& ch, const SortedSpec& sp);
+int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* mom,
+                              i64 cap, const GridGeom& g, double dt, const UndulParams& und, const SortedSpec& sp);
 // field gather from a shared-memory tile of the EB grid + undulator + Boris push
 int launch_gather_push_tiled(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
                              const GridGeom& g, double dt, const UndulParams& und, i64 np);

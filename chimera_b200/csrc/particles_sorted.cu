@@ -352,26 +352,127 @@ int launch_gather_push_tiled(cudaStream_t st, int env, CPView x, const double* w
 }
 
 // ================================================================================================
-// Binned deposit (see kernels.cuh).  Shared memory per CTA: NF record fields x 1024 particles
-// (shape fractions, azimuthal phase, amplitudes), the 64 x 32 cell histogram / offsets, the sorted
-// order and keys.  Phases: (A) one thread per particle: shape, phase, amplitude -> record, cell key,
-// histogram; (B) block scan of the histogram; (C) scatter particle ids to their sorted slot;
-// (D) one task per (run of 16 sorted particles, component, mode slot): 4 complex node accumulators
-// in registers, flushed with 8 red.global.add.f64 whenever the cell changes.
+// CTA-binned particle kernels (see kernels.cuh).  A CTA takes kDepNPB consecutive particles of ONE
+// x-chunk and
+//  (A) computes every particle's cell inside a 64 x 32 cell box anchored at the CTA's first particle
+//      and histograms the cells in shared memory,
+//  (B) block-scans the histogram (cell -> first sorted slot) and cuts every cell's particles into
+//      SEGMENTS of at most 16: a segment's particles share a cell, so whatever belongs to the cell is
+//      held in registers for the whole segment,
+//  (C) writes a per-particle record (shape fractions, azimuthal phase, amplitudes) to its sorted slot,
+//  (D) runs one thread per (segment, component):
+//        deposit: 4 nodes x nm modes of complex accumulators in registers, ONE red.global.add.f64
+//                 per node value and segment (instead of one per particle);
+//        gather : the 4 x nm node values of the component are loaded ONCE per segment, the
+//                 per-particle field goes to shared memory,
+//  (E) gather only: one thread per particle: external device, Boris push.
+// Particles that drifted out of the box since the last re-binning take the direct path (L2 atomics
+// / L2 loads); the result is identical, only slower.
 // ================================================================================================
 }  // namespace chb
 #include <cub/block/block_scan.cuh>
 namespace chb {
 namespace {
-constexpr int DB_THREADS = 192, DB_RUN = 16, DB_NRUN = kDepNPB / DB_RUN;
-constexpr int DB_BX = 64, DB_BR = 32, DB_BINS = DB_BX * DB_BR, DB_ITEMS = (DB_BINS + DB_THREADS - 1) / DB_THREADS;
+constexpr int DB_THREADS = 192, DB_RUN = 16;
+constexpr int DB_BX = 64, DB_BR = 32, DB_BINS = DB_BX * DB_BR;
 constexpr int DB_PPT = (kDepNPB + DB_THREADS - 1) / DB_THREADS;
+constexpr int DB_MAXTASK = kDepNPB / DB_RUN + kDepNPB;  // worst case: every particle alone in its cell
+
+template <int THREADS>
+struct BinShared {  // static shared memory of the binning stage
+  int anchor[2];
+  int total, ntask;
+  typename cub::BlockScan<int, THREADS>::TempStorage scan;
+};
+
+struct CtaRange {
+  int chunk;
+  i64 first;
+  int count;
+};
+
+__device__ __forceinline__ CtaRange cta_range(const SortedSpec& sp) {
+  int lo = 0, hi = sp.nchnk;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)blockIdx.x >= __ldg(sp.cta + mid)) lo = mid; else hi = mid;
+  }
+  CtaRange r;
+  r.chunk = lo;
+  r.first = (i64)__ldg(sp.ind + lo) + (i64)((int)blockIdx.x - __ldg(sp.cta + lo)) * kDepNPB;
+  const i64 n = (i64)__ldg(sp.ind + lo + 1) - r.first;
+  r.count = (int)(n < kDepNPB ? n : kDepNPB);
+  return r;
+}
+
+// anchor of the CTA's cell box: the re-binning tile of the first particle, centred in the 64-cell
+// window, and 6 rows below the first particle's r-cell
+__device__ __forceinline__ void cta_anchor(const double* __restrict__ x, i64 cap, const GridGeom& g, const SortedSpec& sp,
+                                           const CtaRange& cr, int* anchor) {
+  const double xp = __ldg(x + cr.first), yp = __ldg(x + cap + cr.first), zp = __ldg(x + 2 * cap + cr.first);
+  const i64 ix = (i64)floor((xp - g.leftX) * g.dx_inv);
+  const i64 ir = (i64)floor((sqrt(yp * yp + zp * zp) - g.r0) * g.dr_inv);
+  i64 ax = ix - DB_BX / 2;
+  if (sp.tile_w > 0) {
+    i64 lx = ix - (i64)cr.chunk * sp.cs;
+    lx = lx < 0 ? 0 : (lx > sp.cs - 1 ? sp.cs - 1 : lx);
+    ax = (i64)cr.chunk * sp.cs + (lx / sp.tile_w) * sp.tile_w - (DB_BX - sp.tile_w) / 2;
+  }
+  anchor[0] = (int)ax;
+  anchor[1] = (int)(ir - 6);
+}
+
+// stage (B): packed scan (low 16 bits: particles, high 16 bits: segments) and the segment table
+//   task word = key | start << 11 | n << 22
+template <int THREADS>
+__device__ __forceinline__ void cta_scan_and_tasks(int* bins, int* tasks, BinShared<THREADS>& sh, int tid) {
+  constexpr int DB_ITEMS = (DB_BINS + THREADS - 1) / THREADS;
+  int items[DB_ITEMS], cnt[DB_ITEMS];
+  int total = 0;
+#pragma unroll
+  for (int i = 0; i < DB_ITEMS; ++i) {
+    const int b = tid * DB_ITEMS + i;
+    cnt[i] = (b < DB_BINS) ? bins[b] : 0;
+    items[i] = cnt[i] | (((cnt[i] + DB_RUN - 1) / DB_RUN) << 16);
+  }
+  cub::BlockScan<int, THREADS>(sh.scan).ExclusiveSum(items, items, total);
+#pragma unroll
+  for (int i = 0; i < DB_ITEMS; ++i) {
+    const int b = tid * DB_ITEMS + i;
+    if (b < DB_BINS) {
+      bins[b] = items[i] & 0xFFFF;
+      int start = items[i] & 0xFFFF, t = items[i] >> 16, left = cnt[i];
+      while (left > 0) {
+        const int n = left < DB_RUN ? left : DB_RUN;
+        tasks[t++] = b | (start << 11) | (n << 22);
+        start += n;
+        left -= n;
+      }
+    }
+  }
+  if (tid == 0) { sh.total = total & 0xFFFF; sh.ntask = total >> 16; }
+}
+
+// x-node range a particle of chunk `c` may write (the chunk-edge rule of grid_deps_chnk.f90:95-115,
+// identical to chunk_keep() for every node, evaluated once per CTA)
+__device__ __forceinline__ void keep_range(const ChunkSpec& ch, int c, i64 nxn, i64& lo, i64& hi) {
+  lo = 0;
+  hi = nxn - 1;
+  if (ch.on) {
+    const i64 left = (i64)c * ch.cs;
+    const i64 l2 = (left - ch.guards >= 0) ? left - ch.guards : left + 1;
+    const i64 h2 = (left + ch.cs + ch.guards <= nxn - 1) ? left + ch.cs + ch.guards : left + ch.cs - 1;
+    lo = l2 > lo ? l2 : lo;
+    hi = h2 < hi ? h2 : hi;
+  }
+}
 
 template <int ENV, int CURR>
 struct DepLayout {
   static constexpr int NAMP = ENV ? 2 : (CURR ? 3 : 1);
   static constexpr int NF = 4 + NAMP;
-  static constexpr size_t smem = sizeof(double) * NF * kDepNPB + sizeof(int) * DB_BINS + 2 * sizeof(unsigned short) * kDepNPB;
+  static constexpr size_t smem =
+      sizeof(double) * NF * kDepNPB + sizeof(int) * (DB_BINS + DB_MAXTASK) + 2 * sizeof(unsigned short) * kDepNPB;
 };
 
 template <int ENV, int CURR, int NM>
@@ -380,181 +481,156 @@ deposit_binned_k(const double* __restrict__ x, const double* __restrict__ mom, c
                  cd* __restrict__ grid, GridGeom g, ChunkSpec ch, SortedSpec sp) {
   using L = DepLayout<ENV, CURR>;
   constexpr int NF = L::NF;
-  constexpr int NC = CURR ? (ENV ? 1 : 3) : 1;
-  constexpr int NSUB = NC * NM;
+  constexpr int NC = CURR ? (ENV ? 1 : 3) : 1;   // components (Q1: the envelope current has l = 3 only)
+  constexpr int SL = CURR ? NM : 1;              // mode slots per thread: all for J, one for rho
+  constexpr int NS = NM / SL;                    // threads per (segment, component)
   constexpr int NKO = ENV ? (NM - 1) / 2 : NM - 1;
+  constexpr int HB = DB_PPT / 2;                 // particles per load batch
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* rec = reinterpret_cast<double*>(smem_raw);                       // [NF][kDepNPB]
-  int* bins = reinterpret_cast<int*>(rec + NF * kDepNPB);                  // [DB_BINS]
-  unsigned short* order = reinterpret_cast<unsigned short*>(bins + DB_BINS);  // [kDepNPB] sorted slot -> local id
-  unsigned short* skey = order + kDepNPB;                                  // [kDepNPB] local id -> key, then slot -> key
-  __shared__ int s_anchor[2];
-  __shared__ typename cub::BlockScan<int, DB_THREADS>::TempStorage scan_tmp;
+  double* rec = reinterpret_cast<double*>(smem_raw);            // [NF][kDepNPB], indexed by local particle id
+  int* bins = reinterpret_cast<int*>(rec + NF * kDepNPB);       // [DB_BINS]
+  int* tasks = bins + DB_BINS;                                  // [DB_MAXTASK]
+  unsigned short* skey = reinterpret_cast<unsigned short*>(tasks + DB_MAXTASK);  // [kDepNPB] local id -> cell key
+  unsigned short* order = skey + kDepNPB;                       // [kDepNPB] sorted slot -> local id
+  __shared__ BinShared<DB_THREADS> sh;
   const int tid = threadIdx.x;
 
-  // CTA -> (chunk, particle range)
-  int c = 0;
-  {
-    int lo = 0, hi = sp.nchnk;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if ((int)blockIdx.x >= __ldg(sp.cta + mid)) lo = mid; else hi = mid;
-    }
-    c = lo;
-  }
-  const i64 first = (i64)__ldg(sp.ind + c) + (i64)((int)blockIdx.x - __ldg(sp.cta + c)) * kDepNPB;
-  const i64 cend = __ldg(sp.ind + c + 1);
-  const int count = (int)((cend - first < kDepNPB) ? (cend - first) : kDepNPB);
-  if (count <= 0) return;
-
+  const CtaRange cr = cta_range(sp);
+  if (cr.count <= 0) return;
   for (int i = tid; i < DB_BINS; i += DB_THREADS) bins[i] = 0;
-  if (tid == 0) {  // anchor of the cell box from the first particle of the (sorted) range
-    const double xp = __ldg(x + first), yp = __ldg(x + cap + first), zp = __ldg(x + 2 * cap + first);
-    const i64 ix = (i64)floor((xp - g.leftX) * g.dx_inv);
-    const i64 ir = (i64)floor((sqrt(yp * yp + zp * zp) - g.r0) * g.dr_inv);
-    i64 ax = ix - DB_BX / 2;
-    if (sp.tile_w > 0) {
-      i64 lx = ix - (i64)c * sp.cs;
-      lx = lx < 0 ? 0 : (lx > sp.cs - 1 ? sp.cs - 1 : lx);
-      ax = (i64)c * sp.cs + (lx / sp.tile_w) * sp.tile_w - (DB_BX - sp.tile_w) / 2;
-    }
-    s_anchor[0] = (int)ax;
-    s_anchor[1] = (int)(ir - 6);
-  }
+  if (tid == 0) cta_anchor(x, cap, g, sp, cr, sh.anchor);
   __syncthreads();
-  const int ix0 = s_anchor[0], ir0 = s_anchor[1];
+  const int ix0 = sh.anchor[0], ir0 = sh.anchor[1];
 
-  // ---- (A) records + histogram
+  // ---- (A) per-particle record, cell key, histogram.  Loads of a batch are issued together.
 #pragma unroll 1
-  for (int j = 0; j < DB_PPT; ++j) {
-    const int li = tid + j * DB_THREADS;
-    if (li >= kDepNPB) break;
-    unsigned short key = 0xFFFFu;
-    if (li < count) {
-      const i64 ip = first + li;
-      const double wp = __ldg(w + ip);
-      const double xp = __ldg(x + ip), yp = __ldg(x + cap + ip), zp = __ldg(x + 2 * cap + ip);
-      double p0 = 0, p1 = 0, p2 = 0;
-      if (CURR) { p0 = __ldg(mom + ip); p1 = __ldg(mom + cap + ip); p2 = __ldg(mom + 2 * cap + ip); }
+  for (int jb = 0; jb < DB_PPT; jb += HB) {
+    double xs[HB], ys[HB], zs[HB], ws[HB], ps[3][HB];
+#pragma unroll
+    for (int j = 0; j < HB; ++j) {
+      const int li = tid + (jb + j) * DB_THREADS;
+      const bool in = li < cr.count;
+      const i64 ip = cr.first + (in ? li : 0);
+      xs[j] = __ldg(x + ip); ys[j] = __ldg(x + cap + ip); zs[j] = __ldg(x + 2 * cap + ip);
+      ws[j] = in ? __ldg(w + ip) : 0.0;
+      if (CURR) { ps[0][j] = __ldg(mom + ip); ps[1][j] = __ldg(mom + cap + ip); ps[2][j] = __ldg(mom + 2 * cap + ip); }
+    }
+#pragma unroll
+    for (int j = 0; j < HB; ++j) {
+      const int li = tid + (jb + j) * DB_THREADS;
+      if (li >= kDepNPB) continue;
+      unsigned short key = 0xFFFFu;
+      const double wp = ws[j], xp = xs[j], yp = ys[j], zp = zs[j];
       Shape s;
-      bool live = (wp != 0.0) && make_shape(g, xp, yp, zp, s);
-      if (live && CURR && fabs(p0) + fabs(p1) + fabs(p2) == 0.0) live = false;
-      if (live) {
+      if (wp != 0.0 && make_shape(g, xp, yp, zp, s)) {
         const i64 kx = s.ix - ix0, kr = s.ir - ir0;
         if (kx >= 0 && kx < DB_BX && kr >= 0 && kr < DB_BR) {
           key = (unsigned short)(kr * DB_BX + kx);
-          rec[0 * kDepNPB + li] = s.sx1;
-          rec[1 * kDepNPB + li] = s.sr1;
-          const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;
-          rec[2 * kDepNPB + li] = (s.rp > 0.0) ? yp / s.rp : 0.0;
-          rec[3 * kDepNPB + li] = (s.rp > 0.0) ? -zp / s.rp : 0.0;
-          (void)rinv;
-          double gp = 1.0;
-          if (CURR) gp = sqrt(1.0 + p0 * p0 + p1 * p1 + p2 * p2);
+          atomicAdd(&bins[key], 1);
+          rec[li] = s.sx1;
+          rec[kDepNPB + li] = s.sr1;
+          const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // deposit phase exp(-i theta); 0 on the axis
+          rec[2 * kDepNPB + li] = yp * rinv;
+          rec[3 * kDepNPB + li] = -zp * rinv;
+          double ginv = 1.0;
+          if (CURR) ginv = 1.0 / sqrt(1.0 + ps[0][j] * ps[0][j] + ps[1][j] * ps[1][j] + ps[2][j] * ps[2][j]);
           if (ENV) {
             double sn, cs;
             sincos(xp * g.kx0, &sn, &cs);
             const cd wpc = cmake(wp * cs, -wp * sn);
-            const cd base = CURR ? cscale(p2 / gp, wpc) : cmul(wpc, wpc);  // Q1: l = 3 only; Q2: weight twice
+            const cd base = CURR ? cscale(ps[2][j] * ginv, wpc) : cmul(wpc, wpc);  // Q1: l = 3 only; Q2: weight twice
             rec[4 * kDepNPB + li] = base.x;
             rec[5 * kDepNPB + li] = base.y;
           } else if (CURR) {
-            rec[4 * kDepNPB + li] = p0 * wp / gp;
-            rec[5 * kDepNPB + li] = p1 * wp / gp;
-            rec[6 * kDepNPB + li] = p2 * wp / gp;
+            const double wg = wp * ginv;
+            rec[4 * kDepNPB + li] = ps[0][j] * wg;
+            rec[5 * kDepNPB + li] = ps[1][j] * wg;
+            rec[6 * kDepNPB + li] = ps[2][j] * wg;
           } else {
             rec[4 * kDepNPB + li] = wp;
           }
-          atomicAdd(&bins[key], 1);
-        } else {
-          deposit_one<ENV, CURR>(g, ch, c, grid, xp, yp, zp, p0, p1, p2, wp);  // drifted out of the box
+        } else {  // drifted out of the box: straight to the grid
+          deposit_one<ENV, CURR>(g, ch, cr.chunk, grid, xp, yp, zp, CURR ? ps[0][j] : 0.0, CURR ? ps[1][j] : 0.0,
+                                 CURR ? ps[2][j] : 0.0, wp);
         }
       }
+      skey[li] = key;
     }
-    skey[li] = key;
   }
   __syncthreads();
-
-  // ---- (B) exclusive scan of the histogram -> first sorted slot of every cell
-  int items[DB_ITEMS];
-  int total = 0;
-#pragma unroll
-  for (int i = 0; i < DB_ITEMS; ++i) {
-    const int b = tid * DB_ITEMS + i;
-    items[i] = (b < DB_BINS) ? bins[b] : 0;
-  }
-  cub::BlockScan<int, DB_THREADS>(scan_tmp).ExclusiveSum(items, items, total);
-#pragma unroll
-  for (int i = 0; i < DB_ITEMS; ++i) {
-    const int b = tid * DB_ITEMS + i;
-    if (b < DB_BINS) bins[b] = items[i];
-  }
+  // ---- (B)
+  cta_scan_and_tasks(bins, tasks, sh, tid);
   __syncthreads();
-
-  // ---- (C) scatter local ids to sorted slots
-  unsigned short mykey[DB_PPT];
+  // ---- (C) local ids to sorted slots
 #pragma unroll
   for (int j = 0; j < DB_PPT; ++j) {
     const int li = tid + j * DB_THREADS;
-    mykey[j] = (li < kDepNPB) ? skey[li] : (unsigned short)0xFFFFu;
-  }
-  __syncthreads();  // every key read before `skey` is re-used as slot -> key
-#pragma unroll
-  for (int j = 0; j < DB_PPT; ++j) {
-    const int li = tid + j * DB_THREADS;
-    if (li < kDepNPB && mykey[j] != 0xFFFFu) {
-      const int pos = atomicAdd(&bins[mykey[j]], 1);
-      order[pos] = (unsigned short)li;
-      skey[pos] = mykey[j];
+    if (li < kDepNPB) {
+      const int key = skey[li];
+      if (key != 0xFFFF) order[atomicAdd(&bins[key], 1)] = (unsigned short)li;
     }
   }
   __syncthreads();
 
-  // ---- (D) run accumulation
+  // ---- (D) one thread per (segment, component[, mode slot]): node accumulators in registers
   const i64 plane = g.nxn * g.nrn;
-  const int nruns = (total + DB_RUN - 1) / DB_RUN;
+  i64 klo, khi;
+  keep_range(ch, cr.chunk, g.nxn, klo, khi);
+  const int ntask = sh.ntask;
 #pragma unroll 1
-  for (int t = tid; t < nruns * NSUB; t += DB_THREADS) {
-    const int run = t / NSUB, sub = t - run * NSUB;
-    const int lc = sub / NM, slot = sub - lc * NM;
+  for (int t = tid; t < ntask * NC * NS; t += DB_THREADS) {
+    const int task = t / (NC * NS), sub = t - task * (NC * NS);
+    const int lc = sub / NS, s0 = (sub - lc * NS) * SL;  // first mode slot of this thread
     const int l = CURR ? (ENV ? 2 : lc) : 0;
-    const int mode = ENV ? slot - NKO : slot;
-    const int am = mode < 0 ? -mode : mode;
-    cd* const gl = grid + plane * (slot + g.nm * l);
-    cd a00 = cmake(0, 0), a01 = a00, a10 = a00, a11 = a00;
-    int ckey = -1;
-    auto flush = [&]() {
-      if (ckey < 0) return;
-      const int kr = ckey / DB_BX, kx = ckey - kr * DB_BX;
-      const i64 gx = (i64)ix0 + kx, gr = (i64)ir0 + kr;
-      cd* pl = gl + gx + g.nxn * gr;
-      const bool k0 = (gx >= 0 && gx <= g.nxn - 1) && (ch.on ? chunk_keep(ch, c, gx, g.nxn) : true);
-      const bool k1 = (gx + 1 >= 0 && gx + 1 <= g.nxn - 1) && (ch.on ? chunk_keep(ch, c, gx + 1, g.nxn) : true);
-      if (k0) { red_add(pl, a00); red_add(pl + g.nxn, a01); }
-      if (k1) { red_add(pl + 1, a10); red_add(pl + 1 + g.nxn, a11); }
-      a00 = a01 = a10 = a11 = cmake(0, 0);
-    };
-    const int p0 = run * DB_RUN;
-    const int p1 = (p0 + DB_RUN < total) ? p0 + DB_RUN : total;
-    for (int pos = p0; pos < p1; ++pos) {
-      const int key = skey[pos];
-      if (key != ckey) { flush(); ckey = key; }
-      const int li = order[pos];
+    const int tw = tasks[task];
+    const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = tw >> 22;
+    cd a[2][2][SL];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int m = 0; m < SL; ++m) a[i][k][m] = cmake(0.0, 0.0);
+    const double* ra = rec + (4 + (ENV ? 0 : (CURR ? l : 0))) * kDepNPB;
+#pragma unroll 2
+    for (int q = 0; q < n; ++q) {
+      const int li = order[start + q];
       const double fx = rec[li], fr = rec[kDepNPB + li];
       const cd ph1 = cmake(rec[2 * kDepNPB + li], rec[3 * kDepNPB + li]);
-      cd ph = cmake(1.0, 0.0);
-      for (int q = 0; q < am; ++q) ph = cmul(ph, ph1);
-      if (mode < 0) ph = cconj(ph);
-      cd f;
-      if (ENV) f = cmul(cmake(rec[4 * kDepNPB + li], rec[5 * kDepNPB + li]), ph);
-      else f = cscale(rec[(4 + (CURR ? l : 0)) * kDepNPB + li], ph);
+      const cd amp = ENV ? cmake(ra[li], ra[kDepNPB + li]) : cmake(ra[li], 0.0);
       const double w00 = (1.0 - fx) * (1.0 - fr), w01 = (1.0 - fx) * fr, w10 = fx * (1.0 - fr), w11 = fx * fr;
-      a00.x += w00 * f.x; a00.y += w00 * f.y;
-      a01.x += w01 * f.x; a01.y += w01 * f.y;
-      a10.x += w10 * f.x; a10.y += w10 * f.y;
-      a11.x += w11 * f.x; a11.y += w11 * f.y;
+      cd phs[NM];  // exp(-i m theta) per mode slot
+      cd ph = cmake(1.0, 0.0);
+#pragma unroll
+      for (int iO = 0; iO <= NKO; ++iO) {
+        if (iO > 0) ph = cmul(ph, ph1);
+        if (ENV) { phs[NKO + iO] = ph; phs[NKO - iO] = cconj(ph); }
+        else phs[iO] = ph;
+      }
+#pragma unroll
+      for (int m = 0; m < SL; ++m) {
+        cd pm = phs[0];
+        if (SL == NM) pm = phs[m];
+        else {
+#pragma unroll
+          for (int z = 1; z < NM; ++z) pm = (s0 == z) ? phs[z] : pm;
+        }
+        const cd f = ENV ? cmul(amp, pm) : cscale(amp.x, pm);
+        a[0][0][m].x += w00 * f.x; a[0][0][m].y += w00 * f.y;
+        a[0][1][m].x += w01 * f.x; a[0][1][m].y += w01 * f.y;
+        a[1][0][m].x += w10 * f.x; a[1][0][m].y += w10 * f.y;
+        a[1][1][m].x += w11 * f.x; a[1][1][m].y += w11 * f.y;
+      }
     }
-    flush();
+    const int kr = key / DB_BX, kx = key - kr * DB_BX;
+    const i64 gx = (i64)ix0 + kx, gr = (i64)ir0 + kr;
+    cd* pl = grid + plane * (g.nm * l + s0) + gx + g.nxn * gr;
+    const bool k0 = gx >= klo && gx <= khi, k1 = gx + 1 >= klo && gx + 1 <= khi;
+#pragma unroll
+    for (int m = 0; m < SL; ++m) {
+      if (k0) { red_add(pl + plane * m, a[0][0][m]); red_add(pl + plane * m + g.nxn, a[0][1][m]); }
+      if (k1) { red_add(pl + plane * m + 1, a[1][0][m]); red_add(pl + plane * m + 1 + g.nxn, a[1][1][m]); }
+    }
   }
 }
 
@@ -585,6 +661,194 @@ int launch_binned_nm(cudaStream_t st, const double* x, const double* mom, const 
   return 0;
 }
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Binned gather + push: stages (A)-(C) as above, (D) one thread per (segment, field component) keeps the
+// 4 x nm node values of its cell and component in registers, (E) device + Boris push per particle.
+namespace {
+constexpr int GB_THREADS = 256, GB_PPT = kDepNPB / GB_THREADS;
+
+template <int ENV>
+struct GatLayout {
+  static constexpr int NF = ENV ? 6 : 4;
+  static constexpr size_t smem = sizeof(double) * (NF + 6) * kDepNPB + sizeof(int) * (DB_BINS + DB_MAXTASK) +
+                                 2 * sizeof(unsigned short) * kDepNPB;
+};
+
+template <int ENV, int NM>
+__global__ void __launch_bounds__(GB_THREADS, 2)
+gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w, const cd* __restrict__ Fld,
+                     double* __restrict__ mom, i64 cap, GridGeom g, double dt_2, UndulParams und, SortedSpec sp) {
+  constexpr int NF = GatLayout<ENV>::NF;
+  constexpr int NKO = ENV ? (NM - 1) / 2 : NM - 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* rec = reinterpret_cast<double*>(smem_raw);            // [NF][kDepNPB] by local id
+  double* fbuf = rec + NF * kDepNPB;                            // [6][kDepNPB] gathered field by local id
+  int* bins = reinterpret_cast<int*>(fbuf + 6 * kDepNPB);
+  int* tasks = bins + DB_BINS;
+  unsigned short* skey = reinterpret_cast<unsigned short*>(tasks + DB_MAXTASK);
+  unsigned short* order = skey + kDepNPB;
+  __shared__ BinShared<GB_THREADS> sh;
+  const int tid = threadIdx.x;
+
+  const CtaRange cr = cta_range(sp);
+  if (cr.count <= 0) return;
+  for (int i = tid; i < DB_BINS; i += GB_THREADS) bins[i] = 0;
+  if (tid == 0) cta_anchor(x, cap, g, sp, cr, sh.anchor);
+  __syncthreads();
+  const int ix0 = sh.anchor[0], ir0 = sh.anchor[1];
+
+  // ---- (A)
+  {
+    double xs[GB_PPT], ys[GB_PPT], zs[GB_PPT], ws[GB_PPT];
+#pragma unroll
+    for (int j = 0; j < GB_PPT; ++j) {
+      const int li = tid + j * GB_THREADS;
+      const bool in = li < cr.count;
+      const i64 ip = cr.first + (in ? li : 0);
+      xs[j] = __ldg(x + ip); ys[j] = __ldg(x + cap + ip); zs[j] = __ldg(x + 2 * cap + ip);
+      ws[j] = in ? __ldg(w + ip) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < GB_PPT; ++j) {
+      const int li = tid + j * GB_THREADS;
+      unsigned short key = 0xFFFFu;
+      const double xp = xs[j], yp = ys[j], zp = zs[j];
+      double F[6] = {0, 0, 0, 0, 0, 0};
+      Shape s;
+      if (ws[j] != 0.0 && make_shape(g, xp, yp, zp, s) && s.ix >= 0 && s.ix <= g.nxn - 2) {
+        const i64 kx = s.ix - ix0, kr = s.ir - ir0;
+        if (kx >= 0 && kx < DB_BX && kr >= 0 && kr < DB_BR) {
+          key = (unsigned short)(kr * DB_BX + kx);
+          atomicAdd(&bins[key], 1);
+          rec[li] = s.sx1;
+          rec[kDepNPB + li] = s.sr1;
+          // gather phase exp(+i theta); on the axis 0 (real solver) or 1 (envelope solver), Q4
+          const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;
+          rec[2 * kDepNPB + li] = (s.rp > 0.0) ? yp * rinv : (ENV ? 1.0 : 0.0);
+          rec[3 * kDepNPB + li] = zp * rinv;
+          if (ENV) {
+            double sn, cs;
+            sincos(xp * g.kx0, &sn, &cs);
+            rec[4 * kDepNPB + li] = cs;
+            rec[5 * kDepNPB + li] = sn;
+          }
+        } else {
+          gather_one<ENV>(g, Fld, xp, yp, zp, F);  // drifted out of the box
+        }
+      }
+      if (key == 0xFFFFu) {
+#pragma unroll
+        for (int l = 0; l < 6; ++l) fbuf[l * kDepNPB + li] = F[l];
+      }
+      skey[li] = key;
+    }
+  }
+  __syncthreads();
+  cta_scan_and_tasks(bins, tasks, sh, tid);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < GB_PPT; ++j) {
+    const int li = tid + j * GB_THREADS;
+    const int key = skey[li];
+    if (key != 0xFFFF) order[atomicAdd(&bins[key], 1)] = (unsigned short)li;
+  }
+  __syncthreads();
+
+  // ---- (D)
+  const i64 plane = g.nxn * g.nrn;
+  const int ntask = sh.ntask;
+#pragma unroll 1
+  for (int t = tid; t < ntask * 6; t += GB_THREADS) {
+    const int task = t / 6, l = t - task * 6;
+    const int tw = tasks[task];
+    const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = tw >> 22;
+    const int kr = key / DB_BX, kx = key - kr * DB_BX;
+    const cd* pl = Fld + plane * g.nm * l + ((i64)ix0 + kx) + g.nxn * ((i64)ir0 + kr);
+    cd N[NM][4];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      N[m][0] = __ldg(pl + plane * m); N[m][1] = __ldg(pl + plane * m + 1);
+      N[m][2] = __ldg(pl + plane * m + g.nxn); N[m][3] = __ldg(pl + plane * m + g.nxn + 1);
+    }
+#pragma unroll 2
+    for (int q = 0; q < n; ++q) {
+      const int li = order[start + q];
+      const double fx = rec[li], fr = rec[kDepNPB + li];
+      const cd ph1 = cmake(rec[2 * kDepNPB + li], rec[3 * kDepNPB + li]);
+      const double w00 = (1.0 - fr) * (1.0 - fx), w10 = (1.0 - fr) * fx, w01 = fr * (1.0 - fx), w11 = fr * fx;
+      cd car = cmake(1.0, 0.0);
+      if (ENV) car = cmake(rec[4 * kDepNPB + li], rec[5 * kDepNPB + li]);  // carrier exp(+i kx0 x)
+      cd ph = cmake(1.0, 0.0);
+      double F = 0.0;
+#pragma unroll
+      for (int iO = 0; iO <= NKO; ++iO) {
+        if (iO > 0) ph = cmul(ph, ph1);
+#pragma unroll
+        for (int sgn = 0; sgn < ((ENV && iO > 0) ? 2 : 1); ++sgn) {
+          const int slot = ENV ? (NKO + (sgn ? -iO : iO)) : iO;
+          const cd pm = ENV ? cmul(car, sgn ? cconj(ph) : ph) : ph;
+          const double sx = w00 * N[slot][0].x + w10 * N[slot][1].x + w01 * N[slot][2].x + w11 * N[slot][3].x;
+          const double sy = w00 * N[slot][0].y + w10 * N[slot][1].y + w01 * N[slot][2].y + w11 * N[slot][3].y;
+          F += pm.x * sx - pm.y * sy;
+        }
+      }
+      fbuf[l * kDepNPB + li] = F;
+    }
+  }
+  __syncthreads();
+
+  // ---- (E) external device + Boris push
+#pragma unroll
+  for (int j = 0; j < GB_PPT; ++j) {
+    const int li = tid + j * GB_THREADS;
+    if (li >= cr.count) continue;
+    const i64 ip = cr.first + li;
+    double F[6];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) F[l] = fbuf[l * kDepNPB + li];
+    if (und.on) undul_field(und, __ldg(x + ip), __ldg(x + cap + ip), F);
+    double px = mom[ip], py = mom[cap + ip], pz = mom[2 * cap + ip];
+    boris(px, py, pz, F[0], F[1], F[2], F[3], F[4], F[5], dt_2);
+    mom[ip] = px; mom[cap + ip] = py; mom[2 * cap + ip] = pz;
+  }
+}
+
+template <int ENV>
+int launch_gather_binned_nm(cudaStream_t st, const double* x, const double* w, const cd* Fld, double* mom, i64 cap,
+                            const GridGeom& g, double dt_2, const UndulParams& und, const SortedSpec& sp) {
+  const size_t smem = GatLayout<ENV>::smem;
+#define CHB_GB(NMV)                                                                                               \
+  case NMV: {                                                                                                     \
+    static bool attr = false;                                                                                     \
+    if (!attr) {                                                                                                  \
+      CHB_CUDA(cudaFuncSetAttribute(gather_push_binned_k<ENV, NMV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    (int)smem));                                                                  \
+      attr = true;                                                                                                \
+    }                                                                                                             \
+    gather_push_binned_k<ENV, NMV><<<sp.ncta, GB_THREADS, smem, st>>>(x, w, Fld, mom, cap, g, dt_2, und, sp);     \
+  } break;
+  switch ((int)g.nm) {
+    CHB_GB(1)
+    CHB_GB(2)
+    CHB_GB(3)
+    CHB_GB(4)
+    CHB_GB(5)
+    default: return -1;
+  }
+#undef CHB_GB
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
+int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* mom,
+                              i64 cap, const GridGeom& g, double dt, const UndulParams& und, const SortedSpec& sp) {
+  if (sp.ncta <= 0) return 0;
+  if (env && (g.nm % 2) != 1) { set_error("envelope gather needs an odd number of mode slots"); return 2; }
+  return env ? launch_gather_binned_nm<1>(st, x, w, Fld, mom, cap, g, 0.5 * dt, und, sp)
+             : launch_gather_binned_nm<0>(st, x, w, Fld, mom, cap, g, 0.5 * dt, und, sp);
+}
 
 int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, const double* mom, const double* w,
                           i64 cap, cd* grid, const GridGeom& g, const ChunkSpec& ch, const SortedSpec& sp) {
