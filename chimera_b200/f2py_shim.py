@@ -8,7 +8,8 @@ library that exports ``<prefix>_<name>`` entry points with the signatures declar
 ``include/chimera_b200.h``.  It is instantiated twice:
 
   * ``chimera_b200.fimera``  -> libchimera_b200.so (CUDA, prefix ``chimera``)   [the product]
-  * ``oracle.fimera``        -> liboracle.so       (CPU,  prefix ``oracle``)    [test checker]
+  * ``oracle.fimera``        -> the CPU checker's library (prefix ``oracle``) [test infrastructure; it
+                                imports this module, never the other way round]
 
 f2py semantics reproduced here
   * ``intent(in,out)`` arguments are returned; the same object is returned (modified in place)

@@ -1,0 +1,253 @@
+"""Second, independent restatement of the real-solver hot path in vectorised numpy (TEST INFRASTRUCTURE).
+
+oracle/chimera_oracle.cpp restates the reference's Fortran loop for loop.  Nothing the reference ships
+pins that restatement (no golden vectors, Fortran not buildable here), so this module restates the same
+mathematics a second time in a *different form* -- whole-array numpy: ``np.add.at`` scatter for the
+deposition, fancy-index gather, ``einsum``/``matmul`` + ``numpy.fft`` for the transforms, matrix notation
+for the spectral calculus -- written from the Fortran sources cited per function.  tests/test_np_ref.py
+requires the two restatements to agree to round-off; a transcription slip in either shows up there.
+
+Only the real ("PIC") solver family is covered (the envelope variants differ by the carrier factor and
+the mode slot range and are covered by the KATs in tests/test_oracle_kat.py).  Array conventions as in
+the reference: Fortran order, grids (Nx, Nr, M[, c]) with radial node 0 the r = -dr/2 ghost.
+"""
+import numpy as np
+
+
+# ---- f90/particle_tools.f90 -------------------------------------------------------------------
+def push_velocs(momenta, fld, dt):
+    """Boris rotation, particle_tools.f90:18-56 (dt already carries 2 pi q/m)."""
+    p = np.array(momenta, dtype=float)
+    e, b = 0.5 * dt * fld[:3], fld[3:]
+    um = p + e
+    g = np.sqrt(1.0 + (um ** 2).sum(0))
+    t = 0.5 * dt * b / g
+    s = 2.0 * t / (1.0 + (t ** 2).sum(0))
+    u0 = um + np.cross(um, t, axis=0)
+    up = um + np.cross(u0, s, axis=0)
+    return up + e
+
+
+def push_coords(coord, momenta, dt):
+    """leap-frog, particle_tools.f90:58-82: returns (new coord, centred coord)."""
+    g = np.sqrt(1.0 + (momenta ** 2).sum(0))
+    new = coord + dt * momenta / g
+    return new, 0.5 * (coord + new)
+
+
+# ---- f90/grid_deps.f90 ------------------------------------------------------------------------
+def _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv):
+    x, y, z = coord
+    r = np.sqrt(y * y + z * z)
+    ok = (wghts != 0.0) & (r < Rgrid[-1])
+    ix = np.floor((x - leftX) * dx_inv).astype(int)
+    ir = np.floor((r - Rgrid[0]) * dr_inv).astype(int)
+    sx = (x - leftX) * dx_inv - ix
+    sr = (r - Rgrid[np.clip(ir, 0, len(Rgrid) - 1)]) * dr_inv
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ph = np.where(r > 0, (y - 1j * z) / np.where(r > 0, r, 1.0), 0.0)  # exp(-i theta); 0 on the axis
+    return ok, ix, ir, sx, sr, ph
+
+
+def _scatter(grid, ok, ix, ir, sx, sr, ph, amp):
+    """grid(Nx,Nr,M) += amp * exp(-i m theta) * Sx * Sr on the 4 nodes of each particle's cell."""
+    nm = grid.shape[2]
+    for m in range(nm):
+        v = amp * ph ** m if m else amp.astype(complex)
+        for i, wx in ((0, 1.0 - sx), (1, sx)):
+            for k, wr in ((0, 1.0 - sr), (1, sr)):
+                np.add.at(grid[:, :, m], (ix[ok] + i, ir[ok] + k), (v * wx * wr)[ok])
+
+
+def _fold_ghost(grid):
+    grid[:, 1] -= grid[:, 0]
+    grid[:, 0] = 0.0
+
+
+def dep_dens(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv):
+    """grid_deps.f90:89-147"""
+    ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
+    _scatter(dens, ok, ix, ir, sx, sr, ph, wghts)
+    _fold_ghost(dens)
+    return dens
+
+
+def dep_curr(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv):
+    """grid_deps.f90:18-87"""
+    ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
+    ok = ok & (np.abs(momenta).sum(0) != 0.0)
+    g = np.sqrt(1.0 + (momenta ** 2).sum(0))
+    for l in range(3):
+        _scatter(curr[..., l], ok, ix, ir, sx, sr, ph, momenta[l] * wghts / g)
+        _fold_ghost(curr[..., l])
+    return curr
+
+
+def proj_fld(coord, wghts, Fld, Fld_tot, leftX, Rgrid, dx_inv, dr_inv):
+    """grid_deps.f90:149-217 (gather phase exp(+i theta), 0 on the axis)"""
+    ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
+    ph = np.conj(ph)
+    out = np.array(Fld_tot, dtype=float)
+    nm = Fld.shape[2]
+    idx = np.nonzero(ok)[0]
+    for l in range(6):
+        acc = np.zeros(idx.size)
+        for m in range(nm):
+            pm = ph[idx] ** m if m else np.ones(idx.size, dtype=complex)
+            for i, wx in ((0, 1.0 - sx[idx]), (1, sx[idx])):
+                for k, wr in ((0, 1.0 - sr[idx]), (1, sr[idx])):
+                    acc += (wx * wr * pm * Fld[ix[idx] + i, ir[idx] + k, m, l]).real
+        out[l, idx] += acc
+    return out
+
+
+def eb_correction(eb):
+    """grid_deps.f90:219-266"""
+    eb = np.array(eb)
+    eb[:, :, 0] /= 2 * np.pi
+    eb[:, :, 1:] /= np.pi
+    eb[:, 0, 0] = eb[:, 1, 0]
+    eb[:, 0, 1:] = -eb[:, 1, 1:]
+    return eb
+
+
+# ---- f90/fb_io.f90 ----------------------------------------------------------------------------
+def fb_in(vec, leftX, kx, In):
+    """fb_vec_in / fb_scl_in, fb_io.f90:18-98: DHT over r (ghost node skipped), FFT over x, phase."""
+    a = np.einsum("xrm...,rkm->xkm...", vec[:, 1:], In)
+    a = np.fft.fft(a, axis=0)
+    ph = np.exp(-1j * leftX * kx)
+    return a * ph.reshape((-1,) + (1,) * (a.ndim - 1))
+
+
+def fb_out(vec_fb, leftX, kx, Out):
+    """fb_vec_out / fb_scl_out, fb_io.f90:100-180: DHT, phase, unnormalised inverse FFT; ghost row 0."""
+    a = np.einsum("xkm...,krm->xrm...", vec_fb, Out)
+    ph = np.exp(1j * leftX * kx)
+    a = np.fft.ifft(a * ph.reshape((-1,) + (1,) * (a.ndim - 1)), axis=0) * vec_fb.shape[0]
+    out = np.zeros((a.shape[0], a.shape[1] + 1) + a.shape[2:], dtype=complex)
+    out[:, 1:] = a
+    return out
+
+
+def fb_eb_out(e_fb, b_fb, leftX, kx, Out):
+    """fb_io.f90:182-228"""
+    return np.concatenate((fb_out(e_fb[..., :3], leftX, kx, Out), fb_out(b_fb, leftX, kx, Out)), axis=-1)
+
+
+# ---- f90/fb_math.f90 --------------------------------------------------------------------------
+MIRROR_SHIFT = 0  # 0: rows are a full kx axis (or the rank-0 slab); 1: a rank>0 kx slab (chimera_b200/sharding.py)
+
+
+def _mirror(f):
+    """-conj(f(-kx)): rows (Nx - i) mod Nx, fb_math.f90:35-36 (slab-local form: (L - i - shift) mod L)"""
+    n = f.shape[0]
+    return -np.conj(f[(n - np.arange(n) - MIRROR_SHIFT) % n])
+
+
+def _con(D, f):
+    """(D . f)[x, k'] = sum_k D[k, k'] f[x, k]"""
+    return f @ D
+
+
+def _lower(f, m):
+    """the mode-(m-1) neighbour of slot m; for m = 0 the mirrored slot 1 (0 when there is none: Q7)"""
+    if m > 0:
+        return f[:, :, m - 1]
+    return _mirror(f[:, :, 1]) if f.shape[2] > 1 else np.zeros_like(f[:, :, 0])
+
+
+def fb_grad(scl, Dp, Dm, kx):
+    """fb_math.f90:96-149"""
+    nm = scl.shape[2]
+    out = np.zeros(scl.shape + (3,), dtype=complex)
+    ikx = 1j * kx[:, None]
+    for m in range(nm):
+        out[:, :, m, 0] = ikx * scl[:, :, m]
+        t = _con(Dm[:, :, m], _lower(scl, m))
+        out[:, :, m, 1] -= t
+        out[:, :, m, 2] += 1j * t
+        if m < nm - 1:
+            t = _con(Dp[:, :, m], scl[:, :, m + 1])
+            out[:, :, m, 1] += t
+            out[:, :, m, 2] += 1j * t
+    return out
+
+
+def fb_div(vec, Dp, Dm, kx, extra_mode=False):
+    """fb_math.f90:151-199; extra_mode: the (M+1)-slot scalar fb_graddiv builds internally (:232-262)"""
+    nm = vec.shape[2]
+    n_out = nm + 1 if extra_mode else nm
+    out = np.zeros(vec.shape[:2] + (n_out,), dtype=complex)
+    ikx = 1j * kx[:, None]
+    y, z = vec[..., 1], vec[..., 2]
+    for m in range(n_out):
+        if m < nm:
+            out[:, :, m] += ikx * vec[:, :, m, 0]
+        out[:, :, m] += _con(Dm[:, :, m], 1j * _lower(z, m) - _lower(y, m))
+        if m < nm - 1:
+            out[:, :, m] += _con(Dp[:, :, m], 1j * z[:, :, m + 1] + y[:, :, m + 1])
+    return out
+
+
+def fb_rot(vec, Dp, Dm, kx):
+    """fb_math.f90:18-94"""
+    nm = vec.shape[2]
+    out = np.zeros_like(vec)
+    ikx = 1j * kx[:, None]
+    x, y, z = vec[..., 0], vec[..., 1], vec[..., 2]
+    for m in range(nm):
+        out[:, :, m, 1] -= ikx * z[:, :, m]
+        out[:, :, m, 2] += ikx * y[:, :, m]
+        if m < nm - 1:
+            out[:, :, m, 0] -= _con(Dp[:, :, m], 1j * y[:, :, m + 1] - z[:, :, m + 1])
+            t = _con(Dp[:, :, m], x[:, :, m + 1])
+            out[:, :, m, 1] += 1j * t
+            out[:, :, m, 2] -= t
+        out[:, :, m, 0] -= _con(Dm[:, :, m], 1j * _lower(y, m) + _lower(z, m))
+        t = _con(Dm[:, :, m], _lower(x, m))
+        out[:, :, m, 1] += 1j * t
+        out[:, :, m, 2] += t
+    return out
+
+
+def fb_graddiv(vec, Dp, Dm, kx):
+    """fb_math.f90:201-293: grad of the (M+1)-slot divergence; the mirror terms only when M > 1 (:217)"""
+    nm = vec.shape[2]
+    s = fb_div(vec, Dp, Dm, kx, extra_mode=True)
+    out = np.zeros_like(vec)
+    ikx = 1j * kx[:, None]
+    for m in range(nm):
+        out[:, :, m, 0] = ikx * s[:, :, m]
+        low = s[:, :, m - 1] if m > 0 else (_mirror(s[:, :, 1]) if nm > 1 else np.zeros_like(s[:, :, 0]))
+        t = _con(Dm[:, :, m], low)
+        out[:, :, m, 1] -= t
+        out[:, :, m, 2] += 1j * t
+        t = _con(Dp[:, :, m], s[:, :, m + 1])
+        out[:, :, m, 1] += t
+        out[:, :, m, 2] += 1j * t
+    return out
+
+
+# ---- f90/maxwell_solvers.f90 --------------------------------------------------------------------
+def maxwell_push_with_spchrg(EG, J, g_n, g_np1, C1, C2):
+    """maxwell_solvers.f90:18-60"""
+    E, G = EG[..., :3], EG[..., 3:]
+    src = (E, G, J, g_n, g_np1)
+    newE = sum(C1[..., i, None] * s for i, s in enumerate(src))
+    newG = sum(C2[..., i, None] * s for i, s in enumerate(src))
+    return np.concatenate((newE, newG), axis=-1)
+
+
+def maxwell_push_wo_spchrg(EG, J, C1, C2):
+    """maxwell_solvers.f90:62-96"""
+    E, G = EG[..., :3], EG[..., 3:]
+    src = (E, G, J)
+    newE = sum(C1[..., i, None] * s for i, s in enumerate(src))
+    newG = sum(C2[..., i, None] * s for i, s in enumerate(src))
+    return np.concatenate((newE, newG), axis=-1)
+
+
+def poiss_corr(J, gdj, g_n, g_np1, dt_inv, w2_inv):
+    """maxwell_solvers.f90:131-164"""
+    return J + w2_inv[..., None] * (gdj + dt_inv * (g_np1 - g_n))

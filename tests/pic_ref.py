@@ -25,7 +25,8 @@ class RefSpecies:
 
 
 class RefRun:
-    def __init__(self, fim, setup, species, chunked=None, sort_every=None, poisson_iters=None, background=False):
+    def __init__(self, fim, setup, species, chunked=None, sort_every=None, poisson_iters=None, background=False,
+                 reduce=None, rank=0):
         self.f, self.S, self.sp = fim, setup, species
         a = self.a = setup.Args
         feats = a.get("Features", ())
@@ -36,6 +37,8 @@ class RefRun:
         self.sort_every = (self.guards + 1 if self.chunked else 0) if sort_every is None else sort_every
         self.npoiss = (0 if "NoPoissonCorrection" in feats else 3) if poisson_iters is None else poisson_iters
         self.background = background
+        # multi-rank runs (particles sharded): `reduce` sums a deposited grid over the ranks in place
+        self.reduce, self.rank = reduce, rank
         S = setup
         self.J, self.Rho, self.Bck = S.zeros_sp(3), S.zeros_sp(), S.zeros_sp()
         self.EB = S.zeros_sp(6)
@@ -79,6 +82,8 @@ class RefRun:
             if s.still or s.coords.shape[1] == 0:
                 continue
             self.J = self._dep("curr", self.J, s, s.coords_halfstep)
+        if self.reduce:
+            self.reduce(self.J)
         a, f = self.a, self.f
         self.J_fb = f.fb_vec_in(self.J_fb, self.J, a["leftX"], *a["FBCurrIn"])
         self.J_fb = f.omp_mult_vec(self.J_fb, a["DepFact"])
@@ -88,6 +93,8 @@ class RefRun:
         for s in self.sp:
             if s.still and s.coords.shape[1]:
                 self.Bck = self._dep("dens", self.Bck, s, s.coords)
+        if self.reduce:
+            self.reduce(self.Bck)
 
     def project_density(self):
         if not self.space_charge:
@@ -95,11 +102,14 @@ class RefRun:
         a, f = self.a, self.f
         self.g_prv[:] = self.g_nxt
         self.Rho[:] = 0.0
-        self.Rho += self.Bck
+        if self.rank == 0:  # the (already summed) background enters the all-reduced density once
+            self.Rho += self.Bck
         for s in self.sp:
             if s.still or s.coords.shape[1] == 0:
                 continue
             self.Rho = self._dep("dens", self.Rho, s, s.coords)
+        if self.reduce:
+            self.reduce(self.Rho)
         self.Rho_fb = f.fb_scl_in(self.Rho_fb, self.Rho, a["leftX"], *a["FBCurrIn"])
         self.Rho_fb = f.omp_mult_scl(self.Rho_fb, a["DepFact"])
         grad = f.fb_grad_env if self.env else f.fb_grad

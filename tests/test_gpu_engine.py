@@ -10,52 +10,10 @@ import numpy as np
 import pytest
 
 from pic_ref import RefRun, RefSpecies
-from util import SETUPS, TOL, assert_close, rel_l2
+from util import SETUPS, TOL, assert_close, carrier_tol, match, plasma, rel_l2, seed_fields
 from chimera_b200.solver_setup import SolverSetup
 
 pytestmark = pytest.mark.gpu
-
-
-def plasma(S, ppc_x, ppc_r, seed, frac=(0.15, 0.85), thermal=0.05, dens=0.005):
-    """Uniform plasma slab with unique (label) weights; coordinates inside the grid."""
-    rng = np.random.default_rng(seed)
-    a = S.Args
-    nx, nr, dx, dr = a["Nx"], a["Nr"], a["dx"], a["dr"]
-    ix = np.arange(int(frac[0] * nx), int(frac[1] * nx))
-    ir = np.arange(0, int(0.8 * (nr - 1)))
-    X, R, px, pr = np.meshgrid(ix, ir, np.arange(ppc_x), np.arange(ppc_r), indexing="ij")
-    x = a["leftX"] + dx * (X + (px + 0.5) / ppc_x)
-    r = dr * (R + (pr + 0.5) / ppc_r)
-    x, r = x.ravel(), r.ravel()
-    # jitter: on a perfectly regular lattice the envelope deposit (carrier exp(-i kx0 x)) cancels almost
-    # exactly and the relative error of the tiny remainder is meaningless
-    x = x + dx * 0.4 / ppc_x * (rng.random(x.size) - 0.5)
-    r = r + dr * 0.4 / ppc_r * (rng.random(x.size) - 0.5)
-    th = 2 * np.pi * rng.random(x.size)
-    coords = np.asfortranarray(np.vstack((x, r * np.cos(th), r * np.sin(th))))
-    mom = np.asfortranarray(thermal * rng.standard_normal((3, x.size)))
-    w = -dens * dr * dx * 2 * np.pi * r / (ppc_x * ppc_r) * (1.0 + 1e-3 * rng.random(x.size))
-    return coords, mom, np.asfortranarray(w)
-
-
-def seed_fields(S, seed, amp=0.5):
-    """A smooth, band-limited initial EG_fb so that gather/push see non-trivial fields."""
-    rng = np.random.default_rng(seed)
-    nx, nkr, nm = S.shape_fb
-    eg = S.zeros_fb(6)
-    kx = np.fft.fftfreq(nx) * nx
-    env = np.exp(-(kx / (0.08 * nx)) ** 2)[:, None, None, None] * np.exp(-(np.arange(nkr) / (0.2 * nkr)) ** 2)[None, :, None, None]
-    eg[:] = amp * env * (rng.standard_normal(eg.shape) + 1j * rng.standard_normal(eg.shape))
-    return np.asfortranarray(eg)
-
-
-def match(w_ref, w_eng):
-    """permutation taking engine order to reference order via the (unique) weights"""
-    a, b = np.argsort(w_ref, kind="stable"), np.argsort(w_eng, kind="stable")
-    perm = np.empty_like(a)
-    perm[a] = b
-    assert np.array_equal(w_ref, w_eng[perm])
-    return perm
 
 
 def build_pair(ofim, name, seed, ppc=(2, 2), still_ions=False, undulator=None, amp=0.5):
@@ -81,6 +39,7 @@ def build_pair(ofim, name, seed, ppc=(2, 2), still_ions=False, undulator=None, a
 
 
 def compare_state(ref, eng, tol, names=("J", "Rho", "EG_fb", "J_fb", "EB")):
+    tol = carrier_tol(ref.S, tol)
     for n in names:
         want = {"J": ref.J, "Rho": ref.Rho, "EG_fb": ref.EG_fb, "J_fb": ref.J_fb, "EB": ref.EB, "B_fb": ref.B_fb}[n]
         if n == "Rho" and not ref.space_charge:

@@ -1,0 +1,87 @@
+"""CPU: the C++ oracle (oracle/chimera_oracle.cpp, loop-for-loop) against the independent vectorised
+numpy restatement (oracle/np_ref.py) of the same Fortran.  Neither is the reference -- the Fortran
+cannot be built here -- but two restatements in different forms agreeing to round-off is the strongest
+pin available for the kernels themselves ("parity unpinned")."""
+import numpy as np
+import pytest
+
+from oracle import np_ref
+from util import assert_close, crandn, particles, setup
+
+REAL = ["real_m1", "real_m2", "real_m3"]
+TOL = 2e-13
+
+
+@pytest.mark.parametrize("n", [1, 257, 5000])
+def test_push(ofim, n):
+    rng = np.random.default_rng(n)
+    p = np.asfortranarray(rng.standard_normal((3, n)) * 2)
+    f = np.asfortranarray(rng.standard_normal((6, n)))
+    x = np.asfortranarray(rng.standard_normal((3, n)))
+    assert_close(ofim.push_velocs(p.copy(order="F"), f, -0.37), np_ref.push_velocs(p, f, -0.37), TOL, "push_velocs")
+    xn, xc = ofim.push_coords(x.copy(order="F"), p, np.zeros_like(x), 0.05)
+    rn, rc = np_ref.push_coords(x, p, 0.05)
+    assert_close(xn, rn, TOL, "coord")
+    assert_close(xc, rc, TOL, "coord_cntr")
+
+
+@pytest.mark.parametrize("name", REAL)
+def test_deposit_and_gather(ofim, name):
+    S = setup(name)
+    a = S.Args
+    x, p, w = particles(S, 4000, 5, inside_only=True)
+    dp = a["DepProj"]
+    rho = ofim.dep_dens(x, w, S.zeros_sp(), a["leftX"], *dp)
+    assert_close(rho, np_ref.dep_dens(x, w, S.zeros_sp(), a["leftX"], *dp), TOL, "dep_dens")
+    cur = ofim.dep_curr(x, p, w, S.zeros_sp(3), a["leftX"], *dp)
+    assert_close(cur, np_ref.dep_curr(x, p, w, S.zeros_sp(3), a["leftX"], *dp), TOL, "dep_curr")
+    fld = crandn(np.random.default_rng(3), S.shape_sp + (6,))
+    got = ofim.proj_fld(x, w, fld, np.zeros((6, x.shape[1]), order="F"), a["leftX"], *dp)
+    assert_close(got, np_ref.proj_fld(x, w, fld, np.zeros((6, x.shape[1])), a["leftX"], *dp), TOL, "proj_fld")
+    assert_close(ofim.eb_correction(fld.copy(order="F")), np_ref.eb_correction(fld), TOL, "eb_correction")
+
+
+@pytest.mark.parametrize("name", REAL)
+def test_transforms(ofim, name):
+    S = setup(name)
+    a = S.Args
+    rng = np.random.default_rng(11)
+    vec = crandn(rng, S.shape_sp + (3,))
+    kx, In = a["FBCurrIn"]
+    assert_close(ofim.fb_vec_in(S.zeros_fb(3), vec, a["leftX"], kx, In), np_ref.fb_in(vec, a["leftX"], kx, In), TOL, "fb_vec_in")
+    assert_close(ofim.fb_scl_in(S.zeros_fb(), vec[..., 0], a["leftX"], kx, In), np_ref.fb_in(vec[..., 0], a["leftX"], kx, In),
+                 TOL, "fb_scl_in")
+    e, b = crandn(rng, S.shape_fb + (6,)), crandn(rng, S.shape_fb + (3,))
+    kxo, Out = a["FBout"]
+    assert_close(ofim.fb_eb_out(S.zeros_sp(6), e, b, a["leftX"], kxo, Out), np_ref.fb_eb_out(e, b, a["leftX"], kxo, Out), TOL,
+                 "fb_eb_out")
+    assert_close(ofim.fb_vec_out(b, a["leftX"], kxo, Out), np_ref.fb_out(b, a["leftX"], kxo, Out), TOL, "fb_vec_out")
+
+
+@pytest.mark.parametrize("name", ["real_m2", "real_m3"])
+def test_spectral_calculus(ofim, name):
+    S = setup(name)
+    a = S.Args
+    rng = np.random.default_rng(13)
+    Dp, Dm, kx = a["FBDiff"]
+    v, s = crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb)
+    assert_close(ofim.fb_grad(S.zeros_fb(3), s, Dp, Dm, kx), np_ref.fb_grad(s, Dp, Dm, kx), TOL, "fb_grad")
+    assert_close(ofim.fb_div(S.zeros_fb(), v, Dp, Dm, kx), np_ref.fb_div(v, Dp, Dm, kx), TOL, "fb_div")
+    assert_close(ofim.fb_rot(S.zeros_fb(3), v, Dp, Dm, kx), np_ref.fb_rot(v, Dp, Dm, kx), TOL, "fb_rot")
+    assert_close(ofim.fb_graddiv(v.copy(order="F"), Dp, Dm, kx), np_ref.fb_graddiv(v, Dp, Dm, kx), TOL, "fb_graddiv")
+
+
+def test_maxwell_family(ofim):
+    S = setup("real_m2")  # SpaceCharge: 5 real coefficients
+    rng = np.random.default_rng(17)
+    eg, j = crandn(rng, S.shape_fb + (6,)), crandn(rng, S.shape_fb + (3,))
+    g0, g1 = crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb + (3,))
+    got = ofim.maxwell_push_with_spchrg(eg.copy(order="F"), j, g0, g1, S.PSATD_E, S.PSATD_G)
+    assert_close(got, np_ref.maxwell_push_with_spchrg(eg, j, g0, g1, S.PSATD_E, S.PSATD_G), TOL, "with_spchrg")
+    a = S.Args
+    got = ofim.poiss_corr(j.copy(order="F"), eg[..., :3], g0, g1, a["dt_inv"], a["PoissFact"])
+    assert_close(got, np_ref.poiss_corr(j, eg[..., :3], g0, g1, a["dt_inv"], a["PoissFact"]), TOL, "poiss_corr")
+    S3 = setup("real_m3")  # no space charge: 3 coefficients
+    eg, j = crandn(rng, S3.shape_fb + (6,)), crandn(rng, S3.shape_fb + (3,))
+    got = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, S3.PSATD_E, S3.PSATD_G)
+    assert_close(got, np_ref.maxwell_push_wo_spchrg(eg, j, S3.PSATD_E, S3.PSATD_G), TOL, "wo_spchrg")

@@ -1,0 +1,172 @@
+"""CPU: analytic known-answer tests of the oracle -- answers that need no reference run
+(SURVEY.md section 8c (ii)).  They pin conventions (signs, normalisations, index offsets) that a
+self-consistent-but-wrong restatement would still get wrong."""
+import numpy as np
+import pytest
+
+from util import ALL_SETUPS, crandn, particles, rel_l2, setup
+
+
+@pytest.mark.parametrize("name", ALL_SETUPS)
+def test_dht_matrices_are_inverse_pairs(name):
+    """In = inv(Out) per mode (solvers.py:742-743); InCurr = In * 1/cell-volume (:107-110)"""
+    S = setup(name)
+    a = S.Args
+    if "Rcut" in a:
+        pytest.skip("R-cut operators are rectangular slices of the full pair (solvers.py:123-136)")
+    for m in range(a["In"].shape[2]):
+        # Out(k, r) = J_m(k_k r_r); In(r, k) its inverse: sum_r Out(k, r) In(r, k') = delta(k, k')
+        np.testing.assert_allclose(a["Out"][:, :, m] @ a["In"][:, :, m], np.eye(a["In"].shape[1]), atol=1e-9)
+        vol = a["InCurr"][:, :, m] / a["In"][:, :, m]
+        np.testing.assert_allclose(vol, np.broadcast_to(vol[:, :1], vol.shape), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["real_m2", "real_m3", "env_m3"])
+def test_forward_backward_transform_roundtrip(ofim, name):
+    """fb_vec_out(fb_vec_in(v)) = Nx * v on the non-ghost rows: unnormalised FFT pair (Q9) and In.Out = 1"""
+    S = setup(name)
+    a = S.Args
+    v = crandn(np.random.default_rng(2), S.shape_sp + (3,))
+    v[:, 0] = 0.0
+    kx = a["FBIn"][0]
+    fb = ofim.fb_vec_in(S.zeros_fb(3), v, a["leftX"], kx, a["In"])
+    back = ofim.fb_vec_out(fb, a["leftX"], kx, a["Out"])
+    assert rel_l2(back[:, 1:] / a["Nx"], v[:, 1:]) < 1e-9
+
+
+def test_boris_push_pure_magnetic_rotation(ofim):
+    """|p| conserved exactly to round-off; rotation angle 2 atan(dt/2 |B| / gamma)"""
+    n = 1000
+    rng = np.random.default_rng(4)
+    p = np.asfortranarray(rng.standard_normal((3, n)) * 3)
+    f = np.zeros((6, n), order="F")
+    f[5] = 0.7  # Bz
+    dt = 0.31
+    q = ofim.push_velocs(p.copy(order="F"), f, dt)
+    np.testing.assert_allclose((q ** 2).sum(0), (p ** 2).sum(0), rtol=1e-13)
+    np.testing.assert_allclose(q[2], p[2], rtol=1e-14)
+    g = np.sqrt(1 + (p ** 2).sum(0))
+    ang = np.angle((q[0] + 1j * q[1]) / (p[0] + 1j * p[1]))
+    np.testing.assert_allclose(np.abs(ang), 2 * np.arctan(0.5 * dt * 0.7 / g), rtol=1e-11)
+
+
+def test_boris_push_pure_electric(ofim):
+    p = np.zeros((3, 5), order="F")
+    f = np.zeros((6, 5), order="F")
+    f[0] = np.arange(5.0)
+    q = ofim.push_velocs(p.copy(order="F"), f, 0.5)
+    np.testing.assert_allclose(q[0], 0.5 * np.arange(5.0), rtol=1e-15)
+
+
+def test_push_coords_is_leapfrog(ofim):
+    x = np.zeros((3, 3), order="F")
+    p = np.asfortranarray([[3.0, 0, 0], [0, 4.0, 0], [0, 0, 0]]).T.copy(order="F")  # particle 0: (3,0,0); 1: (0,4,0)
+    xn, xc = ofim.push_coords(x.copy(order="F"), p, np.zeros_like(x), 2.0)
+    np.testing.assert_allclose(xn[0, 0], 2.0 * 3 / np.sqrt(10.0), rtol=1e-15)
+    np.testing.assert_allclose(xn[1, 1], 2.0 * 4 / np.sqrt(17.0), rtol=1e-15)
+    np.testing.assert_allclose(xc, 0.5 * xn, rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["real_m2", "real_m3"])
+def test_charge_conservation_of_deposit(ofim, name):
+    """sum over nodes of the m=0 density equals the total weight (the ghost fold moves, never loses, charge:
+    grid_deps.f90:80-85 subtracts row 0 from row 1 -- the reflected ghost contribution)"""
+    S = setup(name)
+    a = S.Args
+    x, p, w = particles(S, 3000, 9, edge_cases=False)
+    r = np.hypot(x[1], x[2])
+    keep = r > 1.01 * a["dr"] * 0.5  # away from the axis cell, where the fold changes the sum by design
+    x, w = np.asfortranarray(x[:, keep]), np.asfortranarray(w[keep])
+    rho = ofim.dep_dens(x, w, S.zeros_sp(), a["leftX"], *a["DepProj"])
+    assert abs(rho[:, :, 0].sum().real - w.sum()) < 1e-12 * abs(w.sum())
+    assert abs(rho[:, :, 0].sum().imag) < 1e-20
+
+
+def test_single_particle_deposit_weights(ofim):
+    """one particle at (x, r) inside cell (ix, ir): the 4 bilinear weights and the exp(-i m theta) phases"""
+    S = setup("real_m3")
+    a = S.Args
+    ix, ir, fx, fr, th = 7, 4, 0.25, 0.6, 0.9
+    xp = a["leftX"] + (ix + fx) * a["dx"]
+    rp = a["Rgrid"][ir] + fr * a["dr"]
+    x = np.asfortranarray([[xp], [rp * np.cos(th)], [rp * np.sin(th)]])
+    w = np.asfortranarray([2.0])
+    rho = ofim.dep_dens(x, w, S.zeros_sp(), a["leftX"], *a["DepProj"])
+    for m in range(3):
+        ph = np.exp(-1j * m * th)
+        want = 2.0 * ph * np.array([[(1 - fx) * (1 - fr), (1 - fx) * fr], [fx * (1 - fr), fx * fr]])
+        np.testing.assert_allclose(rho[ix:ix + 2, ir:ir + 2, m], want, rtol=1e-12, atol=1e-14)
+    assert np.count_nonzero(rho) == 12
+
+
+def test_gather_of_uniform_field_returns_it(ofim):
+    """a field constant over the grid in mode 0 is gathered unchanged (weights sum to 1); mode-1 content
+    picks up cos(theta)"""
+    S = setup("real_m2")
+    a = S.Args
+    x, p, w = particles(S, 500, 3, edge_cases=False)
+    fld = S.zeros_sp(6)
+    fld[:, :, 0, 2] = 1.5
+    fld[:, :, 1, 4] = 2.0
+    got = ofim.proj_fld(x, w, fld, np.zeros((6, 500), order="F"), a["leftX"], *a["DepProj"])
+    np.testing.assert_allclose(got[2], 1.5, rtol=1e-13)
+    th = np.arctan2(x[2], x[1])
+    np.testing.assert_allclose(got[4], 2.0 * np.cos(th), rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["real_m2", "real_m3"])
+def test_vector_identities_in_fb_space(ofim, name):
+    """div(rot v) = 0 and rot(grad f) = 0 for the real solver: the D+/D- couplings and the kx-mirror term
+    (fb_math.f90:35-36) are mutually consistent only with the right signs.  The highest stored mode is
+    truncated (its m+1 neighbour does not exist), so the identities are checked with it empty."""
+    S = setup(name)
+    a = S.Args
+    Dp, Dm, kx = a["FBDiff"]
+    rng = np.random.default_rng(6)
+    v, f = crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb)
+    v[:, :, -1], f[:, :, -1] = 0.0, 0.0
+    # hermitian-symmetric in kx so that mode 0 is a real field (what the mirror term assumes)
+    rev = (-np.arange(a["Nx"])) % a["Nx"]
+    v[:, :, 0] = 0.5 * (v[:, :, 0] + np.conj(v[rev][:, :, 0]))
+    f[:, :, 0] = 0.5 * (f[:, :, 0] + np.conj(f[rev][:, :, 0]))
+    ny = a["Nx"] // 2  # the Nyquist row is its own mirror with kx = -kx: leave it empty
+    v[ny], f[ny] = 0.0, 0.0
+    assert np.allclose(np.delete(kx, ny), -np.delete(kx[rev], ny))
+    rot = ofim.fb_rot(S.zeros_fb(3), v, Dp, Dm, kx)
+    d = ofim.fb_div(S.zeros_fb(), rot, Dp, Dm, kx)
+    nm = S.shape_fb[2]
+    lo = slice(0, max(nm - 2, 1))  # modes whose both neighbours were complete
+    assert np.linalg.norm(d[:, :, lo]) < 1e-9 * np.linalg.norm(rot)
+    g = ofim.fb_grad(S.zeros_fb(3), f, Dp, Dm, kx)
+    r2 = ofim.fb_rot(S.zeros_fb(3), g, Dp, Dm, kx)
+    assert np.linalg.norm(r2[:, :, lo]) < 1e-9 * np.linalg.norm(g) * np.abs(kx).max()
+
+
+def test_vacuum_psatd_conserves_field_energy(ofim):
+    """no current, no charge: the PSATD rotation is unitary on (E, G/w) for every (kx, kr, m) (solvers.py:227-279)"""
+    S = setup("real_m3")
+    a = S.Args
+    eg = crandn(np.random.default_rng(8), S.shape_fb + (6,))
+    w = a["w"][..., None]
+    nrg0 = (np.abs(eg[..., :3]) ** 2 + np.abs(eg[..., 3:] / w) ** 2).sum()
+    j = S.zeros_fb(3)
+    for _ in range(7):
+        eg = ofim.maxwell_push_wo_spchrg(eg, j, S.PSATD_E, S.PSATD_G)
+    nrg1 = (np.abs(eg[..., :3]) ** 2 + np.abs(eg[..., 3:] / w) ** 2).sum()
+    assert abs(nrg1 / nrg0 - 1) < 1e-12
+
+
+def test_envelope_quirks(ofim):
+    """Q1: the envelope current deposit fills component 3 only; Q2: the envelope density carries the complex
+    weight squared (grid_deps_env.f90:76,145-147)"""
+    S = setup("env_m3")
+    a = S.Args
+    x, p, w = particles(S, 800, 12, edge_cases=False)
+    j = ofim.dep_curr_env(x, p, w, S.zeros_sp(3), a["leftX"], *a["DepProj"])
+    assert np.count_nonzero(j[..., 0]) == 0 and np.count_nonzero(j[..., 1]) == 0 and np.count_nonzero(j[..., 2]) > 0
+    one = (np.asfortranarray(x[:, :1]), np.asfortranarray(w[:1]))
+    rho = ofim.dep_dens_env(one[0], one[1], S.zeros_sp(), a["leftX"], *a["DepProj"])
+    kx0 = a["DepProj"][3]
+    wp = one[1][0] * np.exp(-1j * kx0 * one[0][0, 0])
+    nko = (S.shape_sp[2] - 1) // 2
+    np.testing.assert_allclose(rho[:, :, nko].sum(), wp * wp, rtol=1e-9)

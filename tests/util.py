@@ -15,6 +15,17 @@ def rel_l2(a, b):
     return num / den if den > 0 else num
 
 
+def carrier_tol(S, tol=TOL):
+    """Tolerance for quantities that went through the envelope gather/deposit.  Those multiply by the
+    carrier exp(+-i kx0 x) (grid_deps_env.f90:47,219) with kx0 x up to ~4e5 rad in the FEL setups: a 1-ulp
+    difference in x (any two compilers: FMA contraction, -ffast-math of the reference Makefile:14) moves
+    the phase by eps * kx0 * |x|, so two correct implementations agree to that, not to 1e-12."""
+    if not S.env:
+        return tol
+    a = S.Args
+    return max(tol, np.finfo(float).eps * abs(a["kx0"]) * max(abs(a["leftX"]), abs(a["rightX"])))
+
+
 def assert_close(a, b, tol=TOL, what=""):
     assert a.shape == b.shape, (what, a.shape, b.shape)
     e = rel_l2(a, b)
@@ -37,6 +48,7 @@ SETUPS = {
     "env_m3": dict(Grid=(-2.0, 2.0, 6.0, 0.1, 0.3), TimeStep=0.05, MaxAzimuthMode=1, KxShift=30.0, Features=()),
 }
 
+ALL_SETUPS = list(SETUPS)
 _cache = {}
 
 
@@ -88,3 +100,46 @@ def chunk_sorted(S, coords, mom, w, fim, nchnk):
     order = np.argsort(ids, kind="stable")[go_out:]
     return (np.asfortranarray(coords[:, order]), np.asfortranarray(mom[:, order]), np.asfortranarray(w[order]),
             chunks)
+
+
+# ---- inputs of the step-level (engine / driver) parity tests --------------------------------------
+def plasma(S, ppc_x, ppc_r, seed, frac=(0.15, 0.85), thermal=0.05, dens=0.005):
+    """Uniform plasma slab with unique (label) weights; coordinates inside the grid."""
+    rng = np.random.default_rng(seed)
+    a = S.Args
+    nx, nr, dx, dr = a["Nx"], a["Nr"], a["dx"], a["dr"]
+    ix = np.arange(int(frac[0] * nx), int(frac[1] * nx))
+    ir = np.arange(0, int(0.8 * (nr - 1)))
+    X, R, px, pr = np.meshgrid(ix, ir, np.arange(ppc_x), np.arange(ppc_r), indexing="ij")
+    x = a["leftX"] + dx * (X + (px + 0.5) / ppc_x)
+    r = dr * (R + (pr + 0.5) / ppc_r)
+    x, r = x.ravel(), r.ravel()
+    # jitter: on a perfectly regular lattice the envelope deposit (carrier exp(-i kx0 x)) cancels almost
+    # exactly and the relative error of the tiny remainder is meaningless
+    x = x + dx * 0.4 / ppc_x * (rng.random(x.size) - 0.5)
+    r = r + dr * 0.4 / ppc_r * (rng.random(x.size) - 0.5)
+    th = 2 * np.pi * rng.random(x.size)
+    coords = np.asfortranarray(np.vstack((x, r * np.cos(th), r * np.sin(th))))
+    mom = np.asfortranarray(thermal * rng.standard_normal((3, x.size)))
+    w = -dens * dr * dx * 2 * np.pi * r / (ppc_x * ppc_r) * (1.0 + 1e-3 * rng.random(x.size))
+    return coords, mom, np.asfortranarray(w)
+
+
+def seed_fields(S, seed, amp=0.5):
+    """A smooth, band-limited initial EG_fb so that gather/push see non-trivial fields."""
+    rng = np.random.default_rng(seed)
+    nx, nkr, nm = S.shape_fb
+    eg = S.zeros_fb(6)
+    kx = np.fft.fftfreq(nx) * nx
+    env = np.exp(-(kx / (0.08 * nx)) ** 2)[:, None, None, None] * np.exp(-(np.arange(nkr) / (0.2 * nkr)) ** 2)[None, :, None, None]
+    eg[:] = amp * env * (rng.standard_normal(eg.shape) + 1j * rng.standard_normal(eg.shape))
+    return np.asfortranarray(eg)
+
+
+def match(w_ref, w_eng):
+    """permutation taking engine order to reference order via the (unique) weights"""
+    a, b = np.argsort(w_ref, kind="stable"), np.argsort(w_eng, kind="stable")
+    perm = np.empty_like(a)
+    perm[a] = b
+    assert np.array_equal(w_ref, w_eng[perm])
+    return perm

@@ -1,0 +1,133 @@
+"""Generate the golden fixtures under tests/golden/ (BUILD CONTAINER ONLY: needs /root/reference).
+
+What pins what
+--------------
+The reference's hot path is Fortran (f90/*.f90) that cannot be compiled in this image (no gfortran,
+no FFTW3), and the reference ships no golden vectors (doc/tests/*.py assert the exit code only).
+What CAN be run here is the reference's *unmodified Python*: ``Solver`` (moduls/solvers.py -- builds
+every DHT / mode-coupling / PSATD table the kernels consume), ``Specie`` (moduls/species.py) and
+``ChimeraRun`` (moduls/chimera_main.py -- the per-step call sequence).  This script imports them from
+/root/reference (tools/ref_driver.py; nothing is copied) with the CPU oracle installed as
+``chimera.moduls.fimera`` and records, per configuration:
+
+  * ``tab_*``   the operator / coefficient tables of the reference's own ``Solver``
+                (pins chimera_b200/solver_setup.py, slot for slot, on the GPU box too);
+  * ``in_*``    seeded particles and a seeded initial field;
+  * ``h_*``     the state after ``ChimeraRun.__init__`` (= make_halfstep, chimera_main.py:61-80);
+  * ``s_*``     the state after NSTEPS x ``ChimeraRun.make_step`` (chimera_main.py:82-92).
+
+So the *sequence* (which kernel is called when, with which arrays, including the driver's numpy-side
+mutations) is the reference's own; the *kernels underneath* are the oracle restatement -- the Fortran
+itself stays unpinned ("parity unpinned", DESIGN.md section Oracle).  tests/test_golden.py replays the
+fixtures on the oracle through tests/pic_ref.py (CPU) and on the CUDA engine and the CUDA drop-in
+(GPU).
+
+  python tools/gen_golden.py            # rewrites tests/golden/*.npz
+"""
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+NSTEPS = 4
+
+# name -> (solver setup in tests/util.SETUPS, still ions?, undulator params or None, field amplitude)
+CASES = {
+    "real_m2": dict(setup="real_m2", ions=True, und=None, amp=0.5),     # LPA-like: space charge, background, chunked
+    "real_m3": dict(setup="real_m3", ions=False, und=None, amp=0.5),    # 3 modes, no space charge, not chunked
+    "env_m1": dict(setup="env_m1", ions=False, und=dict(a0=0.3, lam=1.3, X0=-1.0, Lx=9.0), amp=0.5),  # FEL-like
+    "env_m3": dict(setup="env_m3", ions=False, und=None, amp=0.5),      # envelope solver with +-1 modes
+}
+
+TABLES = ("In", "InCurr", "Out", "DpS2S", "DmS2S", "DepFact", "PoissFact", "kx", "kx_env", "Rgrid", "Xgrid", "VGrid")
+
+
+def species_dict(cfg, **extra):
+    d = {"Grid": cfg["Grid"], "TimeStep": cfg["TimeStep"]}
+    if "Xchunked" in cfg:
+        d["Xchunked"] = cfg["Xchunked"]
+    d.update(extra)
+    return d
+
+
+def snapshot(prefix, run, out, grids=("J", "Rho", "BckGrndRho", "EB", "EG_fb")):
+    sol = run.Solvers[0]
+    for k in grids:
+        if k in sol.Data:
+            out["%s_%s" % (prefix, k)] = np.array(sol.Data[k], order="F")
+    sp = run.Particles[0]
+    for k in ("coords", "coords_halfstep", "momenta", "weights"):
+        out["%s_%s" % (prefix, k)] = np.array(sp.Data[k], order="F")
+    if hasattr(sp, "chunks"):
+        out["%s_chunks" % prefix] = np.array(sp.chunks)
+
+
+def generate(name, case, R, ofim):
+    from util import SETUPS, plasma, seed_fields
+    from chimera_b200.solver_setup import SolverSetup
+
+    cfg = copy.deepcopy(SETUPS[case["setup"]])
+    np.random.seed(20260101)
+    solver = R.Solver(copy.deepcopy(cfg))
+    out = {"cfg": np.array(json.dumps({"case": case, "nsteps": NSTEPS}))}
+    for k in TABLES:
+        out["tab_" + k] = np.array(solver.Args[k], order="F")
+    out["tab_PSATD_E"] = np.array(solver.Data["PSATD_E"], order="F")
+    out["tab_PSATD_G"] = np.array(solver.Data["PSATD_G"], order="F")
+    for i, v in enumerate(solver.Args["DepProj"][1:]):
+        out["tab_DepProj%d" % (i + 1)] = np.array(v)
+
+    S = SolverSetup(copy.deepcopy(cfg))  # only used to shape the seeded inputs
+    x, p, w = plasma(S, 2, 2, 11)
+    eg0 = seed_fields(S, 12, case["amp"])
+    out["in_coords"], out["in_momenta"], out["in_weights"], out["in_EG_fb"] = x, p, w, eg0
+    solver.Data["EG_fb"][:] = eg0
+
+    e_in = species_dict(cfg)
+    if case["und"]:
+        u = case["und"]
+        e_in["Devices"] = ([ofim.undul_analytic, np.array([u["a0"], u["lam"], u["X0"], u["Lx"]])],)
+    electrons = R.Specie(e_in)
+    electrons.add_particles(x.copy(order="F"), p.copy(order="F"), w.copy())
+    parts = [electrons]
+    if case["ions"]:
+        xi, pi_, wi = plasma(S, 2, 2, 18)
+        out["in_ion_coords"], out["in_ion_weights"] = xi, -wi
+        ions = R.Specie(species_dict(cfg, Charge=1.0, Mass=1886.0, Features=("Still",)))
+        ions.add_particles(xi.copy(order="F"), 0 * pi_, -wi.copy())
+        parts.append(ions)
+    # a window that never moves: frame_act still runs every step (chimera_main.py:292-304) and, for a
+    # SpaceCharge solver, re-deposits the background of the still species (postframe_corr :277-284)
+    run = R.ChimeraRun({"Solvers": (solver,), "Particles": tuple(parts), "MovingFrames": ({"Velocity": 0.0},)})
+    snapshot("h", run, out, grids=("EG_fb",))
+    for i in range(1, NSTEPS + 1):
+        run.make_step(i)
+    snapshot("s", run, out)
+    return out
+
+
+def main():
+    import ref_driver
+    from oracle import fimera as ofim
+
+    R = ref_driver.install(ofim)
+    dst = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(dst, exist_ok=True)
+    for name, case in CASES.items():
+        out = generate(name, case, R, ofim)
+        path = os.path.join(dst, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-8s %6.1f kB  particles %d -> %d  |EG_fb| %.6e" % (
+            name, os.path.getsize(path) / 1e3, out["in_weights"].size, out["s_weights"].size,
+            np.linalg.norm(out["s_EG_fb"].ravel())))
+
+
+if __name__ == "__main__":
+    main()
