@@ -17,6 +17,8 @@
 
 namespace chb {
 
+extern long long g_h2d_bytes, g_d2h_bytes;  // api_host.cu: host<->device traffic counters
+
 struct NamedArray {
   void* p = nullptr;
   size_t bytes = 0;
@@ -42,6 +44,11 @@ using namespace chb;
 struct chimera_engine {
   chimera_engine_config cfg;
   cudaStream_t st = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of chimera_engine_step_host
+  std::vector<cudaEvent_t> host_evs;
+  double *host_EG = nullptr, *host_G = nullptr, *host_mom = nullptr;  // between step_host_begin / _end
+  int host_id = -1;
+  double host_rho_from_bg = 1.0;  // 0 on the ranks that must not add BckGrndRho before an all-reduce
   bool own_stream = false;
   Scratch scr;
   FFTCache fft;
@@ -561,6 +568,7 @@ int chimera_engine_destroy(chimera_engine* e) {
   for (auto& pe : e->pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
   for (auto v : e->ev_pool) cudaEventDestroy(v);
   if (e->own_stream) cudaStreamDestroy(e->st);
+  if (e->s_h2d) { cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h); }
   g_host.erase(e);
   delete e;
   return 0;
@@ -706,6 +714,180 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
     CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
     CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// One make_step with the whole PIC state in HOST buffers (the reference's calling model: numpy owns
+// every array, moduls/chimera_main.py:82-92), pipelined over three streams so that PCIe runs in both
+// directions while the device computes:
+//   h2d stream : coords / momenta / weights in NCHUNK pieces, then EG_fb and gradRho_fb_nxt
+//   engine     : per piece transpose to SoA + push_coords (+ transpose back); then deposit .. gather+push
+//   d2h stream : coords / coords_halfstep pieces as soon as they are pushed, EG_fb after the PSATD
+//                advance, momenta after the Boris push
+// ------------------------------------------------------------------------------------------
+static int host_mark(chimera_engine* e, cudaStream_t on, cudaStream_t waiter) {
+  cudaEvent_t ev;
+  CHB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  e->host_evs.push_back(ev);
+  CHB_CUDA(cudaEventRecord(ev, on));
+  CHB_CUDA(cudaStreamWaitEvent(waiter, ev, 0));
+  return 0;
+}
+
+int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
+                                   double* weights, chb_i64 np, double* EG_fb, double* gradRho_fb_nxt, chb_i64 istep,
+                                   int rebin) {
+  ENG_CHECK(e);
+  if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  Species& s = e->sp[id];
+  if (s.still) { set_error("step_host: species %d is still", id); return 2; }
+  if (np < 0 || np > s.cap) { set_error("step_host: np=%lld exceeds the species capacity %lld", np, s.cap); return 2; }
+  if (!coords || !coords_half || !momenta || !weights) { set_error("step_host: null particle buffer"); return 2; }
+  const auto& c = e->cfg;
+  CHB_TRY(ensure_ops(e));
+  if (!e->s_h2d) {
+    CHB_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+    CHB_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+  }
+  auto mark = [&](cudaStream_t on, cudaStream_t waiter) -> int { return host_mark(e, on, waiter); };
+  const bool sort_now = rebin || (c.sort_every > 0 && istep % c.sort_every == 0);
+  if (np != s.np && !sort_now) { set_error("step_host: particle count changed (%lld -> %lld) without rebin", s.np, np); return 2; }
+  s.np = np;
+  const size_t D = sizeof(double);
+  // the copy streams start after whatever the engine stream did before
+  CHB_TRY(mark(e->st, e->s_h2d));
+  CHB_TRY(mark(e->st, e->s_d2h));
+  constexpr int NCHUNK = 16;
+  const i64 csz = ((np + NCHUNK - 1) / NCHUNK + 31) & ~31LL;
+  for (i64 a = 0; a < np; a += csz) {
+    const i64 n = (np - a < csz) ? np - a : csz;
+    CHB_CUDA(cudaMemcpyAsync(s.x2 + 3 * a, coords + 3 * a, D * 3 * n, cudaMemcpyHostToDevice, e->s_h2d));
+    CHB_CUDA(cudaMemcpyAsync(s.p2 + 3 * a, momenta + 3 * a, D * 3 * n, cudaMemcpyHostToDevice, e->s_h2d));
+    CHB_CUDA(cudaMemcpyAsync(s.w + a, weights + a, D * n, cudaMemcpyHostToDevice, e->s_h2d));
+    g_h2d_bytes += (long long)(D * 7 * n);
+    CHB_TRY(mark(e->s_h2d, e->st));
+    aos_to_soa_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.x + a, s.x2 + 3 * a, 3, s.cap, n);
+    CHB_LAUNCH_CHECK();
+    aos_to_soa_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.p + a, s.p2 + 3 * a, 3, s.cap, n);
+    CHB_LAUNCH_CHECK();
+    CHB_TRY(launch_push_coords(e->st, soa(s.x + a, s.cap), soa((const double*)(s.p + a), s.cap), soa(s.xh + a, s.cap), c.dt, n));
+    if (!sort_now) {
+      soa_to_aos_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.x2 + 3 * a, s.x + a, 3, s.cap, n);
+      CHB_LAUNCH_CHECK();
+      soa_to_aos_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.xh2 + 3 * a, s.xh + a, 3, s.cap, n);
+      CHB_LAUNCH_CHECK();
+      CHB_TRY(mark(e->st, e->s_d2h));
+      CHB_CUDA(cudaMemcpyAsync(coords + 3 * a, s.x2 + 3 * a, D * 3 * n, cudaMemcpyDeviceToHost, e->s_d2h));
+      CHB_CUDA(cudaMemcpyAsync(coords_half + 3 * a, s.xh2 + 3 * a, D * 3 * n, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)(D * 6 * n);
+    }
+  }
+  // spectral state of the solver: needed from the density transform on
+  NamedArray *aEG = nullptr, *aG = nullptr;
+  CHB_TRY(find_array(e, "EG_fb", &aEG));
+  if (EG_fb) {
+    CHB_CUDA(cudaMemcpyAsync(aEG->p, EG_fb, aEG->bytes, cudaMemcpyHostToDevice, e->s_h2d));
+    g_h2d_bytes += (long long)aEG->bytes;
+  }
+  if (gradRho_fb_nxt && c.space_charge) {
+    CHB_TRY(find_array(e, "gradRho_fb_nxt", &aG));
+    CHB_CUDA(cudaMemcpyAsync(aG->p, gradRho_fb_nxt, aG->bytes, cudaMemcpyHostToDevice, e->s_h2d));
+    g_h2d_bytes += (long long)aG->bytes;
+  }
+  if (sort_now) {
+    CHB_TRY(run_phase(e, CHB_SORT, 1));  // synchronises the engine stream; s.np may shrink
+    const i64 m = s.np;
+    if (m > 0) {
+      soa_to_aos_k<<<grid_for(3 * m, 256), 256, 0, e->st>>>(s.x2, s.x, 3, s.cap, m);
+      CHB_LAUNCH_CHECK();
+      soa_to_aos_k<<<grid_for(3 * m, 256), 256, 0, e->st>>>(s.xh2, s.xh, 3, s.cap, m);
+      CHB_LAUNCH_CHECK();
+      CHB_TRY(mark(e->st, e->s_d2h));
+      CHB_CUDA(cudaMemcpyAsync(coords, s.x2, D * 3 * m, cudaMemcpyDeviceToHost, e->s_d2h));
+      CHB_CUDA(cudaMemcpyAsync(coords_half, s.xh2, D * 3 * m, cudaMemcpyDeviceToHost, e->s_d2h));
+      CHB_CUDA(cudaMemcpyAsync(weights, s.w, D * m, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)(D * 7 * m);
+    }
+  }
+  CHB_TRY(run_phase(e, CHB_DEPOSIT_J, 0));
+  if (c.space_charge) CHB_TRY(run_phase(e, CHB_DEPOSIT_RHO, e->host_rho_from_bg));
+  e->host_EG = EG_fb;
+  e->host_G = (gradRho_fb_nxt && c.space_charge) ? gradRho_fb_nxt : nullptr;
+  e->host_mom = momenta;
+  e->host_id = id;
+  return 0;
+}
+
+// second half: (the caller may all-reduce J / Rho on the engine stream in between) transforms, Poisson
+// correction, PSATD advance, fields out, gather + push, copies out; synchronises everything
+int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out) {
+  ENG_CHECK(e);
+  if (e->host_id < 0) { set_error("step_host_end without step_host_begin"); return 2; }
+  Species& s = e->sp[e->host_id];
+  const auto& c = e->cfg;
+  const size_t D = sizeof(double);
+  auto mark = [&](cudaStream_t on, cudaStream_t waiter) -> int { return host_mark(e, on, waiter); };
+  double* EG_fb = e->host_EG;
+  double* gradRho_fb_nxt = e->host_G;
+  double* momenta = e->host_mom;
+  NamedArray *aEG = nullptr, *aG = nullptr;
+  CHB_TRY(find_array(e, "EG_fb", &aEG));
+  if (gradRho_fb_nxt) CHB_TRY(find_array(e, "gradRho_fb_nxt", &aG));
+  CHB_TRY(mark(e->s_h2d, e->st));  // EG_fb / gradRho_fb_nxt have landed
+  CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
+  if (c.space_charge) CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
+  CHB_TRY(run_phase(e, CHB_POISSON, 0));
+  CHB_TRY(run_phase(e, CHB_MAXWELL, 0));
+  if (EG_fb || aG) {
+    CHB_TRY(mark(e->st, e->s_d2h));
+    if (EG_fb) {
+      CHB_CUDA(cudaMemcpyAsync(EG_fb, aEG->p, aEG->bytes, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)aEG->bytes;
+    }
+    if (aG) {
+      CHB_CUDA(cudaMemcpyAsync(gradRho_fb_nxt, aG->p, aG->bytes, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)aG->bytes;
+    }
+  }
+  CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
+  CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
+  if (s.np > 0) {
+    soa_to_aos_k<<<grid_for(3 * s.np, 256), 256, 0, e->st>>>(s.p2, s.p, 3, s.cap, s.np);
+    CHB_LAUNCH_CHECK();
+    CHB_TRY(mark(e->st, e->s_d2h));
+    CHB_CUDA(cudaMemcpyAsync(momenta, s.p2, D * 3 * s.np, cudaMemcpyDeviceToHost, e->s_d2h));
+    g_d2h_bytes += (long long)(D * 3 * s.np);
+  }
+  CHB_CUDA(cudaStreamSynchronize(e->s_h2d));
+  CHB_CUDA(cudaStreamSynchronize(e->s_d2h));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  for (auto ev : e->host_evs) cudaEventDestroy(ev);
+  e->host_evs.clear();
+  e->host_id = -1;
+  if (np_out) *np_out = s.np;
+  return 0;
+}
+
+int chimera_engine_step_host(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
+                             double* weights, chb_i64 np, chb_i64* np_out, double* EG_fb, double* gradRho_fb_nxt,
+                             chb_i64 istep, int rebin) {
+  CHB_TRY(chimera_engine_step_host_begin(e, id, coords, coords_half, momenta, weights, np, EG_fb, gradRho_fb_nxt, istep, rebin));
+  return chimera_engine_step_host_end(e, np_out);
+}
+
+int chimera_engine_set_rho_from_bg(chimera_engine* e, int from_bg) {
+  ENG_CHECK(e);
+  e->host_rho_from_bg = from_bg ? 1.0 : 0.0;
+  return 0;
+}
+
+int chimera_host_register(void* ptr, chb_i64 nbytes) {
+  CHB_CUDA(cudaHostRegister(ptr, (size_t)nbytes, cudaHostRegisterPortable));
+  return 0;
+}
+int chimera_host_unregister(void* ptr) {
+  CHB_CUDA(cudaHostUnregister(ptr));
   return 0;
 }
 

@@ -116,6 +116,7 @@ class Engine:
             self.upload(name, arr)
         self.nspecies = 0
         self.istep = 0
+        self._pinned = []
         self.group = group
         self.rank, self.world = 0, 1
         if group is not None:
@@ -135,6 +136,8 @@ class Engine:
             raise EngineError("libchimera_b200: status %d: %s" % (rc, self.lib.chimera_last_error().decode()))
 
     def close(self):
+        if getattr(self, "_pinned", None):
+            self.unpin_all()
         if getattr(self, "_h", None):
             self.lib.chimera_engine_destroy(self._h)
             self._h = None
@@ -283,6 +286,53 @@ class Engine:
             self.run("maxwell")
             self.run("fields_out")
             self.run("gather_push", 1.0)
+
+    # -- host-buffer stepping ------------------------------------------------------------------
+    def step_host(self, coords, coords_half, momenta, weights, EG_fb=None, gradRho_fb_nxt=None, sid=0, rebin=False):
+        """One ``ChimeraRun.make_step`` (chimera_main.py:82-92) on HOST arrays, the reference's calling model.
+
+        ``coords``/``momenta`` (3,Np) and ``weights`` (Np,) are the species' numpy arrays (Fortran order,
+        float64), updated in place; ``coords_half`` (3,Np) receives the centred positions; ``EG_fb`` and
+        ``gradRho_fb_nxt`` are the solver's spectral state, updated in place (``None``: keep the
+        engine-resident copy).  Host<->device copies are pipelined with the kernels inside the call
+        (csrc/engine.cu ``chimera_engine_step_host``); page-lock the arrays once with :meth:`pin` for full
+        PCIe speed.  Returns the number of particles kept (the first entries of the arrays are valid)."""
+        n = coords.shape[1]
+        for name, arr, shp in (("coords", coords, (3, n)), ("coords_half", coords_half, (3, n)),
+                               ("momenta", momenta, (3, n)), ("weights", weights, (n,))):
+            if arr.dtype != np.float64 or not arr.flags.f_contiguous or arr.shape != shp or not arr.flags.writeable:
+                raise ValueError("step_host: %s must be a writeable Fortran-ordered float64 array of shape %r" % (name, shp))
+        for name, arr in (("EG_fb", EG_fb), ("gradRho_fb_nxt", gradRho_fb_nxt)):
+            if arr is not None and (arr.dtype != np.complex128 or not arr.flags.f_contiguous or arr.shape != self.shape_of(name)):
+                raise ValueError("step_host: %s must be a Fortran-ordered complex128 array of shape %r" % (name, self.shape_of(name)))
+        self.istep += 1
+        n_out = _i64(0)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data if a is not None else None)  # noqa: E731
+        if self.world == 1:
+            self._check(self.lib.chimera_engine_step_host(
+                self._h, int(sid), vp(coords), vp(coords_half), vp(momenta), vp(weights), _i64(n), ctypes.byref(n_out),
+                vp(EG_fb), vp(gradRho_fb_nxt), _i64(self.istep), int(bool(rebin))))
+            return n_out.value
+        # particles sharded over the ranks: deposit locally, sum the grids over NVLink, then the field update
+        self._check(self.lib.chimera_engine_set_rho_from_bg(self._h, int(self.rank == 0)))
+        self._check(self.lib.chimera_engine_step_host_begin(
+            self._h, int(sid), vp(coords), vp(coords_half), vp(momenta), vp(weights), _i64(n), vp(EG_fb),
+            vp(gradRho_fb_nxt), _i64(self.istep), int(bool(rebin))))
+        self._allreduce_grids()
+        self._check(self.lib.chimera_engine_step_host_end(self._h, ctypes.byref(n_out)))
+        return n_out.value
+
+    def pin(self, *arrays):
+        """Page-lock numpy arrays (cudaHostRegister) so that step_host's copies run at PCIe speed."""
+        for a in arrays:
+            if a is not None and a.nbytes:
+                self._check(self.lib.chimera_host_register(ctypes.c_void_p(a.ctypes.data), _i64(a.nbytes)))
+                self._pinned.append(a)
+
+    def unpin_all(self):
+        for a in self._pinned:
+            self.lib.chimera_host_unregister(ctypes.c_void_p(a.ctypes.data))
+        self._pinned = []
 
     # -- profiling ---------------------------------------------------------------------------
     def profile(self, on=True):

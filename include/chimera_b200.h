@@ -220,6 +220,29 @@ int chimera_engine_run(chimera_engine* e, int phase, double arg);
 /* nsteps x make_step on the engine's stream; istep0 = index of the first step (re-binning cadence) */
 int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps);
 int chimera_engine_sync(chimera_engine* e);
+/* One make_step (chimera_main.py:82-92) with the PIC state in HOST buffers, the reference's calling model:
+ * coords/momenta (3,np) Fortran-ordered in-out, coords_half (3,np) out, weights (np) in (rewritten in the
+ * new particle order on re-binning steps), EG_fb (nx,nkr,nm,6) and gradRho_fb_nxt (nx,nkr,nm,3) complex
+ * in-out (either may be NULL: the engine-resident copy is used and nothing is copied).  Operators, tables,
+ * BckGrndRho and still species stay resident.  Copies run on two extra streams and overlap the kernels;
+ * pass page-locked buffers (chimera_host_register) for full PCIe speed.  The call is synchronous.
+ * rebin != 0 forces a re-binning in this step (required after the caller reordered or added particles);
+ * *np_out = particles kept (re-binning culls the ones that left the domain). */
+int chimera_engine_step_host(chimera_engine* e, int species, double* coords, double* coords_half, double* momenta,
+                             double* weights, chb_i64 np, chb_i64* np_out, double* EG_fb, double* gradRho_fb_nxt,
+                             chb_i64 istep, int rebin);
+/* the same in two halves, for multi-GPU runs: _begin copies the particles in, pushes coordinates and
+ * deposits J / Rho (with from_bg = 0 the background charge is left out: ranks > 0 before an all-reduce,
+ * set with chimera_engine_set_rho_from_bg); the caller all-reduces the grids on the engine stream; _end
+ * runs the field update, gather + push and the copies out, and synchronises. */
+int chimera_engine_step_host_begin(chimera_engine* e, int species, double* coords, double* coords_half,
+                                   double* momenta, double* weights, chb_i64 np, double* EG_fb,
+                                   double* gradRho_fb_nxt, chb_i64 istep, int rebin);
+int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out);
+int chimera_engine_set_rho_from_bg(chimera_engine* e, int from_bg);
+/* page-lock / unlock a host buffer the caller owns (cudaHostRegister) */
+int chimera_host_register(void* ptr, chb_i64 nbytes);
+int chimera_host_unregister(void* ptr);
 int chimera_engine_set_stream(chimera_engine* e, void* cuda_stream);
 /* per-phase device time (CUDA events on the engine stream), accumulated since the last reset */
 int chimera_engine_profile(chimera_engine* e, int on);

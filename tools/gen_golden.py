@@ -42,7 +42,10 @@ NSTEPS = 4
 CASES = {
     "real_m2": dict(setup="real_m2", ions=True, und=None, amp=0.5),     # LPA-like: space charge, background, chunked
     "real_m3": dict(setup="real_m3", ions=False, und=None, amp=0.5),    # 3 modes, no space charge, not chunked
-    "env_m1": dict(setup="env_m1", ions=False, und=dict(a0=0.3, lam=1.3, X0=-1.0, Lx=9.0), amp=0.5),  # FEL-like
+    # FEL-like: a gamma = 391 beam.  Slow particles would make this setup a round-off amplifier (a position
+    # error dx changes the gathered carrier phase by kx0 dx ~ 7e5 dx, the push feeds it back into x: x4400 per
+    # step for v << c, x1e-4 for gamma = 391 where dv = dp / gamma^3)
+    "env_m1": dict(setup="env_m1", ions=False, und=dict(a0=0.3, lam=1.3, X0=-1.0, Lx=9.0), amp=0.5, boost=391.0),
     "env_m3": dict(setup="env_m3", ions=False, und=None, amp=0.5),      # envelope solver with +-1 modes
 }
 
@@ -86,6 +89,7 @@ def generate(name, case, R, ofim):
 
     S = SolverSetup(copy.deepcopy(cfg))  # only used to shape the seeded inputs
     x, p, w = plasma(S, 2, 2, 11)
+    p[0] += case.get("boost", 0.0)
     eg0 = seed_fields(S, 12, case["amp"])
     out["in_coords"], out["in_momenta"], out["in_weights"], out["in_EG_fb"] = x, p, w, eg0
     solver.Data["EG_fb"][:] = eg0
