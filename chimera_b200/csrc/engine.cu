@@ -48,6 +48,7 @@ struct chimera_engine {
   std::vector<cudaEvent_t> host_evs;
   double *host_EG = nullptr, *host_G = nullptr, *host_mom = nullptr;  // between step_host_begin / _end
   int host_id = -1;
+  int host_mid_done = 0;
   double host_rho_from_bg = 1.0;  // 0 on the ranks that must not add BckGrndRho before an all-reduce
   bool own_stream = false;
   Scratch scr;
@@ -235,7 +236,13 @@ GridGeom geom_ready(chimera_engine* e) {
 }
 
 FBCtx fbctx(chimera_engine* e) { return FBCtx{e->st, &e->scr, &e->fft}; }
-FBMathDims mdims(chimera_engine* e) { return FBMathDims{e->cfg.nx, e->cfg.nkr, e->cfg.nm, e->cfg.nkr, e->cfg.env}; }
+// kx rows of the spectral state held by this engine: all of them, or one slab of mirror pairs when the
+// spectral solve is sharded over the ranks (chimera_b200/sharding.py)
+inline bool slab(const chimera_engine* e) { return e->cfg.nx_slab > 0 && e->cfg.nx_slab < e->cfg.nx; }
+inline i64 nxs(const chimera_engine* e) { return slab(e) ? e->cfg.nx_slab : e->cfg.nx; }
+FBMathDims mdims(chimera_engine* e) {
+  return FBMathDims{nxs(e), e->cfg.nkr, e->cfg.nm, e->cfg.nkr, e->cfg.env, slab(e) ? e->cfg.mirror_shift : 0};
+}
 
 ChunkSpec chunkspec(chimera_engine* e, const Species& s) {
   if (!e->cfg.chunked) return ChunkSpec{0, nullptr, 1, 0, e->cfg.nx};
@@ -377,6 +384,9 @@ int ph_add_bg(chimera_engine* e) {
 int ph_fb_in_j(chimera_engine* e) {
   const auto& c = e->cfg;
   FBCtx fb = fbctx(e);
+  if (slab(e))
+    return fb_in_slab_dev(fb, e->A("J_fb"), e->A("J"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"),
+                          (const i64*)e->arr["slab_rows"].p, c.nx, nxs(e), c.nrn, c.nm, c.nkr, 3);
   return fb_in_dev(fb, e->A("J_fb"), e->A("J"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"), c.nx, c.nrn, c.nm,
                    c.nkr, 3);
 }
@@ -385,14 +395,18 @@ int ph_fb_in_rho(chimera_engine* e) {
   const auto& c = e->cfg;
   FBCtx fb = fbctx(e);
   std::swap(e->arr["gradRho_fb_prv"], e->arr["gradRho_fb_nxt"]);  // gradRho_fb_prv[:] = gradRho_fb_nxt
-  CHB_TRY(fb_in_dev(fb, e->A("Rho_fb"), e->A("Rho"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"), c.nx, c.nrn,
-                    c.nm, c.nkr, 1));
+  if (slab(e))
+    CHB_TRY(fb_in_slab_dev(fb, e->A("Rho_fb"), e->A("Rho"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"),
+                           (const i64*)e->arr["slab_rows"].p, c.nx, nxs(e), c.nrn, c.nm, c.nkr, 1));
+  else
+    CHB_TRY(fb_in_dev(fb, e->A("Rho_fb"), e->A("Rho"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"), c.nx, c.nrn,
+                      c.nm, c.nkr, 1));
   return fb_grad_dev(fb, e->A("gradRho_fb_nxt"), e->A("Rho_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e));
 }
 
 int ph_poisson(chimera_engine* e) {
   const auto& c = e->cfg;
-  const i64 P = c.nx * c.nkr * c.nm;
+  const i64 P = nxs(e) * c.nkr * c.nm;
   FBCtx fb = fbctx(e);
   for (int it = 0; it < c.poisson_iters; ++it) {
     CHB_CUDA(cudaMemcpyAsync(e->A("vec_fb"), e->A("J_fb"), sizeof(cd) * P * 3, cudaMemcpyDeviceToDevice, e->st));
@@ -410,7 +424,7 @@ int ph_poisson(chimera_engine* e) {
 
 int ph_maxwell(chimera_engine* e) {
   const auto& c = e->cfg;
-  const i64 P = c.nx * c.nkr * c.nm;
+  const i64 P = nxs(e) * c.nkr * c.nm;
   if (c.space_charge)
     return launch_maxwell_push(e->st, e->A("EG_fb"), e->A("J_fb"), e->A("gradRho_fb_prv"), e->A("gradRho_fb_nxt"),
                                e->arr["PSATD_E"].p, e->arr["PSATD_G"].p, 5, 0, P);
@@ -420,19 +434,35 @@ int ph_maxwell(chimera_engine* e) {
 
 int ph_init_push(chimera_engine* e) {
   const auto& c = e->cfg;
-  const i64 P = c.nx * c.nkr * c.nm;
+  const i64 P = nxs(e) * c.nkr * c.nm;
   return launch_maxwell_init_push(e->st, e->A("EG_fb"), e->A("J_fb"), e->A("gradRho_fb_nxt"), e->A("CPSATD1"),
                                   e->A("CPSATD2"), P);
 }
 
-int ph_fields_out(chimera_engine* e) {
+// fields out, first half: B from G, backward DHT (+ phase).  Unsharded: also the inverse x-FFT and the
+// normalisation, i.e. the whole of G2B_FBRot + fb_fld_out (solvers.py:536, 450).  kx-slab mode: stops at
+// "EB_slab"; the caller all-gathers the slabs into "EB_gath" and runs the second half.
+int ph_fields_out_a(chimera_engine* e, bool whole) {
   const auto& c = e->cfg;
-  const i64 P = c.nx * c.nkr * c.nm;
+  const i64 P = nxs(e) * c.nkr * c.nm;
   FBCtx fb = fbctx(e);
   CHB_TRY(fb_rot_dev(fb, e->A("B_fb"), e->A("EG_fb") + P * 3, e->pDp, e->pDm, e->D("kx"), mdims(e)));
   CHB_TRY(launch_mult_real(e->st, e->A("B_fb"), e->D("PoissFact"), P, 3));
   const cd* srcs[2] = {e->A("EG_fb"), e->A("B_fb")};
+  if (slab(e)) {
+    if (whole) { set_error("kx-slab engine: run fields_out_a, all-gather EB_slab into EB_gath, then fields_out_b"); return 2; }
+    return fb_out_slab_dev(fb, e->A("EB_slab"), srcs, 2, 3, c.leftX, e->D("kx_base"), e->pOut, nxs(e), c.nrn, c.nm, c.nkr);
+  }
   CHB_TRY(fb_out_dev(fb, e->A("EB"), srcs, 2, 3, c.leftX, e->D("kx_base"), e->pOut, c.nx, c.nrn, c.nm, c.nkr));
+  return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
+}
+
+int ph_fields_out_b(chimera_engine* e) {
+  const auto& c = e->cfg;
+  if (!slab(e)) return 0;  // everything was done by the first half
+  FBCtx fb = fbctx(e);
+  CHB_TRY(fb_out_finish_dev(fb, e->A("EB"), e->A("EB_gath"), (const i64*)e->arr["gather_map"].p, c.nx, nxs(e),
+                            c.nrn * c.nm * 6));
   return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
 }
 
@@ -493,7 +523,9 @@ int run_phase(chimera_engine* e, int phase, double arg) {
     case CHB_POISSON: rc = ph_poisson(e); break;
     case CHB_MAXWELL: rc = ph_maxwell(e); break;
     case CHB_INIT_PUSH: rc = ph_init_push(e); break;
-    case CHB_FIELDS_OUT: rc = ph_fields_out(e); break;
+    case CHB_FIELDS_OUT: rc = ph_fields_out_a(e, true); break;
+    case CHB_FIELDS_OUT_A: rc = ph_fields_out_a(e, false); break;
+    case CHB_FIELDS_OUT_B: rc = ph_fields_out_b(e); break;
     case CHB_GATHER_PUSH: rc = ph_gather_push(e, arg); break;
     case CHB_ADD_BG: rc = ph_add_bg(e); break;
     default: set_error("unknown engine phase %d", phase); rc = 2;
@@ -530,7 +562,9 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
   for (int i = 0; i < CHB_NPHASES; ++i) { e->ms[i] = 0; e->calls[i] = 0; }
   CHB_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   e->own_stream = true;
-  const size_t Pg = (size_t)c.nx * c.nrn * c.nm, Pf = (size_t)c.nx * c.nkr * c.nm, C = sizeof(cd);
+  if (c.nx_slab < 0 || c.nx_slab > c.nx || (c.nx_slab & 1)) { set_error("engine_create: bad kx slab size"); chimera_engine_destroy(e); return 2; }
+  const size_t nxf = (size_t)nxs(e);  // kx rows of the spectral state held here
+  const size_t Pg = (size_t)c.nx * c.nrn * c.nm, Pf = nxf * c.nkr * c.nm, C = sizeof(cd);
   const i64 nr = c.nrn - 1;
   const int nd = (int)(c.env ? c.nm + 2 : c.nm + 1);
   const int ncoef = c.space_charge ? 5 : 3;
@@ -540,7 +574,7 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
       {"gradRho_fb_prv", Pf * 3 * C}, {"gradRho_fb_nxt", Pf * 3 * C}, {"vec_fb", Pf * 3 * C},
       {"InCurr", sizeof(double) * nr * c.nkr * c.nm}, {"Out", sizeof(double) * nr * c.nkr * c.nm},
       {"DpS2S", sizeof(double) * c.nkr * c.nkr * nd}, {"DmS2S", sizeof(double) * c.nkr * c.nkr * nd},
-      {"kx", sizeof(double) * c.nx}, {"kx_base", sizeof(double) * c.nx},
+      {"kx", sizeof(double) * nxf}, {"kx_base", sizeof(double) * nxf},
       {"DepFact", sizeof(double) * Pf}, {"PoissFact", sizeof(double) * Pf},
       {"PSATD_E", (c.coef_complex ? C : sizeof(double)) * Pf * ncoef},
       {"PSATD_G", (c.coef_complex ? C : sizeof(double)) * Pf * ncoef},
@@ -548,6 +582,15 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
   for (auto& s : spec) {
     int rc = alloc_named(e, s.n, s.b);
     if (rc) { chimera_engine_destroy(e); return rc; }
+  }
+  if (slab(e)) {
+    struct { const char* n; size_t b; } extra[] = {
+        {"slab_rows", sizeof(i64) * nxf}, {"gather_map", sizeof(i64) * (size_t)c.nx},
+        {"EB_slab", nxf * c.nrn * c.nm * 6 * C}, {"EB_gath", Pg * 6 * C}};
+    for (auto& s : extra) {
+      int rc = alloc_named(e, s.n, s.b);
+      if (rc) { chimera_engine_destroy(e); return rc; }
+    }
   }
   *out = e;
   return 0;
@@ -699,6 +742,7 @@ int chimera_engine_run(chimera_engine* e, int phase, double arg) {
 int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
   ENG_CHECK(e);
   const auto& c = e->cfg;
+  if (slab(e)) { set_error("kx-slab engine: sequence the phases from the host (all-gather between fields_out_a / _b)"); return 2; }
   for (i64 k = 0; k < nsteps; ++k) {
     const i64 istep = istep0 + k;
     CHB_TRY(run_phase(e, CHB_PUSH_COORDS, 0));
@@ -819,6 +863,36 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
   return 0;
 }
 
+// kx-slab mode only: field update on this rank's slab and the first half of fields out (-> "EB_slab")
+int chimera_engine_step_host_mid(chimera_engine* e) {
+  ENG_CHECK(e);
+  if (e->host_id < 0) { set_error("step_host_mid without step_host_begin"); return 2; }
+  const auto& c = e->cfg;
+  auto mark = [&](cudaStream_t on, cudaStream_t waiter) -> int { return host_mark(e, on, waiter); };
+  NamedArray *aEG = nullptr, *aG = nullptr;
+  CHB_TRY(find_array(e, "EG_fb", &aEG));
+  if (e->host_G) CHB_TRY(find_array(e, "gradRho_fb_nxt", &aG));
+  CHB_TRY(mark(e->s_h2d, e->st));  // EG_fb / gradRho_fb_nxt have landed
+  CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
+  if (c.space_charge) CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
+  CHB_TRY(run_phase(e, CHB_POISSON, 0));
+  CHB_TRY(run_phase(e, CHB_MAXWELL, 0));
+  if (e->host_EG || aG) {
+    CHB_TRY(mark(e->st, e->s_d2h));
+    if (e->host_EG) {
+      CHB_CUDA(cudaMemcpyAsync(e->host_EG, aEG->p, aEG->bytes, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)aEG->bytes;
+    }
+    if (aG) {
+      CHB_CUDA(cudaMemcpyAsync(e->host_G, aG->p, aG->bytes, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)aG->bytes;
+    }
+  }
+  CHB_TRY(run_phase(e, CHB_FIELDS_OUT_A, 0));
+  e->host_mid_done = 1;
+  return 0;
+}
+
 // second half: (the caller may all-reduce J / Rho on the engine stream in between) transforms, Poisson
 // correction, PSATD advance, fields out, gather + push, copies out; synchronises everything
 int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out) {
@@ -834,6 +908,10 @@ int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out) {
   NamedArray *aEG = nullptr, *aG = nullptr;
   CHB_TRY(find_array(e, "EG_fb", &aEG));
   if (gradRho_fb_nxt) CHB_TRY(find_array(e, "gradRho_fb_nxt", &aG));
+  if (e->host_mid_done) {  // chimera_engine_step_host_mid already ran the field update and the first half of fields out
+    CHB_TRY(run_phase(e, CHB_FIELDS_OUT_B, 0));
+  } else {
+  if (slab(e)) { set_error("kx-slab engine: call step_host_mid, all-gather EB_slab into EB_gath, then step_host_end"); return 2; }
   CHB_TRY(mark(e->s_h2d, e->st));  // EG_fb / gradRho_fb_nxt have landed
   CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
   if (c.space_charge) CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
@@ -851,6 +929,8 @@ int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out) {
     }
   }
   CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
+  }
+  e->host_mid_done = 0;
   CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
   if (s.np > 0) {
     soa_to_aos_k<<<grid_for(3 * s.np, 256), 256, 0, e->st>>>(s.p2, s.p, 3, s.cap, s.np);

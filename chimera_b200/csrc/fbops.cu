@@ -140,6 +140,66 @@ int fb_out_dev(FBCtx& c, cd* out, const cd* const* srcs, int nsrc, int ncomp_eac
   return 0;
 }
 
+namespace {
+__global__ void __launch_bounds__(256) take_rows_k(cd* __restrict__ dst, const cd* __restrict__ src,
+                                                   const i64* __restrict__ rows, i64 nxs, i64 nkx, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const i64 col = e / nxs, j = e - col * nxs;
+  dst[e] = __ldg(src + __ldg(rows + j) + nkx * col);
+}
+// out(i, col) = gathered[rank r][j, col] with map[i] = r * nxs + j; each rank's block is (nxs, ncols)
+__global__ void __launch_bounds__(256) put_rows_k(cd* __restrict__ out, const cd* __restrict__ gath,
+                                                  const i64* __restrict__ map, i64 nkx, i64 nxs, i64 ncols, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const i64 col = e / nkx, i = e - col * nkx;
+  const i64 m = __ldg(map + i), r = m / nxs, j = m - r * nxs;
+  out[e] = __ldg(gath + r * nxs * ncols + j + nxs * col);
+}
+}  // namespace
+
+int fb_in_slab_dev(FBCtx& c, cd* out_fb, const cd* in, double leftX, const double* kx_slab, const PackedOps& In,
+                   const double* fact_slab, const i64* rows, i64 nkx, i64 nxs, i64 nrn, i64 nm, i64 nkr, int ncomp) {
+  const i64 nr = nrn - 1, ncols = nrn * nm * ncomp;
+  cd* full = c.scr->take_n<cd>(nkx * ncols);
+  cd* slab = c.scr->take_n<cd>(nxs * ncols);
+  if (!full || !slab) return 6;
+  CHB_CUDA(cudaMemcpyAsync(full, in, sizeof(cd) * nkx * ncols, cudaMemcpyDeviceToDevice, c.st));
+  CHB_TRY(c.fft->exec(c.st, full, nkx, ncols, CUFFT_FORWARD));
+  take_rows_k<<<grid_for(nxs * ncols, 256), 256, 0, c.st>>>(slab, full, rows, nxs, nkx, nxs * ncols);
+  CHB_LAUNCH_CHECK();
+  Batcher gb(c.st, 2 * nxs, nkr, nr, 2 * nxs, 2 * nxs);
+  for (int l = 0; l < ncomp; ++l)
+    for (i64 m = 0; m < nm; ++m)
+      gb.add(slab + nxs * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nxs * nkr * (m + nm * l), 1.0, 0.0);
+  CHB_TRY(gb.flush());
+  CHB_TRY(launch_rowscale_phase(c.st, out_fb, kx_slab, leftX, -1.0, 1.0, fact_slab, nxs, nkr * nm * ncomp, nkr * nm));
+  return 0;
+}
+
+int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int ncomp_each, double leftX,
+                    const double* kx_slab, const PackedOps& Out, i64 nxs, i64 nrn, i64 nm, i64 nkr) {
+  const i64 nr = nrn - 1;
+  const int ncomp = nsrc * ncomp_each;
+  CHB_CUDA(cudaMemsetAsync(out_slab, 0, sizeof(cd) * nxs * nrn * nm * ncomp, c.st));
+  Batcher gb(c.st, 2 * nxs, nr, nkr, 2 * nxs, 2 * nxs);
+  for (int j = 0; j < nsrc; ++j)
+    for (int l = 0; l < ncomp_each; ++l)
+      for (i64 m = 0; m < nm; ++m)
+        gb.add(srcs[j] + nxs * nkr * (m + nm * l), Out.slot[m],
+               out_slab + nxs * (1 + nrn * (m + nm * (l + ncomp_each * j))), 1.0, 0.0);
+  CHB_TRY(gb.flush());
+  CHB_TRY(launch_rowscale_phase(c.st, out_slab, kx_slab, leftX, +1.0, 1.0, nullptr, nxs, nrn * nm * ncomp, 1));
+  return 0;
+}
+
+int fb_out_finish_dev(FBCtx& c, cd* out, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols) {
+  put_rows_k<<<grid_for(nkx * ncols, 256), 256, 0, c.st>>>(out, gathered, gather_map, nkx, nxs, ncols, nkx * ncols);
+  CHB_LAUNCH_CHECK();
+  return c.fft->exec(c.st, out, nkx, ncols, CUFFT_INVERSE);
+}
+
 int fb_filtr_dev(FBCtx& c, cd* vec, double leftX, const double* kx, const double* filtr, int modefilt, i64 nkx,
                  i64 nkr, i64 nm, i64 nxfilt) {
   const i64 ncols = nkr * nm * 3;
@@ -190,7 +250,7 @@ int div_like(FBCtx& c, cd* S, i64 slo, i64 shi, const cd* vec, const PackedOps& 
   if (!d.env && mo.nko > 0) {  // Q7: with nko = 0 the missing mode 1 is taken as zero
     T1ext = c.scr->take_n<cd>(Pv);
     if (!T1ext) return 6;
-    CHB_TRY(launch_combine(c.st, T1ext, v3 + Pv * mo.vslot(1), Ui, v2 + Pv * mo.vslot(1), Um1, 1, d.nkx, d.nkr));
+    CHB_TRY(launch_combine(c.st, T1ext, v3 + Pv * mo.vslot(1), Ui, v2 + Pv * mo.vslot(1), Um1, 1 + d.mirror_shift, d.nkx, d.nkr));
   }
   for (i64 mode = slo; mode <= shi; ++mode) {
     cd* o = S + Ps * (mode - slo);
@@ -230,7 +290,7 @@ int grad_like(FBCtx& c, cd* out, const cd* S, i64 slo, i64 shi, const PackedOps&
   if (!d.env && mo.nko > 0) {
     Sext = c.scr->take_n<cd>(Pin);
     if (!Sext) return 6;
-    CHB_TRY(launch_combine(c.st, Sext, Sp(1), U1, nullptr, U0, 1, d.nkx, d.nkr));
+    CHB_TRY(launch_combine(c.st, Sext, Sp(1), U1, nullptr, U0, 1 + d.mirror_shift, d.nkx, d.nkr));
   }
   for (i64 mode = mo.lo; mode <= mo.hi; ++mode)
     CHB_TRY(ikx_plane(c.st, out + Ps * mo.vslot(mode), Sp(mode), kx, +1.0, 0, d));
@@ -301,8 +361,8 @@ int fb_rot_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const Pack
     R2ext = c.scr->take_n<cd>(Pv);
     V1ext = c.scr->take_n<cd>(Pv);
     if (!R2ext || !V1ext) return 6;
-    CHB_TRY(launch_combine(c.st, R2ext, v2 + Pv * mo.vslot(1), Ui, v3 + Pv * mo.vslot(1), U1, 1, d.nkx, d.nkr));
-    CHB_TRY(launch_combine(c.st, V1ext, v1 + Pv * mo.vslot(1), U1, nullptr, U0, 1, d.nkx, d.nkr));
+    CHB_TRY(launch_combine(c.st, R2ext, v2 + Pv * mo.vslot(1), Ui, v3 + Pv * mo.vslot(1), U1, 1 + d.mirror_shift, d.nkx, d.nkr));
+    CHB_TRY(launch_combine(c.st, V1ext, v1 + Pv * mo.vslot(1), U1, nullptr, U0, 1 + d.mirror_shift, d.nkx, d.nkr));
   }
   CHB_CUDA(cudaMemsetAsync(out, 0, sizeof(cd) * Ps * d.nm, c.st));  // component 1
   CHB_CUDA(cudaMemsetAsync(GP, 0, sizeof(cd) * Ps * d.nm, c.st));

@@ -63,7 +63,17 @@ int fb_filtr_dev(FBCtx& c, cd* vec, double leftX, const double* kx, const double
 struct FBMathDims {
   i64 nkx, nkr, nm, nkr_loc;
   int env;
+  int mirror_shift = 0;  // rows are a kx slab of mirror pairs: partner of row i is (nkx - i - shift) mod nkx
 };
+// forward transform of a kx slab: x-FFT of the full grid first, then the DHT on the rows `rows` only
+// (the two are linear maps on different axes and commute); out_fb has nxs rows
+int fb_in_slab_dev(FBCtx& c, cd* out_fb, const cd* in, double leftX, const double* kx_slab, const PackedOps& In,
+                   const double* fact_slab, const i64* rows, i64 nkx, i64 nxs, i64 nrn, i64 nm, i64 nkr, int ncomp);
+// backward DHT + phase of a kx slab into out_slab (nxs, nrn, nm, ncomp); the inverse x-FFT follows the all-gather
+int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int ncomp_each, double leftX,
+                    const double* kx_slab, const PackedOps& Out, i64 nxs, i64 nrn, i64 nm, i64 nkr);
+// rows of the gathered slabs back to natural kx order, inverse x-FFT
+int fb_out_finish_dev(FBCtx& c, cd* out, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols);
 int fb_grad_dev(FBCtx& c, cd* out, const cd* scl, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
                 const FBMathDims& d);
 int fb_div_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx,

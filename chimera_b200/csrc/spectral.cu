@@ -271,8 +271,10 @@ __global__ void __launch_bounds__(TPB) combine_k(cd* __restrict__ out, const cd*
   if (e >= n) return;
   i64 src = e;
   if (mirror) {
-    const i64 i = e % nkx;
-    src = e - i + (i == 0 ? 0 : nkx - i);
+    const i64 i = e % nkx;  // mirror = 1 + shift: partner row (nkx - i - shift) mod nkx (kx slabs: chimera_b200/sharding.py)
+    i64 j = nkx - i - (mirror - 1);
+    if (j >= nkx) j -= nkx;
+    src = e - i + j;
   }
   cd va = ldg(a + src);
   if (mirror) va = cmake(-va.x, va.y);

@@ -8,7 +8,9 @@ the operator tables once and exposes the state.
 
 Multi-GPU (one process per GPU, ``torch.distributed``): particles are sharded across ranks, every
 rank deposits into its own J / Rho grids, the grids are summed with an NCCL all-reduce over NVLink and
-every rank then advances the (replicated) spectral fields and gathers to its own particles.  There is
+the spectral solve is sharded by kx slab (mirror pairs of rows, chimera_b200/sharding.py): every rank
+x-FFTs the summed grids, transforms / corrects / advances only its rows, and the backward-transformed
+slabs are all-gathered before the inverse x-FFT and the gather to the rank's own particles.  There is
 no CPU fallback: without the CUDA library the import of :mod:`chimera_b200._lib` fails.
 """
 from __future__ import annotations
@@ -17,13 +19,13 @@ import ctypes
 
 import numpy as np
 
-from . import _lib
+from . import _lib, sharding
 
 _i64 = ctypes.c_longlong
 
 PHASES = (
     "push_coords", "sort", "deposit_J", "deposit_rho", "deposit_bg", "fb_in_J", "fb_in_rho", "poisson",
-    "maxwell", "init_push", "fields_out", "gather_push", "add_bg",
+    "maxwell", "init_push", "fields_out", "gather_push", "add_bg", "fields_out_a", "fields_out_b",
 )
 PHASE_ID = {n: i for i, n in enumerate(PHASES)}
 
@@ -40,7 +42,7 @@ class EngineConfig(ctypes.Structure):
         ("dr", ctypes.c_double), ("dt", ctypes.c_double), ("kx0", ctypes.c_double),
         ("rcull2", ctypes.c_double), ("chunk_len", ctypes.c_double),
         ("und_a0", ctypes.c_double), ("und_lambda", ctypes.c_double), ("und_X0", ctypes.c_double),
-        ("und_Lx", ctypes.c_double),
+        ("und_Lx", ctypes.c_double), ("nx_slab", _i64), ("mirror_shift", ctypes.c_int),
     ]
 
 
@@ -75,9 +77,13 @@ class Engine:
         ``{'a0','lambda','X0','Lx'}`` of ``undul_analytic`` (devices.f90:162)
     group : torch.distributed process group or True, optional
         shard particles over the ranks of the group and all-reduce the deposited grids
+    slab : bool or (rank, world), optional
+        shard the spectral solve by kx slab (chimera_b200.sharding): this engine then holds ``Nx/world``
+        rows of every spectral array.  Default: on under a process group whenever ``Nx`` is divisible by
+        ``2*world``.  ``(rank, world)`` selects a slab without a process group (tests drive the exchange).
     """
 
-    def __init__(self, setup, chunked=None, sort_every=None, poisson_iters=None, undulator=None, group=None):
+    def __init__(self, setup, chunked=None, sort_every=None, poisson_iters=None, undulator=None, group=None, slab=None):
         self.lib = _lib.load()
         self.setup = setup
         a = setup.Args
@@ -104,6 +110,27 @@ class Engine:
         if undulator:
             cfg.undulator = 1
             cfg.und_a0, cfg.und_lambda, cfg.und_X0, cfg.und_Lx = (float(undulator[k]) for k in ("a0", "lambda", "X0", "Lx"))
+        self.group = group
+        self.rank, self.world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+
+            self._dist = dist
+            self._group = None if group is True else group
+            self.rank, self.world = dist.get_rank(self._group), dist.get_world_size(self._group)
+        # kx-slab sharding of the spectral solve
+        self.slab_rank, self.slab_world = self.rank, self.world
+        if isinstance(slab, tuple):
+            self.slab_rank, self.slab_world = int(slab[0]), int(slab[1])
+            slab = True
+        if slab is None:
+            slab = self.slab_world > 1 and sharding.slab_supported(a["Nx"], self.slab_world)
+        self.slab = bool(slab) and self.slab_world > 1
+        self.rows = None
+        if self.slab:
+            self.rows = sharding.kx_slab_rows(a["Nx"], self.slab_rank, self.slab_world)
+            cfg.nx_slab = int(self.rows.size)
+            cfg.mirror_shift = sharding.mirror_shift(self.slab_rank, self.slab_world)
         self.cfg = cfg
         self._h = ctypes.c_void_p()
         self._check(self.lib.chimera_engine_create(ctypes.byref(cfg), ctypes.byref(self._h)))
@@ -114,17 +141,17 @@ class Engine:
             ("PSATD_E", setup.PSATD_E), ("PSATD_G", setup.PSATD_G), ("Rgrid", a["Rgrid"]),
         ):
             self.upload(name, arr)
+        if self.slab:
+            gmap = np.empty(a["Nx"], dtype=np.int64)
+            for r in range(self.slab_world):
+                rr = sharding.kx_slab_rows(a["Nx"], r, self.slab_world)
+                gmap[rr] = r * rr.size + np.arange(rr.size)
+            self._upload_raw("slab_rows", self.rows.astype(np.int64))
+            self._upload_raw("gather_map", gmap)
         self.nspecies = 0
         self.istep = 0
         self._pinned = []
-        self.group = group
-        self.rank, self.world = 0, 1
         if group is not None:
-            import torch.distributed as dist
-
-            self._dist = dist
-            self._group = None if group is True else group
-            self.rank, self.world = dist.get_rank(self._group), dist.get_world_size(self._group)
             import torch
 
             # run on torch's current stream so that the NCCL collectives are ordered with the kernels
@@ -148,13 +175,25 @@ class Engine:
         except Exception:
             pass
 
-    def upload(self, name, arr):
+    _KX_FIRST = ("kx", "kx_base", "DepFact", "PoissFact", "PSATD_E", "PSATD_G", "CPSATD1", "CPSATD2", "EG_fb", "J_fb",
+                 "B_fb", "Rho_fb", "gradRho_fb_prv", "gradRho_fb_nxt", "vec_fb")
+
+    def _upload_raw(self, name, arr):
         arr = np.asfortranarray(arr)
         self._check(self.lib.chimera_engine_upload(self._h, name.encode(), ctypes.c_void_p(arr.ctypes.data), _i64(arr.nbytes)))
 
+    def upload(self, name, arr):
+        """Upload a named array.  On a kx-slab engine, arrays whose first axis is kx may be given in full:
+        this rank's rows are taken (chimera_b200.sharding.kx_slab_rows)."""
+        arr = np.asarray(arr)
+        if self.slab and name in self._KX_FIRST and arr.shape[0] == self.cfg.nx:
+            arr = arr[self.rows]
+        self._upload_raw(name, arr)
+
     def shape_of(self, name):
         c = self.cfg
-        g, f = (c.nx, c.nrn, c.nm), (c.nx, c.nkr, c.nm)
+        nxf = c.nx_slab if self.slab else c.nx
+        g, f = (c.nx, c.nrn, c.nm), (nxf, c.nkr, c.nm)
         table = {"J": g + (3,), "Rho": g, "BckGrndRho": g, "EB": g + (6,), "EG_fb": f + (6,), "J_fb": f + (3,),
                  "B_fb": f + (3,), "Rho_fb": f, "gradRho_fb_prv": f + (3,), "gradRho_fb_nxt": f + (3,), "vec_fb": f + (3,)}
         return table[name]
@@ -234,6 +273,19 @@ class Engine:
         for n in names:
             self._dist.all_reduce(self.device_tensor(n), group=self._group)
 
+    def _fields_out(self):
+        """``Solver.G2B_FBRot`` + ``fb_fld_out`` (solvers.py:536, 450); on kx-slab engines the backward DHT runs
+        on this rank's rows, the slabs are all-gathered over NVLink and every rank finishes with the x-FFT."""
+        if not self.slab:
+            self.run("fields_out")
+            return
+        self.run("fields_out_a")
+        self._allgather_eb()
+        self.run("fields_out_b")
+
+    def _allgather_eb(self):
+        self._dist.all_gather_into_tensor(self.device_tensor("EB_gath"), self.device_tensor("EB_slab"), group=self._group)
+
     def _deposit_and_reduce(self):
         self.run("deposit_J")
         if self.cfg.space_charge:
@@ -263,12 +315,12 @@ class Engine:
                 self.upload("CPSATD1", c1)
                 self.upload("CPSATD2", c2)
                 self.run("init_push")
-        self.run("fields_out")
+        self._fields_out()
         self.run("gather_push", 0.5)
 
     def step(self, nsteps=1):
         """``nsteps`` x ``ChimeraRun.make_step`` (chimera_main.py:82-92)."""
-        if self.world == 1:
+        if self.world == 1 and not self.slab:
             self._check(self.lib.chimera_engine_step(self._h, _i64(self.istep + 1), _i64(nsteps)))
             self.istep += nsteps
             return
@@ -284,7 +336,7 @@ class Engine:
                 self.run("fb_in_rho")
             self.run("poisson")
             self.run("maxwell")
-            self.run("fields_out")
+            self._fields_out()
             self.run("gather_push", 1.0)
 
     # -- host-buffer stepping ------------------------------------------------------------------
@@ -319,6 +371,9 @@ class Engine:
             self._h, int(sid), vp(coords), vp(coords_half), vp(momenta), vp(weights), _i64(n), vp(EG_fb),
             vp(gradRho_fb_nxt), _i64(self.istep), int(bool(rebin))))
         self._allreduce_grids()
+        if self.slab:
+            self._check(self.lib.chimera_engine_step_host_mid(self._h))
+            self._allgather_eb()
         self._check(self.lib.chimera_engine_step_host_end(self._h, ctypes.byref(n_out)))
         return n_out.value
 

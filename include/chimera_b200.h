@@ -177,6 +177,11 @@ typedef struct chimera_engine_config {
   double rcull2;     /* particles with y^2+z^2 > rcull2 are removed at re-binning (SimDom[3])         */
   double chunk_len;  /* Xgrid[Nx/nchnk]-Xgrid[0] (nchnk>1) or Xgrid[Nx-1]-Xgrid[0] (particle_tools.f90:171) */
   double und_a0, und_lambda, und_X0, und_Lx; /* devices.f90:162 parameters                           */
+  /* kx-slab sharding of the spectral solve (multi-GPU): this engine holds nx_slab of the nx kx rows (a set of
+   * mirror pairs, uploaded as "slab_rows"); 0 = all rows.  mirror_shift: partner of local row j is
+   * (nx_slab - j - mirror_shift) mod nx_slab (reference f90/fb_math.f90:35-36 in slab-local form).           */
+  chb_i64 nx_slab;
+  int mirror_shift;
 } chimera_engine_config;
 
 typedef struct chimera_engine chimera_engine;
@@ -185,7 +190,9 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
 int chimera_engine_destroy(chimera_engine* e);
 /* named arrays: grids "J" "Rho" "BckGrndRho" "EB"; spectral "EG_fb" "J_fb" "B_fb" "Rho_fb"
  * "gradRho_fb_prv" "gradRho_fb_nxt" "vec_fb"; tables "InCurr" "Out" "DpS2S" "DmS2S" "kx" "kx_base"
- * "DepFact" "PoissFact" "PSATD_E" "PSATD_G" "CPSATD1" "CPSATD2" "Rgrid".  Shapes as in solvers.py:160-212;
+ * "DepFact" "PoissFact" "PSATD_E" "PSATD_G" "CPSATD1" "CPSATD2" "Rgrid"; kx-slab engines also "slab_rows"
+ * (int64 global row of each local row), "gather_map" (int64, nx entries: rank * nx_slab + local row of each
+ * global row), "EB_slab", "EB_gath".  Shapes as in solvers.py:160-212 (spectral arrays: nx_slab rows);
  * `src`/`dst` may be host or device pointers; nbytes must equal the array size. */
 int chimera_engine_upload(chimera_engine* e, const char* name, const void* src, chb_i64 nbytes);
 int chimera_engine_download(chimera_engine* e, const char* name, void* dst, chb_i64 nbytes);
@@ -214,7 +221,9 @@ enum chimera_engine_phase {
   CHB_FIELDS_OUT = 10, /* solvers.py:536 G2B_FBRot + :450 fb_fld_out                              */
   CHB_GATHER_PUSH = 11,/* chimera_main.py:139 proj_fld + devices + species.py:279 push_velocs; arg: dt_frac */
   CHB_ADD_BG = 12,     /* Rho += BckGrndRho (for ranks that deposited from zero before an all-reduce) */
-  CHB_NPHASES = 13
+  CHB_FIELDS_OUT_A = 13, /* kx-slab mode: G2B_FBRot + backward DHT of this rank's rows -> "EB_slab"          */
+  CHB_FIELDS_OUT_B = 14, /* kx-slab mode: rows of the all-gathered "EB_gath" -> EB, inverse x-FFT, eb_correction */
+  CHB_NPHASES = 15
 };
 int chimera_engine_run(chimera_engine* e, int phase, double arg);
 /* nsteps x make_step on the engine's stream; istep0 = index of the first step (re-binning cadence) */
@@ -238,6 +247,8 @@ int chimera_engine_step_host(chimera_engine* e, int species, double* coords, dou
 int chimera_engine_step_host_begin(chimera_engine* e, int species, double* coords, double* coords_half,
                                    double* momenta, double* weights, chb_i64 np, double* EG_fb,
                                    double* gradRho_fb_nxt, chb_i64 istep, int rebin);
+/* kx-slab engines: _begin, all-reduce, _mid, all-gather "EB_slab" -> "EB_gath", _end */
+int chimera_engine_step_host_mid(chimera_engine* e);
 int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out);
 int chimera_engine_set_rho_from_bg(chimera_engine* e, int from_bg);
 /* page-lock / unlock a host buffer the caller owns (cudaHostRegister) */

@@ -1,0 +1,85 @@
+"""Worker of tests/test_gpu_multi.py: one rank of an N-GPU NCCL job.  Particles sharded over the ranks,
+deposited grids all-reduced, spectral solve sharded by kx slab, backward-transformed slabs all-gathered.
+Compares every rank's state with the single-process oracle sequence and exits non-zero on a mismatch."""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main(name, slab):
+    from oracle import fimera as ofim
+    from pic_ref import RefRun, RefSpecies
+    from util import SETUPS, TOL, assert_close, carrier_tol, match, plasma, seed_fields
+    from chimera_b200 import sharding
+    from chimera_b200.engine import Engine
+    from chimera_b200.solver_setup import SolverSetup
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from chimera_b200 import _lib
+
+    _lib.load().chimera_set_device(local)
+    S = SolverSetup(copy.deepcopy(SETUPS[name]))
+    x, p, w = plasma(S, 2, 2, 71)
+    xi, pi_, wi = plasma(S, 2, 2, 77)
+    ions = "SpaceCharge" in S.Args.get("Features", ())
+    eg0 = seed_fields(S, 72)
+    sp = [RefSpecies(x, p, w)]
+    if ions:
+        sp.append(RefSpecies(xi, 0 * pi_, -wi, charge=1.0, mass=1886.0, still=True))
+    ref = RefRun(ofim, S, sp, background=ions)
+    ref.EG_fb[:] = eg0
+    px0 = (0.0,) * len(sp)
+    ref.make_halfstep(px0=px0)
+    for _ in range(3):
+        ref.make_step()
+
+    eng = Engine(S, group=True, slab=bool(slab))
+    lo, hi = sharding.particle_range(x.shape[1], rank, world)
+    eng.add_species(x[:, lo:hi], p[:, lo:hi], w[lo:hi])
+    if ions:
+        ilo, ihi = sharding.particle_range(xi.shape[1], rank, world)
+        eng.add_species(xi[:, ilo:ihi], 0 * pi_[:, ilo:ihi], -wi[ilo:ihi], charge=1.0, mass=1886.0, still=True)
+    eng.upload("EG_fb", eg0)
+    eng.make_halfstep(px0=px0, background=ions)
+    eng.step(2)
+    # third step through the host-buffer entry point (begin / all-reduce / mid / all-gather / end)
+    xs, xh, ps, ws = eng.particles(0)
+    eg = eng.download("EG_fb")
+    g = eng.download("gradRho_fb_nxt") if eng.cfg.space_charge else None
+    n = eng.step_host(xs, xh, ps, ws, eg, g)
+    tol = carrier_tol(S, 4 * TOL)
+    rows = eng.rows if eng.slab else slice(None)
+    assert_close(eg, ref.EG_fb[rows], tol, "EG_fb")
+    assert_close(eng.download("EG_fb"), ref.EG_fb[rows], tol, "EG_fb (device)")
+    assert_close(eng.download("EB"), ref.EB, tol, "EB")
+    assert_close(eng.download("J"), ref.J, 20 * tol if S.env else tol, "J")
+    # this rank's particles are a subset of the reference's
+    order = np.argsort(ref.sp[0].weights)
+    pos = np.searchsorted(ref.sp[0].weights[order], ws[:n])
+    idx = order[pos]
+    assert np.array_equal(ref.sp[0].weights[idx], ws[:n])
+    assert_close(ps[:, :n], ref.sp[0].momenta[:, idx], tol, "momenta")
+    assert_close(xs[:, :n], ref.sp[0].coords[:, idx], tol, "coords")
+    cnt = torch.tensor([float(n)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(cnt)
+    assert int(cnt.item()) == ref.sp[0].weights.size, (int(cnt.item()), ref.sp[0].weights.size)
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("OK", name, "world", world, "slab", bool(slab))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]))
