@@ -130,6 +130,7 @@ ALG_BYTES = {
     "deposit_J": 56.0,     # R x_half,p,w   (+ grid RW, added below)
     "deposit_rho": 32.0,   # R x,w
     "gather_push": 80.0,   # fused proj_fld + push_velocs: R x,w,p  W p  (the per-particle EB never hits HBM)
+    "particles_fused": 128.0,  # gather+push of step k and push_coords+deposits of step k+1: R x,p,w  W x,x_half,p
 }
 
 
@@ -235,6 +236,8 @@ def run_ours(a):
             ent = {"ms_per_call": per, "share": ms / ms_total}
             if name in ALG_BYTES:
                 by = ALG_BYTES[name] * n_local
+                if name == "particles_fused":
+                    by += (96.0 + 2 * 48.0 + 2 * 16.0) * grid_pts  # EB read once, J and Rho read-modify-write
                 if name == "deposit_J":
                     by += 2 * 48.0 * grid_pts
                 if name == "deposit_rho":

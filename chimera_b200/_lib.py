@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchimera_b200.so")
+LIB_PATH = os.environ.get("CHIMERA_B200_LIB") or os.path.join(_HERE, "libchimera_b200.so")  # override: kernel tuning builds
 _lib = None
 
 

@@ -34,6 +34,8 @@ struct Species {
   std::vector<int> h_ind;
   int* d_cta = nullptr;          // prefix of binned-deposit CTA counts per chunk (0:nchnk)
   int ncta = 0;
+  int* d_cta_f = nullptr;        // the same for the fused kernel (kFusedNPB particles per CTA)
+  int ncta_f = 0;
   i64 tile_w = 0;                // x cells per re-binning tile of the current particle order (0: unsorted)
 };
 
@@ -49,6 +51,7 @@ struct chimera_engine {
   double *host_EG = nullptr, *host_G = nullptr, *host_mom = nullptr;  // between step_host_begin / _end
   int host_id = -1;
   int host_mid_done = 0;
+  int fuse = 1;  // use the fused particle kernel inside multi-step calls (chimera_engine_set_fuse)
   double host_rho_from_bg = 1.0;  // 0 on the ranks that must not add BckGrndRho before an all-reduce
   bool own_stream = false;
   Scratch scr;
@@ -259,6 +262,13 @@ int update_cta_table(chimera_engine* e, Species& s) {
   }
   s.ncta = cta[nchnk];
   CHB_CUDA(cudaMemcpyAsync(s.d_cta, cta.data(), sizeof(int) * (nchnk + 1), cudaMemcpyHostToDevice, e->st));
+  std::vector<int> ctaf(nchnk + 1, 0);
+  for (int c = 0; c < nchnk; ++c) {
+    const int n = s.h_ind[c + 1] - s.h_ind[c];
+    ctaf[c + 1] = ctaf[c] + (n > 0 ? (n + kFusedNPB - 1) / kFusedNPB : 0);
+  }
+  s.ncta_f = ctaf[nchnk];
+  CHB_CUDA(cudaMemcpyAsync(s.d_cta_f, ctaf.data(), sizeof(int) * (nchnk + 1), cudaMemcpyHostToDevice, e->st));
   CHB_CUDA(cudaStreamSynchronize(e->st));
   return 0;
 }
@@ -482,6 +492,50 @@ int ph_gather_push(chimera_engine* e, double dt_frac) {
   return 0;
 }
 
+// gather + push_velocs of step k fused with push_coords + dep_curr + dep_dens of step k+1 (particles_fused.cu);
+// species without a fused instantiation (or still ones) take the separate kernels
+int ph_particles_fused(chimera_engine* e, int rho_from_bg) {
+  const auto& c = e->cfg;
+  GridGeom g = geom_ready(e);
+  UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
+  const i64 n = c.nx * c.nrn * c.nm;
+  CHB_CUDA(cudaMemsetAsync(e->A("J"), 0, sizeof(cd) * n * 3, e->st));
+  if (c.space_charge) {
+    if (rho_from_bg) CHB_CUDA(cudaMemcpyAsync(e->A("Rho"), e->A("BckGrndRho"), sizeof(cd) * n, cudaMemcpyDeviceToDevice, e->st));
+    else CHB_CUDA(cudaMemsetAsync(e->A("Rho"), 0, sizeof(cd) * n, e->st));
+  }
+  for (auto& s : e->sp) {
+    if (s.still || s.np == 0) continue;
+    SortedSpec spf = sortedspec(e, s);
+    spf.cta = s.d_cta_f;
+    spf.ncta = s.ncta_f;
+    int rc = launch_fused_particles(e->st, c.env, c.space_charge, s.x, s.xh, s.p, s.w, s.cap, e->A("EB"), e->A("J"),
+                                    e->A("Rho"), g, chunkspec(e, s), s.push_fact * c.dt, c.dt, und, spf);
+    if (rc == -1) {  // no fused instantiation for this mode count: the separate kernels, same order of operations
+      rc = launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt, und, sortedspec(e, s));
+      if (rc == -1)
+        rc = launch_gather_push_tiled(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
+                                      s.push_fact * c.dt, und, s.np);
+      CHB_TRY(rc);
+      CHB_TRY(launch_push_coords(e->st, soa(s.x, s.cap), soa((const double*)s.p, s.cap), soa(s.xh, s.cap), c.dt, s.np));
+      for (int curr = 1; curr >= (c.space_charge ? 0 : 1); --curr) {
+        cd* grid = curr ? e->A("J") : e->A("Rho");
+        const double* xs = curr ? s.xh : s.x;
+        rc = launch_deposit_binned(e->st, c.env, curr, xs, s.p, s.w, s.cap, grid, g, chunkspec(e, s), sortedspec(e, s));
+        if (rc == -1)
+          rc = launch_deposit_runs(e->st, c.env, curr, soa(xs, s.cap), soa((const double*)s.p, s.cap), s.w, grid, g,
+                                   chunkspec(e, s), s.np);
+        CHB_TRY(rc);
+      }
+      rc = 0;
+    }
+    CHB_TRY(rc);
+  }
+  CHB_TRY(launch_ghost_fold(e->st, e->A("J"), c.nx, c.nrn, c.nm * 3));
+  if (c.space_charge) CHB_TRY(launch_ghost_fold(e->st, e->A("Rho"), c.nx, c.nrn, c.nm));
+  return 0;
+}
+
 cudaEvent_t get_event(chimera_engine* e) {
   if (!e->ev_pool.empty()) { cudaEvent_t v = e->ev_pool.back(); e->ev_pool.pop_back(); return v; }
   cudaEvent_t v;
@@ -526,6 +580,7 @@ int run_phase(chimera_engine* e, int phase, double arg) {
     case CHB_FIELDS_OUT: rc = ph_fields_out_a(e, true); break;
     case CHB_FIELDS_OUT_A: rc = ph_fields_out_a(e, false); break;
     case CHB_FIELDS_OUT_B: rc = ph_fields_out_b(e); break;
+    case CHB_PARTICLES_FUSED: rc = ph_particles_fused(e, arg != 0.0); break;
     case CHB_GATHER_PUSH: rc = ph_gather_push(e, arg); break;
     case CHB_ADD_BG: rc = ph_add_bg(e); break;
     default: set_error("unknown engine phase %d", phase); rc = 2;
@@ -602,7 +657,7 @@ int chimera_engine_destroy(chimera_engine* e) {
   for (auto& kv : e->arr) cudaFree(kv.second.p);
   for (auto& s : e->sp) {
     cudaFree(s.x); cudaFree(s.xh); cudaFree(s.p); cudaFree(s.w);
-    cudaFree(s.x2); cudaFree(s.xh2); cudaFree(s.p2); cudaFree(s.w2); cudaFree(s.d_ind); cudaFree(s.d_cta);
+    cudaFree(s.x2); cudaFree(s.xh2); cudaFree(s.p2); cudaFree(s.w2); cudaFree(s.d_ind); cudaFree(s.d_cta); cudaFree(s.d_cta_f);
   }
   cudaFree(e->packed);
   cudaFree(e->key_a); cudaFree(e->key_b); cudaFree(e->idx_a); cudaFree(e->idx_b); cudaFree(e->cub_tmp);
@@ -675,6 +730,7 @@ int chimera_engine_add_species(chimera_engine* e, const double* coords, const do
   const int nchnk = e->cfg.chunked ? e->cfg.nchnk : 1;
   CHB_CUDA(cudaMalloc((void**)&s.d_ind, sizeof(int) * (nchnk + 1)));
   CHB_CUDA(cudaMalloc((void**)&s.d_cta, sizeof(int) * (nchnk + 1)));
+  CHB_CUDA(cudaMalloc((void**)&s.d_cta_f, sizeof(int) * (nchnk + 1)));
   s.h_ind.assign(nchnk + 1, 0);
   // placeholder until the first re-binning (CHB_SORT must run before a chunked deposit, as the
   // reference's make_halfstep does, chimera_main.py:62-70)
@@ -743,21 +799,31 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
   ENG_CHECK(e);
   const auto& c = e->cfg;
   if (slab(e)) { set_error("kx-slab engine: sequence the phases from the host (all-gather between fields_out_a / _b)"); return 2; }
+  // The particle work between two field solves -- gather + push_velocs of step k, then push_coords + deposits
+  // of step k+1 -- is independent per particle, so inside a multi-step call it runs as ONE kernel
+  // (CHB_PARTICLES_FUSED); the first step's head, the last step's tail and re-binning steps (the sort sits
+  // between push_coords and the deposits, chimera_main.py:82-86) use the separate phases.
+  bool gather_pending = false;
   for (i64 k = 0; k < nsteps; ++k) {
     const i64 istep = istep0 + k;
-    CHB_TRY(run_phase(e, CHB_PUSH_COORDS, 0));
-    if (c.sort_every > 0 && istep % c.sort_every == 0) CHB_TRY(run_phase(e, CHB_SORT, 1));
-    CHB_TRY(run_phase(e, CHB_DEPOSIT_J, 0));
-    CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
-    if (c.space_charge) {
-      CHB_TRY(run_phase(e, CHB_DEPOSIT_RHO, 1));
-      CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
+    const bool sort_now = c.sort_every > 0 && istep % c.sort_every == 0;
+    if (gather_pending && !sort_now && e->fuse) {
+      CHB_TRY(run_phase(e, CHB_PARTICLES_FUSED, 1));
+    } else {
+      if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
+      CHB_TRY(run_phase(e, CHB_PUSH_COORDS, 0));
+      if (sort_now) CHB_TRY(run_phase(e, CHB_SORT, 1));
+      CHB_TRY(run_phase(e, CHB_DEPOSIT_J, 0));
+      if (c.space_charge) CHB_TRY(run_phase(e, CHB_DEPOSIT_RHO, 1));
     }
+    CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
+    if (c.space_charge) CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
     CHB_TRY(run_phase(e, CHB_POISSON, 0));
     CHB_TRY(run_phase(e, CHB_MAXWELL, 0));
     CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
-    CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
+    gather_pending = true;
   }
+  if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
   return 0;
 }
 
@@ -954,6 +1020,12 @@ int chimera_engine_step_host(chimera_engine* e, int id, double* coords, double* 
                              chb_i64 istep, int rebin) {
   CHB_TRY(chimera_engine_step_host_begin(e, id, coords, coords_half, momenta, weights, np, EG_fb, gradRho_fb_nxt, istep, rebin));
   return chimera_engine_step_host_end(e, np_out);
+}
+
+int chimera_engine_set_fuse(chimera_engine* e, int on) {
+  ENG_CHECK(e);
+  e->fuse = on ? 1 : 0;
+  return 0;
 }
 
 int chimera_engine_set_rho_from_bg(chimera_engine* e, int from_bg) {

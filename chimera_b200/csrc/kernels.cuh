@@ -68,6 +68,12 @@ int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, c
                           i64 cap, cd* grid, const GridGeom& g, const ChunkSpec& ch, const SortedSpec& sp);
 int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* mom,
                               i64 cap, const GridGeom& g, double dt, const UndulParams& und, const SortedSpec& sp);
+// particles_fused.cu: gather + device + Boris push + position update + J / rho deposit in one kernel.
+// `sp.cta` must be the CTA table for kFusedNPB particles per CTA.  push_dt = 2 pi q/m dt, dt = time step.
+constexpr int kFusedNPB = 512;
+int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
+                           const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
+                           const ChunkSpec& ch, double push_dt, double dt, const UndulParams& und, const SortedSpec& sp);
 // field gather from a shared-memory tile of the EB grid + undulator + Boris push
 int launch_gather_push_tiled(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
                              const GridGeom& g, double dt, const UndulParams& und, i64 np);

@@ -1,0 +1,523 @@
+// particles_fused.cu -- the whole particle half of a PIC step in ONE kernel.
+//
+// Between two field solves the reference does, per particle and with no dependence on other particles,
+//   proj_fld (gather E,B at x_n)           grid_deps.f90:149 / grid_deps_env.f90:164   [end of make_step k]
+//   device field (undul_analytic)           devices.f90:162
+//   push_velocs (Boris)                     particle_tools.f90:18
+//   push_coords (x_n -> x_n+1, x_n+1/2)     particle_tools.f90:58                        [start of make_step k+1]
+//   dep_curr at x_n+1/2, dep_dens at x_n+1  grid_deps*.f90:18,89 (+ _chnk / _env variants)
+// (moduls/chimera_main.py:82-92: the tail of one make_step followed by the head of the next).  Run as four
+// kernels this moves 408 B per particle through HBM and bins the particles three times; fused it reads
+// x, p, w once and writes x, x_half, p once (128 B per particle) and bins once:
+//
+//  (A) a CTA takes FNPB consecutive particles of the cell-sorted order (one x-chunk), builds the gather
+//      record of each (shape fractions, e^{+i theta}, carrier) keyed by its cell inside a FBX x FBR cell
+//      window, and histograms the cells in shared memory;
+//  (B) block scan -> segments of <= FRUN same-cell particles; (C) counting sort of the local ids;
+//  (D) gather: one thread per (segment, field component) holds the 4 x NM node values in registers;
+//  (E) one thread per particle: device field, Boris push, strict-IEEE position update, global stores;
+//      then the deposit records at x_half (J) and x_new (rho).  A particle whose deposit cell is still the
+//      cell it was binned under (the common case: |v| dt << dx for all but the laser-driven few) is marked
+//      "fast"; the others are queued;
+//  (F) deposit: one thread per (segment, J component | rho) accumulates the 4 x NM node values of the
+//      segment's fast particles in registers and issues one red.global.add.f64 per node value;
+//  (G) the queued cell-changers: one thread per (particle, component, mode, node) -> red.global.add.f64.
+// Arithmetic per particle is the same as in the separate kernels (same helpers), so the result differs
+// from them only in the order of the floating-point sums on the grid.
+#include <cub/block/block_scan.cuh>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "particle_dev.cuh"
+
+namespace chb {
+namespace {
+#ifndef CHB_FT
+#define CHB_FT 256
+#endif
+#ifndef CHB_FRUN
+#define CHB_FRUN 24
+#endif
+#ifndef CHB_FMINB
+#define CHB_FMINB 3
+#endif
+constexpr int FNPB = kFusedNPB, FT = CHB_FT, FRUN = CHB_FRUN;
+constexpr int FBX = 40, FBR = 16, FBINS = FBX * FBR;
+constexpr int FPPT = (FNPB + FT - 1) / FT;
+constexpr int FMAXTASK = FNPB / FRUN + (FBINS < FNPB ? FBINS : FNPB);
+constexpr int FITEMS = (FBINS + FT - 1) / FT;
+constexpr int FNF = 12;  // doubles per particle in the record area (gather: 4|6 + 6 field values; deposit: 7|6 + 5|6)
+
+struct FShared {
+  int anchor[2];
+  int total, ntask;
+  int nslow[2];
+  typename cub::BlockScan<int, FT>::TempStorage scan;
+};
+
+struct FRange {
+  int chunk;
+  i64 first;
+  int count;
+};
+
+__device__ __forceinline__ FRange f_range(const SortedSpec& sp) {
+  int lo = 0, hi = sp.nchnk;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)blockIdx.x >= __ldg(sp.cta + mid)) lo = mid; else hi = mid;
+  }
+  FRange r;
+  r.chunk = lo;
+  r.first = (i64)__ldg(sp.ind + lo) + (i64)((int)blockIdx.x - __ldg(sp.cta + lo)) * FNPB;
+  const i64 n = (i64)__ldg(sp.ind + lo + 1) - r.first;
+  r.count = (int)(n < FNPB ? n : FNPB);
+  return r;
+}
+
+__device__ __forceinline__ void f_keep_range(const ChunkSpec& ch, int c, i64 nxn, i64& lo, i64& hi) {
+  lo = 0;
+  hi = nxn - 1;
+  if (ch.on) {  // the chunk-edge rule of grid_deps_chnk.f90:95-115 as a node interval (== chunk_keep per node)
+    const i64 left = (i64)c * ch.cs;
+    const i64 l2 = (left - ch.guards >= 0) ? left - ch.guards : left + 1;
+    const i64 h2 = (left + ch.cs + ch.guards <= nxn - 1) ? left + ch.cs + ch.guards : left + ch.cs - 1;
+    lo = l2 > lo ? l2 : lo;
+    hi = h2 < hi ? h2 : hi;
+  }
+}
+
+template <int ENV, int NM, int SC>
+__global__ void __launch_bounds__(FT, CHB_FMINB)
+fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __restrict__ mom, const double* __restrict__ w,
+                  i64 cap, const cd* __restrict__ Fld, cd* __restrict__ J, cd* __restrict__ Rho, GridGeom g, ChunkSpec ch,
+                  double dt_2, double dt, UndulParams und, SortedSpec sp) {
+  constexpr int NKO = ENV ? (NM - 1) / 2 : NM - 1;
+  constexpr int NCJ = ENV ? 1 : 3;  // Q1: the envelope current has l = 3 only
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* rec = reinterpret_cast<double*>(smem_raw);             // [FNF][FNPB], by local particle id
+  int* bins = reinterpret_cast<int*>(rec + FNF * FNPB);          // [FBINS]
+  int* tasks = bins + FBINS;                                     // [FMAXTASK]  key | start << 11 | n << 22
+  unsigned short* skey = reinterpret_cast<unsigned short*>(tasks + FMAXTASK);  // [FNPB]
+  unsigned short* order = skey + FNPB;                           // [FNPB]
+  unsigned short* slowJ = order + FNPB;                          // [FNPB] local ids that changed cell (J)
+  unsigned short* slowR = slowJ + FNPB;                          // [FNPB] ... (rho)
+  unsigned* cellJ = reinterpret_cast<unsigned*>(slowR + FNPB);   // [FNPB] (ix + 1) | ir << 20 of the J deposit cell
+  unsigned* cellR = cellJ + FNPB;                                // [FNPB]
+  unsigned char* fast = reinterpret_cast<unsigned char*>(cellR + FNPB);        // [FNPB] bit0: J, bit1: rho
+  __shared__ FShared sh;
+  const int tid = threadIdx.x;
+
+  const FRange cr = f_range(sp);
+  if (cr.count <= 0) return;
+  for (int i = tid; i < FBINS; i += FT) bins[i] = 0;
+  if (tid == 0) {
+    const double xp = __ldg(x + cr.first), yp = __ldg(x + cap + cr.first), zp = __ldg(x + 2 * cap + cr.first);
+    const i64 ix = (i64)floor((xp - g.leftX) * g.dx_inv);
+    const i64 ir = (i64)floor((sqrt(yp * yp + zp * zp) - g.r0) * g.dr_inv);
+    i64 ax = ix - FBX / 2;
+    if (sp.tile_w > 0 && sp.tile_w <= FBX) {
+      i64 lx = ix - (i64)cr.chunk * sp.cs;
+      lx = lx < 0 ? 0 : (lx > sp.cs - 1 ? sp.cs - 1 : lx);
+      ax = (i64)cr.chunk * sp.cs + (lx / sp.tile_w) * sp.tile_w - (FBX - sp.tile_w) / 2;
+    }
+    sh.anchor[0] = (int)ax;
+    sh.anchor[1] = (int)(ir - 3);
+    sh.nslow[0] = 0;
+    sh.nslow[1] = 0;
+  }
+  __syncthreads();
+  const int ix0 = sh.anchor[0], ir0 = sh.anchor[1];
+  double* fbuf = rec + 6 * FNPB;  // [6][FNPB] gathered field, phase (D)-(E)
+
+  // ---- (A) loads, gather records, histogram
+  {
+  double xs[FPPT], ys[FPPT], zs[FPPT], ws[FPPT];
+#pragma unroll
+  for (int j = 0; j < FPPT; ++j) {
+    const int li = tid + j * FT;
+    const bool in = li < cr.count;
+    const i64 ip = cr.first + (in ? li : 0);
+    xs[j] = __ldg(x + ip); ys[j] = __ldg(x + cap + ip); zs[j] = __ldg(x + 2 * cap + ip);
+    ws[j] = in ? __ldg(w + ip) : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < FPPT; ++j) {
+    const int li = tid + j * FT;
+    if (li >= FNPB) continue;
+    unsigned short key = 0xFFFFu;
+    const double xp = xs[j], yp = ys[j], zp = zs[j];
+    double F[6] = {0, 0, 0, 0, 0, 0};
+    Shape s;
+    if (ws[j] != 0.0 && make_shape(g, xp, yp, zp, s) && s.ix >= 0 && s.ix <= g.nxn - 2) {
+      const i64 kx = s.ix - ix0, kr = s.ir - ir0;
+      if (kx >= 0 && kx < FBX && kr >= 0 && kr < FBR) {
+        key = (unsigned short)(kr * FBX + kx);
+        atomicAdd(&bins[key], 1);
+        rec[li] = s.sx1;
+        rec[FNPB + li] = s.sr1;
+        const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // gather phase e^{+i theta}; axis: 0 | 1 (Q4)
+        rec[2 * FNPB + li] = (s.rp > 0.0) ? yp * rinv : (ENV ? 1.0 : 0.0);
+        rec[3 * FNPB + li] = zp * rinv;
+        if (ENV) {
+          double sn, cs;
+          sincos(xp * g.kx0, &sn, &cs);
+          rec[4 * FNPB + li] = cs;
+          rec[5 * FNPB + li] = sn;
+        }
+      } else {
+        gather_one<ENV>(g, Fld, xp, yp, zp, F);  // drifted out of the window: L2 path
+      }
+    }
+    if (key == 0xFFFFu) {
+#pragma unroll
+      for (int l = 0; l < 6; ++l) fbuf[l * FNPB + li] = F[l];
+    }
+    skey[li] = key;
+  }
+  }
+  __syncthreads();
+  // ---- (B) packed scan (low 16 bits: particles, high 16: segments) and the segment table
+  {
+    int items[FITEMS], cnt[FITEMS];
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < FITEMS; ++i) {
+      const int b = tid * FITEMS + i;
+      cnt[i] = (b < FBINS) ? bins[b] : 0;
+      items[i] = cnt[i] | (((cnt[i] + FRUN - 1) / FRUN) << 16);
+    }
+    cub::BlockScan<int, FT>(sh.scan).ExclusiveSum(items, items, total);
+#pragma unroll
+    for (int i = 0; i < FITEMS; ++i) {
+      const int b = tid * FITEMS + i;
+      if (b < FBINS) {
+        bins[b] = items[i] & 0xFFFF;
+        int start = items[i] & 0xFFFF, t = items[i] >> 16, left = cnt[i];
+        while (left > 0) {
+          const int n = left < FRUN ? left : FRUN;
+          tasks[t++] = b | (start << 11) | (n << 22);
+          start += n;
+          left -= n;
+        }
+      }
+    }
+    if (tid == 0) { sh.total = total & 0xFFFF; sh.ntask = total >> 16; }
+  }
+  __syncthreads();
+  // ---- (C) local ids to sorted slots
+#pragma unroll
+  for (int j = 0; j < FPPT; ++j) {
+    const int li = tid + j * FT;
+    if (li < FNPB) {
+      const int key = skey[li];
+      if (key != 0xFFFF) order[atomicAdd(&bins[key], 1)] = (unsigned short)li;
+    }
+  }
+  __syncthreads();
+  const i64 plane = g.nxn * g.nrn;
+  const int ntask = sh.ntask;
+  // ---- (D) gather: one thread per (segment, field component)
+#pragma unroll 1
+  for (int t = tid; t < ntask * 6; t += FT) {
+    const int task = t / 6, l = t - task * 6;
+    const int tw = tasks[task];
+    const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = tw >> 22;
+    const int kr = key / FBX, kx = key - kr * FBX;
+    const cd* pl = Fld + plane * g.nm * l + ((i64)ix0 + kx) + g.nxn * ((i64)ir0 + kr);
+    cd N[NM][4];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      N[m][0] = __ldg(pl + plane * m); N[m][1] = __ldg(pl + plane * m + 1);
+      N[m][2] = __ldg(pl + plane * m + g.nxn); N[m][3] = __ldg(pl + plane * m + g.nxn + 1);
+    }
+#pragma unroll 2
+    for (int q = 0; q < n; ++q) {
+      const int li = order[start + q];
+      const double fx = rec[li], fr = rec[FNPB + li];
+      const cd ph1 = cmake(rec[2 * FNPB + li], rec[3 * FNPB + li]);
+      const double w00 = (1.0 - fr) * (1.0 - fx), w10 = (1.0 - fr) * fx, w01 = fr * (1.0 - fx), w11 = fr * fx;
+      cd car = cmake(1.0, 0.0);
+      if (ENV) car = cmake(rec[4 * FNPB + li], rec[5 * FNPB + li]);  // carrier e^{+i kx0 x}
+      cd ph = cmake(1.0, 0.0);
+      double Fv = 0.0;
+#pragma unroll
+      for (int iO = 0; iO <= NKO; ++iO) {
+        if (iO > 0) ph = cmul(ph, ph1);
+#pragma unroll
+        for (int sgn = 0; sgn < ((ENV && iO > 0) ? 2 : 1); ++sgn) {
+          const int slot = ENV ? (NKO + (sgn ? -iO : iO)) : iO;
+          const cd pm = ENV ? cmul(car, sgn ? cconj(ph) : ph) : ph;
+          const double sx = w00 * N[slot][0].x + w10 * N[slot][1].x + w01 * N[slot][2].x + w11 * N[slot][3].x;
+          const double sy = w00 * N[slot][0].y + w10 * N[slot][1].y + w01 * N[slot][2].y + w11 * N[slot][3].y;
+          Fv += pm.x * sx - pm.y * sy;
+        }
+      }
+      fbuf[l * FNPB + li] = Fv;
+    }
+  }
+  __syncthreads();
+
+  // ---- (E) device field, Boris push, position update, deposit records.  The deposit records reuse the
+  // whole record area, gathered field included: slot li of every plane belongs to the one thread that handles
+  // particle li here, and it reads the particle's field values before it writes the particle's records.
+  double* recJ = rec;                         // [7 | 6][FNPB]: fx, fr, ph.x, ph.y, amplitude(s)
+  double* recR = rec + (ENV ? 6 : 7) * FNPB;  // [5 | 6][FNPB]
+  double xs[FPPT], ys[FPPT], zs[FPPT], ws[FPPT], pxs[FPPT], pys[FPPT], pzs[FPPT];
+#pragma unroll
+  for (int j = 0; j < FPPT; ++j) {  // x, w were read a moment ago by this CTA: L1/L2 hits
+    const int li = tid + j * FT;
+    const bool in = li < cr.count;
+    const i64 ip = cr.first + (in ? li : 0);
+    xs[j] = __ldg(x + ip); ys[j] = __ldg(x + cap + ip); zs[j] = __ldg(x + 2 * cap + ip);
+    ws[j] = in ? __ldg(w + ip) : 0.0;
+    pxs[j] = mom[ip]; pys[j] = mom[cap + ip]; pzs[j] = mom[2 * cap + ip];
+  }
+#pragma unroll
+  for (int j = 0; j < FPPT; ++j) {
+    const int li = tid + j * FT;
+    if (li >= cr.count) {
+      if (li < FNPB) fast[li] = 0;
+      continue;
+    }
+    const i64 ip = cr.first + li;
+    double Fp[6];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) Fp[l] = fbuf[l * FNPB + li];
+    if (und.on) undul_field(und, xs[j], ys[j], Fp);
+    double px = pxs[j], py = pys[j], pz = pzs[j];
+    boris(px, py, pz, Fp[0], Fp[1], Fp[2], Fp[3], Fp[4], Fp[5], dt_2);
+    mom[ip] = px; mom[cap + ip] = py; mom[2 * cap + ip] = pz;
+    // push_coords (particle_tools.f90:58-82) in strict IEEE arithmetic, see push_coords_k
+    const double p2 = __dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz));
+    const double dt_gp = __ddiv_rn(dt, __dsqrt_rn(__dadd_rn(1.0, p2)));
+    const double x0[3] = {xs[j], ys[j], zs[j]}, pp[3] = {px, py, pz};
+    double x1[3], xc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      x1[c] = __dadd_rn(x0[c], __dmul_rn(pp[c], dt_gp));
+      xc[c] = __dmul_rn(0.5, __dadd_rn(x0[c], x1[c]));
+      x[c * cap + ip] = x1[c];
+      xh[c * cap + ip] = xc[c];
+    }
+    const int key = skey[li];
+    const double wp = ws[j];
+    unsigned char fl = 0;
+    // Deposit records: a particle whose deposit cell is the cell it was binned under goes the register path
+    // of stage (F); one that changed cell (or was outside the window) is queued for stage (G).
+    {  // current at the centred position
+      Shape s;
+      bool direct = false;
+      if (wp != 0.0 && make_shape(g, xc[0], xc[1], xc[2], s) && fabs(px) + fabs(py) + fabs(pz) != 0.0 &&
+          s.ix >= -1 && s.ix <= g.nxn - 1) {  // dep_curr skips w = 0, r >= rmax and particles at rest (grid_deps.f90:36-42)
+        if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
+          recJ[li] = s.sx1;
+          recJ[FNPB + li] = s.sr1;
+          const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // deposit phase e^{-i theta}; 0 on the axis
+          recJ[2 * FNPB + li] = xc[1] * rinv;
+          recJ[3 * FNPB + li] = -xc[2] * rinv;
+          const double ginv = 1.0 / sqrt(1.0 + px * px + py * py + pz * pz);
+          if (ENV) {
+            double sn, cs;
+            sincos(xc[0] * g.kx0, &sn, &cs);
+            const cd base = cscale(pz * ginv, cmake(wp * cs, -wp * sn));
+            recJ[4 * FNPB + li] = base.x;
+            recJ[5 * FNPB + li] = base.y;
+          } else {
+            const double wg = wp * ginv;
+            recJ[4 * FNPB + li] = px * wg;
+            recJ[5 * FNPB + li] = py * wg;
+            recJ[6 * FNPB + li] = pz * wg;
+          }
+          const i64 kx = s.ix - ix0, kr = s.ir - ir0;
+          if (key != 0xFFFF && kx >= 0 && kx < FBX && kr >= 0 && kr < FBR && (int)(kr * FBX + kx) == key) fl |= 1;
+          else {
+            cellJ[li] = (unsigned)(s.ix + 1) | ((unsigned)s.ir << 20);
+            slowJ[atomicAdd(&sh.nslow[0], 1)] = (unsigned short)li;
+          }
+        } else direct = true;
+      }
+      if (direct) deposit_one<ENV, 1>(g, ch, cr.chunk, J, xc[0], xc[1], xc[2], px, py, pz, wp);
+    }
+    if (SC) {  // charge at the new position
+      Shape s;
+      bool direct = false;
+      if (wp != 0.0 && make_shape(g, x1[0], x1[1], x1[2], s) && s.ix >= -1 && s.ix <= g.nxn - 1) {
+        if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
+          recR[li] = s.sx1;
+          recR[FNPB + li] = s.sr1;
+          const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;
+          recR[2 * FNPB + li] = x1[1] * rinv;
+          recR[3 * FNPB + li] = -x1[2] * rinv;
+          if (ENV) {
+            double sn, cs;
+            sincos(x1[0] * g.kx0, &sn, &cs);
+            const cd wpc = cmake(wp * cs, -wp * sn);
+            const cd base = cmul(wpc, wpc);  // Q2: the complex weight enters twice
+            recR[4 * FNPB + li] = base.x;
+            recR[5 * FNPB + li] = base.y;
+          } else {
+            recR[4 * FNPB + li] = wp;
+          }
+          const i64 kx = s.ix - ix0, kr = s.ir - ir0;
+          if (key != 0xFFFF && kx >= 0 && kx < FBX && kr >= 0 && kr < FBR && (int)(kr * FBX + kx) == key) fl |= 2;
+          else {
+            cellR[li] = (unsigned)(s.ix + 1) | ((unsigned)s.ir << 20);
+            slowR[atomicAdd(&sh.nslow[1], 1)] = (unsigned short)li;
+          }
+        } else direct = true;
+      }
+      if (direct) deposit_one<ENV, 0>(g, ch, cr.chunk, Rho, x1[0], x1[1], x1[2], 0.0, 0.0, 0.0, wp);
+    }
+    fast[li] = fl;
+  }
+  __syncthreads();
+
+  // ---- (F) deposit: one thread per (segment, unit), unit = J component(s) then rho
+  constexpr int NU = NCJ + (SC ? 1 : 0);
+  i64 klo, khi;
+  f_keep_range(ch, cr.chunk, g.nxn, klo, khi);
+#pragma unroll 1
+  for (int t = tid; t < ntask * NU; t += FT) {
+    const int task = t / NU, u = t - task * NU;
+    const bool isJ = u < NCJ;
+    const int tw = tasks[task];
+    const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = tw >> 22;
+    const double* rb = isJ ? recJ : recR;
+    const double* ra = rb + (4 + ((!ENV && isJ) ? u : 0)) * FNPB;
+    const unsigned char bit = isJ ? 1 : 2;
+    cd a[2][2][NM];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int m = 0; m < NM; ++m) a[i][k][m] = cmake(0.0, 0.0);
+    bool any = false;
+#pragma unroll 2
+    for (int q = 0; q < n; ++q) {
+      const int li = order[start + q];
+      if (!(fast[li] & bit)) continue;
+      any = true;
+      const double fx = rb[li], fr = rb[FNPB + li];
+      const cd ph1 = cmake(rb[2 * FNPB + li], rb[3 * FNPB + li]);
+      const cd amp = ENV ? cmake(ra[li], ra[FNPB + li]) : cmake(ra[li], 0.0);
+      const double w00 = (1.0 - fx) * (1.0 - fr), w01 = (1.0 - fx) * fr, w10 = fx * (1.0 - fr), w11 = fx * fr;
+      cd ph = cmake(1.0, 0.0);
+#pragma unroll
+      for (int iO = 0; iO <= NKO; ++iO) {
+        if (iO > 0) ph = cmul(ph, ph1);
+#pragma unroll
+        for (int sgn = 0; sgn < ((ENV && iO > 0) ? 2 : 1); ++sgn) {
+          const int m = ENV ? (NKO + (sgn ? -iO : iO)) : iO;
+          const cd pm = sgn ? cconj(ph) : ph;
+          const cd f = ENV ? cmul(amp, pm) : cscale(amp.x, pm);
+          a[0][0][m].x += w00 * f.x; a[0][0][m].y += w00 * f.y;
+          a[0][1][m].x += w01 * f.x; a[0][1][m].y += w01 * f.y;
+          a[1][0][m].x += w10 * f.x; a[1][0][m].y += w10 * f.y;
+          a[1][1][m].x += w11 * f.x; a[1][1][m].y += w11 * f.y;
+        }
+      }
+    }
+    if (!any) continue;
+    const int kr = key / FBX, kx = key - kr * FBX;
+    const i64 gx = (i64)ix0 + kx, gr = (i64)ir0 + kr;
+    const int l = isJ ? (ENV ? 2 : u) : 0;
+    cd* pl = (isJ ? J : Rho) + plane * (g.nm * l) + gx + g.nxn * gr;
+    const bool k0 = gx >= klo && gx <= khi, k1 = gx + 1 >= klo && gx + 1 <= khi;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      if (k0) { red_add(pl + plane * m, a[0][0][m]); red_add(pl + plane * m + g.nxn, a[0][1][m]); }
+      if (k1) { red_add(pl + plane * m + 1, a[1][0][m]); red_add(pl + plane * m + 1 + g.nxn, a[1][1][m]); }
+    }
+  }
+
+  // ---- (G) particles that changed cell: one thread per (particle, component, node), so that the few of
+  // them cost a few warp-wide red.global.add instead of serialising inside divergent warps
+#pragma unroll 1
+  for (int pass = 0; pass < (SC ? 2 : 1); ++pass) {
+    const bool isJ = pass == 0;
+    const int per = (isJ ? NCJ : 1) * 4;
+    const int nitems = sh.nslow[pass] * per;
+    const double* rb = isJ ? recJ : recR;
+    const unsigned short* lst = isJ ? slowJ : slowR;
+    const unsigned* cells = isJ ? cellJ : cellR;
+    cd* grid = isJ ? J : Rho;
+#pragma unroll 1
+    for (int t = tid; t < nitems; t += FT) {
+      const int q = t / per, r = t - q * per;
+      const int u = r >> 2, node = r & 3;
+      const int i = node >> 1, k = node & 1;
+      const int li = lst[q];
+      const unsigned cell = cells[li];
+      const i64 gx = (i64)(cell & 0xFFFFFu) - 1 + i, gr = (i64)(cell >> 20) + k;
+      const bool keep = gx >= 0 && gx <= g.nxn - 1 && (!ch.on || chunk_keep(ch, cr.chunk, gx, g.nxn));
+      if (!keep) continue;
+      const double fx = rb[li], fr = rb[FNPB + li];
+      const cd ph1 = cmake(rb[2 * FNPB + li], rb[3 * FNPB + li]);
+      const double* ra = rb + (4 + ((!ENV && isJ) ? u : 0)) * FNPB;
+      const cd amp = ENV ? cmake(ra[li], ra[FNPB + li]) : cmake(ra[li], 0.0);
+      const double wgt = (i ? fx : 1.0 - fx) * (k ? fr : 1.0 - fr);
+      const int l = isJ ? (ENV ? 2 : u) : 0;
+      cd* pl = grid + plane * (g.nm * l) + gx + g.nxn * gr;
+      cd ph = cmake(1.0, 0.0);
+#pragma unroll
+      for (int iO = 0; iO <= NKO; ++iO) {
+        if (iO > 0) ph = cmul(ph, ph1);
+#pragma unroll
+        for (int sgn = 0; sgn < ((ENV && iO > 0) ? 2 : 1); ++sgn) {
+          const int m = ENV ? (NKO + (sgn ? -iO : iO)) : iO;
+          const cd pm = sgn ? cconj(ph) : ph;
+          const cd f = ENV ? cmul(amp, pm) : cscale(amp.x, pm);
+          red_add(pl + plane * m, cscale(wgt, f));
+        }
+      }
+    }
+  }
+}
+
+constexpr size_t F_SMEM = sizeof(double) * FNF * FNPB + sizeof(int) * (FBINS + FMAXTASK) +
+                          4 * sizeof(unsigned short) * FNPB + 2 * sizeof(unsigned) * FNPB + FNPB;
+
+template <int ENV, int SC>
+int launch_fused_nm(cudaStream_t st, double* x, double* xh, double* mom, const double* w, i64 cap, const cd* Fld, cd* J,
+                    cd* Rho, const GridGeom& g, const ChunkSpec& ch, double dt_2, double dt, const UndulParams& und,
+                    const SortedSpec& sp) {
+#define CHB_FUSED(NMV)                                                                                                 \
+  case NMV: {                                                                                                          \
+    static bool attr = false;                                                                                          \
+    if (!attr) {                                                                                                       \
+      CHB_CUDA(cudaFuncSetAttribute(fused_particles_k<ENV, NMV, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    (int)F_SMEM));                                                                     \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    fused_particles_k<ENV, NMV, SC><<<sp.ncta, FT, F_SMEM, st>>>(x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp); \
+  } break;
+  switch ((int)g.nm) {
+    CHB_FUSED(1)
+    CHB_FUSED(2)
+    CHB_FUSED(3)
+    CHB_FUSED(5)
+    default: return -1;
+  }
+#undef CHB_FUSED
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
+// returns -1 when the mode count has no instantiation (the caller falls back to the separate kernels)
+int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
+                           const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
+                           const ChunkSpec& ch, double push_dt, double dt, const UndulParams& und, const SortedSpec& sp) {
+  if (sp.ncta <= 0) return 0;
+  if (env && (g.nm % 2) != 1) { set_error("envelope kernels need an odd number of mode slots"); return 2; }
+  const double dt_2 = 0.5 * push_dt;
+  if (env) {
+    if (space_charge) return launch_fused_nm<1, 1>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
+    return launch_fused_nm<1, 0>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
+  }
+  if (space_charge) return launch_fused_nm<0, 1>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
+  return launch_fused_nm<0, 0>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
+}
+
+}  // namespace chb

@@ -26,6 +26,7 @@ _i64 = ctypes.c_longlong
 PHASES = (
     "push_coords", "sort", "deposit_J", "deposit_rho", "deposit_bg", "fb_in_J", "fb_in_rho", "poisson",
     "maxwell", "init_push", "fields_out", "gather_push", "add_bg", "fields_out_a", "fields_out_b",
+    "particles_fused",
 )
 PHASE_ID = {n: i for i, n in enumerate(PHASES)}
 
@@ -151,6 +152,7 @@ class Engine:
         self.nspecies = 0
         self.istep = 0
         self._pinned = []
+        self.fuse = True
         if group is not None:
             import torch
 
@@ -265,6 +267,11 @@ class Engine:
     def sync(self):
         self._check(self.lib.chimera_engine_sync(self._h))
 
+    def set_fuse(self, on=True):
+        """Fuse the particle work between two field solves into one kernel inside multi-step calls (default)."""
+        self.fuse = bool(on)
+        self._check(self.lib.chimera_engine_set_fuse(self._h, int(self.fuse)))
+
     def use_stream(self, cuda_stream_ptr):
         self._check(self.lib.chimera_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
 
@@ -324,19 +331,32 @@ class Engine:
             self._check(self.lib.chimera_engine_step(self._h, _i64(self.istep + 1), _i64(nsteps)))
             self.istep += nsteps
             return
+        # same schedule as chimera_engine_step (csrc/engine.cu): inside a multi-step call the particle work between
+        # two field solves (gather + push of step k, push_coords + deposits of step k+1) is one fused kernel
         c = self.cfg
+        gather_pending = False
         for _ in range(nsteps):
             self.istep += 1
-            self.run("push_coords")
-            if c.sort_every > 0 and self.istep % c.sort_every == 0:
-                self.run("sort", 1.0)
-            self._deposit_and_reduce()
+            sort_now = c.sort_every > 0 and self.istep % c.sort_every == 0
+            if gather_pending and not sort_now and self.fuse:
+                self.run("particles_fused", 1.0 if self.rank == 0 else 0.0)
+                if self.world > 1:
+                    self._allreduce_grids()
+            else:
+                if gather_pending:
+                    self.run("gather_push", 1.0)
+                self.run("push_coords")
+                if sort_now:
+                    self.run("sort", 1.0)
+                self._deposit_and_reduce()
             self.run("fb_in_J")
             if c.space_charge:
                 self.run("fb_in_rho")
             self.run("poisson")
             self.run("maxwell")
             self._fields_out()
+            gather_pending = True
+        if gather_pending:
             self.run("gather_push", 1.0)
 
     # -- host-buffer stepping ------------------------------------------------------------------

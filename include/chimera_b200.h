@@ -223,12 +223,16 @@ enum chimera_engine_phase {
   CHB_ADD_BG = 12,     /* Rho += BckGrndRho (for ranks that deposited from zero before an all-reduce) */
   CHB_FIELDS_OUT_A = 13, /* kx-slab mode: G2B_FBRot + backward DHT of this rank's rows -> "EB_slab"          */
   CHB_FIELDS_OUT_B = 14, /* kx-slab mode: rows of the all-gathered "EB_gath" -> EB, inverse x-FFT, eb_correction */
-  CHB_NPHASES = 15
+  CHB_PARTICLES_FUSED = 15, /* gather + device + push_velocs of one step and push_coords + dep_curr + dep_dens of the
+                             next in one kernel (the per-particle work between two field solves); arg as DEPOSIT_RHO */
+  CHB_NPHASES = 16
 };
 int chimera_engine_run(chimera_engine* e, int phase, double arg);
 /* nsteps x make_step on the engine's stream; istep0 = index of the first step (re-binning cadence) */
 int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps);
 int chimera_engine_sync(chimera_engine* e);
+/* multi-step calls fuse the particle work between two field solves into one kernel (default on) */
+int chimera_engine_set_fuse(chimera_engine* e, int on);
 /* One make_step (chimera_main.py:82-92) with the PIC state in HOST buffers, the reference's calling model:
  * coords/momenta (3,np) Fortran-ordered in-out, coords_half (3,np) out, weights (np) in (rewritten in the
  * new particle order on re-binning steps), EG_fb (nx,nkr,nm,6) and gradRho_fb_nxt (nx,nkr,nm,3) complex

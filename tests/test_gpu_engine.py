@@ -240,3 +240,27 @@ def test_kx_slab_sharded_solve_matches_reference(ofim, gfim, name, world):
         perm = match(ref.sp[0].weights, we)
         assert_close(pe[:, perm], ref.sp[0].momenta, tol, "momenta on rank %d" % r)
         e.close()
+
+
+@pytest.mark.parametrize("name,ions", [("real_m2", True), ("real_m3", False), ("env_m3", False), ("env_m1", False)])
+@pytest.mark.parametrize("nsteps", [3, 6])
+def test_fused_particle_kernel_matches_reference_sequence(ofim, gfim, name, ions, nsteps):
+    """Engine.step(n>1) runs gather + push_velocs of step k and push_coords + deposits of step k+1 as one kernel
+    (csrc/particles_fused.cu); 6 steps cross a re-binning step for Xchunked=(4,3).  Also checked against the
+    unfused engine, which must agree to summation order."""
+    und = dict(a0=0.3, **{"lambda": 1.3}, X0=-1.0, Lx=9.0) if name == "env_m1" else None
+    S, ref, eng = build_pair(ofim, name, 81, still_ions=ions, undulator=und)
+    _, _, eng2 = build_pair(ofim, name, 81, still_ions=ions, undulator=und)
+    eng2.set_fuse(False)
+    ref.make_halfstep()
+    for e in (eng, eng2):
+        e.make_halfstep(background=ions)
+    for _ in range(nsteps):
+        ref.make_step()
+    eng.step(nsteps)
+    eng2.step(nsteps)
+    compare_state(ref, eng, nsteps * TOL)
+    for n in ("J", "EB", "EG_fb"):
+        assert_close(eng.download(n), eng2.download(n), carrier_tol(S, 20 * nsteps * TOL if S.env else nsteps * TOL), n + " fused vs unfused")
+    eng.close()
+    eng2.close()
