@@ -108,6 +108,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_substr):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/traffic.json,
+    written by tools/ncu_summary.py traffic); None when the kernel is not in the capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    for name, v in json.load(open(p)).get("kernels", {}).items():
+        if kernel_substr in name:
+            return v["dram_bytes_per_launch"]
+    return None
+
+
 def dgemm_peak_tflops(torch, n=8192, reps=5):
     """cuBLAS DGEMM n^3: the FP64-tensor denominator (MEASURED_PEAKS.json has no FP64 figure)."""
     a = torch.randn(n, n, dtype=torch.float64, device="cuda")
@@ -132,6 +144,10 @@ ALG_BYTES = {
     "gather_push": 80.0,   # fused proj_fld + push_velocs: R x,w,p  W p  (the per-particle EB never hits HBM)
     "particles_fused": 128.0,  # gather+push of step k and push_coords+deposits of step k+1: R x,p,w  W x,x_half,p
 }
+
+
+TRAFFIC_KERNEL = {"particles_fused": "fused_particles_k", "gather_push": "gather_push_binned_k",
+                  "deposit_J": "deposit_binned_k<0, 1", "deposit_rho": "deposit_binned_k<0, 0", "push_coords": "push_coords_k"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,6 +179,30 @@ def build_problem(a, torch, rank, world, group):
     return S, eng, n
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the
+    host arrays of the end-to-end leg are first-touched on the GPU's NUMA node.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        cpus = set()
+        for part in open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_ours(a):
     import torch
 
@@ -170,6 +210,8 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa_node(local)
     group = None
     if world > 1:
         import torch.distributed as dist
@@ -253,12 +295,13 @@ def run_ours(a):
         if top is None or gemm["share"] >= cand[top]:
             roof = {"kernel": "gemm_dmma_k (DHT + mode-coupling contractions)", "bound": "tensor",
                     "achieved": gemm["tflops"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm["tflops"] / fp64_peak,
-                    "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor; MEASURED_PEAKS.json has no FP64 figure)",
+                    "traffic": ncu_traffic("gemm_dmma_k"), "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor; MEASURED_PEAKS.json has no FP64 figure)",
                     "share_of_step": gemm["share"]}
         else:
             s = stages[top]
             roof = {"kernel": top, "bound": "hbm", "achieved": s["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": s["frac"], "traffic": None, "peak_source": hbm_src, "share_of_step": s["share"]}
+                    "frac": s["frac"], "traffic": ncu_traffic(TRAFFIC_KERNEL.get(top, top)), "peak_source": hbm_src,
+                    "share_of_step": s["share"]}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -270,6 +313,9 @@ def run_ours(a):
                        "l2": "inputs larger than L2 (particle arrays %.1f GB, grids %.2f GB)"
                              % (n_local * 80 / 1e9, grid_pts * 16 * 10 / 1e9)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": stages, "gemm": gemm,
+            # second half of BASELINE.json's metric: "DHT+PSATD ms/step" = every spectral phase of one step
+            "dht_psatd_ms_per_step": sum(v["ms_per_call"] for k, v in stages.items()
+                                         if k in ("fb_in_J", "fb_in_rho", "poisson", "maxwell", "fields_out", "fields_out_a", "fields_out_b")),
             "fp64_peak_tflops": fp64_peak,
         }
     # ---- end to end through the reference-facing drop-in (host buffers, copies inside the timed region)

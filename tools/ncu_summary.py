@@ -25,7 +25,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def short(n):
     n = re.sub(r"\(.*", "", n)
     n = re.sub(r"^void ", "", n)
-    n = re.sub(r"chb::|<unnamed>::", "", n)
+    n = re.sub(r"chb::|<?unnamed>::", "", n)
     return n
 
 
@@ -35,11 +35,13 @@ def launches(src, dst):
     h = rows[hi]
     ki, vi = h.index("Kernel Name"), h.index("Metric Value")
     data = [(short(r[ki]), float(r[vi].replace(",", ""))) for r in rows[hi + 1:] if len(r) > vi]
-    idx = [i for i, d in enumerate(data) if d[0].startswith("push_coords_k")]
+    idx = [i for i, d in enumerate(data) if d[0].startswith("fused_particles_k")]
+    if len(idx) < 2:
+        idx = [i for i, d in enumerate(data) if d[0].startswith("push_coords_k")]
     out = ["ncu --metrics gpu__time_duration.sum --clock-control none: %d launches in %s" % (len(data), src)]
     if len(idx) >= 2:
         seg = data[idx[-2]:idx[-1]]
-        out.append("one full PIC step (between the last two push_coords_k launches): %d launches" % len(seg))
+        out.append("one full PIC step (between the last two %s launches): %d launches" % (data[idx[-1]][0].split("<")[0], len(seg)))
     else:
         seg = data
     agg = collections.OrderedDict()
@@ -71,5 +73,31 @@ def full(src, dst):
     print("\n".join(out))
 
 
+def traffic(src, dst):
+    """per-kernel DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured
+    launches) -> JSON consumed by bench.py for roofline.traffic"""
+    import json
+
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units = rows[0], rows[1]
+    ir, iw, it = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        name = short(r[h.index("Kernel Name")])
+        by = float(r[ir].replace(",", "")) * scale[units[ir]] + float(r[iw].replace(",", "")) * scale[units[iw]]
+        a = agg.setdefault(name, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += by
+        a[2] += float(r[it].replace(",", "")) * tscale[units[it]]
+    out = {"source": src, "note": "ncu --set full --clock-control none; mean per launch over the captured launches",
+           "kernels": {k: {"launches": v[0], "dram_bytes_per_launch": v[1] / v[0], "ms_per_launch_under_ncu": v[2] / v[0]}
+                       for k, v in agg.items()}}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
