@@ -34,6 +34,7 @@ struct Species {
   std::vector<int> h_ind;
   int* d_cta = nullptr;          // prefix of binned-deposit CTA counts per chunk (0:nchnk)
   int ncta = 0;
+  std::vector<int> h_cta;        // host copy of d_cta
   int* d_cta_f = nullptr;        // the same for the fused kernel (kFusedNPB particles per CTA)
   int ncta_f = 0;
   i64 tile_w = 0;                // x cells per re-binning tile of the current particle order (0: unsorted)
@@ -261,6 +262,7 @@ int update_cta_table(chimera_engine* e, Species& s) {
     cta[c + 1] = cta[c] + (n > 0 ? (n + kDepNPB - 1) / kDepNPB : 0);
   }
   s.ncta = cta[nchnk];
+  s.h_cta = cta;
   CHB_CUDA(cudaMemcpyAsync(s.d_cta, cta.data(), sizeof(int) * (nchnk + 1), cudaMemcpyHostToDevice, e->st));
   std::vector<int> ctaf(nchnk + 1, 0);
   for (int c = 0; c < nchnk; ++c) {
@@ -997,13 +999,49 @@ int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out) {
   CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
   }
   e->host_mid_done = 0;
-  CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
-  if (s.np > 0) {
-    soa_to_aos_k<<<grid_for(3 * s.np, 256), 256, 0, e->st>>>(s.p2, s.p, 3, s.cap, s.np);
-    CHB_LAUNCH_CHECK();
-    CHB_TRY(mark(e->st, e->s_d2h));
-    CHB_CUDA(cudaMemcpyAsync(momenta, s.p2, D * 3 * s.np, cudaMemcpyDeviceToHost, e->s_d2h));
-    g_d2h_bytes += (long long)(D * 3 * s.np);
+  // gather + push in pieces of whole CTAs (consecutive CTAs own consecutive particles), each piece's momenta
+  // copied out while the next piece is being pushed
+  bool piecewise = false;
+  if (s.np > 0 && s.ncta >= 2 && (c.nm == 1 || c.nm == 2 || c.nm == 3 || c.nm == 4 || c.nm == 5)) {
+    piecewise = true;
+    GridGeom g = geom_ready(e);
+    UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
+    const int nchnk = (int)s.h_ind.size() - 1;
+    auto first_of = [&](int cta) -> i64 {  // first particle of CTA `cta` (== np for cta == ncta)
+      if (cta >= s.ncta) return s.np;
+      int ck = 0;
+      while (ck + 1 < nchnk && cta >= s.h_cta[ck + 1]) ++ck;
+      return (i64)s.h_ind[ck] + (i64)(cta - s.h_cta[ck]) * kDepNPB;
+    };
+    constexpr int NPIECE = 8;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e->profile) { e0 = get_event(e); e1 = get_event(e); cudaEventRecord(e0, e->st); }
+    for (int k = 0; k < NPIECE; ++k) {
+      const int c0 = (int)((i64)s.ncta * k / NPIECE), c1 = (int)((i64)s.ncta * (k + 1) / NPIECE);
+      if (c1 <= c0) continue;
+      SortedSpec spk = sortedspec(e, s);
+      spk.cta_base = c0;
+      spk.ncta = c1 - c0;
+      CHB_TRY(launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt, und, spk));
+      const i64 a = first_of(c0), b = first_of(c1), n = b - a;
+      if (n <= 0) continue;
+      soa_to_aos_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.p2 + 3 * a, s.p + a, 3, s.cap, n);
+      CHB_LAUNCH_CHECK();
+      CHB_TRY(mark(e->st, e->s_d2h));
+      CHB_CUDA(cudaMemcpyAsync(momenta + 3 * a, s.p2 + 3 * a, D * 3 * n, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)(D * 3 * n);
+    }
+    if (e->profile) { cudaEventRecord(e1, e->st); e->pending.push_back({CHB_GATHER_PUSH, {e0, e1}}); }
+  }
+  if (!piecewise) {
+    CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
+    if (s.np > 0) {
+      soa_to_aos_k<<<grid_for(3 * s.np, 256), 256, 0, e->st>>>(s.p2, s.p, 3, s.cap, s.np);
+      CHB_LAUNCH_CHECK();
+      CHB_TRY(mark(e->st, e->s_d2h));
+      CHB_CUDA(cudaMemcpyAsync(momenta, s.p2, D * 3 * s.np, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)(D * 3 * s.np);
+    }
   }
   CHB_CUDA(cudaStreamSynchronize(e->s_h2d));
   CHB_CUDA(cudaStreamSynchronize(e->s_d2h));

@@ -63,6 +63,7 @@ struct SortedSpec {
   const int* cta;   // device prefix of CTA counts per chunk (0:nchnk), cta[c+1]-cta[c] = ceil(n_c / kDepNPB)
   int nchnk, ncta;
   i64 cs, tile_w;   // x cells per chunk and per re-binning tile (0: unknown / never re-binned)
+  int cta_base;     // launch covers CTAs [cta_base, cta_base + ncta) of the table (partial launches)
 };
 int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, const double* mom, const double* w,
                           i64 cap, cd* grid, const GridGeom& g, const ChunkSpec& ch, const SortedSpec& sp);

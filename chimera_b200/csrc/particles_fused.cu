@@ -45,7 +45,16 @@ constexpr int FBX = 40, FBR = 16, FBINS = FBX * FBR;
 constexpr int FPPT = (FNPB + FT - 1) / FT;
 constexpr int FMAXTASK = FNPB / FRUN + (FBINS < FNPB ? FBINS : FNPB);
 constexpr int FITEMS = (FBINS + FT - 1) / FT;
+constexpr int FSTR = FNPB + 1;  // plane stride of the record area: the 6 component threads of a segment write the same
+                                // particle slot of 6 planes at once -> odd stride keeps them in different banks
 constexpr int FNF = 12;  // doubles per particle in the record area (gather: 4|6 + 6 field values; deposit: 7|6 + 5|6)
+
+// a cell's particles are cut into runs of FRUN; a tail of up to FSLACK particles joins the last run instead of
+// becoming a segment of its own (a segment costs 4 x NM node loads / red.global.adds whatever its length)
+constexpr int FSLACK = FRUN / 3;
+__device__ __forceinline__ int f_nseg(int cnt) {
+  return cnt <= 0 ? 0 : 1 + (cnt > FRUN + FSLACK ? (cnt - FSLACK - 1) / FRUN : 0);
+}
 
 struct FShared {
   int anchor[2];
@@ -95,7 +104,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   constexpr int NCJ = ENV ? 1 : 3;  // Q1: the envelope current has l = 3 only
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* rec = reinterpret_cast<double*>(smem_raw);             // [FNF][FNPB], by local particle id
-  int* bins = reinterpret_cast<int*>(rec + FNF * FNPB);          // [FBINS]
+  int* bins = reinterpret_cast<int*>(rec + FNF * FSTR);          // [FBINS]
   int* tasks = bins + FBINS;                                     // [FMAXTASK]  key | start << 11 | n << 22
   unsigned short* skey = reinterpret_cast<unsigned short*>(tasks + FMAXTASK);  // [FNPB]
   unsigned short* order = skey + FNPB;                           // [FNPB]
@@ -127,7 +136,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   }
   __syncthreads();
   const int ix0 = sh.anchor[0], ir0 = sh.anchor[1];
-  double* fbuf = rec + 6 * FNPB;  // [6][FNPB] gathered field, phase (D)-(E)
+  double* fbuf = rec + 6 * FSTR;  // [6][FNPB] gathered field, phase (D)-(E)
 
   // ---- (A) loads, gather records, histogram
   {
@@ -154,15 +163,15 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         key = (unsigned short)(kr * FBX + kx);
         atomicAdd(&bins[key], 1);
         rec[li] = s.sx1;
-        rec[FNPB + li] = s.sr1;
+        rec[FSTR + li] = s.sr1;
         const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // gather phase e^{+i theta}; axis: 0 | 1 (Q4)
-        rec[2 * FNPB + li] = (s.rp > 0.0) ? yp * rinv : (ENV ? 1.0 : 0.0);
-        rec[3 * FNPB + li] = zp * rinv;
+        rec[2 * FSTR + li] = (s.rp > 0.0) ? yp * rinv : (ENV ? 1.0 : 0.0);
+        rec[3 * FSTR + li] = zp * rinv;
         if (ENV) {
           double sn, cs;
           sincos(xp * g.kx0, &sn, &cs);
-          rec[4 * FNPB + li] = cs;
-          rec[5 * FNPB + li] = sn;
+          rec[4 * FSTR + li] = cs;
+          rec[5 * FSTR + li] = sn;
         }
       } else {
         gather_one<ENV>(g, Fld, xp, yp, zp, F);  // drifted out of the window: L2 path
@@ -170,7 +179,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     }
     if (key == 0xFFFFu) {
 #pragma unroll
-      for (int l = 0; l < 6; ++l) fbuf[l * FNPB + li] = F[l];
+      for (int l = 0; l < 6; ++l) fbuf[l * FSTR + li] = F[l];
     }
     skey[li] = key;
   }
@@ -184,7 +193,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     for (int i = 0; i < FITEMS; ++i) {
       const int b = tid * FITEMS + i;
       cnt[i] = (b < FBINS) ? bins[b] : 0;
-      items[i] = cnt[i] | (((cnt[i] + FRUN - 1) / FRUN) << 16);
+      items[i] = cnt[i] | (f_nseg(cnt[i]) << 16);
     }
     cub::BlockScan<int, FT>(sh.scan).ExclusiveSum(items, items, total);
 #pragma unroll
@@ -194,7 +203,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         bins[b] = items[i] & 0xFFFF;
         int start = items[i] & 0xFFFF, t = items[i] >> 16, left = cnt[i];
         while (left > 0) {
-          const int n = left < FRUN ? left : FRUN;
+          const int n = left <= FRUN + FSLACK ? left : FRUN;  // the tail joins the last full run
           tasks[t++] = b | (start << 11) | (n << 22);
           start += n;
           left -= n;
@@ -233,11 +242,11 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
 #pragma unroll 2
     for (int q = 0; q < n; ++q) {
       const int li = order[start + q];
-      const double fx = rec[li], fr = rec[FNPB + li];
-      const cd ph1 = cmake(rec[2 * FNPB + li], rec[3 * FNPB + li]);
+      const double fx = rec[li], fr = rec[FSTR + li];
+      const cd ph1 = cmake(rec[2 * FSTR + li], rec[3 * FSTR + li]);
       const double w00 = (1.0 - fr) * (1.0 - fx), w10 = (1.0 - fr) * fx, w01 = fr * (1.0 - fx), w11 = fr * fx;
       cd car = cmake(1.0, 0.0);
-      if (ENV) car = cmake(rec[4 * FNPB + li], rec[5 * FNPB + li]);  // carrier e^{+i kx0 x}
+      if (ENV) car = cmake(rec[4 * FSTR + li], rec[5 * FSTR + li]);  // carrier e^{+i kx0 x}
       cd ph = cmake(1.0, 0.0);
       double Fv = 0.0;
 #pragma unroll
@@ -252,7 +261,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
           Fv += pm.x * sx - pm.y * sy;
         }
       }
-      fbuf[l * FNPB + li] = Fv;
+      fbuf[l * FSTR + li] = Fv;
     }
   }
   __syncthreads();
@@ -261,7 +270,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   // whole record area, gathered field included: slot li of every plane belongs to the one thread that handles
   // particle li here, and it reads the particle's field values before it writes the particle's records.
   double* recJ = rec;                         // [7 | 6][FNPB]: fx, fr, ph.x, ph.y, amplitude(s)
-  double* recR = rec + (ENV ? 6 : 7) * FNPB;  // [5 | 6][FNPB]
+  double* recR = rec + (ENV ? 6 : 7) * FSTR;  // [5 | 6][FNPB]
   double xs[FPPT], ys[FPPT], zs[FPPT], ws[FPPT], pxs[FPPT], pys[FPPT], pzs[FPPT];
 #pragma unroll
   for (int j = 0; j < FPPT; ++j) {  // x, w were read a moment ago by this CTA: L1/L2 hits
@@ -282,7 +291,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     const i64 ip = cr.first + li;
     double Fp[6];
 #pragma unroll
-    for (int l = 0; l < 6; ++l) Fp[l] = fbuf[l * FNPB + li];
+    for (int l = 0; l < 6; ++l) Fp[l] = fbuf[l * FSTR + li];
     if (und.on) undul_field(und, xs[j], ys[j], Fp);
     double px = pxs[j], py = pys[j], pz = pzs[j];
     boris(px, py, pz, Fp[0], Fp[1], Fp[2], Fp[3], Fp[4], Fp[5], dt_2);
@@ -311,22 +320,22 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
           s.ix >= -1 && s.ix <= g.nxn - 1) {  // dep_curr skips w = 0, r >= rmax and particles at rest (grid_deps.f90:36-42)
         if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
           recJ[li] = s.sx1;
-          recJ[FNPB + li] = s.sr1;
+          recJ[FSTR + li] = s.sr1;
           const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // deposit phase e^{-i theta}; 0 on the axis
-          recJ[2 * FNPB + li] = xc[1] * rinv;
-          recJ[3 * FNPB + li] = -xc[2] * rinv;
+          recJ[2 * FSTR + li] = xc[1] * rinv;
+          recJ[3 * FSTR + li] = -xc[2] * rinv;
           const double ginv = 1.0 / sqrt(1.0 + px * px + py * py + pz * pz);
           if (ENV) {
             double sn, cs;
             sincos(xc[0] * g.kx0, &sn, &cs);
             const cd base = cscale(pz * ginv, cmake(wp * cs, -wp * sn));
-            recJ[4 * FNPB + li] = base.x;
-            recJ[5 * FNPB + li] = base.y;
+            recJ[4 * FSTR + li] = base.x;
+            recJ[5 * FSTR + li] = base.y;
           } else {
             const double wg = wp * ginv;
-            recJ[4 * FNPB + li] = px * wg;
-            recJ[5 * FNPB + li] = py * wg;
-            recJ[6 * FNPB + li] = pz * wg;
+            recJ[4 * FSTR + li] = px * wg;
+            recJ[5 * FSTR + li] = py * wg;
+            recJ[6 * FSTR + li] = pz * wg;
           }
           const i64 kx = s.ix - ix0, kr = s.ir - ir0;
           if (key != 0xFFFF && kx >= 0 && kx < FBX && kr >= 0 && kr < FBR && (int)(kr * FBX + kx) == key) fl |= 1;
@@ -344,19 +353,19 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
       if (wp != 0.0 && make_shape(g, x1[0], x1[1], x1[2], s) && s.ix >= -1 && s.ix <= g.nxn - 1) {
         if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
           recR[li] = s.sx1;
-          recR[FNPB + li] = s.sr1;
+          recR[FSTR + li] = s.sr1;
           const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;
-          recR[2 * FNPB + li] = x1[1] * rinv;
-          recR[3 * FNPB + li] = -x1[2] * rinv;
+          recR[2 * FSTR + li] = x1[1] * rinv;
+          recR[3 * FSTR + li] = -x1[2] * rinv;
           if (ENV) {
             double sn, cs;
             sincos(x1[0] * g.kx0, &sn, &cs);
             const cd wpc = cmake(wp * cs, -wp * sn);
             const cd base = cmul(wpc, wpc);  // Q2: the complex weight enters twice
-            recR[4 * FNPB + li] = base.x;
-            recR[5 * FNPB + li] = base.y;
+            recR[4 * FSTR + li] = base.x;
+            recR[5 * FSTR + li] = base.y;
           } else {
-            recR[4 * FNPB + li] = wp;
+            recR[4 * FSTR + li] = wp;
           }
           const i64 kx = s.ix - ix0, kr = s.ir - ir0;
           if (key != 0xFFFF && kx >= 0 && kx < FBX && kr >= 0 && kr < FBR && (int)(kr * FBX + kx) == key) fl |= 2;
@@ -383,7 +392,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     const int tw = tasks[task];
     const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = tw >> 22;
     const double* rb = isJ ? recJ : recR;
-    const double* ra = rb + (4 + ((!ENV && isJ) ? u : 0)) * FNPB;
+    const double* ra = rb + (4 + ((!ENV && isJ) ? u : 0)) * FSTR;
     const unsigned char bit = isJ ? 1 : 2;
     cd a[2][2][NM];
 #pragma unroll
@@ -398,9 +407,9 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
       const int li = order[start + q];
       if (!(fast[li] & bit)) continue;
       any = true;
-      const double fx = rb[li], fr = rb[FNPB + li];
-      const cd ph1 = cmake(rb[2 * FNPB + li], rb[3 * FNPB + li]);
-      const cd amp = ENV ? cmake(ra[li], ra[FNPB + li]) : cmake(ra[li], 0.0);
+      const double fx = rb[li], fr = rb[FSTR + li];
+      const cd ph1 = cmake(rb[2 * FSTR + li], rb[3 * FSTR + li]);
+      const cd amp = ENV ? cmake(ra[li], ra[FSTR + li]) : cmake(ra[li], 0.0);
       const double w00 = (1.0 - fx) * (1.0 - fr), w01 = (1.0 - fx) * fr, w10 = fx * (1.0 - fr), w11 = fx * fr;
       cd ph = cmake(1.0, 0.0);
 #pragma unroll
@@ -452,10 +461,10 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
       const i64 gx = (i64)(cell & 0xFFFFFu) - 1 + i, gr = (i64)(cell >> 20) + k;
       const bool keep = gx >= 0 && gx <= g.nxn - 1 && (!ch.on || chunk_keep(ch, cr.chunk, gx, g.nxn));
       if (!keep) continue;
-      const double fx = rb[li], fr = rb[FNPB + li];
-      const cd ph1 = cmake(rb[2 * FNPB + li], rb[3 * FNPB + li]);
-      const double* ra = rb + (4 + ((!ENV && isJ) ? u : 0)) * FNPB;
-      const cd amp = ENV ? cmake(ra[li], ra[FNPB + li]) : cmake(ra[li], 0.0);
+      const double fx = rb[li], fr = rb[FSTR + li];
+      const cd ph1 = cmake(rb[2 * FSTR + li], rb[3 * FSTR + li]);
+      const double* ra = rb + (4 + ((!ENV && isJ) ? u : 0)) * FSTR;
+      const cd amp = ENV ? cmake(ra[li], ra[FSTR + li]) : cmake(ra[li], 0.0);
       const double wgt = (i ? fx : 1.0 - fx) * (k ? fr : 1.0 - fr);
       const int l = isJ ? (ENV ? 2 : u) : 0;
       cd* pl = grid + plane * (g.nm * l) + gx + g.nxn * gr;
@@ -475,7 +484,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   }
 }
 
-constexpr size_t F_SMEM = sizeof(double) * FNF * FNPB + sizeof(int) * (FBINS + FMAXTASK) +
+constexpr size_t F_SMEM = sizeof(double) * FNF * FSTR + sizeof(int) * (FBINS + FMAXTASK) +
                           4 * sizeof(unsigned short) * FNPB + 2 * sizeof(unsigned) * FNPB + FNPB;
 
 template <int ENV, int SC>

@@ -392,14 +392,15 @@ struct CtaRange {
 };
 
 __device__ __forceinline__ CtaRange cta_range(const SortedSpec& sp) {
+  const int bid = (int)blockIdx.x + sp.cta_base;
   int lo = 0, hi = sp.nchnk;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if ((int)blockIdx.x >= __ldg(sp.cta + mid)) lo = mid; else hi = mid;
+    if (bid >= __ldg(sp.cta + mid)) lo = mid; else hi = mid;
   }
   CtaRange r;
   r.chunk = lo;
-  r.first = (i64)__ldg(sp.ind + lo) + (i64)((int)blockIdx.x - __ldg(sp.cta + lo)) * kDepNPB;
+  r.first = (i64)__ldg(sp.ind + lo) + (i64)(bid - __ldg(sp.cta + lo)) * kDepNPB;
   const i64 n = (i64)__ldg(sp.ind + lo + 1) - r.first;
   r.count = (int)(n < kDepNPB ? n : kDepNPB);
   return r;

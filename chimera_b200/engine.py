@@ -89,6 +89,9 @@ class Engine:
         self.setup = setup
         a = setup.Args
         feats = a.get("Features", ())
+        if "StaticKick" in feats:
+            raise NotImplementedError("the resident engine has no 'StaticKick' schedule (chimera_main.py:118-125); use the "
+                                      "per-function drop-in chimera_b200.fimera for that stage")
         cfg = EngineConfig()
         cfg.env = int(setup.env)
         cfg.space_charge = int("SpaceCharge" in feats)

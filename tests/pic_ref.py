@@ -32,6 +32,7 @@ class RefRun:
         feats = a.get("Features", ())
         self.env = setup.env
         self.space_charge = "SpaceCharge" in feats
+        self.static_kick = "StaticKick" in feats  # chimera_main.py:106-125, 186: quasi-static field of a beam
         self.chunked = ("Xchunked" in a) if chunked is None else chunked
         self.nchnk, self.guards = (a["Xchunked"] if self.chunked else (1, 0))
         self.sort_every = (self.guards + 1 if self.chunked else 0) if sort_every is None else sort_every
@@ -97,17 +98,18 @@ class RefRun:
             self.reduce(self.Bck)
 
     def project_density(self):
-        if not self.space_charge:
+        if not (self.space_charge or self.static_kick):
             return
         a, f = self.a, self.f
-        self.g_prv[:] = self.g_nxt
+        if not self.static_kick:
+            self.g_prv[:] = self.g_nxt
         self.Rho[:] = 0.0
         if self.rank == 0:  # the (already summed) background enters the all-reduced density once
             self.Rho += self.Bck
         for s in self.sp:
             if s.still or s.coords.shape[1] == 0:
                 continue
-            self.Rho = self._dep("dens", self.Rho, s, s.coords)
+            self.Rho = self._dep("dens", self.Rho, s, s.coords_halfstep if self.static_kick else s.coords)
         if self.reduce:
             self.reduce(self.Rho)
         self.Rho_fb = f.fb_scl_in(self.Rho_fb, self.Rho, a["leftX"], *a["FBCurrIn"])
@@ -119,6 +121,18 @@ class RefRun:
     def update_fields(self):
         a, f = self.a, self.f
         graddiv = f.fb_graddiv_env if self.env else f.fb_graddiv
+        if self.static_kick:  # chimera_main.py:118-125, solvers.py:333-406
+            self.EG_fb[:] = 0.0
+            for s in self.sp:
+                px = (s.momenta[0] * s.weights).sum() / s.weights.sum()
+                beta = px / np.sqrt(1 + px ** 2)
+                if self.npoiss:
+                    self.vec_fb[:] = self.J_fb
+                    self.vec_fb = graddiv(self.vec_fb, *a["FBDiff"])
+                    self.J_fb = f.poiss_corr_stat(self.J_fb, self.vec_fb, self.g_nxt, -1j * beta * a["kx"], a["PoissFact"])
+                self.maxwell_solver_stat(px)
+                self.EG_fb = f.field_drift(self.EG_fb, a["kx"], beta, a["dt"])
+            return
         for _ in range(self.npoiss):
             self.vec_fb[:] = self.J_fb
             self.vec_fb = graddiv(self.vec_fb, *a["FBDiff"])
@@ -133,7 +147,7 @@ class RefRun:
             self.EG_fb = f.maxwell_push_wo_spchrg(self.EG_fb, self.J_fb, self.PE, self.PG)
 
     def maxwell_solver_stat(self, px0):  # solvers.py:333-358
-        if not self.space_charge:
+        if not (self.space_charge or self.static_kick):
             return
         c1, c2 = self.S.static_coeffs(px0)
         self.EG_fb = self.f.maxwell_init_push(self.EG_fb, self.J_fb, self.g_nxt, c1, c2)

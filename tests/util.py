@@ -44,6 +44,9 @@ SETUPS = {
     "env_m1": dict(Grid=(-3.55, 3.55, 35.7, 7.1 / 40, 35.7 / 30), TimeStep=1.0 / 30, MaxAzimuthMode=0,
                    KxShift=2 * (391 / (1 + 1.95 ** 2 / 2) ** 0.5) ** 2, Rcut=25.0, CoPropagative=0.999,
                    Xchunked=(4, 6), Features={"NoPoissonCorrection": True}),
+    # quasi-static field of a relativistic beam (space-charge demo, first stage: 'StaticKick'), chunked
+    "static_m2": dict(Grid=(-3.0, 1.0, 3.0, 0.05, 0.2), TimeStep=0.05, MaxAzimuthMode=1, Xchunked=(4, 3),
+                      Features=("StaticKick",)),
     # envelope solver with +-1 modes
     "env_m3": dict(Grid=(-2.0, 2.0, 6.0, 0.1, 0.3), TimeStep=0.05, MaxAzimuthMode=1, KxShift=30.0, Features=()),
 }

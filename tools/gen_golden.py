@@ -47,6 +47,8 @@ CASES = {
     # step for v << c, x1e-4 for gamma = 391 where dv = dp / gamma^3)
     "env_m1": dict(setup="env_m1", ions=False, und=dict(a0=0.3, lam=1.3, X0=-1.0, Lx=9.0), amp=0.5, boost=391.0),
     "env_m3": dict(setup="env_m3", ions=False, und=None, amp=0.5),      # envelope solver with +-1 modes
+    # space-charge demo stage 1: quasi-static kick of a px = 50 beam (poiss_corr_stat, maxwell_init_push, field_drift)
+    "static_m2": dict(setup="static_m2", ions=False, und=None, amp=0.0, boost=50.0),
 }
 
 TABLES = ("In", "InCurr", "Out", "DpS2S", "DmS2S", "DepFact", "PoissFact", "kx", "kx_env", "Rgrid", "Xgrid", "VGrid")
