@@ -8,13 +8,16 @@
 
 namespace chb {
 
+// Boris rotation (particle_tools.f90:18-56).  t = dt/2 B / gamma and s = 2 t / (1 + t^2) are formed with ONE
+// reciprocal each (the reference divides component by component; gfortran -ffast-math, the reference's own
+// build flag, makes the same transformation): 2 FP64 divisions per particle instead of 6.
 __device__ __forceinline__ void boris(double& px, double& py, double& pz, double ex, double ey, double ez,
                                       double bx, double by, double bz, double dt_2) {
   const double umx = px + dt_2 * ex, umy = py + dt_2 * ey, umz = pz + dt_2 * ez;
-  const double gamma = sqrt(1.0 + (umx * umx + umy * umy + umz * umz));
-  const double tx = dt_2 * bx / gamma, ty = dt_2 * by / gamma, tz = dt_2 * bz / gamma;
-  const double t2 = tx * tx + ty * ty + tz * tz;
-  const double sx = 2 * tx / (1 + t2), sy = 2 * ty / (1 + t2), sz = 2 * tz / (1 + t2);
+  const double ginv = dt_2 / sqrt(1.0 + (umx * umx + umy * umy + umz * umz));
+  const double tx = bx * ginv, ty = by * ginv, tz = bz * ginv;
+  const double sfac = 2.0 / (1.0 + (tx * tx + ty * ty + tz * tz));
+  const double sx = tx * sfac, sy = ty * sfac, sz = tz * sfac;
   const double u0x = umx + umy * tz - umz * ty;
   const double u0y = umy - umx * tz + umz * tx;
   const double u0z = umz + umx * ty - umy * tx;

@@ -164,7 +164,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         atomicAdd(&bins[key], 1);
         rec[li] = s.sx1;
         rec[FSTR + li] = s.sr1;
-        const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // gather phase e^{+i theta}; axis: 0 | 1 (Q4)
+        const double rinv = (s.rp > 0.0) ? rsqrt(s.rp * s.rp) : 0.0;  // gather phase e^{+i theta}; axis: 0 | 1 (Q4)
         rec[2 * FSTR + li] = (s.rp > 0.0) ? yp * rinv : (ENV ? 1.0 : 0.0);
         rec[3 * FSTR + li] = zp * rinv;
         if (ENV) {
@@ -269,6 +269,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   // ---- (E) device field, Boris push, position update, deposit records.  The deposit records reuse the
   // whole record area, gathered field included: slot li of every plane belongs to the one thread that handles
   // particle li here, and it reads the particle's field values before it writes the particle's records.
+  const double dt_inv = 1.0 / dt;
   double* recJ = rec;                         // [7 | 6][FNPB]: fx, fr, ph.x, ph.y, amplitude(s)
   double* recR = rec + (ENV ? 6 : 7) * FSTR;  // [5 | 6][FNPB]
   double xs[FPPT], ys[FPPT], zs[FPPT], ws[FPPT], pxs[FPPT], pys[FPPT], pzs[FPPT];
@@ -321,10 +322,10 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
           recJ[li] = s.sx1;
           recJ[FSTR + li] = s.sr1;
-          const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // deposit phase e^{-i theta}; 0 on the axis
+          const double rinv = (s.rp > 0.0) ? rsqrt(s.rp * s.rp) : 0.0;  // deposit phase e^{-i theta}; 0 on the axis
           recJ[2 * FSTR + li] = xc[1] * rinv;
           recJ[3 * FSTR + li] = -xc[2] * rinv;
-          const double ginv = 1.0 / sqrt(1.0 + px * px + py * py + pz * pz);
+          const double ginv = dt_gp * dt_inv;  // 1 / gamma, from the position update's dt / gamma
           if (ENV) {
             double sn, cs;
             sincos(xc[0] * g.kx0, &sn, &cs);
@@ -354,7 +355,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
           recR[li] = s.sx1;
           recR[FSTR + li] = s.sr1;
-          const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;
+          const double rinv = (s.rp > 0.0) ? rsqrt(s.rp * s.rp) : 0.0;
           recR[2 * FSTR + li] = x1[1] * rinv;
           recR[3 * FSTR + li] = -x1[2] * rinv;
           if (ENV) {
