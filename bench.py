@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-per-call", action="store_true", help="skip the per-function drop-in timing (e2e_per_call)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fused-profile", action="store_true",
+                    help="after the timed run: per-stage clock shares of the fused particle kernel (adds barriers; diagnosis)")
     ap.add_argument("--cpu-nx", type=int, default=256)
     return ap.parse_args()
 
@@ -318,6 +320,21 @@ def run_ours(a):
                                          if k in ("fb_in_J", "fb_in_rho", "poisson", "maxwell", "fields_out", "fields_out_a", "fields_out_b")),
             "fp64_peak_tflops": fp64_peak,
         }
+    if a.fused_profile and rank == 0:
+        lib.chimera_fused_profile(1)
+        eng.profile(True)
+        eng.timings(reset=True)
+        eng.step(3)
+        ph = eng.timings(reset=True)
+        eng.profile(False)
+        cyc = (ctypes.c_ulonglong * 8)()
+        lib.chimera_fused_profile_read(cyc)
+        lib.chimera_fused_profile(0)
+        tot = float(sum(cyc[:6])) or 1.0
+        out["fused_stages"] = {n: cyc[i] / tot for i, n in enumerate(
+            ("A_records_histogram", "BC_scan_sort", "D_gather", "E_push", "F_deposit", "G_cell_changers"))}
+        out["fused_stages"]["cycles_per_cta"] = tot / max(int(cyc[7]), 1)
+        out["fused_stages"]["ms_per_call_with_profile_barriers"] = ph["particles_fused"][0] / ph["particles_fused"][1]
     # ---- end to end through the reference-facing drop-in (host buffers, copies inside the timed region)
     if not a.no_e2e:
         e2e, state = run_e2e(a, torch, S, eng, n_local, world)

@@ -638,6 +638,12 @@ int chimera_undul_analytic(const double* coord, double* Fld, double t, const dou
 }
 
 int chimera_gemm_profile(int on) { gemm_profile_enable(on); return 0; }
+int chimera_fused_profile(int on) { fused_profile_enable(on); return 0; }
+int chimera_fused_profile_read(unsigned long long* cycles8) {
+  CHB_CUDA(cudaDeviceSynchronize());
+  fused_profile_read(cycles8);
+  return 0;
+}
 int chimera_gemm_profile_read(double* ms, double* flops, chb_i64* launches, int reset) {
   gemm_profile_read(ms, flops, launches, reset);
   return 0;

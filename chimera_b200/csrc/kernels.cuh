@@ -75,6 +75,8 @@ constexpr int kFusedNPB = 512;
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
                            const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
                            const ChunkSpec& ch, double push_dt, double dt, const UndulParams& und, const SortedSpec& sp);
+void fused_profile_enable(int on);
+void fused_profile_read(unsigned long long out[8]);
 // field gather from a shared-memory tile of the EB grid + undulator + Boris push
 int launch_gather_push_tiled(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
                              const GridGeom& g, double dt, const UndulParams& und, i64 np);

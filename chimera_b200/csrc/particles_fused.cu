@@ -24,6 +24,7 @@
 //  (G) the queued cell-changers: one thread per (particle, component, mode, node) -> red.global.add.f64.
 // Arithmetic per particle is the same as in the separate kernels (same helpers), so the result differs
 // from them only in the order of the floating-point sums on the grid.
+#include <cstdlib>
 #include <cub/block/block_scan.cuh>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -35,12 +36,19 @@ namespace {
 #define CHB_FT 256
 #endif
 #ifndef CHB_FRUN
-#define CHB_FRUN 24
+#define CHB_FRUN 48
+#endif
+#ifndef CHB_FDSPLIT
+#define CHB_FDSPLIT 2
+#endif
+#ifndef CHB_FSYNC
+#define CHB_FSYNC 0
 #endif
 #ifndef CHB_FMINB
 #define CHB_FMINB 3
 #endif
 constexpr int FNPB = kFusedNPB, FT = CHB_FT, FRUN = CHB_FRUN;
+constexpr int FDSPLIT = CHB_FDSPLIT;
 constexpr int FBX = 40, FBR = 16, FBINS = FBX * FBR;
 constexpr int FPPT = (FNPB + FT - 1) / FT;
 constexpr int FMAXTASK = FNPB / FRUN + (FBINS < FNPB ? FBINS : FNPB);
@@ -56,6 +64,19 @@ __device__ __forceinline__ int f_nseg(int cnt) {
   return cnt <= 0 ? 0 : 1 + (cnt > FRUN + FSLACK ? (cnt - FSLACK - 1) / FRUN : 0);
 }
 
+// per-stage clock profile (chimera_fused_profile): cycles summed over CTAs, read after each barrier by thread 0
+__constant__ int c_fprof_on = 0;
+__device__ unsigned long long g_fprof[8];
+#define FPROF_MARK(slot)                                                   \
+  if (c_fprof_on) {                                                        \
+    __syncthreads();                                                       \
+    if (tid == 0) {                                                        \
+      const long long now = clock64();                                     \
+      atomicAdd(&g_fprof[slot], (unsigned long long)(now - fprof_t));      \
+      fprof_t = now;                                                       \
+    }                                                                      \
+  }
+
 struct FShared {
   int anchor[2];
   int total, ntask;
@@ -69,15 +90,15 @@ struct FRange {
   int count;
 };
 
-__device__ __forceinline__ FRange f_range(const SortedSpec& sp) {
+__device__ __forceinline__ FRange f_range(const SortedSpec& sp, int block) {
   int lo = 0, hi = sp.nchnk;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if ((int)blockIdx.x >= __ldg(sp.cta + mid)) lo = mid; else hi = mid;
+    if (block >= __ldg(sp.cta + mid)) lo = mid; else hi = mid;
   }
   FRange r;
   r.chunk = lo;
-  r.first = (i64)__ldg(sp.ind + lo) + (i64)((int)blockIdx.x - __ldg(sp.cta + lo)) * FNPB;
+  r.first = (i64)__ldg(sp.ind + lo) + (i64)(block - __ldg(sp.cta + lo)) * FNPB;
   const i64 n = (i64)__ldg(sp.ind + lo + 1) - r.first;
   r.count = (int)(n < FNPB ? n : FNPB);
   return r;
@@ -115,12 +136,23 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   unsigned char* fast = reinterpret_cast<unsigned char*>(cellR + FNPB);        // [FNPB] bit0: J, bit1: rho
   __shared__ FShared sh;
   const int tid = threadIdx.x;
+  long long fprof_t = c_fprof_on ? clock64() : 0;
 
-  const FRange cr = f_range(sp);
+  const FRange cr = f_range(sp, (int)blockIdx.x);
   if (cr.count <= 0) return;
+  // ---- (A) loads (issued before the anchor barrier so that their latency overlaps it), gather records, histogram
+  double xa[FPPT], ya[FPPT], za[FPPT], wa[FPPT];  // dead after stage (A)
+#pragma unroll
+  for (int j = 0; j < FPPT; ++j) {
+    const int li = tid + j * FT;
+    const bool in = li < cr.count;
+    const i64 ip = cr.first + (in ? li : 0);
+    xa[j] = __ldg(x + ip); ya[j] = __ldg(x + cap + ip); za[j] = __ldg(x + 2 * cap + ip);
+    wa[j] = in ? __ldg(w + ip) : 0.0;
+  }
   for (int i = tid; i < FBINS; i += FT) bins[i] = 0;
   if (tid == 0) {
-    const double xp = __ldg(x + cr.first), yp = __ldg(x + cap + cr.first), zp = __ldg(x + 2 * cap + cr.first);
+    const double xp = xa[0], yp = ya[0], zp = za[0];  // li = 0: the first particle of the block
     const i64 ix = (i64)floor((xp - g.leftX) * g.dx_inv);
     const i64 ir = (i64)floor((sqrt(yp * yp + zp * zp) - g.r0) * g.dr_inv);
     i64 ax = ix - FBX / 2;
@@ -138,26 +170,16 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   const int ix0 = sh.anchor[0], ir0 = sh.anchor[1];
   double* fbuf = rec + 6 * FSTR;  // [6][FNPB] gathered field, phase (D)-(E)
 
-  // ---- (A) loads, gather records, histogram
   {
-  double xs[FPPT], ys[FPPT], zs[FPPT], ws[FPPT];
-#pragma unroll
-  for (int j = 0; j < FPPT; ++j) {
-    const int li = tid + j * FT;
-    const bool in = li < cr.count;
-    const i64 ip = cr.first + (in ? li : 0);
-    xs[j] = __ldg(x + ip); ys[j] = __ldg(x + cap + ip); zs[j] = __ldg(x + 2 * cap + ip);
-    ws[j] = in ? __ldg(w + ip) : 0.0;
-  }
 #pragma unroll
   for (int j = 0; j < FPPT; ++j) {
     const int li = tid + j * FT;
     if (li >= FNPB) continue;
     unsigned short key = 0xFFFFu;
-    const double xp = xs[j], yp = ys[j], zp = zs[j];
+    const double xp = xa[j], yp = ya[j], zp = za[j];
     double F[6] = {0, 0, 0, 0, 0, 0};
     Shape s;
-    if (ws[j] != 0.0 && make_shape(g, xp, yp, zp, s) && s.ix >= 0 && s.ix <= g.nxn - 2) {
+    if (wa[j] != 0.0 && make_shape(g, xp, yp, zp, s) && s.ix >= 0 && s.ix <= g.nxn - 2) {
       const i64 kx = s.ix - ix0, kr = s.ir - ir0;
       if (kx >= 0 && kx < FBX && kr >= 0 && kr < FBR) {
         key = (unsigned short)(kr * FBX + kx);
@@ -185,6 +207,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   }
   }
   __syncthreads();
+  FPROF_MARK(0)
   // ---- (B) packed scan (low 16 bits: particles, high 16: segments) and the segment table
   {
     int items[FITEMS], cnt[FITEMS];
@@ -223,28 +246,35 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     }
   }
   __syncthreads();
+  FPROF_MARK(1)
   const i64 plane = g.nxn * g.nrn;
   const int ntask = sh.ntask;
   // ---- (D) gather: one thread per (segment, field component)
 #pragma unroll 1
-  for (int t = tid; t < ntask * 6; t += FT) {
-    const int task = t / 6, l = t - task * 6;
+  for (int t = tid; t < ntask * 6 * FDSPLIT; t += FT) {
+    const int hd = t % FDSPLIT, td = t / FDSPLIT;  // FDSPLIT lanes share a (segment, component): particle q = hd, hd + FDSPLIT, ..
+    const int task = td / 6, l = td - task * 6;
     const int tw = tasks[task];
     const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = tw >> 22;
     const int kr = key / FBX, kx = key - kr * FBX;
     const cd* pl = Fld + plane * g.nm * l + ((i64)ix0 + kx) + g.nxn * ((i64)ir0 + kr);
+    // node values in difference form: value(fx, fr) = N0 + fx Nx + fr Nr + fx fr Nxr  (3 FMAs per interpolation)
     cd N[NM][4];
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-      N[m][0] = __ldg(pl + plane * m); N[m][1] = __ldg(pl + plane * m + 1);
-      N[m][2] = __ldg(pl + plane * m + g.nxn); N[m][3] = __ldg(pl + plane * m + g.nxn + 1);
+      const cd n00 = __ldg(pl + plane * m), n10 = __ldg(pl + plane * m + 1);
+      const cd n01 = __ldg(pl + plane * m + g.nxn), n11 = __ldg(pl + plane * m + g.nxn + 1);
+      N[m][0] = n00;
+      N[m][1] = csub(n10, n00);
+      N[m][2] = csub(n01, n00);
+      N[m][3] = csub(csub(n11, n01), N[m][1]);
     }
 #pragma unroll 2
-    for (int q = 0; q < n; ++q) {
+    for (int q = hd; q < n; q += FDSPLIT) {
       const int li = order[start + q];
       const double fx = rec[li], fr = rec[FSTR + li];
       const cd ph1 = cmake(rec[2 * FSTR + li], rec[3 * FSTR + li]);
-      const double w00 = (1.0 - fr) * (1.0 - fx), w10 = (1.0 - fr) * fx, w01 = fr * (1.0 - fx), w11 = fr * fx;
+      const double fxr = fx * fr;
       cd car = cmake(1.0, 0.0);
       if (ENV) car = cmake(rec[4 * FSTR + li], rec[5 * FSTR + li]);  // carrier e^{+i kx0 x}
       cd ph = cmake(1.0, 0.0);
@@ -255,16 +285,21 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
 #pragma unroll
         for (int sgn = 0; sgn < ((ENV && iO > 0) ? 2 : 1); ++sgn) {
           const int slot = ENV ? (NKO + (sgn ? -iO : iO)) : iO;
-          const cd pm = ENV ? cmul(car, sgn ? cconj(ph) : ph) : ph;
-          const double sx = w00 * N[slot][0].x + w10 * N[slot][1].x + w01 * N[slot][2].x + w11 * N[slot][3].x;
-          const double sy = w00 * N[slot][0].y + w10 * N[slot][1].y + w01 * N[slot][2].y + w11 * N[slot][3].y;
-          Fv += pm.x * sx - pm.y * sy;
+          const double sx = fma(fxr, N[slot][3].x, fma(fr, N[slot][2].x, fma(fx, N[slot][1].x, N[slot][0].x)));
+          if (!ENV && iO == 0) {  // mode 0 of the real solver: phase 1, only the real part enters
+            Fv += sx;
+          } else {
+            const cd pm = ENV ? cmul(car, sgn ? cconj(ph) : ph) : ph;
+            const double sy = fma(fxr, N[slot][3].y, fma(fr, N[slot][2].y, fma(fx, N[slot][1].y, N[slot][0].y)));
+            Fv += pm.x * sx - pm.y * sy;
+          }
         }
       }
       fbuf[l * FSTR + li] = Fv;
     }
   }
   __syncthreads();
+  FPROF_MARK(2)
 
   // ---- (E) device field, Boris push, position update, deposit records.  The deposit records reuse the
   // whole record area, gathered field included: slot li of every plane belongs to the one thread that handles
@@ -274,8 +309,8 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   double* recR = rec + (ENV ? 6 : 7) * FSTR;  // [5 | 6][FNPB]
   double xs[FPPT], ys[FPPT], zs[FPPT], ws[FPPT], pxs[FPPT], pys[FPPT], pzs[FPPT];
 #pragma unroll
-  for (int j = 0; j < FPPT; ++j) {  // x, w were read a moment ago by this CTA: L1/L2 hits
-    const int li = tid + j * FT;
+  for (int j = 0; j < FPPT; ++j) {  // x, w were read a moment ago by this CTA (L1/L2 hits); holding them in registers
+    const int li = tid + j * FT;    // since stage (A) costs more in spills than the reload
     const bool in = li < cr.count;
     const i64 ip = cr.first + (in ? li : 0);
     xs[j] = __ldg(x + ip); ys[j] = __ldg(x + cap + ip); zs[j] = __ldg(x + 2 * cap + ip);
@@ -381,17 +416,24 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     fast[li] = fl;
   }
   __syncthreads();
+  FPROF_MARK(3)
 
   // ---- (F) deposit: one thread per (segment, unit), unit = J component(s) then rho
   constexpr int NU = NCJ + (SC ? 1 : 0);
   i64 klo, khi;
   f_keep_range(ch, cr.chunk, g.nxn, klo, khi);
+  // Each (segment, unit) is shared by a lane pair: lane h takes the particles q = h, h + 2, ... of the run; the
+  // halves are exchanged with one shuffle per accumulator (lane 0 ends up with the sums of the left x node pair,
+  // lane 1 with the right pair) and each lane issues its half of the red.global.adds.
+  const int nwork = ntask * NU * 2;
 #pragma unroll 1
-  for (int t = tid; t < ntask * NU; t += FT) {
-    const int task = t / NU, u = t - task * NU;
+  for (int t = tid; t < ((nwork + 31) & ~31); t += FT) {
+    const bool valid = t < nwork;
+    const int h = t & 1, tu = valid ? (t >> 1) : 0;
+    const int task = tu / NU, u = tu - task * NU;
     const bool isJ = u < NCJ;
     const int tw = tasks[task];
-    const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = tw >> 22;
+    const int key = tw & 0x7FF, start = (tw >> 11) & 0x7FF, n = valid ? (tw >> 22) : 0;
     const double* rb = isJ ? recJ : recR;
     const double* ra = rb + (4 + ((!ENV && isJ) ? u : 0)) * FSTR;
     const unsigned char bit = isJ ? 1 : 2;
@@ -402,12 +444,12 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
       for (int k = 0; k < 2; ++k)
 #pragma unroll
         for (int m = 0; m < NM; ++m) a[i][k][m] = cmake(0.0, 0.0);
-    bool any = false;
+    int any = 0;
 #pragma unroll 2
-    for (int q = 0; q < n; ++q) {
+    for (int q = h; q < n; q += 2) {
       const int li = order[start + q];
       if (!(fast[li] & bit)) continue;
-      any = true;
+      any = 1;
       const double fx = rb[li], fr = rb[FSTR + li];
       const cd ph1 = cmake(rb[2 * FSTR + li], rb[3 * FSTR + li]);
       const cd amp = ENV ? cmake(ra[li], ra[FSTR + li]) : cmake(ra[li], 0.0);
@@ -420,6 +462,11 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         for (int sgn = 0; sgn < ((ENV && iO > 0) ? 2 : 1); ++sgn) {
           const int m = ENV ? (NKO + (sgn ? -iO : iO)) : iO;
           const cd pm = sgn ? cconj(ph) : ph;
+          if (!ENV && iO == 0) {  // e^{-i 0 theta} = 1: real amplitude, the imaginary parts stay 0
+            a[0][0][m].x += w00 * amp.x; a[0][1][m].x += w01 * amp.x;
+            a[1][0][m].x += w10 * amp.x; a[1][1][m].x += w11 * amp.x;
+            continue;
+          }
           const cd f = ENV ? cmul(amp, pm) : cscale(amp.x, pm);
           a[0][0][m].x += w00 * f.x; a[0][0][m].y += w00 * f.y;
           a[0][1][m].x += w01 * f.x; a[0][1][m].y += w01 * f.y;
@@ -428,19 +475,39 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         }
       }
     }
-    if (!any) continue;
+    // lane h keeps x node h: send the other node's partial sums to the partner, add what it sends
+    cd mine[2][NM];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        const cd keep = h ? a[1][k][m] : a[0][k][m], give = h ? a[0][k][m] : a[1][k][m];
+        mine[k][m].x = keep.x + __shfl_xor_sync(0xffffffffu, give.x, 1);
+        mine[k][m].y = (!ENV && m == 0) ? 0.0 : keep.y + __shfl_xor_sync(0xffffffffu, give.y, 1);
+      }
+    any |= __shfl_xor_sync(0xffffffffu, any, 1);
+    if (!valid || !any) continue;
     const int kr = key / FBX, kx = key - kr * FBX;
-    const i64 gx = (i64)ix0 + kx, gr = (i64)ir0 + kr;
+    const i64 gx = (i64)ix0 + kx + h, gr = (i64)ir0 + kr;
+    if (gx < klo || gx > khi) continue;
     const int l = isJ ? (ENV ? 2 : u) : 0;
     cd* pl = (isJ ? J : Rho) + plane * (g.nm * l) + gx + g.nxn * gr;
-    const bool k0 = gx >= klo && gx <= khi, k1 = gx + 1 >= klo && gx + 1 <= khi;
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-      if (k0) { red_add(pl + plane * m, a[0][0][m]); red_add(pl + plane * m + g.nxn, a[0][1][m]); }
-      if (k1) { red_add(pl + plane * m + 1, a[1][0][m]); red_add(pl + plane * m + 1 + g.nxn, a[1][1][m]); }
+      if (!ENV && m == 0) {  // imaginary sums are exactly 0
+        atomicAdd(&pl[0].x, mine[0][0].x);
+        atomicAdd(&pl[g.nxn].x, mine[1][0].x);
+        continue;
+      }
+      red_add(pl + plane * m, mine[0][m]);
+      red_add(pl + plane * m + g.nxn, mine[1][m]);
     }
   }
 
+#if CHB_FSYNC & 1
+  __syncthreads();
+#endif
+  FPROF_MARK(4)
   // ---- (G) particles that changed cell: one thread per (particle, component, node), so that the few of
   // them cost a few warp-wide red.global.add instead of serialising inside divergent warps
 #pragma unroll 1
@@ -483,6 +550,11 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
       }
     }
   }
+#if CHB_FSYNC & 2
+  __syncthreads();
+#endif
+  FPROF_MARK(5)
+  if (c_fprof_on && tid == 0) atomicAdd(&g_fprof[7], 1ull);
 }
 
 constexpr size_t F_SMEM = sizeof(double) * FNF * FSTR + sizeof(int) * (FBINS + FMAXTASK) +
@@ -498,6 +570,11 @@ int launch_fused_nm(cudaStream_t st, double* x, double* xh, double* mom, const d
     if (!attr) {                                                                                                       \
       CHB_CUDA(cudaFuncSetAttribute(fused_particles_k<ENV, NMV, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                     (int)F_SMEM));                                                                     \
+      if (getenv("CHB_DEBUG")) {                                                                                       \
+        int nb = 0;                                                                                                    \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_particles_k<ENV, NMV, SC>, FT, F_SMEM);               \
+        fprintf(stderr, "fused_particles_k<%d,%d,%d>: %d CTAs/SM, dyn smem %zu\n", ENV, NMV, SC, nb, (size_t)F_SMEM);   \
+      }                                                                                                                \
       attr = true;                                                                                                     \
     }                                                                                                                  \
     fused_particles_k<ENV, NMV, SC><<<sp.ncta, FT, F_SMEM, st>>>(x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp); \
@@ -514,6 +591,13 @@ int launch_fused_nm(cudaStream_t st, double* x, double* xh, double* mom, const d
   return 0;
 }
 }  // namespace
+
+void fused_profile_enable(int on) {
+  cudaMemcpyToSymbol(c_fprof_on, &on, sizeof(int));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_fprof, z, sizeof(z));
+}
+void fused_profile_read(unsigned long long out[8]) { cudaMemcpyFromSymbol(out, g_fprof, 8 * sizeof(unsigned long long)); }
 
 // returns -1 when the mode count has no instantiation (the caller falls back to the separate kernels)
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,

@@ -156,6 +156,11 @@ int chimera_bench_gemm(chb_i64 nkx, chb_i64 K, chb_i64 N, int batch, int iters, 
  * accumulated milliseconds, flop (2*M*N*K per problem) and launches since the last reset */
 int chimera_gemm_profile(int on);
 int chimera_gemm_profile_read(double* ms, double* flops, chb_i64* launches, int reset);
+/* per-stage clock profile of the fused particle kernel (particles_fused.cu): SM cycles summed over CTAs for
+ * stages A (records + histogram), B+C (scan, counting sort), D (gather), E (push), F (deposit), G (cell
+ * changers) in cycles8[0..5], CTA count in cycles8[7].  Enabling adds a barrier per stage: diagnosis only. */
+int chimera_fused_profile(int on);
+int chimera_fused_profile_read(unsigned long long* cycles8);
 
 /* ---- device-resident PIC engine ------------------------------------------------------------ */
 /* The per-function entry points above take HOST buffers and copy per call (the f2py drop-in).
