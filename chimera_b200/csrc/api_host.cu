@@ -626,15 +626,40 @@ int chimera_omp_add_vec(double* v, const double* A, chb_i64 nkx, chb_i64 nkr, ch
 int chimera_omp_add_scl(double* v, const double* A, chb_i64 nkx, chb_i64 nkr, chb_i64 nm) { return add_host(v, A, nkx * nkr * nm); }
 
 // ------------------------------------------------------------------ devices.f90
-int chimera_undul_analytic(const double* coord, double* Fld, double t, const double* params, chb_i64 np) {
-  (void)t;
+// one device over host arrays: coord (3,np), Fld (6,np) in-out, optional map a0(2,nx)
+static int device_host(int kind, const double* coord, double* Fld, double t, double a0, const double* params, int nparams,
+                       const double* map, chb_i64 nx, chb_i64 np) {
   CALL_BEGIN();
   double* d_x = call.up(coord, 3 * np); NEED(d_x);
   double* d_f = call.up(Fld, 6 * np); NEED(d_f);
-  UndulParams u{1, params[0], params[1], params[2], params[3]};
-  CHB_TRY(launch_undul(call.c.st, aos((const double*)d_x, 3), aos(d_f, 6), u, np));
+  double* d_m = nullptr;
+  if (map) { d_m = call.up(map, 2 * nx); NEED(d_m); }
+  const DeviceSet u = one_device(kind, a0, params, nparams, d_m, (int)nx, t);
+  CHB_TRY(launch_devices(call.c.st, aos((const double*)d_x, 3), aos(d_f, 6), u, np));
   CHB_TRY(call.down(Fld, d_f, 6 * np));
   return call.sync();
+}
+int chimera_undul_analytic(const double* coord, double* Fld, double t, const double* params, chb_i64 np) {
+  return device_host(DEV_UNDUL_ANALYTIC, coord, Fld, t, 0.0, params, 4, nullptr, 0, np);
+}
+int chimera_undul_analytic_taper(const double* coord, double* Fld, double t, const double* params, chb_i64 np) {
+  return device_host(DEV_UNDUL_ANALYTIC_TAPER, coord, Fld, t, 0.0, params, 5, nullptr, 0, np);
+}
+int chimera_undul_mapped(const double* coord, double* Fld, double t, const double* a0, const double* params, chb_i64 np,
+                         chb_i64 nx) {
+  if (nx < 3) { set_error("undul_mapped: nx >= 3 expected"); return 2; }
+  return device_host(DEV_UNDUL_MAPPED, coord, Fld, t, 0.0, params, 3, a0, nx, np);
+}
+int chimera_undul_mapped_tap(const double* coord, double* Fld, double t, const double* a0, const double* params,
+                             chb_i64 np, chb_i64 nx) {
+  if (nx < 3) { set_error("undul_mapped_tap: nx >= 3 expected"); return 2; }
+  return device_host(DEV_UNDUL_MAPPED_TAP, coord, Fld, t, 0.0, params, 5, a0, nx, np);
+}
+int chimera_planewave(const double* coord, double* Fld, double t, const double* params, chb_i64 np) {
+  return device_host(DEV_PLANEWAVE, coord, Fld, t, 0.0, params, 7, nullptr, 0, np);
+}
+int chimera_gaussbeam(const double* coord, double* Fld, double time, double a0, const double* params, chb_i64 np) {
+  return device_host(DEV_GAUSSBEAM, coord, Fld, time, a0, params, 8, nullptr, 0, np);
 }
 
 int chimera_gemm_profile(int on) { gemm_profile_enable(on); return 0; }

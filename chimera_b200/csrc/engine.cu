@@ -38,6 +38,8 @@ struct Species {
   int* d_cta_f = nullptr;        // the same for the fused kernel (kFusedNPB particles per CTA)
   int ncta_f = 0;
   i64 tile_w = 0;                // x cells per re-binning tile of the current particle order (0: unsorted)
+  std::vector<DeviceSpec> devs;  // external-field devices of this species (species.py:55 Args['Devices'])
+  std::vector<double*> dev_maps; // device copies of their maps (owned)
 };
 
 }  // namespace chb
@@ -53,6 +55,7 @@ struct chimera_engine {
   int host_id = -1;
   int host_mid_done = 0;
   int fuse = 1;  // use the fused particle kernel inside multi-step calls (chimera_engine_set_fuse)
+  double dev_time = 0.0;  // i_step * TimeStep seen by time-dependent devices in the next gather + push
   double host_rho_from_bg = 1.0;  // 0 on the ranks that must not add BckGrndRho before an all-reduce
   bool own_stream = false;
   Scratch scr;
@@ -478,12 +481,22 @@ int ph_fields_out_b(chimera_engine* e) {
   return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
 }
 
+// the device list of a species at the engine's current device time (species.py:274-277)
+static DeviceSet devset(const chimera_engine* e, const Species& s) {
+  DeviceSet d;
+  memset(&d, 0, sizeof(d));
+  d.t = e->dev_time;
+  d.n = (int)s.devs.size();
+  for (int i = 0; i < d.n; ++i) d.d[i] = s.devs[i];
+  return d;
+}
+
 int ph_gather_push(chimera_engine* e, double dt_frac) {
   const auto& c = e->cfg;
   GridGeom g = geom_ready(e);
-  UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
   for (auto& s : e->sp) {
     if (s.still || s.np == 0) continue;
+    const DeviceSet und = devset(e, s);
     int rc = launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt * dt_frac, und,
                                        sortedspec(e, s));
     if (rc == -1)
@@ -499,7 +512,6 @@ int ph_gather_push(chimera_engine* e, double dt_frac) {
 int ph_particles_fused(chimera_engine* e, int rho_from_bg) {
   const auto& c = e->cfg;
   GridGeom g = geom_ready(e);
-  UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
   const i64 n = c.nx * c.nrn * c.nm;
   CHB_CUDA(cudaMemsetAsync(e->A("J"), 0, sizeof(cd) * n * 3, e->st));
   if (c.space_charge) {
@@ -508,6 +520,7 @@ int ph_particles_fused(chimera_engine* e, int rho_from_bg) {
   }
   for (auto& s : e->sp) {
     if (s.still || s.np == 0) continue;
+    const DeviceSet und = devset(e, s);
     SortedSpec spf = sortedspec(e, s);
     spf.cta = s.d_cta_f;
     spf.ncta = s.ncta_f;
@@ -660,6 +673,7 @@ int chimera_engine_destroy(chimera_engine* e) {
   for (auto& s : e->sp) {
     cudaFree(s.x); cudaFree(s.xh); cudaFree(s.p); cudaFree(s.w);
     cudaFree(s.x2); cudaFree(s.xh2); cudaFree(s.p2); cudaFree(s.w2); cudaFree(s.d_ind); cudaFree(s.d_cta); cudaFree(s.d_cta_f);
+    for (double* m : s.dev_maps) cudaFree(m);
   }
   cudaFree(e->packed);
   cudaFree(e->key_a); cudaFree(e->key_b); cudaFree(e->idx_a); cudaFree(e->idx_b); cudaFree(e->cub_tmp);
@@ -752,8 +766,44 @@ int chimera_engine_add_species(chimera_engine* e, const double* coords, const do
   }
   CHB_CUDA(cudaStreamSynchronize(e->st));
   CHB_TRY(update_cta_table(e, s));
+  if (e->cfg.undulator && !still) {  // configuration shortcut for the FEL setups: one analytic undulator on every beam
+    const double prm[4] = {e->cfg.und_a0, e->cfg.und_lambda, e->cfg.und_X0, e->cfg.und_Lx};
+    s.devs.push_back(one_device(DEV_UNDUL_ANALYTIC, 0.0, prm, 4, nullptr, 0, 0.0).d[0]);
+  }
   e->sp.push_back(s);
   if (id) *id = (int)e->sp.size() - 1;
+  return 0;
+}
+
+int chimera_engine_add_device(chimera_engine* e, int id, int kind, double a0, const double* params, int nparams,
+                              const double* map, chb_i64 nx) {
+  ENG_CHECK(e);
+  if (id < -1 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  static const int need[7] = {0, 4, 5, 3, 5, 7, 8};
+  if (kind < DEV_UNDUL_ANALYTIC || kind > DEV_GAUSSBEAM) { set_error("add_device: unknown device kind %d", kind); return 2; }
+  if (!params || nparams != need[kind]) { set_error("add_device: kind %d takes %d parameters, got %d", kind, need[kind], nparams); return 2; }
+  const bool mapped = kind == DEV_UNDUL_MAPPED || kind == DEV_UNDUL_MAPPED_TAP;
+  if (mapped && (!map || nx < 3)) { set_error("add_device: mapped undulator needs a0(2,nx), nx >= 3"); return 2; }
+  for (int k = 0; k < (int)e->sp.size(); ++k) {
+    if (id >= 0 && k != id) continue;
+    Species& s = e->sp[k];
+    if (s.still) continue;  // species.py:272
+    if ((int)s.devs.size() >= kMaxDevices) { set_error("add_device: at most %d devices per species", kMaxDevices); return 2; }
+    double* dmap = nullptr;
+    if (mapped) {
+      CHB_CUDA(cudaMalloc(&dmap, sizeof(double) * 2 * nx));
+      CHB_CUDA(cudaMemcpyAsync(dmap, map, sizeof(double) * 2 * nx, cudaMemcpyDefault, e->st));
+      CHB_CUDA(cudaStreamSynchronize(e->st));
+      s.dev_maps.push_back(dmap);
+    }
+    s.devs.push_back(one_device(kind, a0, params, nparams, dmap, (int)nx, 0.0).d[0]);
+  }
+  return 0;
+}
+
+int chimera_engine_set_time(chimera_engine* e, double t) {
+  ENG_CHECK(e);
+  e->dev_time = t;
   return 0;
 }
 
@@ -809,6 +859,7 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
   for (i64 k = 0; k < nsteps; ++k) {
     const i64 istep = istep0 + k;
     const bool sort_now = c.sort_every > 0 && istep % c.sort_every == 0;
+    e->dev_time = (double)(istep - 1) * c.dt;  // the pending gather + push closes step istep - 1 (make_device(istep - 1))
     if (gather_pending && !sort_now && e->fuse) {
       CHB_TRY(run_phase(e, CHB_PARTICLES_FUSED, 1));
     } else {
@@ -825,6 +876,7 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
     CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
     gather_pending = true;
   }
+  e->dev_time = (double)(istep0 + nsteps - 1) * c.dt;
   if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
   return 0;
 }
@@ -864,6 +916,7 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
   }
   auto mark = [&](cudaStream_t on, cudaStream_t waiter) -> int { return host_mark(e, on, waiter); };
   const bool sort_now = rebin || (c.sort_every > 0 && istep % c.sort_every == 0);
+  e->dev_time = (double)istep * c.dt;
   if (np != s.np && !sort_now) { set_error("step_host: particle count changed (%lld -> %lld) without rebin", s.np, np); return 2; }
   s.np = np;
   const size_t D = sizeof(double);
@@ -1005,7 +1058,7 @@ int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out) {
   if (s.np > 0 && s.ncta >= 2 && (c.nm == 1 || c.nm == 2 || c.nm == 3 || c.nm == 4 || c.nm == 5)) {
     piecewise = true;
     GridGeom g = geom_ready(e);
-    UndulParams und{c.undulator, c.und_a0, c.und_lambda, c.und_X0, c.und_Lx};
+    const DeviceSet und = devset(e, s);
     const int nchnk = (int)s.h_ind.size() - 1;
     auto first_of = [&](int cta) -> i64 {  // first particle of CTA `cta` (== np for cta == ncta)
       if (cta >= s.ncta) return s.np;

@@ -1,6 +1,7 @@
 // kernels.cuh -- internal (device-pointer) launch API shared by the C-ABI host layer and the
 // resident engine.  Everything here takes a stream and device pointers; no allocation.
 #pragma once
+#include <cmath>
 #include "common.cuh"
 
 namespace chb {
@@ -21,22 +22,111 @@ struct ChunkSpec {
   i64 cs;          // chunk size in nodes = nxn / nchnk
 };
 
-// analytic planar undulator (devices.f90:162-203)
-struct UndulParams {
-  int on;
-  double a0, lambda, X0, Lx;
+// external-field devices (devices.f90:18-297), evaluated per particle between the field gather and the
+// momentum push (species.py:258-277 make_device).  Up to kMaxDevices per launch; `t` = i_step * TimeStep.
+enum DeviceKind {
+  DEV_UNDUL_ANALYTIC = 1,        // devices.f90:162  p = a0, lambda, X0, Lx
+  DEV_UNDUL_ANALYTIC_TAPER = 2,  // devices.f90:117  p = a0, lambda, X0, Lx, taper
+  DEV_UNDUL_MAPPED = 3,          // devices.f90:18   p = lambda, Xleft, dx ; map a0(2, nx)
+  DEV_UNDUL_MAPPED_TAP = 4,      // devices.f90:64   p = lambda, Xleft, dx, Lx, taper ; map a0(2, nx)
+  DEV_PLANEWAVE = 5,             // devices.f90:205  p = a0, lambda, X0, Lx, ramp, theta, phi0
+  DEV_GAUSSBEAM = 6              // devices.f90:254  a0 ; p = lambda, axis, x0, y0, z0, Lx, Ly, Lz
 };
+constexpr int kMaxDevices = 4;
+struct DeviceSpec {
+  int kind, nx;
+  const double* map;  // device pointer, (2, nx) Fortran order (mapped undulators)
+  double a0;
+  double p[8];
+  double c[3];        // host-side derived constants: wave number; sin, cos of the plane-wave angle
+};
+struct DeviceSet {
+  int n;
+  double t;
+  DeviceSpec d[kMaxDevices];
+};
+// fills the derived constants of a spec from its parameters
+static inline void device_finish(DeviceSpec& d) {
+  const double pi = 4.0 * atan(1.0);
+  const double lambda = (d.kind == DEV_UNDUL_MAPPED || d.kind == DEV_UNDUL_MAPPED_TAP || d.kind == DEV_GAUSSBEAM) ? d.p[0] : d.p[1];
+  d.c[0] = 2.0 * pi / lambda;
+  d.c[1] = d.kind == DEV_PLANEWAVE ? sin(d.p[5]) : 0.0;
+  d.c[2] = d.kind == DEV_PLANEWAVE ? cos(d.p[5]) : 1.0;
+}
+static inline DeviceSet one_device(int kind, double a0, const double* params, int nparams, const double* map, int nx,
+                                   double t) {
+  DeviceSet s;
+  memset(&s, 0, sizeof(s));
+  s.n = 1;
+  s.t = t;
+  s.d[0].kind = kind; s.d[0].nx = nx; s.d[0].map = map; s.d[0].a0 = a0;
+  for (int i = 0; i < nparams && i < 8; ++i) s.d[0].p[i] = params[i];
+  device_finish(s.d[0]);
+  return s;
+}
 
-__device__ __forceinline__ void undul_field(const UndulParams& u, double x, double y, double F[6]) {
-  const double ku = 2.0 * 3.14159265358979323846 / u.lambda;
-  double ampl;
-  if (x <= u.X0 || x >= u.X0 + u.Lx) ampl = 0.0;
-  else if (x > u.X0 && x < u.X0 + u.lambda) ampl = (x - u.X0) / u.lambda;
-  else if (x > u.X0 + u.Lx - u.lambda && x < u.X0 + u.Lx) ampl = (u.X0 + u.Lx - x) / u.lambda;
-  else ampl = 1.0;
-  ampl *= u.a0;
-  F[4] += ampl * sin(ku * (x - u.X0)) * cosh(ku * y);
-  F[3] += ampl * cos(ku * (x - u.X0)) * sinh(ku * y);
+__device__ __forceinline__ double ramp_ampl(double x, double X0, double Lx, double ramp) {
+  if (x <= X0 || x >= X0 + Lx) return 0.0;
+  if (x > X0 && x < X0 + ramp) return (x - X0) / ramp;
+  if (x > X0 + Lx - ramp && x < X0 + Lx) return (X0 + Lx - x) / ramp;
+  return 1.0;
+}
+
+__device__ __forceinline__ void apply_devices(const DeviceSet& ds, double x, double y, double z, double F[6]) {
+  for (int i = 0; i < ds.n; ++i) {
+    const DeviceSpec& d = ds.d[i];
+    const double k = d.c[0];
+    switch (d.kind) {
+      case DEV_UNDUL_ANALYTIC:
+      case DEV_UNDUL_ANALYTIC_TAPER: {
+        const double X0 = d.p[2], Lx = d.p[3];
+        double ampl = ramp_ampl(x, X0, Lx, d.p[1]);
+        if (d.kind == DEV_UNDUL_ANALYTIC_TAPER) ampl = ampl * (1 + d.p[4] * (x - X0 - 0.5 * Lx) / (0.5 * Lx));
+        ampl *= d.p[0];
+        F[4] += ampl * sin(k * (x - X0)) * cosh(k * y);
+        F[3] += ampl * cos(k * (x - X0)) * sinh(k * y);
+      } break;
+      case DEV_UNDUL_MAPPED:
+      case DEV_UNDUL_MAPPED_TAP: {
+        const double Xleft = d.p[1], dx = d.p[2], dx_inv = 1.0 / dx, Xright = Xleft + d.nx * dx;
+        if (x < Xleft + dx || x > Xright - dx) break;
+        const i64 ix = (i64)floor((x - Xleft) * dx_inv + 0.5);
+        const double ddx = (x - Xleft) * dx_inv - (double)ix;
+        const double S0[3] = {0.5 * (0.5 - ddx) * (0.5 - ddx), 0.75 - ddx * ddx, 0.5 * (0.5 + ddx) * (0.5 + ddx)};
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const i64 kk = ix - 1 + j;  // 1-based node; Q12: node 0 (read out of bounds by the reference) counts as 0
+          if (kk < 1 || kk > d.nx) continue;
+          s1 += S0[j] * __ldg(d.map + 2 * (kk - 1));
+          s2 += S0[j] * __ldg(d.map + 2 * (kk - 1) + 1);
+        }
+        double amp = 1.0;
+        if (d.kind == DEV_UNDUL_MAPPED_TAP) {
+          const double Lx = d.p[3], x_shift = 0.5 * (d.nx * dx - Lx);
+          amp = 1 + d.p[4] * (x - x_shift - Xleft - 0.5 * Lx) / (0.5 * Lx);
+        }
+        F[4] += amp * s1 * cosh(k * y);
+        F[3] += amp * s2 * sinh(k * y);
+      } break;
+      case DEV_PLANEWAVE: {
+        const double sinth = d.c[1], costh = d.c[2];
+        const double ampl = d.p[0] * ramp_ampl(x, d.p[2], d.p[3], d.p[4]) * sin(k * (x * costh + y * sinth - ds.t) + d.p[6]);
+        F[2] += ampl;
+        F[3] += ampl * sinth;
+        F[4] -= ampl * costh;
+      } break;
+      case DEV_GAUSSBEAM: {
+        const double axis = d.p[1];
+        const double xp = x - d.p[2] - axis * ds.t, yp = y - d.p[3], zp = z - d.p[4];
+        const double E = d.a0 * exp(-xp * xp / (d.p[5] * d.p[5]) - yp * yp / (d.p[6] * d.p[6]) - zp * zp / (d.p[7] * d.p[7])) *
+                         sin(k * xp);
+        F[2] += E;
+        F[4] -= axis * E;
+      } break;
+      default: break;
+    }
+  }
 }
 
 // ---- particles.cu
@@ -44,8 +134,8 @@ int launch_push_velocs(cudaStream_t st, PView mom, CPView fld, double dt, i64 np
 int launch_push_coords(cudaStream_t st, PView x, CPView mom, PView xc, double dt, i64 np);
 int launch_gather(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView out, const GridGeom& g, i64 np);
 int launch_gather_push(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
-                       const GridGeom& g, double dt, const UndulParams& und, i64 np);
-int launch_undul(cudaStream_t st, CPView x, PView fld, const UndulParams& und, i64 np);
+                       const GridGeom& g, double dt, const DeviceSet& und, i64 np);
+int launch_devices(cudaStream_t st, CPView x, PView fld, const DeviceSet& und, i64 np);
 int launch_deposit_direct(cudaStream_t st, int env, int curr, CPView x, CPView mom, const double* w, cd* grid,
                           const GridGeom& g, const ChunkSpec& ch, i64 np, bool fold);
 int launch_ghost_fold(cudaStream_t st, cd* grid, i64 nxn, i64 nrn, i64 nplanes);
@@ -68,18 +158,18 @@ struct SortedSpec {
 int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, const double* mom, const double* w,
                           i64 cap, cd* grid, const GridGeom& g, const ChunkSpec& ch, const SortedSpec& sp);
 int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* mom,
-                              i64 cap, const GridGeom& g, double dt, const UndulParams& und, const SortedSpec& sp);
+                              i64 cap, const GridGeom& g, double dt, const DeviceSet& und, const SortedSpec& sp);
 // particles_fused.cu: gather + device + Boris push + position update + J / rho deposit in one kernel.
 // `sp.cta` must be the CTA table for kFusedNPB particles per CTA.  push_dt = 2 pi q/m dt, dt = time step.
 constexpr int kFusedNPB = 512;
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
                            const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
-                           const ChunkSpec& ch, double push_dt, double dt, const UndulParams& und, const SortedSpec& sp);
+                           const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp);
 void fused_profile_enable(int on);
 void fused_profile_read(unsigned long long out[8]);
 // field gather from a shared-memory tile of the EB grid + undulator + Boris push
 int launch_gather_push_tiled(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
-                             const GridGeom& g, double dt, const UndulParams& und, i64 np);
+                             const GridGeom& g, double dt, const DeviceSet& und, i64 np);
 int launch_chunk_bin(cudaStream_t st, CPView x, int8_t* chunked, int* counts, int* goout, double x0, double inv,
                      const double lims[4], int nchnk, i64 np);
 int launch_permute(cudaStream_t st, PView dst, CPView src, const i64* idx, int ncomp, i64 np);

@@ -95,7 +95,7 @@ int launch_gather(cudaStream_t st, int env, CPView x, const double* w, const cd*
 template <int ENV>
 __global__ void __launch_bounds__(128) gather_push_k(CPView x, const double* __restrict__ w,
                                                      const cd* __restrict__ Fld, PView mom, GridGeom g,
-                                                     double dt_2, UndulParams und, i64 np) {
+                                                     double dt_2, DeviceSet und, i64 np) {
   const i64 ip = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= np) return;
   double F[6] = {0, 0, 0, 0, 0, 0};
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) gather_push_k(CPView x, const double* __r
       for (int l = 0; l < 6; ++l) F[l] = G[l];
     }
   }
-  if (und.on) undul_field(und, xp, yp, F);
+  if (und.n) apply_devices(und, xp, yp, zp, F);
   double px = mom.at(0, ip), py = mom.at(1, ip), pz = mom.at(2, ip);
   boris(px, py, pz, F[0], F[1], F[2], F[3], F[4], F[5], dt_2);
   mom.at(0, ip) = px;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) gather_push_k(CPView x, const double* __r
 }
 
 int launch_gather_push(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
-                       const GridGeom& g, double dt, const UndulParams& und, i64 np) {
+                       const GridGeom& g, double dt, const DeviceSet& und, i64 np) {
   if (np <= 0) return 0;
   if (env) gather_push_k<1><<<grid_for(np, 128), 128, 0, st>>>(x, w, Fld, mom, g, 0.5 * dt, und, np);
   else     gather_push_k<0><<<grid_for(np, 128), 128, 0, st>>>(x, w, Fld, mom, g, 0.5 * dt, und, np);
@@ -124,19 +124,20 @@ int launch_gather_push(cudaStream_t st, int env, CPView x, const double* w, cons
   return 0;
 }
 
-// devices.f90:162-203 (NEXT-1 row): analytic planar undulator added to the per-particle field
-__global__ void __launch_bounds__(256) undul_k(CPView x, PView fld, UndulParams und, i64 np) {
+// devices.f90:18-297 (NEXT-1 row): external-field devices added to the per-particle field
+__global__ void __launch_bounds__(256) devices_k(CPView x, PView fld, DeviceSet und, i64 np) {
   const i64 ip = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= np) return;
   double F[6] = {0, 0, 0, 0, 0, 0};
-  undul_field(und, x.at(0, ip), x.at(1, ip), F);
+  apply_devices(und, x.at(0, ip), x.at(1, ip), x.at(2, ip), F);
+  fld.at(2, ip) += F[2];
   fld.at(3, ip) += F[3];
   fld.at(4, ip) += F[4];
 }
 
-int launch_undul(cudaStream_t st, CPView x, PView fld, const UndulParams& und, i64 np) {
+int launch_devices(cudaStream_t st, CPView x, PView fld, const DeviceSet& und, i64 np) {
   if (np <= 0) return 0;
-  undul_k<<<grid_for(np, 256), 256, 0, st>>>(x, fld, und, np);
+  devices_k<<<grid_for(np, 256), 256, 0, st>>>(x, fld, und, np);
   CHB_LAUNCH_CHECK();
   return 0;
 }

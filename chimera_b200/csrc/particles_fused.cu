@@ -120,7 +120,7 @@ template <int ENV, int NM, int SC>
 __global__ void __launch_bounds__(FT, CHB_FMINB)
 fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __restrict__ mom, const double* __restrict__ w,
                   i64 cap, const cd* __restrict__ Fld, cd* __restrict__ J, cd* __restrict__ Rho, GridGeom g, ChunkSpec ch,
-                  double dt_2, double dt, UndulParams und, SortedSpec sp) {
+                  double dt_2, double dt, DeviceSet und, SortedSpec sp) {
   constexpr int NKO = ENV ? (NM - 1) / 2 : NM - 1;
   constexpr int NCJ = ENV ? 1 : 3;  // Q1: the envelope current has l = 3 only
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -328,7 +328,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     double Fp[6];
 #pragma unroll
     for (int l = 0; l < 6; ++l) Fp[l] = fbuf[l * FSTR + li];
-    if (und.on) undul_field(und, xs[j], ys[j], Fp);
+    if (und.n) apply_devices(und, xs[j], ys[j], zs[j], Fp);
     double px = pxs[j], py = pys[j], pz = pzs[j];
     boris(px, py, pz, Fp[0], Fp[1], Fp[2], Fp[3], Fp[4], Fp[5], dt_2);
     mom[ip] = px; mom[cap + ip] = py; mom[2 * cap + ip] = pz;
@@ -562,7 +562,7 @@ constexpr size_t F_SMEM = sizeof(double) * FNF * FSTR + sizeof(int) * (FBINS + F
 
 template <int ENV, int SC>
 int launch_fused_nm(cudaStream_t st, double* x, double* xh, double* mom, const double* w, i64 cap, const cd* Fld, cd* J,
-                    cd* Rho, const GridGeom& g, const ChunkSpec& ch, double dt_2, double dt, const UndulParams& und,
+                    cd* Rho, const GridGeom& g, const ChunkSpec& ch, double dt_2, double dt, const DeviceSet& und,
                     const SortedSpec& sp) {
 #define CHB_FUSED(NMV)                                                                                                 \
   case NMV: {                                                                                                          \
@@ -602,7 +602,7 @@ void fused_profile_read(unsigned long long out[8]) { cudaMemcpyFromSymbol(out, g
 // returns -1 when the mode count has no instantiation (the caller falls back to the separate kernels)
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
                            const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
-                           const ChunkSpec& ch, double push_dt, double dt, const UndulParams& und, const SortedSpec& sp) {
+                           const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp) {
   if (sp.ncta <= 0) return 0;
   if (env && (g.nm % 2) != 1) { set_error("envelope kernels need an odd number of mode slots"); return 2; }
   const double dt_2 = 0.5 * push_dt;

@@ -251,7 +251,7 @@ __device__ __forceinline__ void gather_tile(const GridGeom& g, const cd* __restr
 template <int ENV>
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gather_push_tiled_k(const double* __restrict__ x, const double* __restrict__ w, const cd* __restrict__ Fld,
-                    double* __restrict__ mom, i64 cap, GridGeom g, double dt_2, UndulParams und, i64 np, int TX, int TR) {
+                    double* __restrict__ mom, i64 cap, GridGeom g, double dt_2, DeviceSet und, i64 np, int TX, int TR) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* tile = reinterpret_cast<cd*>(smem_raw);  // [6*nm][TR][TX]
   __shared__ int s_box[4];                     // min ix, min ir, max ix, max ir
@@ -319,7 +319,7 @@ gather_push_tiled_k(const double* __restrict__ x, const double* __restrict__ w, 
       if (kx + 1 < ncol && kr + 1 < nrow) gather_tile<ENV>(g, tile, TX, trx, kx, kr, s, xp[j], yp[j], zp[j], F);
       else gather_one<ENV>(g, Fld, xp[j], yp[j], zp[j], F);
     }
-    if (und.on) undul_field(und, xp[j], yp[j], F);
+    if (und.n) apply_devices(und, xp[j], yp[j], zp[j], F);
     double px = mom[ip], py = mom[cap + ip], pz = mom[2 * cap + ip];
     boris(px, py, pz, F[0], F[1], F[2], F[3], F[4], F[5], dt_2);
     mom[ip] = px; mom[cap + ip] = py; mom[2 * cap + ip] = pz;
@@ -328,7 +328,7 @@ gather_push_tiled_k(const double* __restrict__ x, const double* __restrict__ w, 
 }  // namespace
 
 int launch_gather_push_tiled(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
-                             const GridGeom& g, double dt, const UndulParams& und, i64 np) {
+                             const GridGeom& g, double dt, const DeviceSet& und, i64 np) {
   if (np <= 0) return 0;
   if (x.ps != 1 || mom.ps != 1 || mom.cs != x.cs) return launch_gather_push(st, env, x, w, Fld, mom, g, dt, und, np);
   // tile capacity: x extent of one re-binning tile (32 cells) plus drift margin, rows by a 56 KB budget
@@ -679,7 +679,7 @@ struct GatLayout {
 template <int ENV, int NM>
 __global__ void __launch_bounds__(GB_THREADS, 2)
 gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w, const cd* __restrict__ Fld,
-                     double* __restrict__ mom, i64 cap, GridGeom g, double dt_2, UndulParams und, SortedSpec sp) {
+                     double* __restrict__ mom, i64 cap, GridGeom g, double dt_2, DeviceSet und, SortedSpec sp) {
   constexpr int NF = GatLayout<ENV>::NF;
   constexpr int NKO = ENV ? (NM - 1) / 2 : NM - 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -808,7 +808,7 @@ gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w,
     double F[6];
 #pragma unroll
     for (int l = 0; l < 6; ++l) F[l] = fbuf[l * kDepNPB + li];
-    if (und.on) undul_field(und, __ldg(x + ip), __ldg(x + cap + ip), F);
+    if (und.n) apply_devices(und, __ldg(x + ip), __ldg(x + cap + ip), __ldg(x + 2 * cap + ip), F);
     double px = mom[ip], py = mom[cap + ip], pz = mom[2 * cap + ip];
     boris(px, py, pz, F[0], F[1], F[2], F[3], F[4], F[5], dt_2);
     mom[ip] = px; mom[cap + ip] = py; mom[2 * cap + ip] = pz;
@@ -817,7 +817,7 @@ gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w,
 
 template <int ENV>
 int launch_gather_binned_nm(cudaStream_t st, const double* x, const double* w, const cd* Fld, double* mom, i64 cap,
-                            const GridGeom& g, double dt_2, const UndulParams& und, const SortedSpec& sp) {
+                            const GridGeom& g, double dt_2, const DeviceSet& und, const SortedSpec& sp) {
   const size_t smem = GatLayout<ENV>::smem;
 #define CHB_GB(NMV)                                                                                               \
   case NMV: {                                                                                                     \
@@ -844,7 +844,7 @@ int launch_gather_binned_nm(cudaStream_t st, const double* x, const double* w, c
 }  // namespace
 
 int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* mom,
-                              i64 cap, const GridGeom& g, double dt, const UndulParams& und, const SortedSpec& sp) {
+                              i64 cap, const GridGeom& g, double dt, const DeviceSet& und, const SortedSpec& sp) {
   if (sp.ncta <= 0) return 0;
   if (env && (g.nm % 2) != 1) { set_error("envelope gather needs an odd number of mode slots"); return 2; }
   return env ? launch_gather_binned_nm<1>(st, x, w, Fld, mom, cap, g, 0.5 * dt, und, sp)

@@ -243,6 +243,30 @@ class Engine:
         self.nspecies += 1
         return sid.value
 
+    DEVICE_KINDS = {"undul_analytic": (1, 4), "undul_analytic_taper": (2, 5), "undul_mapped": (3, 3),
+                    "undul_mapped_tap": (4, 5), "planewave": (5, 7), "gaussbeam": (6, 8)}
+
+    def add_device(self, kind, params, a0=0.0, a0_map=None, sid=-1):
+        """External-field device of a species, evaluated between the field gather and the momentum push
+        (``Specie.make_device``, species.py:258-277; routines of f90/devices.f90).  ``kind`` is the Fortran
+        routine name in lower case, ``params`` its ``params`` array; ``a0`` (gaussbeam) and ``a0_map`` (the
+        ``a0(2,nx)`` table of the mapped undulators) as in the reference signatures.  ``sid=-1``: every
+        non-still species."""
+        k, npar = self.DEVICE_KINDS[kind]
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.shape != (npar,):
+            raise ValueError("%s takes %d parameters" % (kind, npar))
+        mp, nx = None, 0
+        if a0_map is not None:
+            a0_map = np.asfortranarray(a0_map, dtype=np.float64)
+            mp, nx = ctypes.c_void_p(a0_map.ctypes.data), a0_map.shape[1]
+        self._check(self.lib.chimera_engine_add_device(self._h, int(sid), k, ctypes.c_double(a0),
+                                                       ctypes.c_void_p(params.ctypes.data), npar, mp, _i64(nx)))
+
+    def set_time(self, t):
+        """time seen by time-dependent devices in phases driven through ``run`` (``i_step * TimeStep``)"""
+        self._check(self.lib.chimera_engine_set_time(self._h, ctypes.c_double(t)))
+
     def count(self, sid=0):
         n = _i64()
         self._check(self.lib.chimera_engine_species_count(self._h, sid, ctypes.byref(n)))
@@ -326,6 +350,7 @@ class Engine:
                 self.upload("CPSATD2", c2)
                 self.run("init_push")
         self._fields_out()
+        self.set_time(0.0)  # make_device() (chimera_main.py:78)
         self.run("gather_push", 0.5)
 
     def step(self, nsteps=1):
@@ -341,6 +366,7 @@ class Engine:
         for _ in range(nsteps):
             self.istep += 1
             sort_now = c.sort_every > 0 and self.istep % c.sort_every == 0
+            self.set_time((self.istep - 1) * c.dt)  # the pending gather + push closes the previous step
             if gather_pending and not sort_now and self.fuse:
                 self.run("particles_fused", 1.0 if self.rank == 0 else 0.0)
                 if self.world > 1:
@@ -360,6 +386,7 @@ class Engine:
             self._fields_out()
             gather_pending = True
         if gather_pending:
+            self.set_time(self.istep * c.dt)
             self.run("gather_push", 1.0)
 
     # -- host-buffer stepping ------------------------------------------------------------------

@@ -479,5 +479,35 @@ def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> type
         call("undul_analytic", coord, fld, _dbl(t), params, _i64(n))
         return fld
 
+    def _device(name, npar, has_a0=False, has_map=False):
+        def f(coord, fld, t, *rest):
+            coord = _in(coord, _F8, "coord", (3, None))
+            n = coord.shape[1]
+            fld = _inout(fld, _F8, "fld", (6, n))
+            rest = list(rest)
+            args = [coord, fld, _dbl(t)]
+            nx = None
+            if has_a0:
+                args.append(_dbl(rest.pop(0)))
+            if has_map:
+                a0 = _in(rest.pop(0), _F8, "a0", (2, None))
+                nx = a0.shape[1]
+                args.append(a0)
+            params = _in(rest.pop(0), _F8, "params", (npar,))
+            args += [params, _i64(n)]
+            if nx is not None:
+                args.append(_i64(nx))
+            call(name, *args)
+            return fld
+
+        f.__name__ = name
+        return f
+
+    mod.undul_analytic_taper = _device("undul_analytic_taper", 5)
+    mod.undul_mapped = _device("undul_mapped", 3, has_map=True)
+    mod.undul_mapped_tap = _device("undul_mapped_tap", 5, has_map=True)
+    mod.planewave = _device("planewave", 7)
+    mod.gaussbeam = _device("gaussbeam", 8, has_a0=True)
+
     mod.API_NAMES = sorted(k for k, v in vars(mod).items() if callable(v) and not k.startswith("_") and k != "error")
     return mod

@@ -147,6 +147,15 @@ int chimera_omp_add_scl(double* scl_fb, const double* A, chb_i64 nkx, chb_i64 nk
 
 /* ---- f90/devices.f90 (SURVEY section 8f NEXT-1) ---------------------------------------------- */
 int chimera_undul_analytic(const double* coord, double* Fld, double t, const double* params, chb_i64 np); /* :162 */
+int chimera_undul_analytic_taper(const double* coord, double* Fld, double t, const double* params, chb_i64 np); /* :117 */
+/* a0(2,nx): tabulated on-axis field, node k (1-based) at Xleft + k dx; Q12: the reference reads node 0 (out of
+ * bounds) for Xleft+dx <= x < Xleft+1.5dx -- taken as zero here */
+int chimera_undul_mapped(const double* coord, double* Fld, double t, const double* a0, const double* params,
+                         chb_i64 np, chb_i64 nx); /* :18 */
+int chimera_undul_mapped_tap(const double* coord, double* Fld, double t, const double* a0, const double* params,
+                             chb_i64 np, chb_i64 nx); /* :64 */
+int chimera_planewave(const double* coord, double* Fld, double t, const double* params, chb_i64 np); /* :205 */
+int chimera_gaussbeam(const double* coord, double* Fld, double time, double a0, const double* params, chb_i64 np); /* :254 */
 
 /* ---- microbenchmark hook: the DHT contraction alone on device-resident random data ----------- */
 /* C[2nkx x N] = A[2nkx x K] . B[K x N], `batch` independent problems, `iters` timed launches;
@@ -207,6 +216,15 @@ int chimera_engine_array(chimera_engine* e, const char* name, void** dev_ptr, ch
 int chimera_engine_add_species(chimera_engine* e, const double* coords, const double* coords_half,
                                const double* momenta, const double* weights, chb_i64 np, double push_fact,
                                int still, chb_i64 capacity, int* id);
+/* external-field device of a species (species.py:55 Args['Devices'], applied between gather and push as in
+ * species.py:258-277): kind 1 undul_analytic, 2 undul_analytic_taper, 3 undul_mapped, 4 undul_mapped_tap,
+ * 5 planewave, 6 gaussbeam; params as the Fortran `params` array, a0 / map only where the routine has them;
+ * species -1 = every non-still species; at most 4 devices per species */
+int chimera_engine_add_device(chimera_engine* e, int species, int kind, double a0, const double* params, int nparams,
+                              const double* map, chb_i64 nx);
+/* time seen by time-dependent devices (i_step * TimeStep) in phases driven through chimera_engine_run;
+ * chimera_engine_step / _step_host set it themselves from their istep argument */
+int chimera_engine_set_time(chimera_engine* e, double t);
 int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np);
 int chimera_engine_get_species(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
                                double* weights);

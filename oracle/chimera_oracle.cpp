@@ -1207,6 +1207,111 @@ int oracle_undul_analytic(const double* coord, double* Fld, double t, const doub
   return 0;
 }
 
+// devices.f90:117-160  the same with a linear amplitude taper along the undulator
+int oracle_undul_analytic_taper(const double* coord, double* Fld, double t, const double* params, i64 np) {
+  (void)t;
+  const double pi = 4.0 * std::atan(1.0);
+  const double a0 = params[0], lambda = params[1], X0 = params[2], Lx = params[3], taper = params[4];
+  const double ku = 2.0 * pi / lambda;
+#pragma omp parallel for schedule(static)
+  for (i64 ip = 0; ip < np; ++ip) {
+    const double x = coord[3 * ip], y = coord[3 * ip + 1];
+    double ampl;
+    if (x <= X0 || x >= X0 + Lx) ampl = 0.0;
+    else if (x > X0 && x < X0 + lambda) ampl = (x - X0) / lambda;
+    else if (x > X0 + Lx - lambda && x < X0 + Lx) ampl = (X0 + Lx - x) / lambda;
+    else ampl = 1.0;
+    ampl = ampl * (1 + taper * (x - X0 - 0.5 * Lx) / (0.5 * Lx));
+    ampl = ampl * a0;
+    Fld[6 * ip + 4] += ampl * std::sin(ku * (x - X0)) * std::cosh(ku * y);
+    Fld[6 * ip + 3] += ampl * std::cos(ku * (x - X0)) * std::sinh(ku * y);
+  }
+  return 0;
+}
+
+// devices.f90:18-62 (tap = 0) and :64-115 (tap = 1): undulator field from a tabulated on-axis map a0(2, nx) with
+// node k (1-based) at Xleft + k dx, quadratic-spline weights around the nearest node.
+// Q12: for Xleft + dx <= x < Xleft + 1.5 dx the nearest node is 1 and the reference reads a0(:, 0), one column
+// before the array; that column is taken as zero here (and on the GPU).
+static int undul_mapped_any(const double* coord, double* Fld, const double* a0, const double* params, i64 np, i64 nx,
+                            int tap) {
+  const double pi = 4.0 * std::atan(1.0);
+  const double lambda = params[0], Xleft = params[1], dx = params[2];
+  const double Lx = tap ? params[3] : 0.0, taper = tap ? params[4] : 0.0;
+  const double ku = 2.0 * pi / lambda, dx_inv = 1.0 / dx, Xright = Xleft + nx * dx;
+  const double x_shift = 0.5 * (nx * dx - Lx);
+#pragma omp parallel for schedule(static)
+  for (i64 ip = 0; ip < np; ++ip) {
+    const double xp = coord[3 * ip];
+    if (xp < Xleft + dx || xp > Xright - dx) continue;
+    const double yp = coord[3 * ip + 1];
+    const i64 ix = (i64)std::floor((xp - Xleft) * dx_inv + 0.5);
+    const double ddx = (xp - Xleft) * dx_inv - (double)ix;
+    const double S0[3] = {0.5 * (0.5 - ddx) * (0.5 - ddx), 0.75 - ddx * ddx, 0.5 * (0.5 + ddx) * (0.5 + ddx)};
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      const i64 k = ix - 1 + j;  // 1-based node
+      if (k < 1 || k > nx) continue;
+      s1 += S0[j] * a0[2 * (k - 1)];
+      s2 += S0[j] * a0[2 * (k - 1) + 1];
+    }
+    double amp = 1.0;
+    if (tap) amp = 1 + taper * (xp - x_shift - Xleft - 0.5 * Lx) / (0.5 * Lx);
+    Fld[6 * ip + 4] += amp * s1 * std::cosh(ku * yp);
+    Fld[6 * ip + 3] += amp * s2 * std::sinh(ku * yp);
+  }
+  return 0;
+}
+int oracle_undul_mapped(const double* coord, double* Fld, double t, const double* a0, const double* params, i64 np,
+                        i64 nx) {
+  (void)t;
+  return undul_mapped_any(coord, Fld, a0, params, np, nx, 0);
+}
+int oracle_undul_mapped_tap(const double* coord, double* Fld, double t, const double* a0, const double* params, i64 np,
+                            i64 nx) {
+  (void)t;
+  return undul_mapped_any(coord, Fld, a0, params, np, nx, 1);
+}
+
+// devices.f90:205-251  linearly polarised plane wave at an angle theta in the x-y plane, with linear ramps
+int oracle_planewave(const double* coord, double* Fld, double t, const double* params, i64 np) {
+  const double pi = 4.0 * std::atan(1.0);
+  const double a0 = params[0], lambda = params[1], X0 = params[2], Lx = params[3], ramp = params[4];
+  const double theta = params[5], phi0 = params[6];
+  const double sinth = std::sin(theta), costh = std::cos(theta), k0 = 2.0 * pi / lambda;
+#pragma omp parallel for schedule(static)
+  for (i64 ip = 0; ip < np; ++ip) {
+    const double x = coord[3 * ip], y = coord[3 * ip + 1];
+    double ampl;
+    if (x <= X0 || x >= X0 + Lx) ampl = 0.0;
+    else if (x > X0 && x < X0 + ramp) ampl = (x - X0) / ramp;
+    else if (x > X0 + Lx - ramp && x < X0 + Lx) ampl = (X0 + Lx - x) / ramp;
+    else ampl = 1.0;
+    ampl = a0 * ampl * std::sin(k0 * (x * costh + y * sinth - t) + phi0);
+    Fld[6 * ip + 2] += ampl;
+    Fld[6 * ip + 3] += ampl * sinth;
+    Fld[6 * ip + 4] -= ampl * costh;
+  }
+  return 0;
+}
+
+// devices.f90:253-297  Gaussian wave packet travelling along +-x (axis = +-1)
+int oracle_gaussbeam(const double* coord, double* Fld, double time, double a0, const double* params, i64 np) {
+  const double pi = 4.0 * std::atan(1.0);
+  const double lambda = params[0], axis = params[1], x0 = params[2], y0 = params[3], z0 = params[4];
+  const double Lx2_inv = 1.0 / (params[5] * params[5]), Ly2_inv = 1.0 / (params[6] * params[6]),
+               Lz2_inv = 1.0 / (params[7] * params[7]);
+#pragma omp parallel for schedule(static)
+  for (i64 ip = 0; ip < np; ++ip) {
+    const double xp = coord[3 * ip] - x0 - axis * time, yp = coord[3 * ip + 1] - y0, zp = coord[3 * ip + 2] - z0;
+    const double E = a0 * std::exp(-xp * xp * Lx2_inv - yp * yp * Ly2_inv - zp * zp * Lz2_inv) *
+                     std::sin(2.0 * pi / lambda * xp);
+    Fld[6 * ip + 2] += E;
+    Fld[6 * ip + 4] -= axis * E;
+  }
+  return 0;
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -251,3 +251,80 @@ def maxwell_push_wo_spchrg(EG, J, C1, C2):
 def poiss_corr(J, gdj, g_n, g_np1, dt_inv, w2_inv):
     """maxwell_solvers.f90:131-164"""
     return J + w2_inv[..., None] * (gdj + dt_inv * (g_np1 - g_n))
+
+
+# ------------------------------------------------------------------ devices.f90 (NEXT-1), whole-array form
+def _ramp(x, X0, Lx, ramp):
+    a = np.ones_like(x)
+    a = np.where((x > X0 + Lx - ramp) & (x < X0 + Lx), (X0 + Lx - x) / ramp, a)
+    a = np.where((x > X0) & (x < X0 + ramp), (x - X0) / ramp, a)
+    return np.where((x <= X0) | (x >= X0 + Lx), 0.0, a)
+
+
+def undul_analytic(coord, fld, t, params, taper=None):
+    a0, lam, X0, Lx = params[:4]
+    ku = 2 * np.pi / lam
+    x, y = coord[0], coord[1]
+    ampl = _ramp(x, X0, Lx, lam)
+    if taper is not None:
+        ampl = ampl * (1 + taper * (x - X0 - 0.5 * Lx) / (0.5 * Lx))
+    ampl = ampl * a0
+    out = fld.copy()
+    out[4] += ampl * np.sin(ku * (x - X0)) * np.cosh(ku * y)
+    out[3] += ampl * np.cos(ku * (x - X0)) * np.sinh(ku * y)
+    return out
+
+
+def undul_analytic_taper(coord, fld, t, params):
+    return undul_analytic(coord, fld, t, params, taper=params[4])
+
+
+def undul_mapped(coord, fld, t, a0, params, tap=False):
+    lam, Xleft, dx = params[:3]
+    nx = a0.shape[1]
+    ku = 2 * np.pi / lam
+    x, y = coord[0], coord[1]
+    ok = ~((x < Xleft + dx) | (x > Xleft + nx * dx - dx))
+    s = (x - Xleft) / dx
+    ix = np.floor(s + 0.5).astype(np.int64)
+    d = s - ix
+    S0 = np.stack((0.5 * (0.5 - d) ** 2, 0.75 - d ** 2, 0.5 * (0.5 + d) ** 2))
+    pad = np.zeros((2, nx + 2))  # column k = node k (1-based); node 0 and nx+1 zero (Q12)
+    pad[:, 1:nx + 1] = a0
+    k = np.clip(ix[None, :] + np.arange(-1, 2)[:, None], 0, nx + 1)
+    s1 = (S0 * pad[0][k]).sum(0)
+    s2 = (S0 * pad[1][k]).sum(0)
+    amp = 1.0
+    if tap:
+        Lx, taper = params[3], params[4]
+        amp = 1 + taper * (x - 0.5 * (nx * dx - Lx) - Xleft - 0.5 * Lx) / (0.5 * Lx)
+    out = fld.copy()
+    out[4] += np.where(ok, amp * s1 * np.cosh(ku * y), 0.0)
+    out[3] += np.where(ok, amp * s2 * np.sinh(ku * y), 0.0)
+    return out
+
+
+def undul_mapped_tap(coord, fld, t, a0, params):
+    return undul_mapped(coord, fld, t, a0, params, tap=True)
+
+
+def planewave(coord, fld, t, params):
+    a0, lam, X0, Lx, ramp, theta, phi0 = params
+    x, y = coord[0], coord[1]
+    k0 = 2 * np.pi / lam
+    ampl = a0 * _ramp(x, X0, Lx, ramp) * np.sin(k0 * (x * np.cos(theta) + y * np.sin(theta) - t) + phi0)
+    out = fld.copy()
+    out[2] += ampl
+    out[3] += ampl * np.sin(theta)
+    out[4] -= ampl * np.cos(theta)
+    return out
+
+
+def gaussbeam(coord, fld, t, a0, params):
+    lam, axis, x0, y0, z0, Lx, Ly, Lz = params
+    xp, yp, zp = coord[0] - x0 - axis * t, coord[1] - y0, coord[2] - z0
+    E = a0 * np.exp(-xp * xp / Lx ** 2 - yp * yp / Ly ** 2 - zp * zp / Lz ** 2) * np.sin(2 * np.pi / lam * xp)
+    out = fld.copy()
+    out[2] += E
+    out[4] -= axis * E
+    return out

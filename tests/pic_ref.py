@@ -12,14 +12,15 @@ import numpy as np
 
 
 class RefSpecies:
-    def __init__(self, coords, momenta, weights, charge=-1.0, mass=1.0, still=False, device=None):
+    def __init__(self, coords, momenta, weights, charge=-1.0, mass=1.0, still=False, device=None, devices=None):
         self.coords = np.asfortranarray(coords, dtype=float).copy(order="F")
         self.coords_halfstep = self.coords.copy(order="F")
         self.momenta = np.asfortranarray(momenta, dtype=float).copy(order="F")
         self.weights = np.asfortranarray(weights, dtype=float).copy()
         self.push_fact = 2 * np.pi * charge / mass  # species.py:64
         self.still = still
-        self.device = device  # (callable, params) as in species.py:258-277
+        # species.py:55 Args['Devices']: a list of (callable, *args); `device` is the one-entry short form
+        self.devices = list(devices) if devices else ([tuple(device)] if device is not None else [])
         self.EB = np.zeros((6, 0), order="F")
         self.chunks = None
 
@@ -174,9 +175,9 @@ class RefRun:
         for s in self.sp:
             if s.still or s.coords.shape[1] == 0:
                 continue
-            if s.device is not None:
-                fn, params = s.device
-                s.EB = fn(s.coords, s.EB, self.istep * a["dt"], np.asfortranarray(params, dtype=float))
+            for dev in s.devices:  # species.py:274-277
+                args = [np.asfortranarray(v, dtype=float) if isinstance(v, (list, tuple, np.ndarray)) else v for v in dev[1:]]
+                s.EB = dev[0](s.coords, s.EB, self.istep * a["dt"], *args)
             s.momenta = f.push_velocs(s.momenta, s.EB, s.push_fact * a["dt"] * dt_frac)
 
     # ---- chimera_main.py:61-92 -----------------------------------------------------------------

@@ -25,7 +25,8 @@ def test_header_declares_the_fimera_hot_path():
               "eb_correction_env dep_curr_env_chnk dep_dens_env_chnk fb_vec_in fb_scl_in fb_vec_out fb_scl_out fb_eb_out "
               "fb_filtr fb_rot fb_grad fb_div fb_graddiv fb_rot_env fb_grad_env fb_div_env fb_graddiv_env "
               "maxwell_push_with_spchrg maxwell_push_wo_spchrg maxwell_init_push poiss_corr poiss_corr_stat field_drift "
-              "omp_mult_vec omp_mult_scl omp_add_vec omp_add_scl undul_analytic").split():
+              "omp_mult_vec omp_mult_scl omp_add_vec omp_add_scl undul_analytic undul_analytic_taper undul_mapped "
+              "undul_mapped_tap planewave gaussbeam").split():
         assert "chimera_" + n in names, n
 
 

@@ -264,3 +264,48 @@ def test_fused_particle_kernel_matches_reference_sequence(ofim, gfim, name, ions
         assert_close(eng.download(n), eng2.download(n), carrier_tol(S, 20 * nsteps * TOL if S.env else nsteps * TOL), n + " fused vs unfused")
     eng.close()
     eng2.close()
+
+
+@pytest.mark.parametrize("name", ["real_m2", "env_m1"])
+def test_engine_device_list(ofim, gfim, name):
+    """NEXT-1: every kind of external device (devices.f90) between gather and push inside the resident engine,
+    time-dependent ones included (t = i_step * TimeStep, species.py:274-277), through the separate kernels
+    (first step, re-binning steps) and the fused kernel."""
+    from chimera_b200.engine import Engine
+
+    S = SolverSetup(copy.deepcopy(SETUPS[name]))
+    a = S.Args
+    x, p, w = plasma(S, 2, 2, 31)
+    if name == "env_m1":
+        p[0] += 391.0
+    L = a["rightX"] - a["leftX"]
+    nxm = 64
+    dxm = L / (nxm - 8)
+    amap = np.asfortranarray(np.vstack((np.sin(0.5 * np.arange(nxm)), np.cos(0.5 * np.arange(nxm)))) * 0.7)
+    devs = [
+        ("planewave", (np.array([0.4, 0.3 * L, a["leftX"] + 0.1 * L, 0.8 * L, 0.1 * L, 0.2, 0.5]),), {}),
+        ("gaussbeam", (0.5, np.array([0.25 * L, 1.0, a["leftX"] + 0.4 * L, 0.1, -0.2, 0.2 * L, 1.0, 1.5])), {}),
+        ("undul_mapped_tap", (amap, np.array([0.2 * L, a["leftX"] - 3 * dxm, dxm, 0.7 * L, 0.1])), {}),
+        ("undul_analytic_taper", (np.array([0.9, 0.15 * L, a["leftX"] + 0.05 * L, 0.9 * L, -0.1]),), {}),
+    ]
+    ref = RefRun(ofim, S, [RefSpecies(x, p, w, devices=[(getattr(ofim, n),) + args for n, args, _ in devs])])
+    eng = Engine(S)
+    eng.add_species(x, p, w)
+    for n, args, _ in devs:
+        if n == "gaussbeam":
+            eng.add_device(n, args[1], a0=args[0])
+        elif n.startswith("undul_mapped"):
+            eng.add_device(n, args[1], a0_map=args[0])
+        else:
+            eng.add_device(n, args[0])
+    eg0 = seed_fields(S, 32, 0.3)
+    ref.EG_fb[:] = eg0
+    eng.upload("EG_fb", eg0)
+    ref.make_halfstep()
+    eng.make_halfstep()
+    compare_state(ref, eng, TOL, names=("EB",))
+    for _ in range(5):
+        ref.make_step()
+    eng.step(5)
+    compare_state(ref, eng, 10 * TOL)
+    eng.close()

@@ -150,13 +150,19 @@ def test_eb_correction(ofim, gfim, name):
     assert_close(rg, ro, what="eb_correction")
 
 
-def test_undul_analytic(ofim, gfim):
-    rng = np.random.default_rng(16)
-    n = 5000
-    x = np.asfortranarray(np.vstack((rng.random(n) * 14 - 2, rng.standard_normal(n) * 0.1, rng.standard_normal(n) * 0.1)))
-    f = np.asfortranarray(rng.standard_normal((6, n)))
-    ro, rg = both(ofim, gfim, "undul_analytic", x, f, 0.3, np.array([1.95, 1.0, 1.0, 10.0]))
-    assert_close(rg, ro, what="undul_analytic")
+def test_devices(ofim, gfim):
+    """every routine of devices.f90 (NEXT-1): undulators (analytic, tapered, mapped), plane wave, Gaussian packet"""
+    from util import device_cases
+
+    x, f, cases = device_cases(np.random.default_rng(16), n=5003)
+    for name, args in cases:
+        ro, rg = both(ofim, gfim, name, x, f, 0.3, *args)
+        assert_close(rg, ro, what=name)
+    # empty input and f2py shape errors
+    e = gfim.planewave(np.zeros((3, 0), order="F"), np.zeros((6, 0), order="F"), 0.0, cases[4][1][0])
+    assert e.shape == (6, 0)
+    with pytest.raises(gfim.error):
+        gfim.planewave(x, f, 0.0, np.zeros(4))
 
 
 # ------------------------------------------------------------------ DHT + FFT

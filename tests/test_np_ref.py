@@ -85,3 +85,15 @@ def test_maxwell_family(ofim):
     eg, j = crandn(rng, S3.shape_fb + (6,)), crandn(rng, S3.shape_fb + (3,))
     got = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, S3.PSATD_E, S3.PSATD_G)
     assert_close(got, np_ref.maxwell_push_wo_spchrg(eg, j, S3.PSATD_E, S3.PSATD_G), TOL, "wo_spchrg")
+
+
+def test_devices(ofim):
+    """every routine of devices.f90: C++ loop restatement vs whole-array numpy restatement"""
+    from util import device_cases
+
+    x, f, cases = device_cases(np.random.default_rng(21))
+    for name, args in cases:
+        got = getattr(ofim, name)(x, f.copy(order="F"), 0.37, *args)
+        want = getattr(np_ref, name)(x, f, 0.37, *args)
+        assert_close(got, want, TOL, name)
+        assert np.abs(got - f).max() > 1e-3, name  # the device did something

@@ -170,3 +170,36 @@ def test_envelope_quirks(ofim):
     wp = one[1][0] * np.exp(-1j * kx0 * one[0][0, 0])
     nko = (S.shape_sp[2] - 1) // 2
     np.testing.assert_allclose(rho[:, :, nko].sum(), wp * wp, rtol=1e-9)
+
+
+def test_device_known_answers(ofim):
+    """devices.f90: a map sampled from the analytic undulator reproduces it (quadratic spline, O(dx^3)); the
+    tapered variants with taper 0 equal the untapered ones; a plane wave at theta = 0 has Ez = -By; the
+    Gaussian packet's field at its centre line is a0 sin(k xp) exp(-xp^2/Lx^2) and moves with axis * t; Q12."""
+    rng = np.random.default_rng(5)
+    n = 2000
+    x = np.asfortranarray(np.vstack((rng.random(n) * 6 + 3.0, rng.standard_normal(n) * 0.05, rng.standard_normal(n) * 0.05)))
+    z = np.zeros((6, n), order="F")
+    lam, X0, Lx, a0 = 1.0, 1.0, 10.0, 1.95
+    ana = ofim.undul_analytic(x, z.copy(order="F"), 0.0, np.array([a0, lam, X0, Lx]))
+    dx, nx = 0.01, 1400
+    nodes = 0.0 + dx * np.arange(1, nx + 1)  # node k (1-based) at Xleft + k dx
+    ku = 2 * np.pi / lam
+    amap = np.asfortranarray(np.vstack((a0 * np.sin(ku * (nodes - X0)), a0 * np.cos(ku * (nodes - X0)))))
+    mp = ofim.undul_mapped(x, z.copy(order="F"), 0.0, amap, np.array([lam, 0.0, dx]))
+    assert np.abs(mp - ana).max() < 2e-3 * a0  # spline smoothing error ~ (ku dx)^2 / 8
+    assert np.array_equal(ofim.undul_analytic_taper(x, z.copy(order="F"), 0.0, np.array([a0, lam, X0, Lx, 0.0])), ana)
+    assert np.allclose(ofim.undul_mapped_tap(x, z.copy(order="F"), 0.0, amap, np.array([lam, 0.0, dx, 9.0, 0.0])), mp, rtol=0, atol=1e-15)
+    pw = ofim.planewave(x, z.copy(order="F"), 0.3, np.array([0.7, 0.8, 0.0, 20.0, 1.0, 0.0, 0.1]))
+    assert np.array_equal(pw[2], -pw[4]) and not pw[3].any() and np.abs(pw[2]).max() > 0.5
+    line = np.asfortranarray(np.vstack((np.linspace(0, 10, n), np.full(n, 0.2), np.full(n, -0.1))))
+    prm = np.array([0.8, 1.0, 4.0, 0.2, -0.1, 2.0, 0.5, 0.5])
+    gb = ofim.gaussbeam(line, z.copy(order="F"), 1.5, 0.6, prm)
+    xp = line[0] - 4.0 - 1.5
+    assert np.allclose(gb[2], 0.6 * np.exp(-xp ** 2 / 4.0) * np.sin(2 * np.pi / 0.8 * xp), rtol=0, atol=1e-14)
+    assert np.array_equal(gb[4], -gb[2])
+    # Q12: a particle between Xleft + dx and Xleft + 1.5 dx only sees nodes 1 and 2
+    one = np.asfortranarray(np.array([[0.0 + 1.2 * dx], [0.0], [0.0]]))
+    got = ofim.undul_mapped(one, np.zeros((6, 1), order="F"), 0.0, amap, np.array([lam, 0.0, dx]))
+    d = 1.2 - 1.0
+    assert np.isclose(got[4, 0], (0.75 - d * d) * amap[0, 0] + 0.5 * (0.5 + d) ** 2 * amap[0, 1], rtol=1e-14)

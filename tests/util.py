@@ -146,3 +146,21 @@ def match(w_ref, w_eng):
     perm[a] = b
     assert np.array_equal(w_ref, w_eng[perm])
     return perm
+
+
+def device_cases(rng, n=4000):
+    """(name, args after (coord, fld, t)) for every routine of devices.f90 on a beam spread over the device entry,
+    body and exit; shared by the CPU cross-check, the GPU parity test and the engine test."""
+    x = np.asfortranarray(np.vstack((rng.random(n) * 16 - 3, rng.standard_normal(n) * 0.1, rng.standard_normal(n) * 0.1)))
+    f = np.asfortranarray(rng.standard_normal((6, n)))
+    nx = 96
+    amap = np.asfortranarray(np.vstack((np.sin(0.7 * np.arange(nx)), np.cos(0.7 * np.arange(nx)))) * 1.3)
+    cases = [
+        ("undul_analytic", (np.array([1.95, 1.0, 1.0, 10.0]),)),
+        ("undul_analytic_taper", (np.array([1.95, 1.0, 1.0, 10.0, 0.08]),)),
+        ("undul_mapped", (amap, np.array([1.0, -1.0, 0.125]))),
+        ("undul_mapped_tap", (amap, np.array([1.0, -1.0, 0.125, 9.0, -0.05]))),
+        ("planewave", (np.array([0.8, 0.9, 0.5, 11.0, 2.0, 0.3, 0.4]),)),
+        ("gaussbeam", (0.6, np.array([0.8, -1.0, 9.0, 0.02, -0.03, 3.0, 0.4, 0.5]))),
+    ]
+    return x, f, cases
