@@ -307,7 +307,8 @@ int ensure_sort_scratch(chimera_engine* e, i64 n) {
   return 0;
 }
 
-int ph_sort(chimera_engine* e, int on_halfstep) {
+// left_margin: the absorbing layer of a moving window (species.py:373-376 SimDom[0] = leftX + AbsorbLayer dx)
+int ph_sort(chimera_engine* e, int on_halfstep, double left_margin = 0.0) {
   const auto& c = e->cfg;
   const int nchnk = c.chunked ? c.nchnk : 1;
   for (auto& s : e->sp) {
@@ -318,7 +319,7 @@ int ph_sort(chimera_engine* e, int on_halfstep) {
     const i64 cs = c.nx / nchnk;  // nodes per chunk
     b.x0 = c.leftX;
     b.chunk_inv = 1.0 / c.chunk_len;
-    b.l0 = c.leftX; b.l1 = c.rightX; b.l2 = 0.0; b.l3 = c.rcull2;
+    b.l0 = c.leftX + left_margin; b.l1 = c.rightX; b.l2 = 0.0; b.l3 = c.rcull2;
     b.leftX = c.leftX; b.dx_inv = 1.0 / c.dx; b.r0 = g_host[e].r0; b.dr_inv = 1.0 / c.dr;
     b.nchnk = nchnk; b.nx = c.nx; b.nrc = c.nrn - 1;
     b.cs = cs; b.tile_w = cs < 32 ? cs : 32; b.ntile = (cs + b.tile_w - 1) / b.tile_w;
@@ -805,6 +806,98 @@ int chimera_engine_set_time(chimera_engine* e, double t) {
   ENG_CHECK(e);
   e->dev_time = t;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Moving window on the device (chimera_main.py:250-304 frame_act stage 1; NEXT-2 row)
+// ------------------------------------------------------------------------------------------
+// solvers.py:619-633 damp_field(config, damp_b = False): x-space window on E and G
+int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode) {
+  ENG_CHECK(e);
+  const auto& c = e->cfg;
+  if (slab(e)) { set_error("damp_field needs every kx row (x-FFT): not available on a kx-slab engine"); return 2; }
+  if (!filtr || nxfilt < 1 || nxfilt > c.nx || mode < 0 || mode > 2) { set_error("damp_field: bad filter (%lld points, mode %d)", nxfilt, mode); return 2; }
+  e->scr.reset();
+  double* d_f = e->scr.take_n<double>(nxfilt);
+  if (!d_f) return 6;
+  CHB_CUDA(cudaMemcpyAsync(d_f, filtr, sizeof(double) * nxfilt, cudaMemcpyDefault, e->st));
+  FBCtx fb = fbctx(e);
+  const i64 half = c.nx * c.nkr * c.nm * 3;
+  CHB_TRY(fb_filtr_dev(fb, e->A("EG_fb"), c.leftX, e->D("kx"), d_f, mode, c.nx, c.nkr, c.nm, nxfilt));
+  CHB_TRY(fb_filtr_dev(fb, e->A("EG_fb") + half, c.leftX, e->D("kx"), d_f, mode, c.nx, c.nkr, c.nm, nxfilt));
+  return 0;
+}
+
+// chimera_main.py:286-290 move_frame: Xgrid += shiftX
+int chimera_engine_move_window(chimera_engine* e, double shiftX) {
+  ENG_CHECK(e);
+  e->cfg.leftX += shiftX;
+  e->cfg.rightX += shiftX;
+  return 0;
+}
+
+static int species_reserve(chimera_engine* e, Species& s, i64 need) {
+  if (need <= s.cap) return 0;
+  i64 ncap = s.cap * 3 / 2;
+  if (ncap < need) ncap = need;
+  ncap = (ncap + 31) & ~31LL;
+  const size_t D = sizeof(double);
+  double** cur[4] = {&s.x, &s.xh, &s.p, &s.w};
+  double** alt[4] = {&s.x2, &s.xh2, &s.p2, &s.w2};
+  for (int k = 0; k < 4; ++k) {
+    const int nc = k < 3 ? 3 : 1;
+    double* nb = nullptr;
+    CHB_CUDA(cudaMalloc((void**)&nb, D * nc * ncap));
+    for (int cpt = 0; cpt < nc; ++cpt)
+      if (s.np > 0) CHB_CUDA(cudaMemcpyAsync(nb + cpt * ncap, *cur[k] + cpt * s.cap, D * s.np, cudaMemcpyDeviceToDevice, e->st));
+    CHB_CUDA(cudaStreamSynchronize(e->st));
+    cudaFree(*cur[k]);
+    *cur[k] = nb;
+    cudaFree(*alt[k]);
+    CHB_CUDA(cudaMalloc((void**)alt[k], D * nc * ncap));
+  }
+  s.cap = ncap;
+  return 0;
+}
+
+// species.py:218-244 add_particles: new particles go to the end, coords_halfstep = coords.  The particle order
+// is no longer binned afterwards: a re-binning (chimera_engine_sort) must follow before the next deposit.
+int chimera_engine_append_particles(chimera_engine* e, int id, const double* coords, const double* momenta,
+                                    const double* weights, chb_i64 n) {
+  ENG_CHECK(e);
+  if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  if (n < 0) { set_error("append_particles: n < 0"); return 2; }
+  if (n == 0) return 0;
+  if (!coords || !momenta || !weights) { set_error("append_particles: null buffer"); return 2; }
+  Species& s = e->sp[id];
+  CHB_TRY(species_reserve(e, s, s.np + n));
+  const double* srcs[2] = {coords, momenta};
+  for (int k = 0; k < 2; ++k) {  // stage the (3,n) arrays through the permutation buffer, transpose behind the old particles
+    CHB_CUDA(cudaMemcpyAsync(s.x2, srcs[k], sizeof(double) * 3 * n, cudaMemcpyDefault, e->st));
+    double* dst = k == 0 ? s.x : s.p;
+    aos_to_soa_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(dst + s.np, s.x2, 3, s.cap, n);
+    CHB_LAUNCH_CHECK();
+    if (k == 0) {
+      aos_to_soa_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.xh + s.np, s.x2, 3, s.cap, n);
+      CHB_LAUNCH_CHECK();
+    }
+  }
+  CHB_CUDA(cudaMemcpyAsync(s.w + s.np, weights, sizeof(double) * n, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  s.np += n;
+  s.tile_w = 0;  // unsorted
+  const int nchnk = e->cfg.chunked ? e->cfg.nchnk : 1;
+  for (int c2 = 1; c2 <= nchnk; ++c2) s.h_ind[c2] = (int)s.np;
+  CHB_CUDA(cudaMemcpyAsync(s.d_ind, s.h_ind.data(), sizeof(int) * (nchnk + 1), cudaMemcpyHostToDevice, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return update_cta_table(e, s);
+}
+
+// species.py:351-398 chunk_and_damp with an explicit absorbing layer: particles left of leftX + left_margin, right
+// of rightX or beyond the radial limit are dropped, the rest re-binned (on coords_halfstep when on_halfstep != 0)
+int chimera_engine_sort(chimera_engine* e, int on_halfstep, double left_margin) {
+  ENG_CHECK(e);
+  return ph_sort(e, on_halfstep, left_margin);
 }
 
 int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np) {

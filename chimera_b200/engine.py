@@ -267,6 +267,56 @@ class Engine:
         """time seen by time-dependent devices in phases driven through ``run`` (``i_step * TimeStep``)"""
         self._check(self.lib.chimera_engine_set_time(self._h, ctypes.c_double(t)))
 
+    # -- moving window (chimera_main.py:250-304) ---------------------------------------------
+    def damp_field(self, profile, config="left"):
+        """``Solver.damp_field`` (solvers.py:619): absorbing-layer window on E and G in x-space."""
+        prof = np.ascontiguousarray(profile, dtype=np.float64)
+        self._check(self.lib.chimera_engine_damp_field(self._h, ctypes.c_void_p(prof.ctypes.data), _i64(prof.shape[0]),
+                                                       {"left": 0, "right": 1, "both": 2}[config]))
+
+    def move_window(self, shift):
+        """``ChimeraRun.move_frame`` (chimera_main.py:286): the engine's grid moves by ``shift``.  The solver
+        dictionary ``setup.Args`` belongs to the driver, whose own ``move_frame`` updates it; the engine tracks
+        its window in ``self.cfg.leftX / rightX``."""
+        self._check(self.lib.chimera_engine_move_window(self._h, ctypes.c_double(shift)))
+        self.cfg.leftX += shift
+        self.cfg.rightX += shift
+
+    def append_particles(self, sid, coords, momenta, weights):
+        """``Specie.add_particles`` (species.py:218): (3,n) coords / momenta and weights(n) join species ``sid``."""
+        x = np.asfortranarray(coords, dtype=np.float64)
+        p = np.asfortranarray(momenta, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        n = x.shape[1]
+        assert x.shape == (3, n) and p.shape == (3, n) and w.shape == (n,)
+        self._check(self.lib.chimera_engine_append_particles(self._h, int(sid), ctypes.c_void_p(x.ctypes.data),
+                                                             ctypes.c_void_p(p.ctypes.data), ctypes.c_void_p(w.ctypes.data), _i64(n)))
+
+    def sort(self, on_halfstep=False, left_margin=0.0):
+        """``Specie.chunk_and_damp`` (species.py:351) with the absorbing layer ``left_margin`` (in x units)."""
+        self._check(self.lib.chimera_engine_sort(self._h, int(bool(on_halfstep)), ctypes.c_double(left_margin)))
+
+    def frame_act(self, wind, add=None, background=False):
+        """Stage 1 of ``ChimeraRun.frame_act`` (chimera_main.py:292-302) for one moving window ``wind`` (the
+        reference's dictionary: ``shiftX``, ``AbsorbLayer`` in cells, ...): damp the fields in the absorbing layer,
+        move the grid, add the particles ``add = {species id: (coords, momenta, weights)}`` produced by the
+        driver's ``gen_parts`` (host-side: numpy RNG and the user's density profile), cull + re-bin, and redo the
+        background / charge density (``postframe_corr``).  Call it between two ``step`` calls."""
+        a = self.setup.Args
+        if wind.get("AbsorbLayer", 0) > 0:
+            self.damp_field(self.setup.get_damp_profile(wind["AbsorbLayer"]))
+        self.move_window(wind["shiftX"])
+        for sid, (x, p, w) in (add or {}).items():
+            self.append_particles(sid, x, p, w)
+        if "AbsorbLayer" in wind:
+            self.sort(False, wind["AbsorbLayer"] * a["dx"])
+        if self.cfg.space_charge:
+            if background:
+                self.deposit_background()
+            self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
+            if self.world > 1:
+                self._dist.all_reduce(self.device_tensor("Rho"), group=self._group)
+
     def count(self, sid=0):
         n = _i64()
         self._check(self.lib.chimera_engine_species_count(self._h, sid, ctypes.byref(n)))

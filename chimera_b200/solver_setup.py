@@ -262,6 +262,13 @@ class SolverSetup:
         return anti * band
 
     # -- convenience ---------------------------------------------------------------------------
+    @staticmethod
+    def get_damp_profile(lf):
+        """``Solver.get_damp_profile`` (solvers.py:612-617): cos^2 ramp over the last quarter of ``int(lf)`` cells."""
+        n = int(lf)
+        g = np.arange(n)
+        return (g >= 0.75 * n) * (0.5 - 0.5 * np.cos(np.pi * (g - 0.75 * n) / (0.25 * n))) ** 2
+
     def zeros_sp(self, ncomp=None):
         shp = self.shape_sp + ((ncomp,) if ncomp else ())
         return np.zeros(shp, dtype=complex, order="F")

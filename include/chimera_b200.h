@@ -225,6 +225,18 @@ int chimera_engine_add_device(chimera_engine* e, int species, int kind, double a
 /* time seen by time-dependent devices (i_step * TimeStep) in phases driven through chimera_engine_run;
  * chimera_engine_step / _step_host set it themselves from their istep argument */
 int chimera_engine_set_time(chimera_engine* e, double t);
+/* ---- moving window on the device (chimera_main.py:250-304 frame_act, stage 1) ----
+ * damp_field: solvers.py:619 (x-space window `filtr` of nxfilt points on E and G; mode 0 left, 1 right, 2 both;
+ *             filtr may be a host or device pointer); not available on kx-slab engines (needs the full x-FFT)
+ * move_window: chimera_main.py:286 (leftX, rightX += shiftX)
+ * append_particles: species.py:218 add_particles ((3,n) Fortran-ordered coords / momenta, weights(n); host or
+ *             device pointers; coords_halfstep = coords; the species grows as needed); call _sort before depositing
+ * sort: species.py:351 chunk_and_damp with SimDom = [leftX + left_margin, rightX, 0, upperR^2] */
+int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode);
+int chimera_engine_move_window(chimera_engine* e, double shiftX);
+int chimera_engine_append_particles(chimera_engine* e, int species, const double* coords, const double* momenta,
+                                    const double* weights, chb_i64 n);
+int chimera_engine_sort(chimera_engine* e, int on_halfstep, double left_margin);
 int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np);
 int chimera_engine_get_species(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
                                double* weights);

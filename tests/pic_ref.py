@@ -51,11 +51,11 @@ class RefRun:
         self.istep = 0
 
     # ---- species.py:351-398 -------------------------------------------------------------------
-    def chunk_and_damp(self, s, position):
+    def chunk_and_damp(self, s, position, left_margin=0.0):
         a, f = self.a, self.f
         if s.coords.shape[1] == 0:
             return
-        dom = np.asfortranarray([a["leftX"], a["rightX"], 0.0, a["Rgrid"].max() ** 2])
+        dom = np.asfortranarray([a["leftX"] + left_margin, a["rightX"], 0.0, a["Rgrid"].max() ** 2])
         src = s.coords_halfstep if position == "cntr" else s.coords
         if self.chunked:
             ids, s.chunks, go_out = f.chunk_coords_boundaries(src, dom, a["Xgrid"], self.nchnk)
@@ -179,6 +179,39 @@ class RefRun:
                 args = [np.asfortranarray(v, dtype=float) if isinstance(v, (list, tuple, np.ndarray)) else v for v in dev[1:]]
                 s.EB = dev[0](s.coords, s.EB, self.istep * a["dt"], *args)
             s.momenta = f.push_velocs(s.momenta, s.EB, s.push_fact * a["dt"] * dt_frac)
+
+    # ---- chimera_main.py:250-304: moving window, stage 1 ----------------------------------------
+    def frame_act(self, wind, add=None):
+        """damp_fields, move_frame, add_plasma (``add`` = {species index: (coords, momenta, weights)} as produced
+        by the driver's gen_parts), damp_plasma, postframe_corr -- in the reference's order"""
+        a, f = self.a, self.f
+        if wind.get("AbsorbLayer", 0) > 0:  # solvers.py:619-633 damp_field('left', damp_b=False)
+            prof = self.S.get_damp_profile(wind["AbsorbLayer"])
+            self.EG_fb[:, :, :, :3] = f.fb_filtr(self.EG_fb[:, :, :, :3], a["leftX"], a["kx"], prof, 0)
+            self.EG_fb[:, :, :, 3:] = f.fb_filtr(self.EG_fb[:, :, :, 3:], a["leftX"], a["kx"], prof, 0)
+        a["Xgrid"] = a["Xgrid"] + wind["shiftX"]
+        a["leftX"], a["rightX"] = a["Xgrid"][0], a["Xgrid"][-1]
+        for i, (x, p, w) in (add or {}).items():  # species.py:218-244
+            s = self.sp[i]
+            s.coords = np.asfortranarray(np.concatenate((s.coords, x), axis=1))
+            s.coords_halfstep = np.asfortranarray(np.concatenate((s.coords_halfstep, x), axis=1))
+            s.momenta = np.asfortranarray(np.concatenate((s.momenta, p), axis=1))
+            s.weights = np.concatenate((s.weights, w))
+        if "AbsorbLayer" in wind:
+            for s in self.sp:
+                self.chunk_and_damp(s, "stag", left_margin=wind["AbsorbLayer"] * a["dx"])
+        if self.space_charge:  # postframe_corr
+            if self.background:
+                self.dep_bg()
+            self.Rho[:] = 0.0
+            if self.rank == 0:
+                self.Rho += self.Bck
+            for s in self.sp:
+                if s.still or s.coords.shape[1] == 0:
+                    continue
+                self.Rho = self._dep("dens", self.Rho, s, s.coords)
+            if self.reduce:
+                self.reduce(self.Rho)
 
     # ---- chimera_main.py:61-92 -----------------------------------------------------------------
     def make_halfstep(self, px0=(0.0,)):

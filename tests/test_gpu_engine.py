@@ -309,3 +309,41 @@ def test_engine_device_list(ofim, gfim, name):
     eng.step(5)
     compare_state(ref, eng, 10 * TOL)
     eng.close()
+
+
+@pytest.mark.parametrize("name,ions", [("real_m2", True), ("real_m3", False)])
+def test_engine_moving_window(ofim, gfim, name, ions):
+    """NEXT-2: the moving window on the device (chimera_main.py:250-304 frame_act stage 1): absorbing-layer field
+    damping, grid shift, particle injection at the right edge, cull + re-binning, background / density redo -- twice,
+    with steps in between, against the same sequence on the oracle."""
+    S, ref, eng = build_pair(ofim, name, 61, still_ions=ions)
+    a = S.Args
+    ref.make_halfstep()
+    eng.make_halfstep(background=ions)
+    rng = np.random.default_rng(62)
+    wind = {"shiftX": 4 * a["dx"], "AbsorbLayer": 24, "Features": ()}
+    for rnd in range(2):
+        for _ in range(3):
+            ref.make_step()
+        eng.step(3)
+        # a layer of fresh plasma in the cells that enter on the right (gen_parts(Xsteps=...), species.py:171)
+        n = 400
+        xr = a["Xgrid"][-1] + wind["shiftX"]
+        x = np.asfortranarray(np.vstack((xr - rng.random(n) * wind["shiftX"], (rng.random((2, n)) - 0.5) * 1.2 * a["Rgrid"].max())))
+        p = np.asfortranarray(rng.standard_normal((3, n)) * 0.05)
+        w = -np.abs(rng.random(n)) * 1e-3
+        add = {0: (x, p, w)}
+        if ions:
+            add[1] = (x.copy(order="F"), np.zeros_like(p), -w)
+        ref.frame_act(wind, add)
+        eng.frame_act(wind, add, background=ions)
+        assert eng.count(0) == ref.sp[0].weights.shape[0]
+        assert_close(eng.download("EG_fb"), ref.EG_fb, 10 * TOL, "EG_fb after damp_field")
+        assert_close(eng.download("Rho"), ref.Rho, 10 * TOL, "Rho after postframe_corr")
+        if ions:
+            assert_close(eng.download("BckGrndRho"), ref.Bck, 10 * TOL, "BckGrndRho")
+    for _ in range(2):
+        ref.make_step()
+    eng.step(2)
+    compare_state(ref, eng, 20 * TOL)
+    eng.close()
