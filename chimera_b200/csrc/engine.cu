@@ -900,6 +900,80 @@ int chimera_engine_sort(chimera_engine* e, int on_halfstep, double left_margin) 
   return ph_sort(e, on_halfstep, left_margin);
 }
 
+// ------------------------------------------------------------------------------------------
+// Integrated diagnostics on the device (moduls/diagnostics.py; NEXT-3 row)
+// ------------------------------------------------------------------------------------------
+// diagnostics.py:109-124 nrg_out before its roll: out[kx] = sum_{kr,m} EnergyFact * sum_{c<3} |EG_fb[..,c]|^2.
+// energy_fact (nx, nkr, nm) float64, host or device, is kept in HBM after the first call (pass NULL later).
+int chimera_engine_field_energy(chimera_engine* e, const double* energy_fact, double* out) {
+  ENG_CHECK(e);
+  const auto& c = e->cfg;
+  const i64 nkx = nxs(e), ncols = c.nkr * c.nm;
+  if (!out) { set_error("field_energy: null output"); return 2; }
+  if (energy_fact) {
+    if (!e->arr.count("EnergyFact")) CHB_TRY(alloc_named(e, "EnergyFact", sizeof(double) * nkx * ncols, false));
+    CHB_CUDA(cudaMemcpyAsync(e->D("EnergyFact"), energy_fact, sizeof(double) * nkx * ncols, cudaMemcpyDefault, e->st));
+  } else if (!e->arr.count("EnergyFact")) { set_error("field_energy: the EnergyFact table was never supplied"); return 2; }
+  e->scr.reset();
+  double* d_out = e->scr.take_n<double>(nkx);
+  if (!d_out) return 6;
+  CHB_TRY(launch_field_energy(e->st, e->A("EG_fb"), e->D("EnergyFact"), d_out, nkx, ncols));
+  CHB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * nkx, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+// diagnostics.py:174-207 get_beam_envelops: the sums it is built from, on coords_halfstep and momenta
+int chimera_engine_beam_moments(chimera_engine* e, int id, double* out16) {
+  ENG_CHECK(e);
+  if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  Species& s = e->sp[id];
+  e->scr.reset();
+  double* d = e->scr.take_n<double>(16);
+  if (!d) return 6;
+  CHB_TRY(launch_beam_moments(e->st, s.xh, s.p, s.w, s.cap, s.np, d));
+  CHB_CUDA(cudaMemcpyAsync(out16, d, sizeof(double) * 16, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int chimera_engine_spectrum(chimera_engine* e, int id, int quantity, double lo, double hi, chb_i64 nbins, double* hist) {
+  ENG_CHECK(e);
+  if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
+  if (nbins < 1 || nbins > 4096 || !(hi > lo) || quantity < 0 || quantity > 1) { set_error("spectrum: bad binning"); return 2; }
+  Species& s = e->sp[id];
+  e->scr.reset();
+  double* d = e->scr.take_n<double>(nbins);
+  if (!d) return 6;
+  CHB_TRY(launch_spectrum(e->st, s.p, s.w, s.cap, s.np, quantity, lo, hi, (int)nbins, d));
+  CHB_CUDA(cudaMemcpyAsync(hist, d, sizeof(double) * nbins, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+// out[ix] = A[ix, ir, m, l] of a complex grid array (e.g. "EB", ir = 0: the on-axis wake field)
+int chimera_engine_lineout(chimera_engine* e, const char* name, chb_i64 ir, chb_i64 m, chb_i64 l, double* out) {
+  ENG_CHECK(e);
+  NamedArray* a;
+  CHB_TRY(find_array(e, name, &a));
+  const auto& c = e->cfg;
+  const std::string n = name;
+  const bool grid = n == "J" || n == "Rho" || n == "BckGrndRho" || n == "EB";
+  const i64 nx = grid ? c.nx : nxs(e), nr = grid ? c.nrn : c.nkr;
+  const i64 off = nx * (ir + nr * (m + c.nm * l));
+  if (ir < 0 || ir >= nr || m < 0 || m >= c.nm || l < 0 || (size_t)(off + nx) * sizeof(cd) > a->bytes) {
+    set_error("lineout: index (%lld, %lld, %lld) outside '%s'", ir, m, l, name);
+    return 2;
+  }
+  e->scr.reset();
+  cd* d = e->scr.take_n<cd>(nx);
+  if (!d) return 6;
+  CHB_TRY(launch_lineout(e->st, (const cd*)a->p, d, nx, off));
+  CHB_CUDA(cudaMemcpyAsync(out, d, sizeof(cd) * nx, cudaMemcpyDefault, e->st));
+  CHB_CUDA(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
 int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np) {
   ENG_CHECK(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }

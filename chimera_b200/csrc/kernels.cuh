@@ -177,6 +177,13 @@ int launch_inside_flag(cudaStream_t st, CPView x, int* flag, const double lims[4
 int launch_nonzero_flag(cudaStream_t st, const double* v, int* flag, i64 np);
 int launch_compact_index(cudaStream_t st, const int* flag, const int* pos, int* out, i64 np);
 
+// ---- diagnostics.cu : reductions behind moduls/diagnostics.py (NEXT-3)
+int launch_field_energy(cudaStream_t st, const cd* EG, const double* fact, double* out, i64 nkx, i64 ncols);
+int launch_beam_moments(cudaStream_t st, const double* x, const double* p, const double* w, i64 cap, i64 np, double* out16);
+int launch_spectrum(cudaStream_t st, const double* p, const double* w, i64 cap, i64 np, int quantity, double lo, double hi,
+                    int nbins, double* hist);
+int launch_lineout(cudaStream_t st, const cd* A, cd* out, i64 nx, i64 offset);
+
 // ---- gemm.cu : batched real GEMM on complex-interleaved data, FP64 tensor cores (DMMA)
 //   C[M x N] = alpha * A[M x K] * B[K x N] + beta * C      (column-major, M = 2*Nx real rows)
 // B must have been packed with gemm_pack_b (fragment-ordered tiles, zero padded).

@@ -317,6 +317,62 @@ class Engine:
             if self.world > 1:
                 self._dist.all_reduce(self.device_tensor("Rho"), group=self._group)
 
+    # -- integrated diagnostics on the device (moduls/diagnostics.py) ---------------------------
+    def nrg_out(self):
+        """``Diagnostics.nrg_out`` (diagnostics.py:109-124): field energy per kx, rolled as the reference does.
+        On a kx-slab engine every rank returns the energies of its own rows (``self.rows``), unrolled."""
+        a = self.setup.Args
+        nloc = self.cfg.nx_slab if self.slab else a["Nx"]
+        out = np.zeros(nloc)
+        fact = None
+        if not getattr(self, "_energy_fact_up", False):
+            ef = np.asfortranarray(a["EnergyFact"][self.rows] if self.slab else a["EnergyFact"], dtype=np.float64)
+            fact = ctypes.c_void_p(ef.ctypes.data)
+        self._check(self.lib.chimera_engine_field_energy(self._h, fact, ctypes.c_void_p(out.ctypes.data)))
+        self._energy_fact_up = True
+        if self.slab:
+            return out
+        return np.r_[out[nloc // 2 + 1:], out[:nloc // 2 + 1]]
+
+    def beam_moments(self, sid=0):
+        out = np.zeros(16)
+        self._check(self.lib.chimera_engine_beam_moments(self._h, int(sid), ctypes.c_void_p(out.ctypes.data)))
+        if self.world > 1:
+            import torch
+
+            t = torch.from_numpy(out).cuda()
+            self._dist.all_reduce(t, group=self._group)
+            out = t.cpu().numpy()
+        return out
+
+    def get_beam_envelops(self, sid=0):
+        """``Diagnostics.get_beam_envelops`` (diagnostics.py:174-207): centroid, rms size and emittance per axis,
+        from 16 sums reduced on the device."""
+        m = self.beam_moments(sid)
+        sw = m[0]
+        xyz0, rms, emit = [], [], []
+        for c in range(3):
+            wx, wx2, wp2, wxp = m[1 + 5 * c:5 + 5 * c]
+            xyz0.append(wx / sw)
+            rms.append(np.sqrt(wx2 / sw - (wx / sw) ** 2))
+            emit.append(np.sqrt(wx2 / sw * wp2 / sw - wxp ** 2 / sw ** 2))
+        return np.array([xyz0, rms, emit])
+
+    def spectrum(self, lo, hi, nbins, quantity="gamma", sid=0):
+        """weighted histogram of ``gamma`` or ``px`` of a species: ``np.histogram(q, nbins, (lo, hi), weights=w)[0]``"""
+        out = np.zeros(int(nbins))
+        self._check(self.lib.chimera_engine_spectrum(self._h, int(sid), {"gamma": 0, "px": 1}[quantity], ctypes.c_double(lo),
+                                                     ctypes.c_double(hi), _i64(nbins), ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def lineout(self, name, ir=0, m=0, l=0):
+        """``A[:, ir, m, l]`` of a named complex array, e.g. ``lineout('EB', 0, 0, 0)`` = the on-axis wake field"""
+        nx = self.cfg.nx_slab if (self.slab and name not in ("J", "Rho", "BckGrndRho", "EB")) else self.setup.Args["Nx"]
+        out = np.zeros(nx, dtype=np.complex128)
+        self._check(self.lib.chimera_engine_lineout(self._h, name.encode(), _i64(ir), _i64(m), _i64(l),
+                                                    ctypes.c_void_p(out.ctypes.data)))
+        return out
+
     def count(self, sid=0):
         n = _i64()
         self._check(self.lib.chimera_engine_species_count(self._h, sid, ctypes.byref(n)))

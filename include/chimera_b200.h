@@ -237,6 +237,17 @@ int chimera_engine_move_window(chimera_engine* e, double shiftX);
 int chimera_engine_append_particles(chimera_engine* e, int species, const double* coords, const double* momenta,
                                     const double* weights, chb_i64 n);
 int chimera_engine_sort(chimera_engine* e, int on_halfstep, double left_margin);
+/* ---- integrated diagnostics on the device (moduls/diagnostics.py) ----
+ * field_energy: nrg_out (diagnostics.py:109) before its roll: out[kx] = sum_{kr,m} EnergyFact[kx,kr,m] *
+ *               sum_{c<3} |EG_fb[kx,kr,m,c]|^2; energy_fact (nx,nkr,nm) float64 host/device on the first call, NULL later
+ * beam_moments: the sums behind get_beam_envelops (diagnostics.py:174) on coords_halfstep / momenta:
+ *               out[0] = sum w; per axis c: out[1+5c..5+5c] = sum w x, w x^2, w p^2, w x p, w p
+ * spectrum:     weighted histogram (numpy.histogram rule) of gamma (quantity 0) or p_x (quantity 1)
+ * lineout:      out[ix] = A[ix, ir, m, l] (complex, nx values) of a named grid or spectral array */
+int chimera_engine_field_energy(chimera_engine* e, const double* energy_fact, double* out);
+int chimera_engine_beam_moments(chimera_engine* e, int species, double* out16);
+int chimera_engine_spectrum(chimera_engine* e, int species, int quantity, double lo, double hi, chb_i64 nbins, double* hist);
+int chimera_engine_lineout(chimera_engine* e, const char* name, chb_i64 ir, chb_i64 m, chb_i64 l, double* out);
 int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np);
 int chimera_engine_get_species(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
                                double* weights);

@@ -347,3 +347,39 @@ def test_engine_moving_window(ofim, gfim, name, ions):
     eng.step(2)
     compare_state(ref, eng, 20 * TOL)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["real_m2", "env_m3"])
+def test_engine_device_diagnostics(ofim, gfim, name):
+    """NEXT-3: the reductions behind nrg_out / get_beam_envelops / energy spectrum / on-axis line-outs computed on
+    the device against the reference's numpy expressions (moduls/diagnostics.py:109-124, 174-207) on downloaded state"""
+    S, ref, eng = build_pair(ofim, name, 71, amp=0.2)
+    a = S.Args
+    eng.make_halfstep()
+    eng.step(5)
+    eg = eng.download("EG_fb")
+    dat = ((np.abs(eg[:, :, :, :3]) ** 2).sum(-1) * a["EnergyFact"]).sum(-1).sum(-1)
+    want = np.r_[dat[dat.shape[0] // 2 + 1:], dat[:dat.shape[0] // 2 + 1]]
+    for _ in range(2):  # second call: cached table
+        assert_close(eng.nrg_out(), want, 1e-12, "nrg_out")
+    _, xh, p, w = eng.particles(0)
+    sw = w.sum()
+    x0 = [(xh[c] * w).sum() / sw for c in range(3)]
+    rms = [np.sqrt((xh[c] ** 2 * w).sum() / sw - x0[c] ** 2) for c in range(3)]
+    emit = [np.sqrt((xh[c] ** 2 * w).sum() / sw * (p[c] ** 2 * w).sum() / sw - (xh[c] * p[c] * w).sum() ** 2 / sw ** 2) for c in range(3)]
+    got = eng.get_beam_envelops(0)
+    assert np.allclose(got, np.array([x0, rms, emit]), rtol=1e-9, atol=1e-12), (got, x0, rms, emit)
+    assert np.isclose(eng.beam_moments(0)[0], sw, rtol=1e-13)  # total charge
+    gam = np.sqrt(1 + (p ** 2).sum(0))
+    lo, hi = gam.min(), gam.max()
+    h = eng.spectrum(lo, hi, 50, "gamma")
+    hw = np.histogram(gam, 50, (lo, hi), weights=w)[0]
+    assert np.abs(h - hw).max() <= 1e-12 * np.abs(hw).max() + 2 * np.abs(w).max()  # a value on a bin edge may round either way
+    assert np.isclose(h.sum(), hw.sum(), rtol=1e-12)
+    hp = eng.spectrum(p[0].min(), p[0].max(), 33, "px")
+    assert np.isclose(hp.sum(), sw, rtol=1e-12)
+    eb = eng.download("EB")
+    assert np.array_equal(eng.lineout("EB", 0, 0, 0), eb[:, 0, 0, 0])
+    assert np.array_equal(eng.lineout("EB", 3, a["Mtot"] - 1, 4), eb[:, 3, a["Mtot"] - 1, 4])
+    assert np.array_equal(eng.lineout("EG_fb", 2, 0, 5), eg[:, 2, 0, 5])
+    eng.close()
