@@ -377,7 +377,7 @@ int ph_deposit_rho(chimera_engine* e, int from_bg) {
   const i64 n = c.nx * c.nrn * c.nm;
   if (from_bg) CHB_CUDA(cudaMemcpyAsync(e->A("Rho"), e->A("BckGrndRho"), sizeof(cd) * n, cudaMemcpyDeviceToDevice, e->st));
   else CHB_CUDA(cudaMemsetAsync(e->A("Rho"), 0, sizeof(cd) * n, e->st));
-  CHB_TRY(deposit_species(e, 0, e->A("Rho"), false, false));
+  CHB_TRY(deposit_species(e, 0, e->A("Rho"), false, c.static_kick != 0));  // chimera_main.py:186: coords_halfstep
   return launch_ghost_fold(e->st, e->A("Rho"), c.nx, c.nrn, c.nm);
 }
 
@@ -446,6 +446,41 @@ int ph_maxwell(chimera_engine* e) {
                                e->arr["PSATD_E"].p, e->arr["PSATD_G"].p, 5, 0, P);
   return launch_maxwell_push(e->st, e->A("EG_fb"), e->A("J_fb"), nullptr, nullptr, e->arr["PSATD_E"].p, e->arr["PSATD_G"].p,
                              3, c.coef_complex, P);
+}
+
+// chimera_main.py:118-125 update_fields under 'StaticKick': the field is rebuilt from zero every step as the
+// quasi-static field of each species' charge and current moving with its mean momentum
+int ph_static_fields(chimera_engine* e) {
+  const auto& c = e->cfg;
+  if (slab(e)) { set_error("StaticKick schedule is not available on a kx-slab engine"); return 2; }
+  if (!e->arr.count("w")) { set_error("StaticKick schedule: engine was created without static_kick"); return 2; }
+  const i64 P = c.nx * c.nkr * c.nm;
+  FBCtx fb = fbctx(e);
+  CHB_CUDA(cudaMemsetAsync(e->A("EG_fb"), 0, sizeof(cd) * P * 6, e->st));
+  for (auto& s : e->sp) {
+    if (s.np == 0) continue;
+    // PXmean = sum(px w) / sum(w) (chimera_main.py:121-122): reduced on the device, 16 doubles to the host
+    double* d_m = e->scr.take_n<double>(16);
+    if (!d_m) return 6;
+    double m[16];
+    CHB_TRY(launch_beam_moments(e->st, s.xh, s.p, s.w, s.cap, s.np, d_m));
+    CHB_CUDA(cudaMemcpyAsync(m, d_m, sizeof(m), cudaMemcpyDeviceToHost, e->st));
+    CHB_CUDA(cudaStreamSynchronize(e->st));
+    const double px = m[5] / m[0];
+    const double beta0 = px / sqrt(1.0 + px * px);
+    if (c.poisson_iters > 0) {  // solvers.py:360-383 poiss_corr_stat (one pass, unless NoPoissonCorrection)
+      cd* DT = e->scr.take_n<cd>(c.nx);
+      if (!DT) return 6;
+      CHB_TRY(launch_dt_stat(e->st, DT, e->D("kx"), beta0, c.nx));
+      CHB_CUDA(cudaMemcpyAsync(e->A("vec_fb"), e->A("J_fb"), sizeof(cd) * P * 3, cudaMemcpyDeviceToDevice, e->st));
+      CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
+      CHB_TRY(launch_poiss_corr_stat(e->st, e->A("J_fb"), e->A("vec_fb"), e->A("gradRho_fb_nxt"), DT, e->D("PoissFact"), c.nx, P));
+    }
+    CHB_TRY(launch_maxwell_static_push(e->st, e->A("EG_fb"), e->A("J_fb"), e->A("gradRho_fb_nxt"), e->D("w"), e->D("kx"),
+                                       beta0, c.nx, P));
+    CHB_TRY(launch_field_drift(e->st, e->A("EG_fb"), e->D("kx"), beta0, c.dt, c.nx, c.nkr * c.nm * 6));
+  }
+  return 0;
 }
 
 int ph_init_push(chimera_engine* e) {
@@ -599,6 +634,7 @@ int run_phase(chimera_engine* e, int phase, double arg) {
     case CHB_PARTICLES_FUSED: rc = ph_particles_fused(e, arg != 0.0); break;
     case CHB_GATHER_PUSH: rc = ph_gather_push(e, arg); break;
     case CHB_ADD_BG: rc = ph_add_bg(e); break;
+    case CHB_STATIC_FIELDS: rc = ph_static_fields(e); break;
     default: set_error("unknown engine phase %d", phase); rc = 2;
   }
   if (e->profile) {
@@ -652,6 +688,10 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
       {"CPSATD1", Pf * 2 * C}, {"CPSATD2", Pf * 2 * C}, {"Rgrid", sizeof(double) * c.nrn}};
   for (auto& s : spec) {
     int rc = alloc_named(e, s.n, s.b);
+    if (rc) { chimera_engine_destroy(e); return rc; }
+  }
+  if (c.static_kick) {
+    int rc = alloc_named(e, "w", sizeof(double) * Pf);
     if (rc) { chimera_engine_destroy(e); return rc; }
   }
   if (slab(e)) {
@@ -1027,19 +1067,23 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
     const i64 istep = istep0 + k;
     const bool sort_now = c.sort_every > 0 && istep % c.sort_every == 0;
     e->dev_time = (double)(istep - 1) * c.dt;  // the pending gather + push closes step istep - 1 (make_device(istep - 1))
-    if (gather_pending && !sort_now && e->fuse) {
+    if (gather_pending && !sort_now && e->fuse && !c.static_kick) {
       CHB_TRY(run_phase(e, CHB_PARTICLES_FUSED, 1));
     } else {
       if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
       CHB_TRY(run_phase(e, CHB_PUSH_COORDS, 0));
       if (sort_now) CHB_TRY(run_phase(e, CHB_SORT, 1));
       CHB_TRY(run_phase(e, CHB_DEPOSIT_J, 0));
-      if (c.space_charge) CHB_TRY(run_phase(e, CHB_DEPOSIT_RHO, 1));
+      if (c.space_charge || c.static_kick) CHB_TRY(run_phase(e, CHB_DEPOSIT_RHO, 1));
     }
     CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
-    if (c.space_charge) CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
-    CHB_TRY(run_phase(e, CHB_POISSON, 0));
-    CHB_TRY(run_phase(e, CHB_MAXWELL, 0));
+    if (c.space_charge || c.static_kick) CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
+    if (c.static_kick) {
+      CHB_TRY(run_phase(e, CHB_STATIC_FIELDS, 0));
+    } else {
+      CHB_TRY(run_phase(e, CHB_POISSON, 0));
+      CHB_TRY(run_phase(e, CHB_MAXWELL, 0));
+    }
     CHB_TRY(run_phase(e, CHB_FIELDS_OUT, 0));
     gather_pending = true;
   }
@@ -1073,6 +1117,7 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   Species& s = e->sp[id];
   if (s.still) { set_error("step_host: species %d is still", id); return 2; }
+  if (e->cfg.static_kick) { set_error("step_host: no 'StaticKick' schedule; use chimera_engine_step"); return 2; }
   if (np < 0 || np > s.cap) { set_error("step_host: np=%lld exceeds the species capacity %lld", np, s.cap); return 2; }
   if (!coords || !coords_half || !momenta || !weights) { set_error("step_host: null particle buffer"); return 2; }
   const auto& c = e->cfg;

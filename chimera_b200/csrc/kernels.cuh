@@ -211,6 +211,9 @@ int launch_eb_correction(cudaStream_t st, cd* eb, i64 nxn, i64 nrn, i64 nm, int 
 int launch_maxwell_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const cd* gp, const void* C1,
                         const void* C2, int ncoef, int coef_complex, i64 P);
 int launch_maxwell_init_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const cd* C1, const cd* C2, i64 P);
+int launch_maxwell_static_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const double* w, const double* kx,
+                               double beta0, i64 nkx, i64 P);
+int launch_dt_stat(cudaStream_t st, cd* DT, const double* kx, double beta0, i64 nkx);
 int launch_poiss_corr(cudaStream_t st, cd* J, const cd* gdj, const cd* gn, const cd* gp, double dt_inv,
                       const double* w2inv, i64 P);
 int launch_poiss_corr_stat(cudaStream_t st, cd* J, const cd* gdj, const cd* gn, const cd* DT, const double* w2inv,

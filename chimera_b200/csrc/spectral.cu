@@ -152,6 +152,43 @@ int launch_maxwell_init_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn,
   return 0;
 }
 
+// solvers.py:333-358 maxwell_solver_stat with the coefficient tables formed on the fly from w, kx and beta0
+// (CPSATD1 = [i kx beta0 / den, -1 / den], CPSATD2 = [w^2 / den, i kx beta0 / den], den = w^2 - (kx beta0)^2),
+// then the update of maxwell_init_push (maxwell_solvers.f90:98-129)
+__global__ void __launch_bounds__(TPB) maxwell_static_push_k(cd* __restrict__ EG, const cd* __restrict__ J,
+                                                             const cd* __restrict__ gn, const double* __restrict__ w,
+                                                             const double* __restrict__ kx, double beta0, i64 nkx, i64 P) {
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double wv = __ldg(w + p), kxb = beta0 * __ldg(kx + p % nkx);
+  const double w2 = wv * wv, den = w2 - kxb * kxb;
+  const cd c10 = cmake(0.0, kxb / den), c11 = cmake(-1.0 / den, 0.0), c20 = cmake(w2 / den, 0.0), c21 = c10;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const cd j = ldg(J + p + P * l), a = ldg(gn + p + P * l);
+    EG[p + P * l] = cadd(cadd(EG[p + P * l], cmul(c10, j)), cmul(c11, a));
+    EG[p + P * (l + 3)] = cadd(cadd(EG[p + P * (l + 3)], cmul(c20, j)), cmul(c21, a));
+  }
+}
+int launch_maxwell_static_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const double* w, const double* kx,
+                               double beta0, i64 nkx, i64 P) {
+  if (P <= 0) return 0;
+  maxwell_static_push_k<<<grid_for(P, TPB), TPB, 0, st>>>(EG, J, gn, w, kx, beta0, nkx, P);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// DT = -i beta0 kx of solvers.py:376 poiss_corr_stat
+__global__ void __launch_bounds__(TPB) dt_stat_k(cd* __restrict__ DT, const double* __restrict__ kx, double beta0, i64 nkx) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nkx) DT[i] = cmake(0.0, -(beta0 * __ldg(kx + i)));
+}
+int launch_dt_stat(cudaStream_t st, cd* DT, const double* kx, double beta0, i64 nkx) {
+  dt_stat_k<<<grid_for(nkx, TPB), TPB, 0, st>>>(DT, kx, beta0, nkx);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 // maxwell_solvers.f90:131-164
 __global__ void __launch_bounds__(TPB) poiss_corr_k(cd* __restrict__ J, const cd* __restrict__ gdj,
                                                     const cd* __restrict__ gn, const cd* __restrict__ gp,

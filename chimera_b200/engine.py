@@ -26,7 +26,7 @@ _i64 = ctypes.c_longlong
 PHASES = (
     "push_coords", "sort", "deposit_J", "deposit_rho", "deposit_bg", "fb_in_J", "fb_in_rho", "poisson",
     "maxwell", "init_push", "fields_out", "gather_push", "add_bg", "fields_out_a", "fields_out_b",
-    "particles_fused",
+    "particles_fused", "static_fields",
 )
 PHASE_ID = {n: i for i, n in enumerate(PHASES)}
 
@@ -43,7 +43,7 @@ class EngineConfig(ctypes.Structure):
         ("dr", ctypes.c_double), ("dt", ctypes.c_double), ("kx0", ctypes.c_double),
         ("rcull2", ctypes.c_double), ("chunk_len", ctypes.c_double),
         ("und_a0", ctypes.c_double), ("und_lambda", ctypes.c_double), ("und_X0", ctypes.c_double),
-        ("und_Lx", ctypes.c_double), ("nx_slab", _i64), ("mirror_shift", ctypes.c_int),
+        ("und_Lx", ctypes.c_double), ("nx_slab", _i64), ("mirror_shift", ctypes.c_int), ("static_kick", ctypes.c_int),
     ]
 
 
@@ -89,10 +89,8 @@ class Engine:
         self.setup = setup
         a = setup.Args
         feats = a.get("Features", ())
-        if "StaticKick" in feats:
-            raise NotImplementedError("the resident engine has no 'StaticKick' schedule (chimera_main.py:118-125); use the "
-                                      "per-function drop-in chimera_b200.fimera for that stage")
         cfg = EngineConfig()
+        cfg.static_kick = int("StaticKick" in feats)
         cfg.env = int(setup.env)
         cfg.space_charge = int("SpaceCharge" in feats)
         if poisson_iters is None:
@@ -143,7 +141,7 @@ class Engine:
             ("InCurr", a["InCurr"]), ("Out", a["Out"]), ("DpS2S", a["DpS2S"]), ("DmS2S", a["DmS2S"]),
             ("kx", a["kx"]), ("kx_base", kx_base), ("DepFact", a["DepFact"]), ("PoissFact", a["PoissFact"]),
             ("PSATD_E", setup.PSATD_E), ("PSATD_G", setup.PSATD_G), ("Rgrid", a["Rgrid"]),
-        ):
+        ) + ((("w", a["w"]),) if cfg.static_kick else ()):
             self.upload(name, arr)
         if self.slab:
             gmap = np.empty(a["Nx"], dtype=np.int64)
@@ -409,7 +407,7 @@ class Engine:
         self._check(self.lib.chimera_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
 
     def _allreduce_grids(self):
-        names = ("J", "Rho") if self.cfg.space_charge else ("J",)
+        names = ("J", "Rho") if (self.cfg.space_charge or self.cfg.static_kick) else ("J",)
         for n in names:
             self._dist.all_reduce(self.device_tensor(n), group=self._group)
 
@@ -428,7 +426,7 @@ class Engine:
 
     def _deposit_and_reduce(self):
         self.run("deposit_J")
-        if self.cfg.space_charge:
+        if self.cfg.space_charge or self.cfg.static_kick:
             # the background charge enters the sum once (rank 0), chimera_main.py:189-190
             self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
         if self.world > 1:
@@ -448,7 +446,7 @@ class Engine:
             self.deposit_background()
         self._deposit_and_reduce()
         self.run("fb_in_J")
-        if self.cfg.space_charge:
+        if self.cfg.space_charge or self.cfg.static_kick:
             self.run("fb_in_rho")
             for p in px0:  # solvers.py:333-358, one static kick per species
                 c1, c2 = self.setup.static_coeffs(p)
@@ -465,6 +463,8 @@ class Engine:
             self._check(self.lib.chimera_engine_step(self._h, _i64(self.istep + 1), _i64(nsteps)))
             self.istep += nsteps
             return
+        if self.cfg.static_kick:
+            raise NotImplementedError("'StaticKick' schedule: single GPU, unsharded spectral solve only")
         # same schedule as chimera_engine_step (csrc/engine.cu): inside a multi-step call the particle work between
         # two field solves (gather + push of step k, push_coords + deposits of step k+1) is one fused kernel
         c = self.cfg

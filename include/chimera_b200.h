@@ -196,6 +196,10 @@ typedef struct chimera_engine_config {
    * (nx_slab - j - mirror_shift) mod nx_slab (reference f90/fb_math.f90:35-36 in slab-local form).           */
   chb_i64 nx_slab;
   int mirror_shift;
+  /* 'StaticKick' feature (chimera_main.py:106-125, 186): quasi-static field of each species' mean momentum, rebuilt
+   * from zero every step (poiss_corr_stat, maxwell_solver_stat, field_drift); rho is deposited on coords_halfstep.
+   * Needs the table "w" (nx,nkr,nm float64, solvers.py w) uploaded. */
+  int static_kick;
 } chimera_engine_config;
 
 typedef struct chimera_engine chimera_engine;
@@ -271,7 +275,8 @@ enum chimera_engine_phase {
   CHB_FIELDS_OUT_B = 14, /* kx-slab mode: rows of the all-gathered "EB_gath" -> EB, inverse x-FFT, eb_correction */
   CHB_PARTICLES_FUSED = 15, /* gather + device + push_velocs of one step and push_coords + dep_curr + dep_dens of the
                              next in one kernel (the per-particle work between two field solves); arg as DEPOSIT_RHO */
-  CHB_NPHASES = 16
+  CHB_STATIC_FIELDS = 16, /* chimera_main.py:118-125 update_fields with 'StaticKick' (needs every kx row)        */
+  CHB_NPHASES = 17
 };
 int chimera_engine_run(chimera_engine* e, int phase, double arg);
 /* nsteps x make_step on the engine's stream; istep0 = index of the first step (re-binning cadence) */

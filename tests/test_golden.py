@@ -24,7 +24,7 @@ from chimera_b200.solver_setup import SolverSetup
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NAMES = ["real_m2", "real_m3", "env_m1", "env_m3", "static_m2"]
-ENGINE_NAMES = ["real_m2", "real_m3", "env_m1", "env_m3"]  # the resident engine has no StaticKick schedule
+ENGINE_NAMES = NAMES
 
 
 def load(name):

@@ -383,3 +383,25 @@ def test_engine_device_diagnostics(ofim, gfim, name):
     assert np.array_equal(eng.lineout("EB", 3, a["Mtot"] - 1, 4), eb[:, 3, a["Mtot"] - 1, 4])
     assert np.array_equal(eng.lineout("EG_fb", 2, 0, 5), eg[:, 2, 0, 5])
     eng.close()
+
+
+def test_engine_static_kick_schedule(ofim, gfim):
+    """'StaticKick' (BASELINE config 2, space-charge demo stage 1; chimera_main.py:106-125, 186): the field is
+    rebuilt every step as the quasi-static field of the beam moving with its mean momentum (device reduction),
+    rho deposited on coords_halfstep; resident engine against the reference sequence on the oracle."""
+    from chimera_b200.engine import Engine
+
+    S = SolverSetup(copy.deepcopy(SETUPS["static_m2"]))
+    x, p, w = plasma(S, 2, 2, 91)
+    p[0] += 50.0  # the demo's beam: px = 50 (doc/space-charge-demo cell 7)
+    ref = RefRun(ofim, S, [RefSpecies(x, p, w)])
+    eng = Engine(S)
+    eng.add_species(x, p, w)
+    ref.make_halfstep(px0=(50.0,))
+    eng.make_halfstep(px0=(50.0,))
+    compare_state(ref, eng, TOL, names=("J", "Rho", "EG_fb", "EB"))
+    for _ in range(6):
+        ref.make_step()
+    eng.step(6)
+    compare_state(ref, eng, 50 * TOL, names=("J", "Rho", "EG_fb", "EB"))
+    eng.close()
