@@ -418,7 +418,7 @@ def run_e2e_per_call(a, torch, S, eng, state):
     x, xh, p, w, eg, g = state
     sp = RefSpecies.__new__(RefSpecies)
     sp.coords, sp.momenta, sp.weights, sp.coords_halfstep = x, p, w, xh
-    sp.push_fact, sp.still, sp.device, sp.chunks = -2 * np.pi, False, None, eng.chunks(0)
+    sp.push_fact, sp.still, sp.devices, sp.chunks = -2 * np.pi, False, [], eng.chunks(0)
     sp.EB = np.zeros((6, 0), order="F")
     run = RefRun(gfim, S, [sp], sort_every=0)
     run.Bck = eng.download("BckGrndRho")

@@ -5,6 +5,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cstdarg>
 #include <mutex>
+#include <vector>
 #include "../../include/chimera_b200.h"
 #include "fbops.cuh"
 
@@ -266,6 +267,53 @@ __global__ void __launch_bounds__(256) fill_pattern_k(double* __restrict__ a, i6
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;
   a[e] = (double)(long long)(z >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+}
+
+
+// ---- SR.f90 / utils.f90 (NEXT-4): host-buffer staging around the kernels of sr.cu
+static int sr_far_host(double* spect, const double* coords, const double* mprv, const double* mnxt, const double* wghts,
+                       int comp, double dt, const double* omega, const double* SinTh, const double* CosTh,
+                       const double* SinPh, const double* CosPh, i64 nt, i64 np, i64 nom, i64 nth, i64 nph) {
+  CALL_BEGIN();
+  if (nt < 0 || np < 0 || nom < 0 || nth < 0 || nph < 0) { set_error("sr_calc_far: negative extent"); return 2; }
+  if (!(dt != 0.0)) { set_error("sr_calc_far: dt must be non-zero"); return 2; }
+  const i64 ns = nom * nth * nph, ntr = 3 * nt * np;
+  if (ns == 0 || ntr == 0) return 0;
+  double* d_s = call.up(spect, ns); NEED(d_s);
+  double* d_x = call.up(coords, ntr); NEED(d_x);
+  double* d_a = call.up(mprv, ntr); NEED(d_a);
+  double* d_b = call.up(mnxt, ntr); NEED(d_b);
+  double* d_w = call.up(wghts, np); NEED(d_w);
+  double* d_o = call.up(omega, nom); NEED(d_o);
+  double* d_st = call.up(SinTh, nth); NEED(d_st);
+  double* d_ct = call.up(CosTh, nth); NEED(d_ct);
+  double* d_sp = call.up(SinPh, nph); NEED(d_sp);
+  double* d_cp = call.up(CosPh, nph); NEED(d_cp);
+  CHB_TRY(launch_sr_far(call.c.st, d_s, d_x, d_a, d_b, d_w, comp, dt, d_o, d_st, d_ct, d_sp, d_cp, nt, np, nom, nth, nph));
+  CHB_TRY(call.down(spect, d_s, ns));
+  return call.sync();
+}
+
+static int sr_near_host(double* spect, const double* coords, const double* mom, const double* wghts, int comp,
+                        double dt, const double* omega, const double* G1, const double* G2s, const double* G2c,
+                        int circ, double z_scr, i64 nt, i64 np, i64 nom, i64 n1, i64 n2) {
+  CALL_BEGIN();
+  if (nt < 0 || np < 0 || nom < 0 || n1 < 0 || n2 < 0) { set_error("sr_calc_near: negative extent"); return 2; }
+  if (comp < 0 || comp > 3) { set_error("sr_calc_near: comp must be 1, 2 or 3 (got %d)", comp); return 2; }
+  const i64 ns = nom * n1 * n2, ntr = 3 * nt * np;
+  if (ns == 0 || ntr == 0) return 0;
+  double* d_s = call.up(spect, ns); NEED(d_s);
+  double* d_x = call.up(coords, ntr); NEED(d_x);
+  double* d_m = call.up(mom, ntr); NEED(d_m);
+  double* d_w = call.up(wghts, np); NEED(d_w);
+  double* d_o = call.up(omega, nom); NEED(d_o);
+  double* d_1 = call.up(G1, n1); NEED(d_1);
+  double* d_2s = call.up(G2s, n2); NEED(d_2s);
+  double* d_2c = nullptr;
+  if (circ) { d_2c = call.up(G2c, n2); NEED(d_2c); }
+  CHB_TRY(launch_sr_near(call.c.st, d_s, d_x, d_m, d_w, comp, dt, d_o, d_1, d_2s, d_2c, circ, z_scr, nt, np, nom, n1, n2));
+  CHB_TRY(call.down(spect, d_s, ns));
+  return call.sync();
 }
 
 }  // namespace chb
@@ -705,6 +753,92 @@ int chimera_bench_gemm(chb_i64 nkx, chb_i64 K, chb_i64 N, int batch, int iters, 
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return 0;
+}
+
+
+/* ---- f90/SR.f90 ---------------------------------------------------------------------------------- */
+int chimera_sr_calc_far_tot(double* spect, const double* coords, const double* momenta_prv, const double* momenta_nxt,
+                            const double* wghts, double dt, const double* omega, const double* SinTh,
+                            const double* CosTh, const double* SinPh, const double* CosPh, chb_i64 nt, chb_i64 np,
+                            chb_i64 nom, chb_i64 nth, chb_i64 nph) {
+  return sr_far_host(spect, coords, momenta_prv, momenta_nxt, wghts, 0, dt, omega, SinTh, CosTh, SinPh, CosPh, nt, np, nom, nth, nph);
+}
+int chimera_sr_calc_far_comp(double* spect, const double* coords, const double* momenta_prv, const double* momenta_nxt,
+                             const double* wghts, int comp, double dt, const double* omega, const double* SinTh,
+                             const double* CosTh, const double* SinPh, const double* CosPh, chb_i64 nt, chb_i64 np,
+                             chb_i64 nom, chb_i64 nth, chb_i64 nph) {
+  /* SR.f90:219-227: any comp outside 1..3 integrates zero */
+  return sr_far_host(spect, coords, momenta_prv, momenta_nxt, wghts, comp >= 1 && comp <= 3 ? comp : -1, dt, omega, SinTh, CosTh, SinPh, CosPh, nt, np, nom, nth, nph);
+}
+int chimera_sr_calc_near_tot(double* spect, const double* coords, const double* momenta, const double* wghts, double dt,
+                             const double* omega, const double* Xgrid, const double* Ygrid, double z_scr, chb_i64 nt,
+                             chb_i64 np, chb_i64 nom, chb_i64 nx, chb_i64 ny) {
+  return sr_near_host(spect, coords, momenta, wghts, 0, dt, omega, Xgrid, Ygrid, nullptr, 0, z_scr, nt, np, nom, nx, ny);
+}
+int chimera_sr_calc_near_comp(double* spect, const double* coords, const double* momenta, const double* wghts, int comp,
+                              double dt, const double* omega, const double* Xgrid, const double* Ygrid, double z_scr,
+                              chb_i64 nt, chb_i64 np, chb_i64 nom, chb_i64 nx, chb_i64 ny) {
+  if (comp < 1 || comp > 3) { set_error("sr_calc_near_comp: comp must be 1, 2 or 3 (got %d)", comp); return 2; }
+  return sr_near_host(spect, coords, momenta, wghts, comp, dt, omega, Xgrid, Ygrid, nullptr, 0, z_scr, nt, np, nom, nx, ny);
+}
+int chimera_sr_calc_nearcirc_tot(double* spect, const double* coords, const double* momenta, const double* wghts,
+                                 double dt, const double* omega, const double* Rgrid, const double* SinPh,
+                                 const double* CosPh, double z_scr, chb_i64 nt, chb_i64 np, chb_i64 nom, chb_i64 nr,
+                                 chb_i64 nph) {
+  return sr_near_host(spect, coords, momenta, wghts, 0, dt, omega, Rgrid, SinPh, CosPh, 1, z_scr, nt, np, nom, nr, nph);
+}
+int chimera_sr_calc_nearcirc_comp(double* spect, const double* coords, const double* momenta, const double* wghts,
+                                  int comp, double dt, const double* omega, const double* Rgrid, const double* SinPh,
+                                  const double* CosPh, double z_scr, chb_i64 nt, chb_i64 np, chb_i64 nom, chb_i64 nr,
+                                  chb_i64 nph) {
+  if (comp < 1 || comp > 3) { set_error("sr_calc_nearcirc_comp: comp must be 1, 2 or 3 (got %d)", comp); return 2; }
+  return sr_near_host(spect, coords, momenta, wghts, comp, dt, omega, Rgrid, SinPh, CosPh, 1, z_scr, nt, np, nom, nr, nph);
+}
+
+/* ---- f90/utils.f90 ------------------------------------------------------------------------------- */
+int chimera_intens_profo(double* PWR_RO, const double* Fld, int NO, chb_i64 nxn, chb_i64 nrn, chb_i64 nm) {
+  CALL_BEGIN();
+  if (NO < 1 || nxn < 1 || nrn < 2 || nm < 1 || (nm % 2) == 0 || nm > 4096) {
+    set_error("intens_profo: bad shape (NO=%d, Fld %lld x %lld x %lld x 3; mode slots must be 2*nkO+1)", NO, nxn, nrn, nm);
+    return 2;
+  }
+  /* e^{i m theta_iO} by the reference's repeated multiplication (utils.f90:31-45) */
+  const i64 nko = (nm - 1) / 2;
+  const double pi = 4.0 * atan(1.0);
+  std::vector<double> tab((size_t)(2 * NO * nm));
+  auto T = [&](int o, i64 m) -> double* { return tab.data() + 2 * (o + (i64)NO * m); };
+  double osr = 1.0, osi = 0.0;
+  const double pr = cos(2.0 * pi / (double)(NO - 1)), pim = sin(2.0 * pi / (double)(NO - 1));
+  for (int o = 0; o < NO; ++o) {
+    if (o > 0) { const double r = osr * pr - osi * pim, i = osr * pim + osi * pr; osr = r; osi = i; }
+    const double d = osr * osr + osi * osi, pmr = osr / d, pmi = -osi / d;
+    T(o, nko)[0] = 1.0; T(o, nko)[1] = 0.0;
+    for (i64 k = 1; k <= nko; ++k) {
+      const double* a = T(o, nko + k - 1);
+      T(o, nko + k)[0] = a[0] * osr - a[1] * osi; T(o, nko + k)[1] = a[0] * osi + a[1] * osr;
+      const double* b = T(o, nko - k + 1);
+      T(o, nko - k)[0] = b[0] * pmr - b[1] * pmi; T(o, nko - k)[1] = b[0] * pmi + b[1] * pmr;
+    }
+  }
+  double* d_f = call.up(Fld, 2 * nxn * nrn * nm * 3); NEED(d_f);
+  double* d_t = call.up(tab.data(), (i64)tab.size()); NEED(d_t);
+  double* d_p = call.dev<double>((i64)NO * (nrn - 1)); NEED(d_p);
+  CHB_TRY(launch_intens_profo(call.c.st, d_p, (const cd*)d_f, (const cd*)d_t, NO, nxn, nrn, nm));
+  CHB_TRY(call.down(PWR_RO, d_p, (i64)NO * (nrn - 1)));
+  return call.sync();
+}
+int chimera_density_2x(const double* x, const double* y, const double* wght, const double* grid, int bins_x,
+                       int bins_y, double* dens, chb_i64 n_part) {
+  CALL_BEGIN();
+  if (bins_x < 1 || bins_y < 1 || n_part < 0) { set_error("density_2x: bins_x, bins_y >= 1 expected"); return 2; }
+  double* d_x = call.up(x, n_part); NEED(d_x);
+  double* d_y = call.up(y, n_part); NEED(d_y);
+  double* d_w = call.up(wght, n_part); NEED(d_w);
+  const i64 nd = (i64)(bins_x + 5) * (bins_y + 5);
+  double* d_d = call.dev<double>(nd); NEED(d_d);
+  CHB_TRY(launch_density_2x(call.c.st, d_d, d_x, d_y, d_w, grid, bins_x, bins_y, n_part));
+  CHB_TRY(call.down(dens, d_d, nd));
+  return call.sync();
 }
 
 }  // extern "C"

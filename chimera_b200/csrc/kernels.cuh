@@ -233,4 +233,20 @@ int launch_axpby(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, Un
 //   out (+)= i * kx * a   (sign = +-1)
 int launch_ikx(cudaStream_t st, cd* out, const cd* a, const double* kx, double sign, int acc, i64 nkx, i64 ncols);
 
+
+// ---- sr.cu : synchrotron-radiation spectra from stored tracks (SR.f90) and utils.f90 diagnostics helpers
+// comp = 0: all three components (*_tot); 1..3: one component (*_comp)
+int launch_sr_far(cudaStream_t st, double* spect, const double* coords, const double* mprv, const double* mnxt,
+                  const double* wghts, int comp, double dt, const double* omega, const double* SinTh,
+                  const double* CosTh, const double* SinPh, const double* CosPh, i64 nt, i64 np, i64 nom, i64 nth,
+                  i64 nph);
+// circ = 0: Cartesian screen, G1 = Xgrid(n1), G2s = Ygrid(n2); circ = 1: polar screen, G1 = Rgrid, G2s/G2c = Sin/CosPh
+int launch_sr_near(cudaStream_t st, double* spect, const double* coords, const double* mom, const double* wghts,
+                   int comp, double dt, const double* omega, const double* G1, const double* G2s, const double* G2c,
+                   int circ, double z_scr, i64 nt, i64 np, i64 nom, i64 n1, i64 n2);
+// phase(NO, nm): e^{i m theta} table; pwr(NO, nrn-1)
+int launch_intens_profo(cudaStream_t st, double* pwr, const cd* fld, const cd* phase, int NO, i64 nxn, i64 nrn, i64 nm);
+int launch_density_2x(cudaStream_t st, double* dens, const double* x, const double* y, const double* w,
+                      const double grid4[4], int bx, int by, i64 n);
+
 }  // namespace chb

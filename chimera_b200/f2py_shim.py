@@ -509,5 +509,81 @@ def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> type
     mod.planewave = _device("planewave", 7)
     mod.gaussbeam = _device("gaussbeam", 8, has_a0=True)
 
+    # ------------------------------------------------------------------ SR.f90 (NEXT-4)
+    # spect(nom, n1, n2) intent(in,out); tracks (3, nt, np); call sites moduls/SR.py:165-215
+    def _sr_tracks(spect, coords, wghts, omega):
+        spect = _inout(spect, _F8, "spect", (None, None, None))
+        coords = _in(coords, _F8, "coords", (3, None, None))
+        nt, n = coords.shape[1], coords.shape[2]
+        wghts = _in(wghts, _F8, "wghts", (n,))
+        omega = _in(omega, _F8, "omega", (spect.shape[0],))
+        return spect, coords, wghts, omega, nt, n
+
+    def _sr_far(name, has_comp):
+        def f(spect, coords, momenta_prv, momenta_nxt, wghts, *rest):
+            rest = list(rest)
+            comp = [_int(int(rest.pop(0)))] if has_comp else []
+            dt, omega, sinth, costh, sinph, cosph = rest
+            spect, coords, wghts, omega, nt, n = _sr_tracks(spect, coords, wghts, omega)
+            nom, nth, nph = spect.shape
+            mp = _in(momenta_prv, _F8, "momenta_prv", (3, nt, n))
+            mn = _in(momenta_nxt, _F8, "momenta_nxt", (3, nt, n))
+            sinth, costh = _in(sinth, _F8, "sinth", (nth,)), _in(costh, _F8, "costh", (nth,))
+            sinph, cosph = _in(sinph, _F8, "sinph", (nph,)), _in(cosph, _F8, "cosph", (nph,))
+            call(name, spect, coords, mp, mn, wghts, *comp, _dbl(dt), omega, sinth, costh, sinph, cosph,
+                 _i64(nt), _i64(n), _i64(nom), _i64(nth), _i64(nph))
+            return spect
+
+        f.__name__ = name
+        return f
+
+    def _sr_near(name, has_comp, circ):
+        def f(spect, coords, momenta, wghts, *rest):
+            rest = list(rest)
+            comp = [_int(int(rest.pop(0)))] if has_comp else []
+            spect, coords, wghts, omega, nt, n = _sr_tracks(spect, coords, wghts, rest[1])
+            nom, n1, n2 = spect.shape
+            mom = _in(momenta, _F8, "momenta", (3, nt, n))
+            if circ:
+                dt, _, rgrid, sinph, cosph, z_scr = rest
+                grids = [_in(rgrid, _F8, "rgrid", (n1,)), _in(sinph, _F8, "sinph", (n2,)), _in(cosph, _F8, "cosph", (n2,))]
+            else:
+                dt, _, xgrid, ygrid, z_scr = rest
+                grids = [_in(xgrid, _F8, "xgrid", (n1,)), _in(ygrid, _F8, "ygrid", (n2,))]
+            call(name, spect, coords, mom, wghts, *comp, _dbl(dt), omega, *grids, _dbl(z_scr),
+                 _i64(nt), _i64(n), _i64(nom), _i64(n1), _i64(n2))
+            return spect
+
+        f.__name__ = name
+        return f
+
+    mod.sr_calc_far_tot = _sr_far("sr_calc_far_tot", False)
+    mod.sr_calc_far_comp = _sr_far("sr_calc_far_comp", True)
+    mod.sr_calc_near_tot = _sr_near("sr_calc_near_tot", False, False)
+    mod.sr_calc_near_comp = _sr_near("sr_calc_near_comp", True, False)
+    mod.sr_calc_nearcirc_tot = _sr_near("sr_calc_nearcirc_tot", False, True)
+    mod.sr_calc_nearcirc_comp = _sr_near("sr_calc_nearcirc_comp", True, True)
+
+    # ------------------------------------------------------------------ utils.f90 (diagnostics helpers)
+    @export
+    def intens_profo(fld, no):
+        fld = _in(fld, _C16, "fld", (None, None, None, 3))
+        nxn, nrn, nm = fld.shape[:3]
+        if nm % 2 == 0:  # f2py: (shape(Fld,2)-1)/2 must reproduce the extent
+            raise FimeraError("intens_profo: shape(fld,2) must be 2*nko+1, got %d" % nm)
+        pwr = np.zeros((int(no), nrn - 1), dtype=_F8, order="F")
+        call("intens_profo", pwr, fld, _int(int(no)), _i64(nxn), _i64(nrn), _i64(nm))
+        return pwr
+
+    @export
+    def density_2x(x, y, wght, grid, bins_x, bins_y):
+        x = _in(x, _F8, "x", (None,))
+        n = x.shape[0]
+        y, wght = _in(y, _F8, "y", (n,)), _in(wght, _F8, "wght", (n,))
+        grid = _in(grid, _F8, "grid", (4,))
+        dens = np.zeros((int(bins_x) + 5, int(bins_y) + 5), dtype=_F8, order="F")
+        call("density_2x", x, y, wght, grid, _int(int(bins_x)), _int(int(bins_y)), dens, _i64(n))
+        return dens
+
     mod.API_NAMES = sorted(k for k, v in vars(mod).items() if callable(v) and not k.startswith("_") and k != "error")
     return mod

@@ -157,6 +157,41 @@ int chimera_undul_mapped_tap(const double* coord, double* Fld, double t, const d
 int chimera_planewave(const double* coord, double* Fld, double t, const double* params, chb_i64 np); /* :205 */
 int chimera_gaussbeam(const double* coord, double* Fld, double time, double a0, const double* params, chb_i64 np); /* :254 */
 
+/* ---- f90/SR.f90: synchrotron-radiation spectra from stored tracks (moduls/SR.py:165-215) ----------- */
+/* spect(nom,n1,n2) inout (accumulated into); coords/momenta (3,nt,np); comp = 1,2,3 picks x,y,z (SR.py:168).
+ * far field  :18 / :139   angles theta (n1 = nth) x phi (n2 = nph) given as sines and cosines
+ * near field :352 / :256  Cartesian screen Xgrid(nx) x Ygrid(ny) at z_scr
+ * near field :546 / :449  polar screen Rgrid(nr) x phi(nph) at z_scr */
+int chimera_sr_calc_far_tot(double* spect, const double* coords, const double* momenta_prv, const double* momenta_nxt,
+                            const double* wghts, double dt, const double* omega, const double* SinTh,
+                            const double* CosTh, const double* SinPh, const double* CosPh, chb_i64 nt, chb_i64 np,
+                            chb_i64 nom, chb_i64 nth, chb_i64 nph);
+int chimera_sr_calc_far_comp(double* spect, const double* coords, const double* momenta_prv, const double* momenta_nxt,
+                             const double* wghts, int comp, double dt, const double* omega, const double* SinTh,
+                             const double* CosTh, const double* SinPh, const double* CosPh, chb_i64 nt, chb_i64 np,
+                             chb_i64 nom, chb_i64 nth, chb_i64 nph);
+int chimera_sr_calc_near_tot(double* spect, const double* coords, const double* momenta, const double* wghts, double dt,
+                             const double* omega, const double* Xgrid, const double* Ygrid, double z_scr, chb_i64 nt,
+                             chb_i64 np, chb_i64 nom, chb_i64 nx, chb_i64 ny);
+int chimera_sr_calc_near_comp(double* spect, const double* coords, const double* momenta, const double* wghts, int comp,
+                              double dt, const double* omega, const double* Xgrid, const double* Ygrid, double z_scr,
+                              chb_i64 nt, chb_i64 np, chb_i64 nom, chb_i64 nx, chb_i64 ny);
+int chimera_sr_calc_nearcirc_tot(double* spect, const double* coords, const double* momenta, const double* wghts,
+                                 double dt, const double* omega, const double* Rgrid, const double* SinPh,
+                                 const double* CosPh, double z_scr, chb_i64 nt, chb_i64 np, chb_i64 nom, chb_i64 nr,
+                                 chb_i64 nph);
+int chimera_sr_calc_nearcirc_comp(double* spect, const double* coords, const double* momenta, const double* wghts,
+                                  int comp, double dt, const double* omega, const double* Rgrid, const double* SinPh,
+                                  const double* CosPh, double z_scr, chb_i64 nt, chb_i64 np, chb_i64 nom, chb_i64 nr,
+                                  chb_i64 nph);
+
+/* ---- f90/utils.f90: diagnostics helpers the driver reaches through fimera -------------------------- */
+/* intens_profO :18  PWR_RO(NO, nrn-1) out; Fld(nxn,nrn,nm,3) complex, nm = 2 nkO + 1 (diagnostics.py:136,147,158) */
+int chimera_intens_profo(double* PWR_RO, const double* Fld, int NO, chb_i64 nxn, chb_i64 nrn, chb_i64 nm);
+/* DENSITY_2x :210   dens(bins_x+5, bins_y+5) out; grid = (xmin, xmax, ymin, ymax) */
+int chimera_density_2x(const double* x, const double* y, const double* wght, const double* grid, int bins_x,
+                       int bins_y, double* dens, chb_i64 n_part);
+
 /* ---- microbenchmark hook: the DHT contraction alone on device-resident random data ----------- */
 /* C[2nkx x N] = A[2nkx x K] . B[K x N], `batch` independent problems, `iters` timed launches;
  * returns the mean milliseconds per launch (CUDA events) in *ms. */

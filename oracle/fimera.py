@@ -17,9 +17,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 def build(force=False):
     """Compile liboracle.so / liboracle_fast.so from chimera_oracle.cpp (g++, OpenMP)."""
-    src = os.path.join(_HERE, "chimera_oracle.cpp")
+    srcs = [os.path.join(_HERE, n) for n in ("chimera_oracle.cpp", "sr_utils_oracle.cpp")]
     libs = [os.path.join(_HERE, n) for n in ("liboracle.so", "liboracle_fast.so")]
-    stale = force or any((not os.path.exists(l)) or os.path.getmtime(l) < os.path.getmtime(src) for l in libs)
+    newest = max(os.path.getmtime(s) for s in srcs)
+    stale = force or any((not os.path.exists(l)) or os.path.getmtime(l) < newest for l in libs)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "all"])
 

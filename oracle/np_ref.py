@@ -328,3 +328,117 @@ def gaussbeam(coord, fld, t, a0, params):
     out[2] += E
     out[4] -= axis * E
     return out
+
+
+# ---- f90/SR.f90 --------------------------------------------------------------------------------
+# Whole-array form: all (time, particle, pixel) phases and amplitudes at once, the frequency axis last;
+# tracks are (3, nt, np) as in moduls/SR.py:141-151.
+def _guarded_integral(amp, phase, limit, omega):
+    """sum over time of amp * exp(i omega phase) where omega*|phase(it) - phase(it-1)| < limit
+    (phase(0) := 0: the reference starts C3_prev / phase_prv at zero, SR.f90:65,302).
+    amp (..., nt) complex-able, phase (..., nt) -> (..., nom)"""
+    prev = np.concatenate([np.zeros_like(phase[..., :1]), phase[..., :-1]], axis=-1)
+    dph = np.abs(phase - prev)
+    keep = dph[..., None] * omega < limit                      # (..., nt, nom)
+    e = np.exp(1j * phase[..., None] * omega)
+    return (np.where(keep, e, 0.0) * amp[..., None]).sum(-2)
+
+
+def sr_calc_far(spect, coords, mom_prv, mom_nxt, wghts, dt, omega, sin_th, cos_th, sin_ph, cos_ph, comp=0):
+    """SR.f90:18-137 (comp=0) / :139-254 (comp=1..3): far-field Lienard-Wiechert spectrum
+    d2W/dOmega domega ~ |int n x ((n - beta) x beta') / (1 - n.beta)^2 e^{i omega (t - n.r)} dt|^2,
+    in the reference's component form C4 = (C1 (n - beta) - C2 beta') / C2^2."""
+    x = np.moveaxis(np.asarray(coords), 0, -1)[:, :, ::-1].transpose(1, 0, 2)   # (np, nt, [z,y,x] -> reversed)
+    bp = np.asarray(mom_prv) / np.sqrt(1.0 + (np.asarray(mom_prv) ** 2).sum(0))
+    bn = np.asarray(mom_nxt) / np.sqrt(1.0 + (np.asarray(mom_nxt) ** 2).sum(0))
+    acc = np.moveaxis((bn - bp) / dt, 0, -1).transpose(1, 0, 2)                 # (np, nt, 3) index 0 = longitudinal
+    vel = np.moveaxis(0.5 * (bn + bp), 0, -1).transpose(1, 0, 2)
+    xx = np.moveaxis(np.asarray(coords), 0, -1).transpose(1, 0, 2)
+    nt = xx.shape[1]
+    tt = np.arange(1, nt + 1) * dt
+    out = np.array(spect, dtype=float, order="F")
+    for iph in range(len(sin_ph)):
+        for ith in range(len(sin_th)):
+            n = np.array([cos_th[ith], sin_th[ith] * sin_ph[iph], sin_th[ith] * cos_ph[iph]])  # (x, y, z) of the reference
+            c2 = 1.0 - vel @ n
+            c1 = acc @ n
+            c3 = 2.0 * np.pi * (tt[None, :] - xx @ n)
+            c4 = (c1[..., None] * (n - vel) - c2[..., None] * acc) / c2[..., None] ** 2 * dt   # (np, nt, 3)
+            comps = range(3) if comp == 0 else ([comp - 1] if 1 <= comp <= 3 else [])
+            tot = np.zeros((xx.shape[0], len(omega)))
+            for k in comps:
+                tot += np.abs(_guarded_integral(c4[..., k], c3, np.pi, np.asarray(omega))) ** 2
+            out[:, ith, iph] += (np.abs(wghts)[:, None] * tot).sum(0)
+    return out
+
+
+def sr_calc_near(spect, coords, mom, wghts, dt, omega, g1, g2, z_scr, comp=0, circ=None):
+    """SR.f90:256-447 (Cartesian screen: g1 = X, g2 = Y) and :449-642 (polar: g1 = R, circ = (SinPh, CosPh)).
+    Integrand (i omega (beta - n)/R + n / (2 pi R^2)) dt e^{2 pi i omega (t + R)}; the screen x pairs with the
+    third track coordinate, y with the second, z_scr with the first (:305-307)."""
+    xx = np.moveaxis(np.asarray(coords), 0, -1).transpose(1, 0, 2)   # (np, nt, 3)
+    u = np.asarray(mom)
+    vel = np.moveaxis(u / np.sqrt(1.0 + (u ** 2).sum(0)), 0, -1).transpose(1, 0, 2)
+    nt = xx.shape[1]
+    tt = np.arange(1, nt + 1) * dt
+    out = np.array(spect, dtype=float, order="F")
+    n1, n2 = out.shape[1:]
+    om = np.asarray(omega)
+    for i1 in range(n1):
+        for i2 in range(n2):
+            if circ is None:
+                xs, ys = g1[i1], g2[i2]
+            else:
+                xs, ys = g1[i1] * circ[1][i2], g1[i1] * circ[0][i2]
+            d = np.array([z_scr, ys, xs]) - xx
+            r0 = np.sqrt((d ** 2).sum(-1))
+            n = d / r0[..., None]
+            phase = 2.0 * np.pi * (tt[None, :] + r0)
+            a1 = dt / r0[..., None] * (vel - n)
+            a2 = dt / r0[..., None] ** 2 / (2.0 * np.pi) * n
+            prev = np.concatenate([np.zeros_like(phase[:, :1]), phase[:, :-1]], axis=1)
+            keep = np.abs(phase - prev)[..., None] * om < 2.0 * np.pi
+            e = np.where(keep, np.exp(1j * phase[..., None] * om), 0.0)          # (np, nt, nom)
+            comps = range(3) if comp == 0 else [comp - 1]
+            tot = np.zeros((xx.shape[0], len(om)))
+            for k in comps:
+                integ = ((1j * a1[..., k, None] * om + a2[..., k, None]) * e).sum(1)
+                tot += np.abs(integ) ** 2
+            out[:, i1, i2] += (np.abs(wghts)[:, None] * tot).sum(0)
+    return out
+
+
+# ---- f90/utils.f90 -----------------------------------------------------------------------------
+def intens_profo(fld, no):
+    """utils.f90:18-57: |sum_m e^{i m theta} F_m|^2 summed over x and the 3 components, on `no` angles
+    theta_j = 2 pi j/(no-1); mode slots ordered -nko..nko; ghost radial node dropped."""
+    nm = fld.shape[2]
+    nko = (nm - 1) // 2
+    theta = 2.0 * np.pi * np.arange(no) / (no - 1.0)
+    ph = np.exp(1j * np.arange(-nko, nko + 1)[None, :] * theta[:, None])      # (no, nm)
+    s = np.einsum("om,xrml->oxrl", ph, fld[:, 1:])
+    return (np.abs(s) ** 2).sum((1, 3))
+
+
+def density_2x(x, y, wght, grid, bins_x, bins_y):
+    """utils.f90:210-272: weighted 2-D histogram with the reference's 5-node shape
+    S = (|d^3|/3 [d<0], 1/4 - d/2 + d^3/3, 1/2 - |d^3|/3, 1/4 + d/2 - d^3/3, |d^3|/3 [d>=0])."""
+    dxg, dyg = (grid[1] - grid[0]) / bins_x, (grid[3] - grid[2]) / bins_y
+    sel = (x >= grid[0]) & (x <= grid[0] + dxg * bins_x) & (y >= grid[2]) & (y <= grid[2] + dyg * bins_y)
+    x, y, w = x[sel], y[sel], wght[sel]
+
+    def shape(u, orig, dlt):
+        k = np.floor((u - orig) / dlt + 0.5).astype(int)
+        d = (u - (dlt * k + orig)) / dlt
+        d3 = d ** 3
+        s = np.stack([np.where(d < 0, np.abs(d3) / 3, 0.0), 0.25 - 0.5 * d + d3 / 3, 0.5 - np.abs(d3) / 3,
+                      0.25 + 0.5 * d - d3 / 3, np.where(d >= 0, np.abs(d3) / 3, 0.0)])
+        return k, s
+
+    kx, sx = shape(x, grid[0], dxg)
+    ky, sy = shape(y, grid[2], dyg)
+    dens = np.zeros((bins_x + 5, bins_y + 5), order="F")
+    for i in range(5):
+        for j in range(5):
+            np.add.at(dens, (kx + i, ky + j), w * sx[i] * sy[j])
+    return dens / dxg / dyg
