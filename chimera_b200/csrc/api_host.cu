@@ -199,7 +199,7 @@ static int fb_math_host(FBMathOp op, int env, double* out, const double* in, con
     case OP_ROT: CHB_TRY(fb_rot_dev(fb, d_out, d_in, PP, PM, d_kx, d)); break;
     case OP_GRAD: CHB_TRY(fb_grad_dev(fb, d_out, d_in, PP, PM, d_kx, d)); break;
     case OP_DIV: CHB_TRY(fb_div_dev(fb, d_out, d_in, PP, PM, d_kx, d)); break;
-    case OP_GRADDIV: CHB_TRY(fb_graddiv_dev(fb, d_in, PP, PM, d_kx, d)); break;
+    case OP_GRADDIV: CHB_TRY(fb_graddiv_dev(fb, d_in, d_in, PP, PM, d_kx, d)); break;
   }
   CHB_TRY(call.down(out, (double*)d_out, 2 * nkx * nkr_loc * nm * out_comp));
   return call.sync();

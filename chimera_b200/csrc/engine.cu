@@ -425,8 +425,8 @@ int ph_poisson(chimera_engine* e) {
   const i64 P = nxs(e) * c.nkr * c.nm;
   FBCtx fb = fbctx(e);
   for (int it = 0; it < c.poisson_iters; ++it) {
-    CHB_CUDA(cudaMemcpyAsync(e->A("vec_fb"), e->A("J_fb"), sizeof(cd) * P * 3, cudaMemcpyDeviceToDevice, e->st));
-    CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
+    // vec_fb = grad div J_fb (solvers.py:317-319 copies J_fb into vec_fb first; here the source is read in place)
+    CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->A("J_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
     if (c.space_charge) {
       CHB_TRY(launch_poiss_corr(e->st, e->A("J_fb"), e->A("vec_fb"), e->A("gradRho_fb_prv"), e->A("gradRho_fb_nxt"),
                                 1.0 / c.dt, e->D("PoissFact"), P));
@@ -472,8 +472,7 @@ int ph_static_fields(chimera_engine* e) {
       cd* DT = e->scr.take_n<cd>(c.nx);
       if (!DT) return 6;
       CHB_TRY(launch_dt_stat(e->st, DT, e->D("kx"), beta0, c.nx));
-      CHB_CUDA(cudaMemcpyAsync(e->A("vec_fb"), e->A("J_fb"), sizeof(cd) * P * 3, cudaMemcpyDeviceToDevice, e->st));
-      CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
+      CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->A("J_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
       CHB_TRY(launch_poiss_corr_stat(e->st, e->A("J_fb"), e->A("vec_fb"), e->A("gradRho_fb_nxt"), DT, e->D("PoissFact"), c.nx, P));
     }
     CHB_TRY(launch_maxwell_static_push(e->st, e->A("EG_fb"), e->A("J_fb"), e->A("gradRho_fb_nxt"), e->D("w"), e->D("kx"),

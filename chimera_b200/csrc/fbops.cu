@@ -245,8 +245,7 @@ int div_like(FBCtx& c, cd* S, i64 slo, i64 shi, const cd* vec, const PackedOps& 
   cd* T2 = c.scr->take_n<cd>(Pv * d.nm);
   cd* T1ext = nullptr;
   if (!T1 || !T2) return 6;
-  CHB_TRY(launch_combine(c.st, T1, v3, Ui, v2, Um1, 0, d.nkx, d.nkr * d.nm));
-  CHB_TRY(launch_combine(c.st, T2, v3, Ui, v2, U1, 0, d.nkx, d.nkr * d.nm));
+  CHB_TRY(launch_pm(c.st, T1, T2, v3, v2, Pv * d.nm));  // T1 = i v3 - v2, T2 = i v3 + v2
   if (!d.env && mo.nko > 0) {  // Q7: with nko = 0 the missing mode 1 is taken as zero
     T1ext = c.scr->take_n<cd>(Pv);
     if (!T1ext) return 6;
@@ -284,29 +283,27 @@ int grad_like(FBCtx& c, cd* out, const cd* S, i64 slo, i64 shi, const PackedOps&
   cd* G1 = c.scr->take_n<cd>(Ps * d.nm);
   cd* G2 = c.scr->take_n<cd>(Ps * d.nm);
   if (!G1 || !G2) return 6;
-  CHB_CUDA(cudaMemsetAsync(G1, 0, sizeof(cd) * Ps * d.nm, c.st));
-  CHB_CUDA(cudaMemsetAsync(G2, 0, sizeof(cd) * Ps * d.nm, c.st));
   cd* Sext = nullptr;
   if (!d.env && mo.nko > 0) {
     Sext = c.scr->take_n<cd>(Pin);
     if (!Sext) return 6;
     CHB_TRY(launch_combine(c.st, Sext, Sp(1), U1, nullptr, U0, 1 + d.mirror_shift, d.nkx, d.nkr));
   }
-  for (i64 mode = mo.lo; mode <= mo.hi; ++mode)
-    CHB_TRY(ikx_plane(c.st, out + Ps * mo.vslot(mode), Sp(mode), kx, +1.0, 0, d));
   Batcher gb(c.st, 2 * d.nkx, d.nkr_loc, d.nkr, 2 * d.nkx, 2 * d.nkx);
   for (i64 mode = mo.lo; mode <= mo.hi; ++mode) {
     const cd* lower = nullptr;
     if (!d.env) lower = (mode > 0) ? Sp(mode - 1) : Sext;
     else if (always_both || mode > -mo.nko) lower = Sp(mode - 1);
+    // a slot no contraction writes (beta = 0 overwrites the others) has to read as zero in the tail
     if (lower) gb.add(lower, Dm.slot[mo.dslot(mode)], G1 + Ps * mo.vslot(mode), 1.0, 0.0);
+    else CHB_CUDA(cudaMemsetAsync(G1 + Ps * mo.vslot(mode), 0, sizeof(cd) * Ps, c.st));
     if (always_both || mode < mo.nko)
       gb.add(Sp(mode + 1), Dp.slot[mo.dslot(mode)], G2 + Ps * mo.vslot(mode), 1.0, 0.0);
+    else CHB_CUDA(cudaMemsetAsync(G2 + Ps * mo.vslot(mode), 0, sizeof(cd) * Ps, c.st));
   }
   CHB_TRY(gb.flush());
-  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm, G1, Um1, G2, U1, 0, Ps * d.nm));
-  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm * 2, G1, Ui, G2, Ui, 0, Ps * d.nm));
-  return 0;
+  // out1 = i kx S, out2 = -G1 + G2, out3 = i G1 + i G2 in one pass
+  return launch_grad_tail(c.st, out, Sp(mo.lo), G1, G2, kx, d.nkx, Ps, Pin, d.nm);
 }
 }  // namespace
 
@@ -328,13 +325,15 @@ int fb_div_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const Pack
 }
 
 // fb_graddiv (fb_math.f90:201-293) / fb_graddiv_env (fb_math_env.f90:164-233), in place
-int fb_graddiv_dev(FBCtx& c, cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx, const FBMathDims& d) {
+// `in` may alias `vec` (the reference's in-place form): the divergence is complete before the gradient is written
+int fb_graddiv_dev(FBCtx& c, cd* vec, const cd* in, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
+                   const FBMathDims& d) {
   if (d.nkr != d.nkr_loc) { set_error("fb_graddiv needs nkr == nkr_loc"); return 9; }
   const Modes mo(d);
   const i64 slo = d.env ? mo.lo - 1 : 0, shi = mo.hi + 1;
   cd* S = c.scr->take_n<cd>(d.nkx * d.nkr_loc * (shi - slo + 1));
   if (!S) return 6;
-  CHB_TRY(div_like(c, S, slo, shi, vec, Dp, Dm, kx, d));
+  CHB_TRY(div_like(c, S, slo, shi, in, Dp, Dm, kx, d));
   CHB_TRY(grad_like(c, vec, S, slo, shi, Dp, Dm, kx, d, true));
   return 0;
 }
@@ -354,8 +353,8 @@ int fb_rot_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const Pack
   cd* GP = c.scr->take_n<cd>(Ps * d.nm);
   cd* GM = c.scr->take_n<cd>(Ps * d.nm);
   if (!R1 || !R2 || !GP || !GM) return 6;
-  CHB_TRY(launch_combine(c.st, R1, v2, Ui, v3, Um1, 0, d.nkx, d.nkr * d.nm));
-  if (!d.env) CHB_TRY(launch_combine(c.st, R2, v2, Ui, v3, U1, 0, d.nkx, d.nkr * d.nm));
+  if (!d.env) CHB_TRY(launch_pm(c.st, R1, R2, v2, v3, Pv * d.nm));  // R1 = i v2 - v3, R2 = i v2 + v3
+  else CHB_TRY(launch_combine(c.st, R1, v2, Ui, v3, Um1, 0, d.nkx, d.nkr * d.nm));
   cd *R2ext = nullptr, *V1ext = nullptr;
   if (!d.env && mo.nko > 0) {
     R2ext = c.scr->take_n<cd>(Pv);
@@ -364,20 +363,23 @@ int fb_rot_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const Pack
     CHB_TRY(launch_combine(c.st, R2ext, v2 + Pv * mo.vslot(1), Ui, v3 + Pv * mo.vslot(1), U1, 1 + d.mirror_shift, d.nkx, d.nkr));
     CHB_TRY(launch_combine(c.st, V1ext, v1 + Pv * mo.vslot(1), U1, nullptr, U0, 1 + d.mirror_shift, d.nkx, d.nkr));
   }
-  CHB_CUDA(cudaMemsetAsync(out, 0, sizeof(cd) * Ps * d.nm, c.st));  // component 1
-  CHB_CUDA(cudaMemsetAsync(GP, 0, sizeof(cd) * Ps * d.nm, c.st));
-  CHB_CUDA(cudaMemsetAsync(GM, 0, sizeof(cd) * Ps * d.nm, c.st));
+  // slots no beta = 0 contraction writes are zeroed; the others are overwritten
+  auto zero = [&](cd* p, i64 slot) { return cudaMemsetAsync(p + Ps * slot, 0, sizeof(cd) * Ps, c.st); };
   Batcher g1(c.st, 2 * d.nkx, d.nkr_loc, d.nkr, 2 * d.nkx, 2 * d.nkx);
   for (i64 mode = mo.lo; mode <= mo.hi; ++mode) {
     const i64 s = mo.vslot(mode);
     if (mode < mo.nko) {
       g1.add(R1 + Pv * mo.vslot(mode + 1), Dp.slot[mo.dslot(mode)], out + Ps * s, -1.0, 0.0);
       g1.add(v1 + Pv * mo.vslot(mode + 1), Dp.slot[mo.dslot(mode)], GP + Ps * s, 1.0, 0.0);
+    } else {
+      CHB_CUDA(zero(out, s));
+      CHB_CUDA(zero(GP, s));
     }
     const cd* l1 = nullptr;
     if (!d.env) l1 = (mode > 0) ? v1 + Pv * mo.vslot(mode - 1) : V1ext;
     else if (mode > -mo.nko) l1 = v1 + Pv * mo.vslot(mode - 1);
     if (l1) g1.add(l1, Dm.slot[mo.dslot(mode)], GM + Ps * s, 1.0, 0.0);
+    else CHB_CUDA(zero(GM, s));
   }
   CHB_TRY(g1.flush());
   if (!d.env) {  // second term of component 1 accumulates on top of the first => separate launch
@@ -388,14 +390,8 @@ int fb_rot_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const Pack
     }
     CHB_TRY(g2.flush());
   }
-  for (i64 mode = mo.lo; mode <= mo.hi; ++mode) {
-    const i64 s = mo.vslot(mode);
-    CHB_TRY(ikx_plane(c.st, out + Ps * (s + d.nm), v3 + Pv * s, kx, -1.0, 0, d));
-    CHB_TRY(ikx_plane(c.st, out + Ps * (s + d.nm * 2), v2 + Pv * s, kx, +1.0, 0, d));
-  }
-  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm, GP, Ui, GM, Ui, 1, Ps * d.nm));
-  CHB_TRY(launch_axpby(c.st, out + Ps * d.nm * 2, GP, Um1, GM, U1, 1, Ps * d.nm));
-  return 0;
+  // out2 = -i kx v3 + i GP + i GM ; out3 = +i kx v2 - GP + GM in one pass
+  return launch_rot_tail(c.st, out + Ps * d.nm, out + Ps * d.nm * 2, v2, v3, GP, GM, kx, d.nkx, Ps, Pv, d.nm);
 }
 
 }  // namespace chb

@@ -232,6 +232,13 @@ int launch_combine(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, 
 int launch_axpby(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, Unit cb, int acc, i64 n);
 //   out (+)= i * kx * a   (sign = +-1)
 int launch_ikx(cudaStream_t st, cd* out, const cd* a, const double* kx, double sign, int acc, i64 nkx, i64 ncols);
+//   outm = i a - b, outp = i a + b in one pass
+int launch_pm(cudaStream_t st, cd* outm, cd* outp, const cd* a, const cd* b, i64 n);
+//   fused tails of fb_grad/fb_graddiv and fb_rot (i kx planes + the +-1/+-i recombination of the two GEMM results)
+int launch_grad_tail(cudaStream_t st, cd* out, const cd* S, const cd* G1, const cd* G2, const double* kx, i64 nkx,
+                     i64 Ps, i64 Pin, i64 nm);
+int launch_rot_tail(cudaStream_t st, cd* out2, cd* out3, const cd* v2, const cd* v3, const cd* GP, const cd* GM,
+                    const double* kx, i64 nkx, i64 Ps, i64 Pv, i64 nm);
 
 
 // ---- sr.cu : synchrotron-radiation spectra from stored tracks (SR.f90) and utils.f90 diagnostics helpers

@@ -367,4 +367,69 @@ int launch_ikx(cudaStream_t st, cd* out, const cd* a, const double* kx, double s
   return 0;
 }
 
+// outm = i a - b ; outp = i a + b: the two mode-coupling sources of fb_div (a = v3, b = v2) and fb_rot
+// (a = v2, b = v3) in one pass over the inputs (same expressions as two launch_combine calls)
+__global__ void __launch_bounds__(TPB) pm_k(cd* __restrict__ outm, cd* __restrict__ outp, const cd* __restrict__ a,
+                                            const cd* __restrict__ b, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const Unit Ui{0, 1}, U1{1, 0}, Um1{-1, 0};
+  const cd ia = unit_mul(Ui, ldg(a + e)), vb = ldg(b + e);
+  outm[e] = cadd(ia, unit_mul(Um1, vb));
+  outp[e] = cadd(ia, unit_mul(U1, vb));
+}
+int launch_pm(cudaStream_t st, cd* outm, cd* outp, const cd* a, const cd* b, i64 n) {
+  if (n <= 0) return 0;
+  pm_k<<<grid_for(n, TPB), TPB, 0, st>>>(outm, outp, a, b, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// tail of fb_grad / fb_graddiv (fb_math.f90:133-147, :262-291): out1 = i kx S, out2 = -G1 + G2, out3 = i G1 + i G2.
+// out components are (Ps, nm) blocks; S planes are Pin apart (Ps <= Pin leading elements used)
+__global__ void __launch_bounds__(TPB) grad_tail_k(cd* __restrict__ out, const cd* __restrict__ S,
+                                                   const cd* __restrict__ G1, const cd* __restrict__ G2,
+                                                   const double* __restrict__ kx, i64 nkx, i64 Ps, i64 Pin, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const Unit Ui{0, 1}, U1{1, 0}, Um1{-1, 0};
+  const i64 pl = e / Ps, w = e - pl * Ps;
+  const double k = __ldg(kx + w % nkx);
+  const cd s = ldg(S + pl * Pin + w), g1 = ldg(G1 + e), g2 = ldg(G2 + e);
+  out[e] = cmake(-k * s.y, k * s.x);
+  out[e + n] = cadd(unit_mul(Um1, g1), unit_mul(U1, g2));
+  out[e + 2 * n] = cadd(unit_mul(Ui, g1), unit_mul(Ui, g2));
+}
+int launch_grad_tail(cudaStream_t st, cd* out, const cd* S, const cd* G1, const cd* G2, const double* kx, i64 nkx,
+                     i64 Ps, i64 Pin, i64 nm) {
+  const i64 n = Ps * nm;
+  if (n <= 0) return 0;
+  grad_tail_k<<<grid_for(n, TPB), TPB, 0, st>>>(out, S, G1, G2, kx, nkx, Ps, Pin, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
+// tail of fb_rot (fb_math.f90:60-92): out2 = -i kx v3 + (i GP + i GM), out3 = +i kx v2 + (-GP + GM)
+__global__ void __launch_bounds__(TPB) rot_tail_k(cd* __restrict__ out2, cd* __restrict__ out3,
+                                                  const cd* __restrict__ v2, const cd* __restrict__ v3,
+                                                  const cd* __restrict__ GP, const cd* __restrict__ GM,
+                                                  const double* __restrict__ kx, i64 nkx, i64 Ps, i64 Pv, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const Unit Ui{0, 1}, U1{1, 0}, Um1{-1, 0};
+  const i64 pl = e / Ps, w = e - pl * Ps;
+  const double kp = __ldg(kx + w % nkx), km = -1.0 * kp;
+  const cd a2 = ldg(v2 + pl * Pv + w), a3 = ldg(v3 + pl * Pv + w), gp = ldg(GP + e), gm = ldg(GM + e);
+  out2[e] = cadd(cadd(unit_mul(Ui, gp), unit_mul(Ui, gm)), cmake(-km * a3.y, km * a3.x));
+  out3[e] = cadd(cadd(unit_mul(Um1, gp), unit_mul(U1, gm)), cmake(-kp * a2.y, kp * a2.x));
+}
+int launch_rot_tail(cudaStream_t st, cd* out2, cd* out3, const cd* v2, const cd* v3, const cd* GP, const cd* GM,
+                    const double* kx, i64 nkx, i64 Ps, i64 Pv, i64 nm) {
+  const i64 n = Ps * nm;
+  if (n <= 0) return 0;
+  rot_tail_k<<<grid_for(n, TPB), TPB, 0, st>>>(out2, out3, v2, v3, GP, GM, kx, nkx, Ps, Pv, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace chb
