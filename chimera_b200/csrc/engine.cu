@@ -425,12 +425,12 @@ int ph_poisson(chimera_engine* e) {
   const i64 P = nxs(e) * c.nkr * c.nm;
   FBCtx fb = fbctx(e);
   for (int it = 0; it < c.poisson_iters; ++it) {
-    // vec_fb = grad div J_fb (solvers.py:317-319 copies J_fb into vec_fb first; here the source is read in place)
-    CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->A("J_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
     if (c.space_charge) {
-      CHB_TRY(launch_poiss_corr(e->st, e->A("J_fb"), e->A("vec_fb"), e->A("gradRho_fb_prv"), e->A("gradRho_fb_nxt"),
-                                1.0 / c.dt, e->D("PoissFact"), P));
+      // grad div J_fb is consumed by the correction in the same pass; vec_fb (solvers.py:317-319) is not needed
+      CHB_TRY(fb_poiss_iter_dev(fb, e->A("J_fb"), e->A("gradRho_fb_prv"), e->A("gradRho_fb_nxt"), 1.0 / c.dt,
+                                e->D("PoissFact"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
     } else {
+      CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->A("J_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
       CHB_TRY(launch_mult_real(e->st, e->A("vec_fb"), e->D("PoissFact"), P, 3));
       CHB_TRY(launch_add(e->st, e->A("J_fb"), e->A("vec_fb"), P * 3));
     }

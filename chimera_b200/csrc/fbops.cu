@@ -127,7 +127,8 @@ int fb_out_dev(FBCtx& c, cd* out, const cd* const* srcs, int nsrc, int ncomp_eac
                const PackedOps& Out, i64 nkx, i64 nrn, i64 nm, i64 nkr) {
   const i64 nr = nrn - 1;
   const int ncomp = nsrc * ncomp_each;
-  CHB_CUDA(cudaMemsetAsync(out, 0, sizeof(cd) * nkx * nrn * nm * ncomp, c.st));
+  // the contractions overwrite radial nodes 1..nr of every plane; only the ghost node 0 is left to zero (fb_io.f90:203)
+  CHB_CUDA(cudaMemset2DAsync(out, sizeof(cd) * nkx * nrn, 0, sizeof(cd) * nkx, (size_t)(nm * ncomp), c.st));
   Batcher gb(c.st, 2 * nkx, nr, nkr, 2 * nkx, 2 * nkx);
   for (int j = 0; j < nsrc; ++j)
     for (int l = 0; l < ncomp_each; ++l)
@@ -182,7 +183,7 @@ int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int
                     const double* kx_slab, const PackedOps& Out, i64 nxs, i64 nrn, i64 nm, i64 nkr) {
   const i64 nr = nrn - 1;
   const int ncomp = nsrc * ncomp_each;
-  CHB_CUDA(cudaMemsetAsync(out_slab, 0, sizeof(cd) * nxs * nrn * nm * ncomp, c.st));
+  CHB_CUDA(cudaMemset2DAsync(out_slab, sizeof(cd) * nxs * nrn, 0, sizeof(cd) * nxs, (size_t)(nm * ncomp), c.st));
   Batcher gb(c.st, 2 * nxs, nr, nkr, 2 * nxs, 2 * nxs);
   for (int j = 0; j < nsrc; ++j)
     for (int l = 0; l < ncomp_each; ++l)
@@ -274,8 +275,13 @@ int div_like(FBCtx& c, cd* S, i64 slo, i64 shi, const cd* vec, const PackedOps& 
 // out(:,:,mode,1) = i kx S[mode];  G1 = Dm(mode).S[mode-1],  G2 = Dp(mode).S[mode+1];
 // out(..,2) = -G1 + G2 ;  out(..,3) = i G1 + i G2
 // (fb_grad fb_math.f90:96-149, fb_grad_env fb_math_env.f90:18-61, second halves of fb_graddiv[_env])
+struct PoissTail {  // when given, grad_like ends in the Poisson-correction update of `out` (= J_fb) instead of storing
+  const cd *gn, *gp;
+  const double* w2inv;
+  double dt_inv;
+};
 int grad_like(FBCtx& c, cd* out, const cd* S, i64 slo, i64 shi, const PackedOps& Dp, const PackedOps& Dm,
-              const double* kx, const FBMathDims& d, bool always_both) {
+              const double* kx, const FBMathDims& d, bool always_both, const PoissTail* pt = nullptr) {
   const Modes mo(d);
   const i64 Pin = d.nkx * d.nkr, Ps = d.nkx * d.nkr_loc;
   auto Sp = [&](i64 mode) { return S + Pin * (mode - slo); };
@@ -302,6 +308,8 @@ int grad_like(FBCtx& c, cd* out, const cd* S, i64 slo, i64 shi, const PackedOps&
     else CHB_CUDA(cudaMemsetAsync(G2 + Ps * mo.vslot(mode), 0, sizeof(cd) * Ps, c.st));
   }
   CHB_TRY(gb.flush());
+  if (pt)  // needs Ps == Pin (checked by the caller)
+    return launch_grad_poiss_tail(c.st, out, Sp(mo.lo), G1, G2, pt->gn, pt->gp, kx, pt->w2inv, pt->dt_inv, d.nkx, Ps * d.nm);
   // out1 = i kx S, out2 = -G1 + G2, out3 = i G1 + i G2 in one pass
   return launch_grad_tail(c.st, out, Sp(mo.lo), G1, G2, kx, d.nkx, Ps, Pin, d.nm);
 }
@@ -336,6 +344,19 @@ int fb_graddiv_dev(FBCtx& c, cd* vec, const cd* in, const PackedOps& Dp, const P
   CHB_TRY(div_like(c, S, slo, shi, in, Dp, Dm, kx, d));
   CHB_TRY(grad_like(c, vec, S, slo, shi, Dp, Dm, kx, d, true));
   return 0;
+}
+
+// one iteration of Solver.poiss_corr (solvers.py:317-326): J += PoissFact (grad div J + (gradRho_nxt - gradRho_prv)/dt)
+int fb_poiss_iter_dev(FBCtx& c, cd* J, const cd* gn, const cd* gp, double dt_inv, const double* w2inv,
+                      const PackedOps& Dp, const PackedOps& Dm, const double* kx, const FBMathDims& d) {
+  if (d.nkr != d.nkr_loc) { set_error("fb_poiss_iter needs nkr == nkr_loc"); return 9; }
+  const Modes mo(d);
+  const i64 slo = d.env ? mo.lo - 1 : 0, shi = mo.hi + 1;
+  cd* S = c.scr->take_n<cd>(d.nkx * d.nkr_loc * (shi - slo + 1));
+  if (!S) return 6;
+  CHB_TRY(div_like(c, S, slo, shi, J, Dp, Dm, kx, d));
+  const PoissTail pt{gn, gp, w2inv, dt_inv};
+  return grad_like(c, J, S, slo, shi, Dp, Dm, kx, d, true, &pt);
 }
 
 // fb_rot (fb_math.f90:18-94) / fb_rot_env (fb_math_env.f90:106-162)

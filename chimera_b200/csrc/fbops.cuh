@@ -80,6 +80,8 @@ int fb_div_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const Pack
                const FBMathDims& d);
 int fb_rot_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
                const FBMathDims& d);
+int fb_poiss_iter_dev(FBCtx& c, cd* J, const cd* gn, const cd* gp, double dt_inv, const double* w2inv,
+                      const PackedOps& Dp, const PackedOps& Dm, const double* kx, const FBMathDims& d);
 int fb_graddiv_dev(FBCtx& c, cd* vec, const cd* in, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
                    const FBMathDims& d);
 // scratch bytes an fb_* call may take (upper bound), for reserve()

@@ -237,6 +237,9 @@ int launch_pm(cudaStream_t st, cd* outm, cd* outp, const cd* a, const cd* b, i64
 //   fused tails of fb_grad/fb_graddiv and fb_rot (i kx planes + the +-1/+-i recombination of the two GEMM results)
 int launch_grad_tail(cudaStream_t st, cd* out, const cd* S, const cd* G1, const cd* G2, const double* kx, i64 nkx,
                      i64 Ps, i64 Pin, i64 nm);
+//   fb_graddiv tail + poiss_corr in one pass: J_l += w2inv (gdj_l + dt_inv (gp_l - gn_l)), gdj never stored
+int launch_grad_poiss_tail(cudaStream_t st, cd* J, const cd* S, const cd* G1, const cd* G2, const cd* gn, const cd* gp,
+                           const double* kx, const double* w2inv, double dt_inv, i64 nkx, i64 n);
 int launch_rot_tail(cudaStream_t st, cd* out2, cd* out3, const cd* v2, const cd* v3, const cd* GP, const cd* GM,
                     const double* kx, i64 nkx, i64 Ps, i64 Pv, i64 nm);
 

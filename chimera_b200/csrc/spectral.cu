@@ -432,4 +432,37 @@ int launch_rot_tail(cudaStream_t st, cd* out2, cd* out3, const cd* v2, const cd*
   return 0;
 }
 
+// one Poisson-correction iteration's tail (solvers.py:317-326 = fb_graddiv second half + poiss_corr,
+// maxwell_solvers.f90:131-164) without materialising grad(div J):
+//   gdj = (i kx S, -G1 + G2, i G1 + i G2);  J_l += w2inv * (gdj_l + dt_inv * (gp_l - gn_l))
+__global__ void __launch_bounds__(TPB) grad_poiss_tail_k(cd* __restrict__ J, const cd* __restrict__ S,
+                                                         const cd* __restrict__ G1, const cd* __restrict__ G2,
+                                                         const cd* __restrict__ gn, const cd* __restrict__ gp,
+                                                         const double* __restrict__ kx,
+                                                         const double* __restrict__ w2inv, double dt_inv, i64 nkx,
+                                                         i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const Unit Ui{0, 1}, U1{1, 0}, Um1{-1, 0};
+  const double k = __ldg(kx + e % nkx), wi = __ldg(w2inv + e);
+  const cd s = ldg(S + e), g1 = ldg(G1 + e), g2 = ldg(G2 + e);
+  cd gdj[3];
+  gdj[0] = cmake(-k * s.y, k * s.x);
+  gdj[1] = cadd(unit_mul(Um1, g1), unit_mul(U1, g2));
+  gdj[2] = cadd(unit_mul(Ui, g1), unit_mul(Ui, g2));
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const i64 q = e + n * l;
+    const cd d = cscale(dt_inv, csub(ldg(gp + q), ldg(gn + q)));
+    J[q] = cadd(J[q], cscale(wi, cadd(gdj[l], d)));
+  }
+}
+int launch_grad_poiss_tail(cudaStream_t st, cd* J, const cd* S, const cd* G1, const cd* G2, const cd* gn, const cd* gp,
+                           const double* kx, const double* w2inv, double dt_inv, i64 nkx, i64 n) {
+  if (n <= 0) return 0;
+  grad_poiss_tail_k<<<grid_for(n, TPB), TPB, 0, st>>>(J, S, G1, G2, gn, gp, kx, w2inv, dt_inv, nkx, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace chb
