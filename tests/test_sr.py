@@ -211,3 +211,55 @@ def test_gpu_intens_profo_and_density(ofim, gfim):
     grid = np.array([-1.0, 1.0, -0.5, 2.0])
     assert_close(gfim.density_2x(x, y, w, grid, 20, 13), ofim.density_2x(x, y, w, grid, 20, 13), 1e-12, "density_2x")
     assert gfim.density_2x(x[:0], y[:0], w[:0], grid, 4, 4).shape == (9, 9)
+
+
+# ---------------------------------------------------------------- fixture from the reference's SR class
+def _golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sr.npz"))
+
+
+def _replay(fim, z, key, comp):
+    """the calls moduls/SR.py:165-215 made when tools/gen_golden_sr.py recorded the fixture"""
+    dep = [z["%s_depfact%d" % (key, i)] for i in range(6 if key != "near" else 5)]
+    dep = [float(d) if d.ndim == 0 else d for d in dep]
+    rad = np.zeros_like(z[key + "_rad_all"], order="F")
+    x, mp, mn, w = z["coords"], z["momenta_prv"], z["momenta_nxt"], z["weights"]
+    name = {"far": "sr_calc_far", "near": "sr_calc_near", "nearcirc": "sr_calc_nearcirc"}[key] + ("_comp" if comp else "_tot")
+    tr = [x, mp, mn, w] if key == "far" else [x, mn, w]
+    return getattr(fim, name)(rad, *tr, *([comp] if comp else []), *dep)
+
+
+@pytest.mark.parametrize("key", ["far", "near", "nearcirc"])
+def test_golden_sr_class_on_oracle(ofim, key):
+    z = _golden()
+    assert_close(_replay(ofim, z, key, 0), z[key + "_rad_all"], 1e-13, key + " all")
+    assert_close(_replay(ofim, z, key, 2), z[key + "_rad_y"], 1e-13, key + " y")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["far", "near", "nearcirc"])
+def test_gpu_golden_sr_class(gfim, key):
+    z = _golden()
+    rad = _replay(gfim, z, key, 0)
+    assert_close(rad, z[key + "_rad_all"], SR_TOL, key + " all")
+    assert_close(_replay(gfim, z, key, 2), z[key + "_rad_y"], SR_TOL, key + " y")
+    # the integrated diagnostic the reference derives from Rad (SR.get_energy: trapezoid in omega, sum over the screen)
+    want = float(z[key + "_energy"])
+    scale = want / _energy_like(z, key, z[key + "_rad_all"])
+    assert abs(_energy_like(z, key, rad) * scale - want) <= 1e-6 * abs(want)
+
+
+def _energy_like(z, key, rad):
+    """the shape of SR.get_energy (SR.py:238-270) up to its constant factors: trapezoid over omega, weighted
+    screen sum; used as a ratio against the recorded value"""
+    om = z[key + "_depfact1"]
+    dw = np.abs(om[1:] - om[:-1])
+    if key == "far":
+        wgt = z["far_depfact2"][None, :, None]  # sin(theta)
+    elif key == "nearcirc":
+        wgt = z["nearcirc_depfact2"][None, :, None]  # R
+    else:
+        wgt = 1.0
+    return float((((rad[1:] + rad[:-1]) * wgt).sum(-1).sum(-1) * dw).sum())
