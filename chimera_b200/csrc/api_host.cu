@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/chimera_b200.h"
 #include "fbops.cuh"
+#include "staging.cuh"
 
 namespace chb {
 
@@ -29,6 +30,7 @@ struct HostCtx {
   cudaStream_t st = nullptr;
   Scratch scr;
   FFTCache fft;
+  Stager stage;  // pageable numpy buffers <-> device at PCIe speed (staging.cuh)
   std::mutex mu;
   int init() {
     if (ready) return 0;
@@ -62,14 +64,11 @@ struct Call {
   template <typename T> T* up(const T* h, i64 n) {
     T* d = dev<T>(n);
     if (n > 0) g_h2d_bytes += (long long)(sizeof(T) * (size_t)n);
-    if (d && n > 0 && cudaMemcpyAsync(d, h, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, c.st) != cudaSuccess) {
-      set_error("H2D copy failed");
-      return nullptr;
-    }
+    if (d && n > 0 && c.stage.h2d(d, h, sizeof(T) * (size_t)n, c.st) != 0) return nullptr;
     return d;
   }
   template <typename T> int down(T* h, const T* d, i64 n) {
-    if (n > 0) CHB_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, c.st));
+    if (n > 0) CHB_TRY(c.stage.d2h(h, d, sizeof(T) * (size_t)n, c.st));
     if (n > 0) g_d2h_bytes += (long long)(sizeof(T) * (size_t)n);
     return 0;
   }

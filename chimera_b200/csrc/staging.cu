@@ -1,0 +1,145 @@
+// staging.cu -- see staging.cuh
+#include "staging.cuh"
+#include <algorithm>
+
+namespace chb {
+
+bool Stager::pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();  // older runtimes report unregistered host memory as an error
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+int Stager::init() {
+  if (ready_) return 0;
+  for (int i = 0; i < kSlots; ++i) {
+    CHB_CUDA(cudaHostAlloc((void**)&slot_[i], kChunk, cudaHostAllocDefault));
+    CHB_CUDA(cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming));
+    busy_[i] = false;
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  int nthreads = (int)std::min(6u, hw > 2 ? hw / 2 : 1u);  // host memcpy saturates with a few threads
+  nparts_ = nthreads;
+  for (int t = 1; t < nthreads; ++t) pool_.emplace_back(&Stager::worker, this, t);
+  ready_ = true;
+  return 0;
+}
+
+Stager::~Stager() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_ = true;
+  }
+  cv_job_.notify_all();
+  for (auto& t : pool_) t.join();
+  // page-locked slots and events are released with the context at process exit (the destructor may run after
+  // the CUDA runtime has shut down)
+}
+
+static inline void part_range(size_t bytes, int nparts, int id, size_t& lo, size_t& hi) {
+  const size_t per = ((bytes / nparts) + 4095) & ~size_t(4095);
+  lo = std::min(bytes, per * (size_t)id);
+  hi = id == nparts - 1 ? bytes : std::min(bytes, lo + per);
+}
+
+void Stager::worker(int id) {
+  unsigned long long seen = 0;
+  for (;;) {
+    char* dst;
+    const char* src;
+    size_t bytes;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_job_.wait(lk, [&] { return stop_ || job_id_ != seen; });
+      if (stop_) return;
+      seen = job_id_;
+      dst = j_dst_; src = j_src_; bytes = j_bytes_;
+    }
+    size_t lo, hi;
+    part_range(bytes, nparts_, id, lo, hi);
+    if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) cv_done_.notify_one();
+    }
+  }
+}
+
+void Stager::parallel_copy(char* dst, const char* src, size_t bytes) {
+  if (pool_.empty() || bytes < (size_t(1) << 20)) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    j_dst_ = dst; j_src_ = src; j_bytes_ = bytes;
+    pending_ = (int)pool_.size();
+    ++job_id_;
+  }
+  cv_job_.notify_all();
+  size_t lo, hi;
+  part_range(bytes, nparts_, 0, lo, hi);
+  if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
+  std::unique_lock<std::mutex> lk(mu_);
+  cv_done_.wait(lk, [&] { return pending_ == 0; });
+}
+
+int Stager::h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (bytes < kMinBytes || !pageable(src_host)) {
+    CHB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  CHB_TRY(init());
+  int s = 0;
+  for (size_t off = 0; off < bytes; off += kChunk, s = (s + 1) % kSlots) {
+    const size_t len = std::min(kChunk, bytes - off);
+    if (busy_[s]) {  // the DMA that last read this slot
+      CHB_CUDA(cudaEventSynchronize(ev_[s]));
+      busy_[s] = false;
+    }
+    parallel_copy(slot_[s], (const char*)src_host + off, len);
+    CHB_CUDA(cudaMemcpyAsync((char*)dst_dev + off, slot_[s], len, cudaMemcpyHostToDevice, st));
+    CHB_CUDA(cudaEventRecord(ev_[s], st));
+    busy_[s] = true;
+  }
+  return 0;
+}
+
+int Stager::d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (bytes < kMinBytes || !pageable(dst_host)) {
+    CHB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+  CHB_TRY(init());
+  // slots still referenced by earlier H2D chunks have to drain first
+  for (int s = 0; s < kSlots; ++s)
+    if (busy_[s]) {
+      CHB_CUDA(cudaEventSynchronize(ev_[s]));
+      busy_[s] = false;
+    }
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  size_t issued = 0;
+  auto issue = [&](size_t c) -> int {
+    const int s = (int)(c % kSlots);
+    const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+    CHB_CUDA(cudaMemcpyAsync(slot_[s], (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, st));
+    CHB_CUDA(cudaEventRecord(ev_[s], st));
+    return 0;
+  };
+  for (; issued < nchunks && issued < (size_t)kSlots; ++issued) CHB_TRY(issue(issued));
+  for (size_t c = 0; c < nchunks; ++c) {
+    const int s = (int)(c % kSlots);
+    const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+    CHB_CUDA(cudaEventSynchronize(ev_[s]));
+    parallel_copy((char*)dst_host + off, slot_[s], len);
+    if (issued < nchunks) CHB_TRY(issue(issued++));  // the slot just emptied takes the next chunk
+  }
+  return 0;
+}
+
+}  // namespace chb
