@@ -42,6 +42,25 @@ def test_push_coords(ofim, gfim, n):
     assert_close(cg, co, what="coords_halfstep")
 
 
+@pytest.mark.parametrize("n", [174763, 699051, 2100011, 5000003])
+def test_large_pageable_buffers_are_staged_exactly(ofim, gfim, n):
+    """arrays above 4 MB go through the page-locked staging ring (csrc/staging.cu: 16 MB chunks, 6 slots, host
+    thread pool): sizes just above the threshold, exactly one chunk (3 n 8 B = 16 MiB + 8), several chunks with a
+    ragged tail, and more chunks than slots (slot reuse) -- bit-exact pass-through both ways (align_data_vec is a
+    pure permutation), then parity of a compute call on the same sizes"""
+    rng = np.random.default_rng(n)
+    dat = np.asfortranarray(rng.standard_normal((3, n)))
+    idx = rng.permutation(n).astype(np.int64)
+    got = gfim.align_data_vec(dat.copy(order="F"), idx)
+    assert np.array_equal(got[:, :n], dat[:, idx])
+    x = np.asfortranarray(rng.standard_normal((3, n)))
+    p = np.asfortranarray(rng.standard_normal((3, n)) * 3)
+    (xo, co), (xg, cg) = both(ofim, gfim, "push_coords", x, p, np.zeros((3, n), order="F"), 0.05)
+    assert_close(xg, xo, what="coords (staged)")
+    assert_close(cg, co, what="coords_halfstep (staged)")
+    assert np.abs(xg - xo).max() <= 1e-14 * np.abs(xo).max()  # no chunk went astray: element-wise, not just in norm
+
+
 def test_genparts(ofim, gfim):
     rng = np.random.default_rng(3)
     S = setup("real_m2")
