@@ -1,0 +1,90 @@
+"""BASELINE.json configs[3], one GPU's share: unaveraged FEL undulator beam, envelope solver (KxShift), one
+azimuthal mode, NoPoissonCorrection, analytic undulator, 1.25e8 macro-particles (1e9 over 8 GPUs).  Device-
+resident engine, CUDA events around K make_steps; per-phase times from the engine profile.  The beam fills
+x in +-lbx/2, r < lbr of the fel-testrun geometry (doc/tests/fel-testrun.py:12-58) on an Nx x Nr = 2048 x 256
+grid: ~7600 particles per occupied cell, i.e. the deposit is dominated by same-cell accumulation.
+Writes gpurun_out/fel_bench.json.
+
+  python tools/fel_bench.py [--np 1.25e8] [--steps 10] [--warmup 3]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from chimera_b200.engine import Engine  # noqa: E402
+from chimera_b200.solver_setup import SolverSetup  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--np", type=float, default=1.25e8)
+ap.add_argument("--nx", type=int, default=2048)
+ap.add_argument("--nr", type=int, default=256)
+ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+a = ap.parse_args()
+
+K0, lam0, periods = 1.95, 2.8, 10
+g0 = 200 / 0.511
+gg = g0 / (1.0 + K0 ** 2 / 2) ** 0.5
+k_res, vb = 2 * gg ** 2, (1.0 - gg ** -2) ** 0.5
+Lgx, Rg, Rcut = 200e-4 / lam0, 1000e-4 / lam0, 700e-4 / lam0
+lbx = lbr = 80e-4 / lam0
+dt = 1.0 / 30
+cfg = {"Grid": (-0.5 * Lgx, 0.5 * Lgx, Rg, Lgx / a.nx, Rg / a.nr), "TimeStep": dt, "MaxAzimuthMode": 0,
+       "KxShift": k_res, "Rcut": Rcut, "CoPropagative": vb, "Xchunked": (16, 6),
+       "Features": {"NoPoissonCorrection": True}}
+S = SolverSetup(cfg)
+eng = Engine(S)
+eng.use_stream(torch.cuda.current_stream().cuda_stream)
+eng.add_device("undul_analytic", np.array([K0, 1.0, 1.0, float(periods)]))
+
+n = int(a.np)
+g = torch.Generator(device="cuda")
+g.manual_seed(20260101)
+rnd = lambda *s: torch.rand(*s, device="cuda", dtype=torch.float64, generator=g)  # noqa: E731
+rndn = lambda *s: torch.randn(*s, device="cuda", dtype=torch.float64, generator=g)  # noqa: E731
+x = (rnd(n) - 0.5) * lbx
+r = lbr * torch.sqrt(rnd(n))  # uniform in the disc
+th = 2 * np.pi * rnd(n)
+coords = torch.stack((x, r * torch.sin(th), r * torch.cos(th)), dim=1).contiguous()
+mom = torch.stack((g0 + 1e-4 * g0 * rndn(n), 2e-5 * g0 * rndn(n), 2e-5 * g0 * rndn(n)), dim=1).contiguous()
+dens = 20e-12 / 1.6022e-19 / (np.pi * 80e-4 ** 3) / (1.1e21 / 2.8e4 ** 2)
+w = torch.full((n,), -dens * np.pi * lbr ** 2 * lbx / n, device="cuda", dtype=torch.float64)
+torch.cuda.synchronize()
+eng.add_species_device(coords.data_ptr(), mom.data_ptr(), w.data_ptr(), n)
+del x, r, th, coords, mom, w
+torch.cuda.empty_cache()
+eng.make_halfstep(px0=(0.0,))
+eng.step(a.warmup)
+eng.sync()
+eng.profile(True)
+eng.timings(reset=True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+eng.step(a.steps)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+ph = eng.timings(reset=True)
+eng.profile(False)
+kept = eng.count(0)
+hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+per = {k: v[0] / v[1] for k, v in ph.items() if v[1]}
+out = {"workload": "FEL undulator beam, envelope solver Nx=%d Nr=%d 1 mode, undul_analytic K0=1.95, %.3g macro-particles, "
+                   "Xchunked=(16,6), NoPoissonCorrection" % (a.nx, a.nr, n),
+       "metric": "particle-steps/s full PIC cycle", "value": kept / (ms * 1e-3), "ms_per_step": ms, "steps": a.steps,
+       "warmup": a.warmup, "particles": n, "particles_after": kept, "phases_ms_per_call": per,
+       "phase_calls": {k: v[1] for k, v in ph.items()},
+       # envelope cycle, SURVEY 8d basis: push_coords 96 + dep_curr_env 56 + proj_fld_env 128 + push_velocs 96 B
+       "particle_cycle_alg_bytes": 376.0 * kept, "hbm_gbs_peak": hbm}
+if "particles_fused" in per:
+    out["fused_frac_of_hbm"] = 376.0 * kept / (per["particles_fused"] * 1e-3) / 1e9 / hbm
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fel_bench.json"), "w"), indent=1)
+print(json.dumps(out))
+eng.close()
