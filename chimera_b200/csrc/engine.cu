@@ -9,6 +9,7 @@
 //   chunk_and_damp moduls/species.py:351-398 (re-binning; here a device radix sort by
 //                  (x-chunk, r-cell, x-cell) which refines the reference's chunk order)
 #include <cub/device/device_radix_sort.cuh>
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -56,6 +57,10 @@ struct chimera_engine {
   int host_mid_done = 0;
   int fuse = 1;  // use the fused particle kernel inside multi-step calls (chimera_engine_set_fuse)
   double dev_time = 0.0;  // i_step * TimeStep seen by time-dependent devices in the next gather + push
+  // window that moves every step inside chimera_engine_step (chimera_engine_set_window): shift at stage 1 (before
+  // push_coords) and at stage 2 (between dep_curr and dep_dens), chimera_main.py:286-302
+  double win_s1 = 0.0, win_s2 = 0.0;
+  double leftX_J = NAN;  // leftX the deposited J lives on, consumed by the next fb_in_J (NaN: cfg.leftX)
   double host_rho_from_bg = 1.0;  // 0 on the ranks that must not add BckGrndRho before an all-reduce
   bool own_stream = false;
   Scratch scr;
@@ -369,7 +374,16 @@ int ph_deposit_j(chimera_engine* e) {
   const i64 n = c.nx * c.nrn * c.nm * 3;
   CHB_CUDA(cudaMemsetAsync(e->A("J"), 0, sizeof(cd) * n, e->st));
   CHB_TRY(deposit_species(e, 1, e->A("J"), false, true));
+  e->leftX_J = c.leftX;
   return launch_ghost_fold(e->st, e->A("J"), c.nx, c.nrn, c.nm * 3);
+}
+
+// one stage of a window that moves every step (ChimeraRun.move_frame, chimera_main.py:286-290)
+int ph_window(chimera_engine* e, int stage) {
+  const double s = stage == 2 ? e->win_s2 : e->win_s1;
+  e->cfg.leftX += s;
+  e->cfg.rightX += s;
+  return 0;
 }
 
 int ph_deposit_rho(chimera_engine* e, int from_bg) {
@@ -400,10 +414,14 @@ int ph_add_bg(chimera_engine* e) {
 int ph_fb_in_j(chimera_engine* e) {
   const auto& c = e->cfg;
   FBCtx fb = fbctx(e);
+  // the phase exp(-i kx leftX) belongs to the grid J was deposited on: with a 'Staged' window project_current runs
+  // between the two half shifts (chimera_main.py:87-88)
+  const double lx = std::isnan(e->leftX_J) ? c.leftX : e->leftX_J;
+  e->leftX_J = NAN;
   if (slab(e))
-    return fb_in_slab_dev(fb, e->A("J_fb"), e->A("J"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"),
+    return fb_in_slab_dev(fb, e->A("J_fb"), e->A("J"), lx, e->D("kx_base"), e->pInCurr, e->D("DepFact"),
                           (const i64*)e->arr["slab_rows"].p, c.nx, nxs(e), c.nrn, c.nm, c.nkr, 3);
-  return fb_in_dev(fb, e->A("J_fb"), e->A("J"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"), c.nx, c.nrn, c.nm,
+  return fb_in_dev(fb, e->A("J_fb"), e->A("J"), lx, e->D("kx_base"), e->pInCurr, e->D("DepFact"), c.nx, c.nrn, c.nm,
                    c.nkr, 3);
 }
 
@@ -545,8 +563,13 @@ int ph_gather_push(chimera_engine* e, double dt_frac) {
 // gather + push_velocs of step k fused with push_coords + dep_curr + dep_dens of step k+1 (particles_fused.cu);
 // species without a fused instantiation (or still ones) take the separate kernels
 int ph_particles_fused(chimera_engine* e, int rho_from_bg) {
-  const auto& c = e->cfg;
-  GridGeom g = geom_ready(e);
+  auto& c = e->cfg;
+  GridGeom g = geom_ready(e);  // the gather closes the previous step: window where that step left it
+  // window stages of the step whose head is fused in: J on the grid after stage 1, rho after stage 2
+  const double lJ = c.leftX + e->win_s1, lR = lJ + e->win_s2;
+  GridGeom gJ = g, gR = g;
+  gJ.leftX = lJ;
+  gR.leftX = lR;
   const i64 n = c.nx * c.nrn * c.nm;
   CHB_CUDA(cudaMemsetAsync(e->A("J"), 0, sizeof(cd) * n * 3, e->st));
   if (c.space_charge) {
@@ -560,7 +583,7 @@ int ph_particles_fused(chimera_engine* e, int rho_from_bg) {
     spf.cta = s.d_cta_f;
     spf.ncta = s.ncta_f;
     int rc = launch_fused_particles(e->st, c.env, c.space_charge, s.x, s.xh, s.p, s.w, s.cap, e->A("EB"), e->A("J"),
-                                    e->A("Rho"), g, chunkspec(e, s), s.push_fact * c.dt, c.dt, und, spf);
+                                    e->A("Rho"), g, chunkspec(e, s), s.push_fact * c.dt, c.dt, und, spf, lJ, lR);
     if (rc == -1) {  // no fused instantiation for this mode count: the separate kernels, same order of operations
       rc = launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt, und, sortedspec(e, s));
       if (rc == -1)
@@ -571,9 +594,10 @@ int ph_particles_fused(chimera_engine* e, int rho_from_bg) {
       for (int curr = 1; curr >= (c.space_charge ? 0 : 1); --curr) {
         cd* grid = curr ? e->A("J") : e->A("Rho");
         const double* xs = curr ? s.xh : s.x;
-        rc = launch_deposit_binned(e->st, c.env, curr, xs, s.p, s.w, s.cap, grid, g, chunkspec(e, s), sortedspec(e, s));
+        const GridGeom& gd = curr ? gJ : gR;
+        rc = launch_deposit_binned(e->st, c.env, curr, xs, s.p, s.w, s.cap, grid, gd, chunkspec(e, s), sortedspec(e, s));
         if (rc == -1)
-          rc = launch_deposit_runs(e->st, c.env, curr, soa(xs, s.cap), soa((const double*)s.p, s.cap), s.w, grid, g,
+          rc = launch_deposit_runs(e->st, c.env, curr, soa(xs, s.cap), soa((const double*)s.p, s.cap), s.w, grid, gd,
                                    chunkspec(e, s), s.np);
         CHB_TRY(rc);
       }
@@ -583,6 +607,10 @@ int ph_particles_fused(chimera_engine* e, int rho_from_bg) {
   }
   CHB_TRY(launch_ghost_fold(e->st, e->A("J"), c.nx, c.nrn, c.nm * 3));
   if (c.space_charge) CHB_TRY(launch_ghost_fold(e->st, e->A("Rho"), c.nx, c.nrn, c.nm));
+  e->leftX_J = lJ;
+  c.rightX += e->win_s1;  // same two roundings as the separate stages
+  c.rightX += e->win_s2;
+  c.leftX = lR;
   return 0;
 }
 
@@ -634,6 +662,7 @@ int run_phase(chimera_engine* e, int phase, double arg) {
     case CHB_GATHER_PUSH: rc = ph_gather_push(e, arg); break;
     case CHB_ADD_BG: rc = ph_add_bg(e); break;
     case CHB_STATIC_FIELDS: rc = ph_static_fields(e); break;
+    case CHB_WINDOW: rc = ph_window(e, arg == 2.0 ? 2 : 1); break;
     default: set_error("unknown engine phase %d", phase); rc = 2;
   }
   if (e->profile) {
@@ -868,6 +897,17 @@ int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nx
 }
 
 // chimera_main.py:286-290 move_frame: Xgrid += shiftX
+int chimera_engine_set_window(chimera_engine* e, double shift_stage1, double shift_stage2) {
+  ENG_CHECK(e);
+  if (e->cfg.static_kick && (shift_stage1 != 0.0 || shift_stage2 != 0.0)) {
+    set_error("set_window: not available with the 'StaticKick' schedule");
+    return 2;
+  }
+  e->win_s1 = shift_stage1;
+  e->win_s2 = shift_stage2;
+  return 0;
+}
+
 int chimera_engine_move_window(chimera_engine* e, double shiftX) {
   ENG_CHECK(e);
   e->cfg.leftX += shiftX;
@@ -1070,9 +1110,12 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
       CHB_TRY(run_phase(e, CHB_PARTICLES_FUSED, 1));
     } else {
       if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
+      const bool win = e->win_s1 != 0.0 || e->win_s2 != 0.0;
+      if (win) CHB_TRY(ph_window(e, 1));  // frame_act(istep) (chimera_main.py:83)
       CHB_TRY(run_phase(e, CHB_PUSH_COORDS, 0));
       if (sort_now) CHB_TRY(run_phase(e, CHB_SORT, 1));
       CHB_TRY(run_phase(e, CHB_DEPOSIT_J, 0));
+      if (win) CHB_TRY(ph_window(e, 2));  // frame_act(istep, 'stage2') (chimera_main.py:87)
       if (c.space_charge || c.static_kick) CHB_TRY(run_phase(e, CHB_DEPOSIT_RHO, 1));
     }
     CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
@@ -1117,6 +1160,7 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
   Species& s = e->sp[id];
   if (s.still) { set_error("step_host: species %d is still", id); return 2; }
   if (e->cfg.static_kick) { set_error("step_host: no 'StaticKick' schedule; use chimera_engine_step"); return 2; }
+  if (e->win_s1 != 0.0 || e->win_s2 != 0.0) { set_error("step_host: no per-step window; use chimera_engine_step"); return 2; }
   if (np < 0 || np > s.cap) { set_error("step_host: np=%lld exceeds the species capacity %lld", np, s.cap); return 2; }
   if (!coords || !coords_half || !momenta || !weights) { set_error("step_host: null particle buffer"); return 2; }
   const auto& c = e->cfg;

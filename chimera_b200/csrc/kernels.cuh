@@ -164,7 +164,8 @@ int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const d
 constexpr int kFusedNPB = 512;
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
                            const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
-                           const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp);
+                           const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp,
+                           double leftX_J, double leftX_R);  // node 0 of the J / rho deposit grids (moving window)
 void fused_profile_enable(int on);
 void fused_profile_read(unsigned long long out[8]);
 // field gather from a shared-memory tile of the EB grid + undulator + Boris push

@@ -47,10 +47,11 @@ struct Shape {
   double rp;
 };
 
-__device__ __forceinline__ bool make_shape(const GridGeom& g, double xp, double yp, double zp, Shape& s) {
+// leftX: position of node 0 of the grid the shape is taken on (g.leftX, or the moved window's, chimera_main.py:286)
+__device__ __forceinline__ bool make_shape_at(const GridGeom& g, double leftX, double xp, double yp, double zp, Shape& s) {
   s.rp = sqrt(yp * yp + zp * zp);
   if (s.rp >= g.rmax) return false;
-  const double xs = (xp - g.leftX) * g.dx_inv;
+  const double xs = (xp - leftX) * g.dx_inv;
   s.ix = (i64)floor(xs);
   s.ir = (i64)floor((s.rp - g.r0) * g.dr_inv);
   if (s.ir < 0 || s.ir > g.nrn - 2) return false;
@@ -59,6 +60,9 @@ __device__ __forceinline__ bool make_shape(const GridGeom& g, double xp, double 
   s.sr1 = (s.rp - __ldg(g.Rgrid + s.ir)) * g.dr_inv;
   s.sr0 = 1.0 - s.sr1;
   return true;
+}
+__device__ __forceinline__ bool make_shape(const GridGeom& g, double xp, double yp, double zp, Shape& s) {
+  return make_shape_at(g, g.leftX, xp, yp, zp, s);
 }
 
 

@@ -120,7 +120,10 @@ template <int ENV, int NM, int SC>
 __global__ void __launch_bounds__(FT, CHB_FMINB)
 fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __restrict__ mom, const double* __restrict__ w,
                   i64 cap, const cd* __restrict__ Fld, cd* __restrict__ J, cd* __restrict__ Rho, GridGeom g, ChunkSpec ch,
-                  double dt_2, double dt, DeviceSet und, SortedSpec sp) {
+                  double dt_2, double dt, DeviceSet und, SortedSpec sp, double leftX_J, double leftX_R) {
+  // leftX_J / leftX_R: node 0 of the grid the current / the charge is deposited on.  They equal g.leftX unless a
+  // window moves every step (chimera_main.py:286-302: stage 1 before push_coords, stage 2 between dep_curr and
+  // dep_dens for a 'Staged' frame); the gather always uses g.leftX, the window position of the closing step.
   constexpr int NKO = ENV ? (NM - 1) / 2 : NM - 1;
   constexpr int NCJ = ENV ? 1 : 3;  // Q1: the envelope current has l = 3 only
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -352,7 +355,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     {  // current at the centred position
       Shape s;
       bool direct = false;
-      if (wp != 0.0 && make_shape(g, xc[0], xc[1], xc[2], s) && fabs(px) + fabs(py) + fabs(pz) != 0.0 &&
+      if (wp != 0.0 && make_shape_at(g, leftX_J, xc[0], xc[1], xc[2], s) && fabs(px) + fabs(py) + fabs(pz) != 0.0 &&
           s.ix >= -1 && s.ix <= g.nxn - 1) {  // dep_curr skips w = 0, r >= rmax and particles at rest (grid_deps.f90:36-42)
         if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
           recJ[li] = s.sx1;
@@ -381,12 +384,16 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
           }
         } else direct = true;
       }
-      if (direct) deposit_one<ENV, 1>(g, ch, cr.chunk, J, xc[0], xc[1], xc[2], px, py, pz, wp);
+      if (direct) {
+        GridGeom gj = g;
+        gj.leftX = leftX_J;
+        deposit_one<ENV, 1>(gj, ch, cr.chunk, J, xc[0], xc[1], xc[2], px, py, pz, wp);
+      }
     }
     if (SC) {  // charge at the new position
       Shape s;
       bool direct = false;
-      if (wp != 0.0 && make_shape(g, x1[0], x1[1], x1[2], s) && s.ix >= -1 && s.ix <= g.nxn - 1) {
+      if (wp != 0.0 && make_shape_at(g, leftX_R, x1[0], x1[1], x1[2], s) && s.ix >= -1 && s.ix <= g.nxn - 1) {
         if (s.ix + 1 < (1 << 20) && s.ir < (1 << 12)) {
           recR[li] = s.sx1;
           recR[FSTR + li] = s.sr1;
@@ -411,7 +418,11 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
           }
         } else direct = true;
       }
-      if (direct) deposit_one<ENV, 0>(g, ch, cr.chunk, Rho, x1[0], x1[1], x1[2], 0.0, 0.0, 0.0, wp);
+      if (direct) {
+        GridGeom gr = g;
+        gr.leftX = leftX_R;
+        deposit_one<ENV, 0>(gr, ch, cr.chunk, Rho, x1[0], x1[1], x1[2], 0.0, 0.0, 0.0, wp);
+      }
     }
     fast[li] = fl;
   }
@@ -563,7 +574,7 @@ constexpr size_t F_SMEM = sizeof(double) * FNF * FSTR + sizeof(int) * (FBINS + F
 template <int ENV, int SC>
 int launch_fused_nm(cudaStream_t st, double* x, double* xh, double* mom, const double* w, i64 cap, const cd* Fld, cd* J,
                     cd* Rho, const GridGeom& g, const ChunkSpec& ch, double dt_2, double dt, const DeviceSet& und,
-                    const SortedSpec& sp) {
+                    const SortedSpec& sp, double leftX_J, double leftX_R) {
 #define CHB_FUSED(NMV)                                                                                                 \
   case NMV: {                                                                                                          \
     static bool attr = false;                                                                                          \
@@ -577,7 +588,8 @@ int launch_fused_nm(cudaStream_t st, double* x, double* xh, double* mom, const d
       }                                                                                                                \
       attr = true;                                                                                                     \
     }                                                                                                                  \
-    fused_particles_k<ENV, NMV, SC><<<sp.ncta, FT, F_SMEM, st>>>(x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp); \
+    fused_particles_k<ENV, NMV, SC><<<sp.ncta, FT, F_SMEM, st>>>(x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp, \
+                                                               leftX_J, leftX_R);                       \
   } break;
   switch ((int)g.nm) {
     CHB_FUSED(1)
@@ -602,16 +614,17 @@ void fused_profile_read(unsigned long long out[8]) { cudaMemcpyFromSymbol(out, g
 // returns -1 when the mode count has no instantiation (the caller falls back to the separate kernels)
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
                            const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
-                           const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp) {
+                           const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp,
+                           double leftX_J, double leftX_R) {
   if (sp.ncta <= 0) return 0;
   if (env && (g.nm % 2) != 1) { set_error("envelope kernels need an odd number of mode slots"); return 2; }
   const double dt_2 = 0.5 * push_dt;
   if (env) {
-    if (space_charge) return launch_fused_nm<1, 1>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
-    return launch_fused_nm<1, 0>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
+    if (space_charge) return launch_fused_nm<1, 1>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp, leftX_J, leftX_R);
+    return launch_fused_nm<1, 0>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp, leftX_J, leftX_R);
   }
-  if (space_charge) return launch_fused_nm<0, 1>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
-  return launch_fused_nm<0, 0>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp);
+  if (space_charge) return launch_fused_nm<0, 1>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp, leftX_J, leftX_R);
+  return launch_fused_nm<0, 0>(st, x, xh, mom, w, cap, Fld, J, Rho, g, ch, dt_2, dt, und, sp, leftX_J, leftX_R);
 }
 
 }  // namespace chb

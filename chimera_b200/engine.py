@@ -26,7 +26,7 @@ _i64 = ctypes.c_longlong
 PHASES = (
     "push_coords", "sort", "deposit_J", "deposit_rho", "deposit_bg", "fb_in_J", "fb_in_rho", "poisson",
     "maxwell", "init_push", "fields_out", "gather_push", "add_bg", "fields_out_a", "fields_out_b",
-    "particles_fused", "static_fields",
+    "particles_fused", "static_fields", "window",
 )
 PHASE_ID = {n: i for i, n in enumerate(PHASES)}
 
@@ -272,6 +272,20 @@ class Engine:
         self._check(self.lib.chimera_engine_damp_field(self._h, ctypes.c_void_p(prof.ctypes.data), _i64(prof.shape[0]),
                                                        {"left": 0, "right": 1, "both": 2}[config]))
 
+    def set_window(self, velocity, time_step=None, staged=False):
+        """A window that moves EVERY step (``MovingFrames`` entry with ``'Steps': 1``; the FEL runs,
+        doc/tests/fel-testrun.py:61-63), handled inside ``step``: shifts as ``ChimeraRun.init_Moving_Frames``
+        computes them (chimera_main.py:40-51) -- ``'Staged'``: ``Velocity*TimeStep/2`` before ``push_coords`` and again
+        between ``dep_curr`` and ``dep_dens``; otherwise ``Velocity*TimeStep`` once, before ``push_coords``.  The fused
+        particle kernel deposits on the moved grids, so multi-step calls stay fused.  ``velocity=0`` switches it off."""
+        ts = self.cfg.dt if time_step is None else time_step
+        if staged:
+            s1 = s2 = 0.5 * velocity * ts * 1
+        else:
+            s1, s2 = velocity * ts * 1, 0.0
+        self._win = (s1, s2)
+        self._check(self.lib.chimera_engine_set_window(self._h, ctypes.c_double(s1), ctypes.c_double(s2)))
+
     def move_window(self, shift):
         """``ChimeraRun.move_frame`` (chimera_main.py:286): the engine's grid moves by ``shift``.  The solver
         dictionary ``setup.Args`` belongs to the driver, whose own ``move_frame`` updates it; the engine tracks
@@ -480,10 +494,19 @@ class Engine:
             else:
                 if gather_pending:
                     self.run("gather_push", 1.0)
+                win = any(getattr(self, "_win", (0.0, 0.0)))
+                if win:
+                    self.run("window", 1.0)
                 self.run("push_coords")
                 if sort_now:
                     self.run("sort", 1.0)
-                self._deposit_and_reduce()
+                self.run("deposit_J")
+                if win:
+                    self.run("window", 2.0)
+                if c.space_charge:
+                    self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
+                if self.world > 1:
+                    self._allreduce_grids()
             self.run("fb_in_J")
             if c.space_charge:
                 self.run("fb_in_rho")

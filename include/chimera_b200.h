@@ -272,6 +272,12 @@ int chimera_engine_set_time(chimera_engine* e, double t);
  *             device pointers; coords_halfstep = coords; the species grows as needed); call _sort before depositing
  * sort: species.py:351 chunk_and_damp with SimDom = [leftX + left_margin, rightX, 0, upperR^2] */
 int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode);
+/* A window that moves EVERY step (MovingFrame 'Steps': 1, e.g. the FEL runs, doc/tests/fel-testrun.py:61-63) inside
+ * chimera_engine_step: the grid origin advances by shift_stage1 before push_coords (ChimeraRun.frame_act stage 1,
+ * chimera_main.py:83,292-302) and by shift_stage2 between dep_curr and dep_dens (stage 2 of a 'Staged' frame,
+ * :87,303).  init_Moving_Frames (:40-51): 'Staged' -> both = Velocity*TimeStep/2, otherwise (Velocity*TimeStep, 0).
+ * The fused particle kernel deposits on the moved grids, so multi-step calls stay fused.  (0, 0) switches it off. */
+int chimera_engine_set_window(chimera_engine* e, double shift_stage1, double shift_stage2);
 int chimera_engine_move_window(chimera_engine* e, double shiftX);
 int chimera_engine_append_particles(chimera_engine* e, int species, const double* coords, const double* momenta,
                                     const double* weights, chb_i64 n);
@@ -311,7 +317,8 @@ enum chimera_engine_phase {
   CHB_PARTICLES_FUSED = 15, /* gather + device + push_velocs of one step and push_coords + dep_curr + dep_dens of the
                              next in one kernel (the per-particle work between two field solves); arg as DEPOSIT_RHO */
   CHB_STATIC_FIELDS = 16, /* chimera_main.py:118-125 update_fields with 'StaticKick' (needs every kx row)        */
-  CHB_NPHASES = 17
+  CHB_WINDOW = 17,        /* one stage of a window that moves every step (chimera_main.py:286); arg: 1 | 2       */
+  CHB_NPHASES = 18
 };
 int chimera_engine_run(chimera_engine* e, int phase, double arg);
 /* nsteps x make_step on the engine's stream; istep0 = index of the first step (re-binning cadence) */

@@ -49,6 +49,8 @@ class RefRun:
         self.g_prv, self.g_nxt = S.zeros_fb(3), S.zeros_fb(3)
         self.PE, self.PG = S.PSATD_E, S.PSATD_G
         self.istep = 0
+        # a window that moves every step ('Steps': 1): (shift at stage 1, shift at stage 2), chimera_main.py:40-51
+        self.window = (0.0, 0.0)
 
     # ---- species.py:351-398 -------------------------------------------------------------------
     def chunk_and_damp(self, s, position, left_margin=0.0):
@@ -226,9 +228,16 @@ class RefRun:
         self.project_fields()
         self.devices_and_push(0.5)
 
+    def move_frame(self, shift):  # chimera_main.py:286-290
+        a = self.a
+        a["Xgrid"] = a["Xgrid"] + shift
+        a["leftX"], a["rightX"] = a["Xgrid"][0], a["Xgrid"][-1]
+
     def make_step(self):
         f, a = self.f, self.a
         self.istep += 1
+        if any(self.window):
+            self.move_frame(self.window[0])  # frame_act(istep): stage 1 (chimera_main.py:83)
         for s in self.sp:
             if s.still or s.coords.shape[1] == 0:
                 continue
@@ -237,6 +246,8 @@ class RefRun:
             for s in self.sp:
                 self.chunk_and_damp(s, "cntr")
         self.project_current()
+        if any(self.window):
+            self.move_frame(self.window[1])  # frame_act(istep, 'stage2') of a 'Staged' frame (chimera_main.py:87)
         self.project_density()
         self.update_fields()
         self.project_fields()

@@ -266,6 +266,37 @@ def test_fused_particle_kernel_matches_reference_sequence(ofim, gfim, name, ions
     eng2.close()
 
 
+@pytest.mark.parametrize("name,staged", [("env_m1", True), ("env_m1", False), ("real_m2", True)])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_engine_window_moving_every_step(ofim, gfim, name, staged, fuse):
+    """MovingFrame with 'Steps': 1 (the FEL runs, doc/tests/fel-testrun.py:61-63): the grid origin advances inside
+    every make_step -- half before push_coords and half between dep_curr and dep_dens for a 'Staged' frame
+    (chimera_main.py:40-51, 83-87), so J, rho and the gathered fields live on three different window positions.
+    The engine handles it inside step() (the fused kernel deposits on the moved grids); 8 steps cross a re-binning
+    step.  The window velocity is not a multiple of dx/dt, so cell indices do change relative to the binning."""
+    und = dict(a0=0.3, **{"lambda": 1.3}, X0=-1.0, Lx=9.0) if name == "env_m1" else None
+    S, ref, eng = build_pair(ofim, name, 83, undulator=und, still_ions=False)
+    v = 0.37 if name == "real_m2" else 0.999
+    dt = S.Args["dt"]
+    ref.window = (0.5 * v * dt, 0.5 * v * dt) if staged else (v * dt, 0.0)
+    eng.set_window(v, staged=staged)
+    eng.set_fuse(fuse)
+    ref.make_halfstep()
+    eng.make_halfstep()
+    nsteps = 8
+    for _ in range(nsteps):
+        ref.make_step()
+    eng.step(3)
+    eng.step(nsteps - 3)
+    compare_state(ref, eng, nsteps * TOL)
+    eng.set_window(0.0)
+    ref.window = (0.0, 0.0)
+    ref.make_step()
+    eng.step(1)
+    compare_state(ref, eng, (nsteps + 1) * TOL)
+    eng.close()
+
+
 @pytest.mark.parametrize("name", ["real_m2", "env_m1"])
 def test_engine_device_list(ofim, gfim, name):
     """NEXT-1: every kind of external device (devices.f90) between gather and push inside the resident engine,

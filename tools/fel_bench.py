@@ -1,6 +1,7 @@
 """BASELINE.json configs[3], one GPU's share: unaveraged FEL undulator beam, envelope solver (KxShift), one
 azimuthal mode, NoPoissonCorrection, analytic undulator, 1.25e8 macro-particles (1e9 over 8 GPUs).  Device-
-resident engine, CUDA events around K make_steps; per-phase times from the engine profile.  The beam fills
+resident engine with the 'Staged' window moving every step inside it, CUDA events around K make_steps; per-phase
+times from the engine profile.  The beam fills
 x in +-lbx/2, r < lbr of the fel-testrun geometry (doc/tests/fel-testrun.py:12-58) on an Nx x Nr = 2048 x 256
 grid: ~7600 particles per occupied cell, i.e. the deposit is dominated by same-cell accumulation.
 Writes gpurun_out/fel_bench.json.
@@ -41,6 +42,9 @@ S = SolverSetup(cfg)
 eng = Engine(S)
 eng.use_stream(torch.cuda.current_stream().cuda_stream)
 eng.add_device("undul_analytic", np.array([K0, 1.0, 1.0, float(periods)]))
+# MovingFrame {'TimeStep': dt, 'Steps': 1, 'Velocity': vb, 'Features': ('Staged', 'NoSorting')} (fel-testrun.py:61-63):
+# the window follows the beam, half a shift before push_coords and half between dep_curr and dep_dens
+eng.set_window(vb, time_step=dt, staged=True)
 
 n = int(a.np)
 g = torch.Generator(device="cuda")
