@@ -65,21 +65,6 @@ __device__ __forceinline__ bool make_shape(const GridGeom& g, double xp, double 
   return make_shape_at(g, g.leftX, xp, yp, zp, s);
 }
 
-// ctr[key] += 1 for every lane with `act`, returning the lane's slot (old value + rank among the lanes with the same
-// key), with ONE shared-memory atomic per distinct key in the warp: cell-sorted particles put most lanes of a warp on
-// the same counter, where per-lane atomics serialise (32-way for a 48-ppc plasma, 512-way per CTA for an FEL beam
-// with thousands of particles per cell).  All 32 lanes of the warp must call it.
-__device__ __forceinline__ int warp_key_add(int* ctr, int key, bool act) {
-  const unsigned am = __ballot_sync(0xffffffffu, act);
-  if (!act) return 0;
-  const unsigned peers = __match_any_sync(am, key);
-  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(ctr + key, __popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  return base + __popc(peers & ((1u << lane) - 1u));
-}
-
 
 template <int ENV>
 __device__ __forceinline__ bool gather_one(const GridGeom& g, const cd* __restrict__ Fld, double xp, double yp,

@@ -177,15 +177,16 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
 #pragma unroll
   for (int j = 0; j < FPPT; ++j) {
     const int li = tid + j * FT;
-    const bool slot_ok = li < FNPB;  // (no `continue`: every lane has to reach the warp-wide histogram step)
+    if (li >= FNPB) continue;
     unsigned short key = 0xFFFFu;
     const double xp = xa[j], yp = ya[j], zp = za[j];
     double F[6] = {0, 0, 0, 0, 0, 0};
     Shape s;
-    if (slot_ok && wa[j] != 0.0 && make_shape(g, xp, yp, zp, s) && s.ix >= 0 && s.ix <= g.nxn - 2) {
+    if (wa[j] != 0.0 && make_shape(g, xp, yp, zp, s) && s.ix >= 0 && s.ix <= g.nxn - 2) {
       const i64 kx = s.ix - ix0, kr = s.ir - ir0;
       if (kx >= 0 && kx < FBX && kr >= 0 && kr < FBR) {
         key = (unsigned short)(kr * FBX + kx);
+        atomicAdd(&bins[key], 1);
         rec[li] = s.sx1;
         rec[FSTR + li] = s.sr1;
         const double rinv = (s.rp > 0.0) ? rsqrt(s.rp * s.rp) : 0.0;  // gather phase e^{+i theta}; axis: 0 | 1 (Q4)
@@ -201,14 +202,11 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         gather_one<ENV>(g, Fld, xp, yp, zp, F);  // drifted out of the window: L2 path
       }
     }
-    warp_key_add(bins, key, key != 0xFFFFu);
-    if (slot_ok) {
-      if (key == 0xFFFFu) {
+    if (key == 0xFFFFu) {
 #pragma unroll
-        for (int l = 0; l < 6; ++l) fbuf[l * FSTR + li] = F[l];
-      }
-      skey[li] = key;
+      for (int l = 0; l < 6; ++l) fbuf[l * FSTR + li] = F[l];
     }
+    skey[li] = key;
   }
   }
   __syncthreads();
@@ -245,9 +243,10 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
 #pragma unroll
   for (int j = 0; j < FPPT; ++j) {
     const int li = tid + j * FT;
-    const int key = li < FNPB ? skey[li] : 0xFFFF;
-    const int slot = warp_key_add(bins, key, key != 0xFFFF);
-    if (key != 0xFFFF) order[slot] = (unsigned short)li;
+    if (li < FNPB) {
+      const int key = skey[li];
+      if (key != 0xFFFF) order[atomicAdd(&bins[key], 1)] = (unsigned short)li;
+    }
   }
   __syncthreads();
   FPROF_MARK(1)

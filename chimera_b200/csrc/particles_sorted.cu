@@ -519,14 +519,15 @@ deposit_binned_k(const double* __restrict__ x, const double* __restrict__ mom, c
 #pragma unroll
     for (int j = 0; j < HB; ++j) {
       const int li = tid + (jb + j) * DB_THREADS;
-      const bool slot_ok = li < kDepNPB;  // (no `continue`: every lane has to reach the warp-wide histogram step)
+      if (li >= kDepNPB) continue;
       unsigned short key = 0xFFFFu;
       const double wp = ws[j], xp = xs[j], yp = ys[j], zp = zs[j];
       Shape s;
-      if (slot_ok && wp != 0.0 && make_shape(g, xp, yp, zp, s)) {
+      if (wp != 0.0 && make_shape(g, xp, yp, zp, s)) {
         const i64 kx = s.ix - ix0, kr = s.ir - ir0;
         if (kx >= 0 && kx < DB_BX && kr >= 0 && kr < DB_BR) {
           key = (unsigned short)(kr * DB_BX + kx);
+          atomicAdd(&bins[key], 1);
           rec[li] = s.sx1;
           rec[kDepNPB + li] = s.sr1;
           const double rinv = (s.rp > 0.0) ? 1.0 / s.rp : 0.0;  // deposit phase exp(-i theta); 0 on the axis
@@ -554,8 +555,7 @@ deposit_binned_k(const double* __restrict__ x, const double* __restrict__ mom, c
                                  CURR ? ps[2][j] : 0.0, wp);
         }
       }
-      warp_key_add(bins, key, key != 0xFFFFu);
-      if (slot_ok) skey[li] = key;
+      skey[li] = key;
     }
   }
   __syncthreads();
@@ -566,9 +566,10 @@ deposit_binned_k(const double* __restrict__ x, const double* __restrict__ mom, c
 #pragma unroll
   for (int j = 0; j < DB_PPT; ++j) {
     const int li = tid + j * DB_THREADS;
-    const int key = li < kDepNPB ? skey[li] : 0xFFFF;
-    const int slot = warp_key_add(bins, key, key != 0xFFFF);
-    if (key != 0xFFFF) order[slot] = (unsigned short)li;
+    if (li < kDepNPB) {
+      const int key = skey[li];
+      if (key != 0xFFFF) order[atomicAdd(&bins[key], 1)] = (unsigned short)li;
+    }
   }
   __syncthreads();
 
@@ -720,6 +721,7 @@ gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w,
         const i64 kx = s.ix - ix0, kr = s.ir - ir0;
         if (kx >= 0 && kx < DB_BX && kr >= 0 && kr < DB_BR) {
           key = (unsigned short)(kr * DB_BX + kx);
+          atomicAdd(&bins[key], 1);
           rec[li] = s.sx1;
           rec[kDepNPB + li] = s.sr1;
           // gather phase exp(+i theta); on the axis 0 (real solver) or 1 (envelope solver), Q4
@@ -736,7 +738,6 @@ gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w,
           gather_one<ENV>(g, Fld, xp, yp, zp, F);  // drifted out of the box
         }
       }
-      warp_key_add(bins, key, key != 0xFFFFu);
       if (key == 0xFFFFu) {
 #pragma unroll
         for (int l = 0; l < 6; ++l) fbuf[l * kDepNPB + li] = F[l];
@@ -751,8 +752,7 @@ gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w,
   for (int j = 0; j < GB_PPT; ++j) {
     const int li = tid + j * GB_THREADS;
     const int key = skey[li];
-    const int slot = warp_key_add(bins, key, key != 0xFFFF);
-    if (key != 0xFFFF) order[slot] = (unsigned short)li;
+    if (key != 0xFFFF) order[atomicAdd(&bins[key], 1)] = (unsigned short)li;
   }
   __syncthreads();
 
