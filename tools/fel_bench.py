@@ -26,6 +26,7 @@ ap.add_argument("--nx", type=int, default=2048)
 ap.add_argument("--nr", type=int, default=256)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--fused-profile", action="store_true", help="per-stage clock shares of the fused particle kernel (diagnosis)")
 a = ap.parse_args()
 
 K0, lam0, periods = 1.95, 2.8, 10
@@ -88,6 +89,19 @@ out = {"workload": "FEL undulator beam, envelope solver Nx=%d Nr=%d 1 mode, undu
        "particle_cycle_alg_bytes": 376.0 * kept, "hbm_gbs_peak": hbm}
 if "particles_fused" in per:
     out["fused_frac_of_hbm"] = 376.0 * kept / (per["particles_fused"] * 1e-3) / 1e9 / hbm
+if a.fused_profile:
+    import ctypes
+
+    lib = eng.lib
+    lib.chimera_fused_profile(1)
+    eng.step(4)
+    eng.sync()
+    cyc = (ctypes.c_ulonglong * 8)()
+    lib.chimera_fused_profile_read(cyc)
+    lib.chimera_fused_profile(0)
+    tot = float(sum(cyc[:6])) or 1.0
+    out["fused_stages"] = {nm: cyc[i] / tot for i, nm in enumerate(
+        ("A_records_histogram", "BC_scan_sort", "D_gather", "E_push", "F_deposit", "G_cell_changers"))}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fel_bench.json"), "w"), indent=1)
 print(json.dumps(out))
