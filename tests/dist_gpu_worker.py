@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def main(name, slab):
+def main(name, slab, window=0):
     from oracle import fimera as ofim
     from pic_ref import RefRun, RefSpecies
     from util import SETUPS, TOL, assert_close, carrier_tol, match, plasma, seed_fields
@@ -37,9 +37,12 @@ def main(name, slab):
     sp = [RefSpecies(x, p, w)]
     if ions:
         sp.append(RefSpecies(xi, 0 * pi_, -wi, charge=1.0, mass=1886.0, still=True))
-    ref = RefRun(ofim, S, sp, background=ions)
+    # the reference sequence moves the window by editing its solver dictionary: give it its own
+    ref = RefRun(ofim, SolverSetup(copy.deepcopy(SETUPS[name])) if window else S, sp, background=ions)
     ref.EG_fb[:] = eg0
     px0 = (0.0,) * len(sp)
+    if window:  # a 'Staged' frame moving every step (chimera_main.py:40-51, 83-87)
+        ref.window = (0.5 * 0.37 * S.Args["dt"],) * 2
     ref.make_halfstep(px0=px0)
     for _ in range(3):
         ref.make_step()
@@ -51,13 +54,21 @@ def main(name, slab):
         ilo, ihi = sharding.particle_range(xi.shape[1], rank, world)
         eng.add_species(xi[:, ilo:ihi], 0 * pi_[:, ilo:ihi], -wi[ilo:ihi], charge=1.0, mass=1886.0, still=True)
     eng.upload("EG_fb", eg0)
+    if window:
+        eng.set_window(0.37, staged=True)
     eng.make_halfstep(px0=px0, background=ions)
     eng.step(2)
-    # third step through the host-buffer entry point (begin / all-reduce / mid / all-gather / end)
     xs, xh, ps, ws = eng.particles(0)
     eg = eng.download("EG_fb")
-    g = eng.download("gradRho_fb_nxt") if eng.cfg.space_charge else None
-    n = eng.step_host(xs, xh, ps, ws, eg, g)
+    if window:  # the per-step window lives in the step schedule, not in the host-buffer entry point
+        eng.step(1)
+        xs, xh, ps, ws = eng.particles(0)
+        eg = eng.download("EG_fb")
+        n = ws.size
+    else:
+        # third step through the host-buffer entry point (begin / all-reduce / mid / all-gather / end)
+        g = eng.download("gradRho_fb_nxt") if eng.cfg.space_charge else None
+        n = eng.step_host(xs, xh, ps, ws, eg, g)
     tol = carrier_tol(S, 4 * TOL)
     rows = eng.rows if eng.slab else slice(None)
     assert_close(eg, ref.EG_fb[rows], tol, "EG_fb")
@@ -78,8 +89,8 @@ def main(name, slab):
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print("OK", name, "world", world, "slab", bool(slab))
+        print("OK", name, "world", world, "slab", bool(slab), "window", bool(window))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]))
+    main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)

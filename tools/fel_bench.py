@@ -39,8 +39,19 @@ dt = 1.0 / 30
 cfg = {"Grid": (-0.5 * Lgx, 0.5 * Lgx, Rg, Lgx / a.nx, Rg / a.nr), "TimeStep": dt, "MaxAzimuthMode": 0,
        "KxShift": k_res, "Rcut": Rcut, "CoPropagative": vb, "Xchunked": (16, 6),
        "Features": {"NoPoissonCorrection": True}}
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+torch.cuda.set_device(local)
+group = None
+if world > 1:  # one rank per GPU: particles sharded (weak scaling), J all-reduced, spectral solve by kx slab
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    group = True
+from chimera_b200 import _lib  # noqa: E402
+
+_lib.load().chimera_set_device(local)
 S = SolverSetup(cfg)
-eng = Engine(S)
+eng = Engine(S, group=group)
 eng.use_stream(torch.cuda.current_stream().cuda_stream)
 eng.add_device("undul_analytic", np.array([K0, 1.0, 1.0, float(periods)]))
 # MovingFrame {'TimeStep': dt, 'Steps': 1, 'Velocity': vb, 'Features': ('Staged', 'NoSorting')} (fel-testrun.py:61-63):
@@ -49,7 +60,7 @@ eng.set_window(vb, time_step=dt, staged=True)
 
 n = int(a.np)
 g = torch.Generator(device="cuda")
-g.manual_seed(20260101)
+g.manual_seed(20260101 + rank)
 rnd = lambda *s: torch.rand(*s, device="cuda", dtype=torch.float64, generator=g)  # noqa: E731
 rndn = lambda *s: torch.randn(*s, device="cuda", dtype=torch.float64, generator=g)  # noqa: E731
 x = (rnd(n) - 0.5) * lbx
@@ -69,26 +80,40 @@ eng.sync()
 eng.profile(True)
 eng.timings(reset=True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-torch.cuda.synchronize()
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+barrier()
 e0.record()
 eng.step(a.steps)
 e1.record()
-torch.cuda.synchronize()
+barrier()
 ms = e0.elapsed_time(e1) / a.steps
+if world > 1:
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
 ph = eng.timings(reset=True)
 eng.profile(False)
 kept = eng.count(0)
+if world > 1:
+    c = torch.tensor([float(kept)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(c)
+    kept = int(c.item())
 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 per = {k: v[0] / v[1] for k, v in ph.items() if v[1]}
 out = {"workload": "FEL undulator beam, envelope solver Nx=%d Nr=%d 1 mode, undul_analytic K0=1.95, %.3g macro-particles, "
                    "Xchunked=(16,6), NoPoissonCorrection" % (a.nx, a.nr, n),
        "metric": "particle-steps/s full PIC cycle", "value": kept / (ms * 1e-3), "ms_per_step": ms, "steps": a.steps,
-       "warmup": a.warmup, "particles": n, "particles_after": kept, "phases_ms_per_call": per,
+       "warmup": a.warmup, "n_gpus": world, "particles_per_gpu": n, "particles_after": kept, "phases_ms_per_call": per,
        "phase_calls": {k: v[1] for k, v in ph.items()},
        # envelope cycle, SURVEY 8d basis: push_coords 96 + dep_curr_env 56 + proj_fld_env 128 + push_velocs 96 B
-       "particle_cycle_alg_bytes": 376.0 * kept, "hbm_gbs_peak": hbm}
+       "particle_cycle_alg_bytes_per_gpu": 376.0 * kept / world, "hbm_gbs_peak": hbm}
 if "particles_fused" in per:
-    out["fused_frac_of_hbm"] = 376.0 * kept / (per["particles_fused"] * 1e-3) / 1e9 / hbm
+    out["fused_frac_of_hbm"] = 376.0 * kept / world / (per["particles_fused"] * 1e-3) / 1e9 / hbm
 if a.fused_profile:
     import ctypes
 
@@ -102,7 +127,11 @@ if a.fused_profile:
     tot = float(sum(cyc[:6])) or 1.0
     out["fused_stages"] = {nm: cyc[i] / tot for i, nm in enumerate(
         ("A_records_histogram", "BC_scan_sort", "D_gather", "E_push", "F_deposit", "G_cell_changers"))}
-os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fel_bench.json"), "w"), indent=1)
-print(json.dumps(out))
+if rank == 0:
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fel_bench_n%d.json" % world), "w"), indent=1)
+    print(json.dumps(out))
 eng.close()
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
