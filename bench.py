@@ -452,7 +452,7 @@ def cpu_step_model(a, steps, warmup):
     from chimera_b200.solver_setup import SolverSetup
     from pic_ref import RefRun, RefSpecies
 
-    fast = load(fast=True)
+    fast = load(fast=True, native=True)  # -march=native when a compiler is on this host (reference Makefile:14)
     cores = int(fast._lib.oracle_num_threads())
     nx_s = min(a.cpu_nx, a.nx)
     S = SolverSetup(synthetic.lwfa_solver_config(nx=nx_s, nr=a.nr, modes=a.modes, chunks=cores if nx_s % (2 * cores) == 0 else 16))
@@ -496,8 +496,9 @@ def cpu_step_model(a, steps, warmup):
     return {
         "value": n_full / t_full, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": "%d of %d particles (particle kernels, scaled linearly) and %d of %d kx rows (spectral update, scaled linearly); "
-                  "g++ -O3 -ffast-math -fopenmp build of oracle/chimera_oracle.cpp, OMP threads=%d; gfortran/FFTW3 absent so the "
-                  "Fortran itself cannot be built" % (n_s, n_full, nx_s, a.nx, cores),
+                  "g++ -O3 -ffast-math -fopenmp build of oracle/chimera_oracle.cpp (%s), OMP threads=%d; gfortran/FFTW3 absent so the "
+                  "Fortran itself cannot be built" % (n_s, n_full, nx_s, a.nx, "-march=native, built on this host" if
+                                                       fast.build_name == "liboracle_native.so" else "-march=x86-64-v3", cores),
         "particle_s_per_step_full": tp * n_full / n_s, "spectral_s_per_step_full": ts * a.nx / nx_s,
         "ms_per_step_full": t_full * 1e3,
     }

@@ -25,13 +25,24 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "all"])
 
 
-def load(fast=False):
+def load(fast=False, native=False):
+    """fast: the -O3 -ffast-math build (CPU speed baseline).  native: additionally -march=native, compiled on THIS
+    host (the reference Makefile:14 flags); falls back to the portable fast build when no compiler is around."""
     name = "liboracle_fast.so" if fast else "liboracle.so"
+    if fast and native:
+        try:
+            subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle_native.so"], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+            name = "liboracle_native.so"
+        except Exception:
+            pass
     path = os.path.join(_HERE, name)
     if not os.path.exists(path):
         build()
     lib = ctypes.CDLL(path)
-    return build_module(lib, "oracle", "oracle_fimera_fast" if fast else "oracle_fimera")
+    mod = build_module(lib, "oracle", "oracle_fimera_fast" if fast else "oracle_fimera")
+    mod.build_name = name
+    return mod
 
 
 _mod = load(fast=False)
