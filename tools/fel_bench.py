@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 sys.path.insert(0, ROOT)
 from chimera_b200.engine import Engine  # noqa: E402
 from chimera_b200.solver_setup import SolverSetup  # noqa: E402
