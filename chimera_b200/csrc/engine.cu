@@ -510,28 +510,45 @@ int ph_init_push(chimera_engine* e) {
 // fields out, first half: B from G, backward DHT (+ phase).  Unsharded: also the inverse x-FFT and the
 // normalisation, i.e. the whole of G2B_FBRot + fb_fld_out (solvers.py:536, 450).  kx-slab mode: stops at
 // "EB_slab"; the caller all-gathers the slabs into "EB_gath" and runs the second half.
-int ph_fields_out_a(chimera_engine* e, bool whole) {
+// part (kx-slab mode): 0 = E and B together; 1 = the E half only, 2 = the B half only -- so that the all-gather of one
+// half can run while the other half is computed / finished (EB_slab and EB are (.., 6) with the component slowest:
+// each half is contiguous; in split mode EB_gath holds [half][rank][(nx_slab, Nr, M, 3)])
+int ph_fields_out_a(chimera_engine* e, bool whole, int part = 0) {
   const auto& c = e->cfg;
   const i64 P = nxs(e) * c.nkr * c.nm;
   FBCtx fb = fbctx(e);
-  CHB_TRY(fb_rot_dev(fb, e->A("B_fb"), e->A("EG_fb") + P * 3, e->pDp, e->pDm, e->D("kx"), mdims(e)));
-  CHB_TRY(launch_mult_real(e->st, e->A("B_fb"), e->D("PoissFact"), P, 3));
+  if (part != 1) {
+    CHB_TRY(fb_rot_dev(fb, e->A("B_fb"), e->A("EG_fb") + P * 3, e->pDp, e->pDm, e->D("kx"), mdims(e)));
+    CHB_TRY(launch_mult_real(e->st, e->A("B_fb"), e->D("PoissFact"), P, 3));
+  }
   const cd* srcs[2] = {e->A("EG_fb"), e->A("B_fb")};
   if (slab(e)) {
     if (whole) { set_error("kx-slab engine: run fields_out_a, all-gather EB_slab into EB_gath, then fields_out_b"); return 2; }
-    return fb_out_slab_dev(fb, e->A("EB_slab"), srcs, 2, 3, c.leftX, e->D("kx_base"), e->pOut, nxs(e), c.nrn, c.nm, c.nkr);
+    if (part == 0)
+      return fb_out_slab_dev(fb, e->A("EB_slab"), srcs, 2, 3, c.leftX, e->D("kx_base"), e->pOut, nxs(e), c.nrn, c.nm, c.nkr);
+    const i64 half = nxs(e) * c.nrn * c.nm * 3;
+    return fb_out_slab_dev(fb, e->A("EB_slab") + (part - 1) * half, srcs + (part - 1), 1, 3, c.leftX, e->D("kx_base"), e->pOut,
+                           nxs(e), c.nrn, c.nm, c.nkr);
   }
+  if (part != 0) { set_error("fields_out halves are a kx-slab feature"); return 2; }
   CHB_TRY(fb_out_dev(fb, e->A("EB"), srcs, 2, 3, c.leftX, e->D("kx_base"), e->pOut, c.nx, c.nrn, c.nm, c.nkr));
   return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
 }
 
-int ph_fields_out_b(chimera_engine* e) {
+int ph_fields_out_b(chimera_engine* e, int part = 0) {
   const auto& c = e->cfg;
   if (!slab(e)) return 0;  // everything was done by the first half
   FBCtx fb = fbctx(e);
-  CHB_TRY(fb_out_finish_dev(fb, e->A("EB"), e->A("EB_gath"), (const i64*)e->arr["gather_map"].p, c.nx, nxs(e),
-                            c.nrn * c.nm * 6));
-  return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
+  if (part == 0) {
+    CHB_TRY(fb_out_finish_dev(fb, e->A("EB"), e->A("EB_gath"), (const i64*)e->arr["gather_map"].p, c.nx, nxs(e),
+                              c.nrn * c.nm * 6));
+    return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
+  }
+  const i64 half = c.nx * c.nrn * c.nm * 3;  // the same for EB and for the split EB_gath (world * nx_slab = nx)
+  cd* eb = e->A("EB") + (part - 1) * half;
+  CHB_TRY(fb_out_finish_dev(fb, eb, e->A("EB_gath") + (part - 1) * half, (const i64*)e->arr["gather_map"].p, c.nx, nxs(e),
+                            c.nrn * c.nm * 3));
+  return launch_eb_correction(e->st, eb, c.nx, c.nrn, c.nm, c.env, 3);
 }
 
 // the device list of a species at the engine's current device time (species.py:274-277)
@@ -656,8 +673,8 @@ int run_phase(chimera_engine* e, int phase, double arg) {
     case CHB_MAXWELL: rc = ph_maxwell(e); break;
     case CHB_INIT_PUSH: rc = ph_init_push(e); break;
     case CHB_FIELDS_OUT: rc = ph_fields_out_a(e, true); break;
-    case CHB_FIELDS_OUT_A: rc = ph_fields_out_a(e, false); break;
-    case CHB_FIELDS_OUT_B: rc = ph_fields_out_b(e); break;
+    case CHB_FIELDS_OUT_A: rc = ph_fields_out_a(e, false, arg == 1.0 ? 1 : (arg == 2.0 ? 2 : 0)); break;
+    case CHB_FIELDS_OUT_B: rc = ph_fields_out_b(e, arg == 1.0 ? 1 : (arg == 2.0 ? 2 : 0)); break;
     case CHB_PARTICLES_FUSED: rc = ph_particles_fused(e, arg != 0.0); break;
     case CHB_GATHER_PUSH: rc = ph_gather_push(e, arg); break;
     case CHB_ADD_BG: rc = ph_add_bg(e); break;

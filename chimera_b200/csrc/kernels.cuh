@@ -208,7 +208,8 @@ void gemm_profile_read(double* ms, double* flops, long long* launches, int reset
 // ---- spectral.cu : elementwise kernels of the Fourier-Bessel PSATD update
 int launch_rowscale_phase(cudaStream_t st, cd* a, const double* kx, double leftX, double sign, double scale,
                           const double* fact, i64 nkx, i64 ncols, i64 fact_cols);
-int launch_eb_correction(cudaStream_t st, cd* eb, i64 nxn, i64 nrn, i64 nm, int env);
+// ncomp: number of (nxn, nrn, nm) component blocks at `eb` (6 = the whole EB grid; 3 = its E or B half)
+int launch_eb_correction(cudaStream_t st, cd* eb, i64 nxn, i64 nrn, i64 nm, int env, int ncomp = 6);
 int launch_maxwell_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const cd* gp, const void* C1,
                         const void* C2, int ncoef, int coef_complex, i64 P);
 int launch_maxwell_init_push(cudaStream_t st, cd* EG, const cd* J, const cd* gn, const cd* C1, const cd* C2, i64 P);

@@ -78,9 +78,9 @@ __global__ void __launch_bounds__(TPB) eb_correction_k(cd* __restrict__ eb, i64 
     if (ir == 1) pl[ix] = negate ? cneg(v) : v;
   }
 }
-int launch_eb_correction(cudaStream_t st, cd* eb, i64 nxn, i64 nrn, i64 nm, int env) {
+int launch_eb_correction(cudaStream_t st, cd* eb, i64 nxn, i64 nrn, i64 nm, int env, int ncomp) {
   if (nxn <= 0) return 0;
-  dim3 grid(grid_for(nxn, TPB), (unsigned)(nm * 6));
+  dim3 grid(grid_for(nxn, TPB), (unsigned)(nm * ncomp));
   eb_correction_k<<<grid, TPB, 0, st>>>(eb, nxn, nrn, nm, env);
   CHB_LAUNCH_CHECK();
   return 0;

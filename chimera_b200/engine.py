@@ -154,6 +154,7 @@ class Engine:
         self.istep = 0
         self._pinned = []
         self.fuse = True
+        self.overlap = True  # pipeline the collectives with the neighbouring kernels (multi-rank only)
         if group is not None:
             import torch
 
@@ -425,15 +426,38 @@ class Engine:
         for n in names:
             self._dist.all_reduce(self.device_tensor(n), group=self._group)
 
+    def _allreduce_grids_async(self):
+        """J then Rho on the collective stream; returns the two handles: fb_in_J only needs J, so the reduction of Rho
+        runs behind it"""
+        w_j = self._dist.all_reduce(self.device_tensor("J"), group=self._group, async_op=True)
+        w_r = None
+        if self.cfg.space_charge:
+            w_r = self._dist.all_reduce(self.device_tensor("Rho"), group=self._group, async_op=True)
+        return w_j, w_r
+
     def _fields_out(self):
         """``Solver.G2B_FBRot`` + ``fb_fld_out`` (solvers.py:536, 450); on kx-slab engines the backward DHT runs
-        on this rank's rows, the slabs are all-gathered over NVLink and every rank finishes with the x-FFT."""
+        on this rank's rows, the slabs are all-gathered over NVLink and every rank finishes with the x-FFT.
+        Across ranks the E and B halves are pipelined: the all-gather of E runs while B (curl + backward DHT) is
+        computed, the all-gather of B while E gets its inverse x-FFT."""
         if not self.slab:
             self.run("fields_out")
             return
-        self.run("fields_out_a")
-        self._allgather_eb()
-        self.run("fields_out_b")
+        if self.world == 1 or not self.overlap:
+            self.run("fields_out_a")
+            self._allgather_eb()
+            self.run("fields_out_b")
+            return
+        slab, gath = self.device_tensor("EB_slab"), self.device_tensor("EB_gath")
+        hs, hg = slab.numel() // 2, gath.numel() // 2
+        self.run("fields_out_a", 1.0)
+        w_e = self._dist.all_gather_into_tensor(gath[:hg], slab[:hs], group=self._group, async_op=True)
+        self.run("fields_out_a", 2.0)
+        w_b = self._dist.all_gather_into_tensor(gath[hg:], slab[hs:], group=self._group, async_op=True)
+        w_e.wait()
+        self.run("fields_out_b", 1.0)
+        w_b.wait()
+        self.run("fields_out_b", 2.0)
 
     def _allgather_eb(self):
         self._dist.all_gather_into_tensor(self.device_tensor("EB_gath"), self.device_tensor("EB_slab"), group=self._group)
@@ -489,8 +513,6 @@ class Engine:
             self.set_time((self.istep - 1) * c.dt)  # the pending gather + push closes the previous step
             if gather_pending and not sort_now and self.fuse:
                 self.run("particles_fused", 1.0 if self.rank == 0 else 0.0)
-                if self.world > 1:
-                    self._allreduce_grids()
             else:
                 if gather_pending:
                     self.run("gather_push", 1.0)
@@ -505,9 +527,16 @@ class Engine:
                     self.run("window", 2.0)
                 if c.space_charge:
                     self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
-                if self.world > 1:
+            w_j = w_r = None
+            if self.world > 1:
+                if self.overlap:
+                    w_j, w_r = self._allreduce_grids_async()
+                    w_j.wait()
+                else:
                     self._allreduce_grids()
             self.run("fb_in_J")
+            if w_r is not None:
+                w_r.wait()
             if c.space_charge:
                 self.run("fb_in_rho")
             self.run("poisson")

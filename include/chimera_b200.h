@@ -312,8 +312,10 @@ enum chimera_engine_phase {
   CHB_FIELDS_OUT = 10, /* solvers.py:536 G2B_FBRot + :450 fb_fld_out                              */
   CHB_GATHER_PUSH = 11,/* chimera_main.py:139 proj_fld + devices + species.py:279 push_velocs; arg: dt_frac */
   CHB_ADD_BG = 12,     /* Rho += BckGrndRho (for ranks that deposited from zero before an all-reduce) */
-  CHB_FIELDS_OUT_A = 13, /* kx-slab mode: G2B_FBRot + backward DHT of this rank's rows -> "EB_slab"          */
-  CHB_FIELDS_OUT_B = 14, /* kx-slab mode: rows of the all-gathered "EB_gath" -> EB, inverse x-FFT, eb_correction */
+  CHB_FIELDS_OUT_A = 13, /* kx-slab mode: G2B_FBRot + backward DHT of this rank's rows -> "EB_slab"; arg 0: E and B,
+                            1: the E half only, 2: the B half only (each half of EB_slab is contiguous)        */
+  CHB_FIELDS_OUT_B = 14, /* kx-slab mode: rows of the all-gathered "EB_gath" -> EB, inverse x-FFT, eb_correction; arg 0:
+                            EB_gath = [rank][(nx_slab,Nr,M,6)]; 1 | 2: one half of EB_gath = [half][rank][(..,3)]  */
   CHB_PARTICLES_FUSED = 15, /* gather + device + push_velocs of one step and push_coords + dep_curr + dep_dens of the
                              next in one kernel (the per-particle work between two field solves); arg as DEPOSIT_RHO */
   CHB_STATIC_FIELDS = 16, /* chimera_main.py:118-125 update_fields with 'StaticKick' (needs every kx row)        */

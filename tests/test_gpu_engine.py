@@ -160,21 +160,45 @@ def test_engine_step_host_matches_reference_sequence(ofim, gfim, name, ions):
     eng.close()
 
 
-def _exchange_slabs(engines):
-    """what the NCCL all-gather does across ranks, emulated between engines that share one GPU"""
+def _exchange_slabs(engines, split=False):
+    """what the NCCL all-gather does across ranks, emulated between engines that share one GPU; split: the E and B
+    halves gathered separately (EB_gath = [half][rank][...]), as the pipelined multi-rank path does"""
     import torch
 
     torch.cuda.synchronize()
     for e in engines:
         e.sync()
-    gath = torch.cat([e.device_tensor("EB_slab") for e in engines])
+    slabs = [e.device_tensor("EB_slab") for e in engines]
+    if split:
+        h = slabs[0].numel() // 2
+        gath = torch.cat([s[:h] for s in slabs] + [s[h:] for s in slabs])
+    else:
+        gath = torch.cat(slabs)
     for e in engines:
         e.device_tensor("EB_gath").copy_(gath)
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("name,world", [("real_m2", 2), ("real_m2", 4), ("real_m3", 5), ("env_m3", 2)])
-def test_kx_slab_sharded_solve_matches_reference(ofim, gfim, name, world):
+def _fields_out_slabs(engines, split):
+    if not split:
+        for e in engines:
+            e.run("fields_out_a")
+        _exchange_slabs(engines)
+        for e in engines:
+            e.run("fields_out_b")
+        return
+    for e in engines:
+        e.run("fields_out_a", 1.0)
+        e.run("fields_out_a", 2.0)
+    _exchange_slabs(engines, split=True)
+    for e in engines:
+        e.run("fields_out_b", 2.0)  # any order
+        e.run("fields_out_b", 1.0)
+
+
+@pytest.mark.parametrize("name,world,split", [("real_m2", 2, False), ("real_m2", 4, True), ("real_m3", 5, False),
+                                              ("env_m3", 2, True), ("real_m3", 2, True)])
+def test_kx_slab_sharded_solve_matches_reference(ofim, gfim, name, world, split):
     """The spectral solve sharded by kx slab (mirror pairs of rows; x-FFT first, DHT / Poisson / PSATD / rot /
     backward DHT on the slab, all-gather, inverse x-FFT): `world` slab engines on one GPU, each with the full
     particle set, the all-gather emulated by device copies.  Halfstep + 2 steps against the oracle sequence."""
@@ -211,10 +235,8 @@ def test_kx_slab_sharded_solve_matches_reference(ofim, gfim, name, world):
             e.upload("CPSATD1", c1)
             e.upload("CPSATD2", c2)
             e.run("init_push")
-        e.run("fields_out_a")
-    _exchange_slabs(engines)
+    _fields_out_slabs(engines, split)
     for e in engines:
-        e.run("fields_out_b")
         e.run("gather_push", 0.5)
     for istep in (1, 2):
         ref.make_step()
@@ -225,10 +247,8 @@ def test_kx_slab_sharded_solve_matches_reference(ofim, gfim, name, world):
             deposit_and_transform(e)
             e.run("poisson")
             e.run("maxwell")
-            e.run("fields_out_a")
-        _exchange_slabs(engines)
+        _fields_out_slabs(engines, split)
         for e in engines:
-            e.run("fields_out_b")
             e.run("gather_push", 1.0)
     tol = carrier_tol(S, 3 * TOL)
     for r, e in enumerate(engines):
