@@ -197,7 +197,7 @@ def _fields_out_slabs(engines, split):
 
 
 @pytest.mark.parametrize("name,world,split", [("real_m2", 2, False), ("real_m2", 4, True), ("real_m3", 5, False),
-                                              ("env_m3", 2, True), ("real_m3", 2, True)])
+                                              ("env_m3", 2, True), ("real_m3", 5, True)])
 def test_kx_slab_sharded_solve_matches_reference(ofim, gfim, name, world, split):
     """The spectral solve sharded by kx slab (mirror pairs of rows; x-FFT first, DHT / Poisson / PSATD / rot /
     backward DHT on the slab, all-gather, inverse x-FFT): `world` slab engines on one GPU, each with the full
