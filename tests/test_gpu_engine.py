@@ -110,6 +110,53 @@ def test_engine_100_steps_diagnostics(ofim, gfim, name):
     eng.close()
 
 
+def test_engine_100_steps_fel_stage(ofim, gfim):
+    """BASELINE configs[0]/[3] in miniature: envelope solver, gamma = 391 beam close to the axis (the analytic
+    undulator field grows like cosh(ku y), devices.f90:196-197), 'Staged' window moving with the beam every step
+    (doc/tests/fel-testrun.py:61-63), 100 steps resident on the device against the reference sequence on the oracle;
+    integrated diagnostics (total charge, field energy = nrg_out, on-axis amplitude, beam energy and its spectrum)
+    within 1e-6."""
+    from chimera_b200.engine import Engine
+
+    S = SolverSetup(copy.deepcopy(SETUPS["env_m1"]))
+    a = S.Args
+    rng = np.random.default_rng(25)
+    n = 3000
+    x = a["leftX"] + (0.25 + 0.5 * rng.random(n)) * (a["rightX"] - a["leftX"])
+    r, th = 0.3 * np.sqrt(rng.random(n)), 2 * np.pi * rng.random(n)
+    coords = np.asfortranarray(np.vstack((x, r * np.cos(th), r * np.sin(th))))
+    mom = np.asfortranarray(np.vstack((391.0 * (1 + 1e-4 * rng.standard_normal(n)), 2e-5 * 391 * rng.standard_normal(n),
+                                       2e-5 * 391 * rng.standard_normal(n))))
+    w = -1e-4 * (1 + 1e-3 * rng.random(n))
+    und = dict(a0=0.3, **{"lambda": 1.3}, X0=-1.0, Lx=9.0)
+    ref = RefRun(ofim, S, [RefSpecies(coords, mom, w, device=(ofim.undul_analytic, [0.3, 1.3, -1.0, 9.0]))])
+    eng = Engine(S, undulator=und)
+    eng.add_species(coords, mom, w)
+    eg0 = seed_fields(S, 26, 0.03)
+    ref.EG_fb[:] = eg0
+    eng.upload("EG_fb", eg0)
+    v, dt = 0.999, a["dt"]
+    ref.window = (0.5 * v * dt, 0.5 * v * dt)
+    eng.set_window(v, staged=True)
+    ref.make_halfstep()
+    eng.make_halfstep()
+    for _ in range(100):
+        ref.make_step()
+    eng.step(100)
+    xe, xh, pe, we = eng.particles(0)
+    assert we.size == ref.sp[0].weights.size == n
+    gam_ref = float(np.sqrt(1 + (ref.sp[0].momenta ** 2).sum(0)).mean()) * (1 + 1e-4)
+    d_eng = diagnostics(S, eng.download("EG_fb"), xe, pe, we, gam_ref)
+    d_ref = diagnostics(S, ref.EG_fb, ref.sp[0].coords, ref.sp[0].momenta, ref.sp[0].weights, gam_ref)
+    scale = np.maximum(np.abs(d_ref), 1e-3 * np.abs(d_ref).max())
+    err = np.abs(d_eng - d_ref) / scale
+    assert err.max() < 1e-6, (err, d_eng, d_ref)
+    assert rel_l2(eng.download("EG_fb"), ref.EG_fb) < 1e-6
+    perm = match(ref.sp[0].weights, we)
+    assert_close(pe[:, perm], ref.sp[0].momenta, 1e-6, "momenta after 100 steps")
+    eng.close()
+
+
 def test_engine_dropin_sequence_matches(ofim, gfim):
     """the host-buffer drop-in (chimera_b200.fimera) driven by the same step sequence"""
     from chimera_b200.engine import Engine  # noqa: F401
