@@ -23,7 +23,7 @@ from util import SETUPS, assert_close, carrier_tol, match
 from chimera_b200.solver_setup import SolverSetup
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["real_m2", "real_m3", "env_m1", "env_m3", "static_m2"]
+NAMES = ["real_m2", "real_m3", "env_m1", "env_m3", "static_m2", "env_m1_win"]
 ENGINE_NAMES = NAMES
 
 
@@ -62,7 +62,15 @@ def _ref_run(fim, z, case):
         sp.append(RefSpecies(xi, 0 * xi, z["in_ion_weights"], charge=1.0, mass=1886.0, still=True))
     run = RefRun(fim, S, sp, background=False)
     run.EG_fb[:] = z["in_EG_fb"]
+    if case.get("window"):
+        run.window = _window_shifts(case, S)
     return S, run
+
+
+def _window_shifts(case, S):
+    """ChimeraRun.init_Moving_Frames (chimera_main.py:40-51) for a frame with 'Steps': 1, 'TimeStep': dt"""
+    v, dt = case["window"]["Velocity"], S.Args["dt"]
+    return (0.5 * v * dt, 0.5 * v * dt) if case["window"]["Staged"] else (v * dt, 0.0)
 
 
 def _check_particles(z, prefix, x, xh, p, w, tol):
@@ -130,6 +138,8 @@ def test_engine_replays_golden(gfim, name):
         xi = z["in_ion_coords"]
         eng.add_species(xi, 0 * xi, z["in_ion_weights"], charge=1.0, mass=1886.0, still=True)
     eng.upload("EG_fb", z["in_EG_fb"])
+    if case.get("window"):
+        eng.set_window(case["window"]["Velocity"], staged=case["window"]["Staged"])
     eng.make_halfstep(px0=(0.0,) * (2 if case["ions"] else 1), background=False)
     assert_close(eng.download("EG_fb"), z["h_EG_fb"], tol, "EG_fb after make_halfstep")
     x, xh, p, w = eng.particles(0)

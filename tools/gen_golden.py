@@ -22,7 +22,7 @@ itself stays unpinned ("parity unpinned", DESIGN.md section Oracle).  tests/test
 fixtures on the oracle through tests/pic_ref.py (CPU) and on the CUDA engine and the CUDA drop-in
 (GPU).
 
-  python tools/gen_golden.py            # rewrites tests/golden/*.npz
+  python tools/gen_golden.py [case ...]  # rewrites tests/golden/<case>.npz (all cases without arguments)
 """
 import copy
 import json
@@ -49,6 +49,12 @@ CASES = {
     "env_m3": dict(setup="env_m3", ions=False, und=None, amp=0.5),      # envelope solver with +-1 modes
     # space-charge demo stage 1: quasi-static kick of a px = 50 beam (poiss_corr_stat, maxwell_init_push, field_drift)
     "static_m2": dict(setup="static_m2", ions=False, und=None, amp=0.0, boost=50.0),
+    # FEL stage with its moving frame (doc/tests/fel-testrun.py:61-63): 'Staged' window every step -- half a shift in
+    # frame_act(istep) before push_coords, half in frame_act(istep, 'stage2') between project_current and
+    # project_density (chimera_main.py:40-51, 82-92, 292-304).  Beam close to the axis: the analytic undulator field
+    # grows like cosh(ku y) (devices.f90:196-197).
+    "env_m1_win": dict(setup="env_m1", ions=False, und=dict(a0=0.3, lam=1.3, X0=-1.0, Lx=9.0), amp=0.03, beam=True,
+                       window=dict(Velocity=0.999, Staged=True)),
 }
 
 TABLES = ("In", "InCurr", "Out", "DpS2S", "DmS2S", "DepFact", "PoissFact", "kx", "kx_env", "Rgrid", "Xgrid", "VGrid")
@@ -92,6 +98,14 @@ def generate(name, case, R, ofim):
     S = SolverSetup(copy.deepcopy(cfg))  # only used to shape the seeded inputs
     x, p, w = plasma(S, 2, 2, 11)
     p[0] += case.get("boost", 0.0)
+    if case.get("beam"):
+        a, rng, n = S.Args, np.random.default_rng(11), 3000
+        xs = a["leftX"] + (0.25 + 0.5 * rng.random(n)) * (a["rightX"] - a["leftX"])
+        r, th = 0.3 * np.sqrt(rng.random(n)), 2 * np.pi * rng.random(n)
+        x = np.asfortranarray(np.vstack((xs, r * np.cos(th), r * np.sin(th))))
+        p = np.asfortranarray(np.vstack((391.0 * (1 + 1e-4 * rng.standard_normal(n)), 2e-5 * 391 * rng.standard_normal(n),
+                                         2e-5 * 391 * rng.standard_normal(n))))
+        w = -1e-4 * (1 + 1e-3 * rng.random(n))
     eg0 = seed_fields(S, 12, case["amp"])
     out["in_coords"], out["in_momenta"], out["in_weights"], out["in_EG_fb"] = x, p, w, eg0
     solver.Data["EG_fb"][:] = eg0
@@ -111,7 +125,12 @@ def generate(name, case, R, ofim):
         parts.append(ions)
     # a window that never moves: frame_act still runs every step (chimera_main.py:292-304) and, for a
     # SpaceCharge solver, re-deposits the background of the still species (postframe_corr :277-284)
-    run = R.ChimeraRun({"Solvers": (solver,), "Particles": tuple(parts), "MovingFrames": ({"Velocity": 0.0},)})
+    frame = {"Velocity": 0.0}
+    if case.get("window"):
+        wn = case["window"]
+        frame = {"TimeStep": cfg["TimeStep"], "Steps": 1, "Velocity": wn["Velocity"],
+                 "Features": ("Staged",) if wn["Staged"] else ()}
+    run = R.ChimeraRun({"Solvers": (solver,), "Particles": tuple(parts), "MovingFrames": (frame,)})
     snapshot("h", run, out, grids=("EG_fb",))
     for i in range(1, NSTEPS + 1):
         run.make_step(i)
@@ -126,7 +145,10 @@ def main():
     R = ref_driver.install(ofim)
     dst = os.path.join(ROOT, "tests", "golden")
     os.makedirs(dst, exist_ok=True)
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         out = generate(name, case, R, ofim)
         path = os.path.join(dst, name + ".npz")
         np.savez_compressed(path, **out)
