@@ -313,7 +313,8 @@ int ensure_sort_scratch(chimera_engine* e, i64 n) {
 }
 
 // left_margin: the absorbing layer of a moving window (species.py:373-376 SimDom[0] = leftX + AbsorbLayer dx)
-int ph_sort(chimera_engine* e, int on_halfstep, double left_margin = 0.0) {
+// r2max > 0: radial cull limit of this call (the window's, species.py:373-376) instead of cfg.rcull2
+int ph_sort(chimera_engine* e, int on_halfstep, double left_margin = 0.0, double r2max = 0.0) {
   const auto& c = e->cfg;
   const int nchnk = c.chunked ? c.nchnk : 1;
   for (auto& s : e->sp) {
@@ -324,7 +325,7 @@ int ph_sort(chimera_engine* e, int on_halfstep, double left_margin = 0.0) {
     const i64 cs = c.nx / nchnk;  // nodes per chunk
     b.x0 = c.leftX;
     b.chunk_inv = 1.0 / c.chunk_len;
-    b.l0 = c.leftX + left_margin; b.l1 = c.rightX; b.l2 = 0.0; b.l3 = c.rcull2;
+    b.l0 = c.leftX + left_margin; b.l1 = c.rightX; b.l2 = 0.0; b.l3 = r2max > 0.0 ? r2max : c.rcull2;
     b.leftX = c.leftX; b.dx_inv = 1.0 / c.dx; b.r0 = g_host[e].r0; b.dr_inv = 1.0 / c.dr;
     b.nchnk = nchnk; b.nx = c.nx; b.nrc = c.nrn - 1;
     b.cs = cs; b.tile_w = cs < 32 ? cs : 32; b.ntile = (cs + b.tile_w - 1) / b.tile_w;
@@ -994,6 +995,12 @@ int chimera_engine_append_particles(chimera_engine* e, int id, const double* coo
 int chimera_engine_sort(chimera_engine* e, int on_halfstep, double left_margin) {
   ENG_CHECK(e);
   return ph_sort(e, on_halfstep, left_margin);
+}
+// the same with the radial limit of the call given explicitly: a window's damp_plasma culls at the SPECIES' upperR
+// (species.py:92,376: its r grid has one node less than the solver's), not at the solver's like the per-step re-binning
+int chimera_engine_sort_window(chimera_engine* e, int on_halfstep, double left_margin, double upper_r2) {
+  ENG_CHECK(e);
+  return ph_sort(e, on_halfstep, left_margin, upper_r2);
 }
 
 // ------------------------------------------------------------------------------------------

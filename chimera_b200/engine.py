@@ -305,9 +305,20 @@ class Engine:
         self._check(self.lib.chimera_engine_append_particles(self._h, int(sid), ctypes.c_void_p(x.ctypes.data),
                                                              ctypes.c_void_p(p.ctypes.data), ctypes.c_void_p(w.ctypes.data), _i64(n)))
 
-    def sort(self, on_halfstep=False, left_margin=0.0):
-        """``Specie.chunk_and_damp`` (species.py:351) with the absorbing layer ``left_margin`` (in x units)."""
-        self._check(self.lib.chimera_engine_sort(self._h, int(bool(on_halfstep)), ctypes.c_double(left_margin)))
+    def sort(self, on_halfstep=False, left_margin=0.0, upper_r=None):
+        """``Specie.chunk_and_damp`` (species.py:351) with the absorbing layer ``left_margin`` (in x units);
+        ``upper_r``: radial limit of this call (default: the solver's ``Rgrid.max()``, chimera_main.py:318)."""
+        if upper_r is None:
+            self._check(self.lib.chimera_engine_sort(self._h, int(bool(on_halfstep)), ctypes.c_double(left_margin)))
+        else:
+            self._check(self.lib.chimera_engine_sort_window(self._h, int(bool(on_halfstep)), ctypes.c_double(left_margin),
+                                                            ctypes.c_double(upper_r ** 2)))
+
+    def species_upper_r(self):
+        """``Specie.Args['upperR']`` of a species built on the solver's ``Grid`` (species.py:85-92): its r grid has
+        ``round(lengthR/dr)`` nodes, one less than the solver's, so a window's ``damp_plasma`` culls one cell earlier"""
+        a = self.setup.Args
+        return a["dr"] * ((a["Nkr"] - 1) - 0.5)
 
     def frame_act(self, wind, add=None, background=False):
         """Stage 1 of ``ChimeraRun.frame_act`` (chimera_main.py:292-302) for one moving window ``wind`` (the
@@ -322,7 +333,7 @@ class Engine:
         for sid, (x, p, w) in (add or {}).items():
             self.append_particles(sid, x, p, w)
         if "AbsorbLayer" in wind:
-            self.sort(False, wind["AbsorbLayer"] * a["dx"])
+            self.sort(False, wind["AbsorbLayer"] * a["dx"], upper_r=self.species_upper_r())
         if self.cfg.space_charge:
             if background:
                 self.deposit_background()

@@ -282,6 +282,9 @@ int chimera_engine_move_window(chimera_engine* e, double shiftX);
 int chimera_engine_append_particles(chimera_engine* e, int species, const double* coords, const double* momenta,
                                     const double* weights, chb_i64 n);
 int chimera_engine_sort(chimera_engine* e, int on_halfstep, double left_margin);
+/* chunk_and_damp called by a moving window (chimera_main.py:258-260): radial limit upper_r2 = the species' upperR^2
+ * (species.py:92,376), one radial cell inside the solver's Rgrid.max() when both use the same Grid */
+int chimera_engine_sort_window(chimera_engine* e, int on_halfstep, double left_margin, double upper_r2);
 /* ---- integrated diagnostics on the device (moduls/diagnostics.py) ----
  * field_energy: nrg_out (diagnostics.py:109) before its roll: out[kx] = sum_{kr,m} EnergyFact[kx,kr,m] *
  *               sum_{c<3} |EG_fb[kx,kr,m,c]|^2; energy_fact (nx,nkr,nm) float64 host/device on the first call, NULL later

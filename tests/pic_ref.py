@@ -53,11 +53,13 @@ class RefRun:
         self.window = (0.0, 0.0)
 
     # ---- species.py:351-398 -------------------------------------------------------------------
-    def chunk_and_damp(self, s, position, left_margin=0.0):
+    def chunk_and_damp(self, s, position, left_margin=0.0, upper_r=None):
         a, f = self.a, self.f
         if s.coords.shape[1] == 0:
             return
-        dom = np.asfortranarray([a["leftX"] + left_margin, a["rightX"], 0.0, a["Rgrid"].max() ** 2])
+        if upper_r is None:  # make_halfstep / chunk_particles: the solver's limit (chimera_main.py:67-68, 317-318)
+            upper_r = a["Rgrid"].max()
+        dom = np.asfortranarray([a["leftX"] + left_margin, a["rightX"], 0.0, upper_r ** 2])
         src = s.coords_halfstep if position == "cntr" else s.coords
         if self.chunked:
             ids, s.chunks, go_out = f.chunk_coords_boundaries(src, dom, a["Xgrid"], self.nchnk)
@@ -200,8 +202,11 @@ class RefRun:
             s.momenta = np.asfortranarray(np.concatenate((s.momenta, p), axis=1))
             s.weights = np.concatenate((s.weights, w))
         if "AbsorbLayer" in wind:
+            # species.py:373-376: the window culls at the SPECIES' upperR; its r grid (species.py:85-92) has
+            # round(lengthR/dr) nodes, one less than the solver's
+            upper_r = a["dr"] * ((a["Nkr"] - 1) - 0.5)
             for s in self.sp:
-                self.chunk_and_damp(s, "stag", left_margin=wind["AbsorbLayer"] * a["dx"])
+                self.chunk_and_damp(s, "stag", left_margin=wind["AbsorbLayer"] * a["dx"], upper_r=upper_r)
         if self.space_charge:  # postframe_corr
             if self.background:
                 self.dep_bg()

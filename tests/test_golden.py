@@ -156,3 +156,84 @@ def test_engine_replays_golden(gfim, name):
     if "s_chunks" in z.files:
         assert np.array_equal(eng.chunks(0), z["s_chunks"])
     eng.close()
+
+
+# ------------------------------------------------------------------ LPA stage with its moving window
+def _check_particles_by_position(z, prefix, x, xh, p, w, tol):
+    """gen_parts gives every particle of a radial row the same weight, so particles are identified by position
+    (nearest neighbour in 3-D; the match has to be one to one)"""
+    from scipy.spatial import cKDTree
+
+    want = z[prefix + "_coords"]
+    assert x.shape == want.shape, (x.shape, want.shape)
+    dist, perm = cKDTree(x.T).query(want.T)
+    assert np.unique(perm).size == perm.size and dist.max() <= 1e-9
+    assert_close(x[:, perm], want, tol, prefix + " coords")
+    assert_close(xh[:, perm], z[prefix + "_coords_halfstep"], tol, prefix + " coords_halfstep")
+    assert_close(p[:, perm], z[prefix + "_momenta"], tol, prefix + " momenta")
+    assert np.array_equal(w[perm], z[prefix + "_weights"])
+
+
+def _lpa_fixture():
+    z = np.load(os.path.join(GOLDEN, "real_m2_lpa.npz"))
+    meta = json.loads(str(z["cfg"]))
+    case = meta["case"]
+    adds = {}
+    for k, (st, si) in enumerate(zip(z["add_steps"], z["add_species"])):
+        adds.setdefault(int(st), {})[int(si)] = (z["add%d_coords" % k], z["add%d_momenta" % k], z["add%d_weights" % k])
+    wind = {"shiftX": float(z["shiftX"]), "AbsorbLayer": case["wind"]["AbsorbLayer"], "Steps": case["wind"]["Steps"]}
+    return z, case, meta["nsteps"], adds, wind
+
+
+def test_lpa_window_sequence_replays_reference_driver_on_oracle(ofim):
+    """doc/tests/lpa-testrun.py in miniature, recorded from the reference's own ChimeraRun (tools/gen_golden.py
+    generate_lpa): species that start EMPTY, a window acting every 3 steps (damp_fields, move_frame, add_plasma with
+    'IonsOnTop', damp_plasma, postframe_corr -- chimera_main.py:250-304).  tests/pic_ref.RefRun.frame_act + make_step
+    on the oracle reproduce the recorded states; the particles the driver's gen_parts produced are replayed."""
+    z, case, nsteps, adds, wind = _lpa_fixture()
+    S = SolverSetup(copy.deepcopy(SETUPS[case["setup"]]))
+    e0 = np.zeros((3, 0), order="F")
+    sp = [RefSpecies(e0, e0, np.zeros(0)), RefSpecies(e0, e0, np.zeros(0), charge=1.0, mass=1886.0, still=True)]
+    run = RefRun(ofim, S, sp, sort_every=0, background=True)  # species feature 'NoSorting': only the window re-bins
+    run.EG_fb[:] = z["in_EG_fb"]
+    run.make_halfstep(px0=(0.0, 0.0))
+    assert_close(run.EG_fb, z["h_EG_fb"], 5e-13, "EG_fb after make_halfstep (no particles)")
+    for i in range(1, nsteps + 1):
+        if i % wind["Steps"] == 0:
+            run.frame_act(wind, add=adds.get(i))
+        run.make_step()
+        if "s%d_EG_fb" % i in z.files:
+            pre = "s%d" % i
+            for k, got in (("J", run.J), ("Rho", run.Rho), ("BckGrndRho", run.Bck), ("EB", run.EB), ("EG_fb", run.EG_fb)):
+                assert_close(got, z[pre + "_" + k], 5e-12, "%s at step %d" % (k, i))
+            s = run.sp[0]
+            _check_particles_by_position(z, pre, s.coords, s.coords_halfstep, s.momenta, s.weights, 5e-12)
+            assert run.sp[1].weights.size == z[pre + "_ion_weights"].size
+
+
+@pytest.mark.gpu
+def test_engine_replays_lpa_window_golden(gfim):
+    """the same recorded LPA-window run on the device-resident engine: Engine.frame_act between step() calls"""
+    from chimera_b200.engine import Engine
+
+    z, case, nsteps, adds, wind = _lpa_fixture()
+    S = SolverSetup(copy.deepcopy(SETUPS[case["setup"]]))
+    e0 = np.zeros((3, 0), order="F")
+    eng = Engine(S, sort_every=0)
+    eng.add_species(e0, e0, np.zeros(0), capacity=4096)
+    eng.add_species(e0, e0, np.zeros(0), charge=1.0, mass=1886.0, still=True, capacity=4096)
+    eng.upload("EG_fb", z["in_EG_fb"])
+    eng.make_halfstep(px0=(0.0, 0.0), background=True)
+    assert_close(eng.download("EG_fb"), z["h_EG_fb"], 1e-11, "EG_fb after make_halfstep (no particles)")
+    for i in range(1, nsteps + 1):
+        if i % wind["Steps"] == 0:
+            eng.frame_act(wind, add=adds.get(i), background=True)
+        eng.step(1)
+        if "s%d_EG_fb" % i in z.files:
+            pre = "s%d" % i
+            for k in ("J", "Rho", "BckGrndRho", "EB", "EG_fb"):
+                assert_close(eng.download(k), z[pre + "_" + k], 2e-11, "%s at step %d" % (k, i))
+            x, xh, p, w = eng.particles(0)
+            _check_particles_by_position(z, pre, x, xh, p, w, 2e-11)
+            assert eng.count(1) == z[pre + "_ion_weights"].size
+    eng.close()

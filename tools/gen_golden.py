@@ -138,6 +138,59 @@ def generate(name, case, R, ofim):
     return out
 
 
+# LPA stage with its moving window (doc/tests/lpa-testrun.py:41-64, shrunk): both species start EMPTY, the plasma
+# enters through 'AddPlasma' as the window moves every LPA_WIND['Steps'] steps; absorbing layer on the left
+LPA_NSTEPS = 13
+LPA_WIND = dict(Steps=3, AbsorbLayer=8)
+LPA_PROFILE = ([1.0, 1.3, 30.0], [0.0, 1.0, 1.0])  # np.interp nodes of the density profile along x
+
+
+def generate_lpa(R, ofim):
+    from util import SETUPS, seed_fields
+    from chimera_b200.solver_setup import SolverSetup
+
+    cfg = copy.deepcopy(SETUPS["real_m2"])
+    np.random.seed(20260102)
+    solver = R.Solver(copy.deepcopy(cfg))
+    S = SolverSetup(copy.deepcopy(cfg))
+    eg0 = seed_fields(S, 14, 0.5)
+    solver.Data["EG_fb"][:] = eg0
+    out = {"cfg": np.array(json.dumps({"case": dict(setup="real_m2", wind=LPA_WIND, profile=LPA_PROFILE), "nsteps": LPA_NSTEPS})),
+           "in_EG_fb": eg0}
+    e_in = species_dict(cfg, Density=0.005, FixedCell=(2, 2, 4), Features=("NoSorting",))
+    i_in = species_dict(cfg, Density=0.005, FixedCell=(2, 2, 4), Charge=1, Mass=1886, Features=("NoSorting", "Still"))
+    electrons, ions = R.Specie(e_in), R.Specie(i_in)
+    adds = []  # (step, species index, coords, momenta, weights) of every add_particles call
+    step = [0]
+    for idx, sp in enumerate((electrons, ions)):
+        orig = sp.add_particles
+
+        def rec(coords, momenta, weights, idx=idx, orig=orig):
+            adds.append((step[0], idx, np.array(coords, order="F"), np.array(momenta, order="F"), np.array(weights)))
+            return orig(coords, momenta, weights)
+
+        sp.add_particles = rec
+    prof_x, prof_y = LPA_PROFILE
+    wind = {"TimeStep": cfg["TimeStep"], "Steps": LPA_WIND["Steps"], "AbsorbLayer": LPA_WIND["AbsorbLayer"],
+            "AddPlasma": lambda x: np.interp(x, prof_x, prof_y), "Features": ("IonsOnTop",)}
+    run = R.ChimeraRun({"Solvers": (solver,), "Particles": (electrons, ions), "MovingFrames": (wind,)})
+    out["h_EG_fb"] = np.array(solver.Data["EG_fb"], order="F")
+    out["shiftX"] = np.array(wind["shiftX"])
+    for i in range(1, LPA_NSTEPS + 1):
+        step[0] = i
+        run.make_step(i)
+        if i in (7, LPA_NSTEPS):
+            pre = "s%d" % i
+            snapshot(pre, run, out)
+            out[pre + "_ion_coords"] = np.array(ions.Data["coords"], order="F")
+            out[pre + "_ion_weights"] = np.array(ions.Data["weights"])
+    out["add_steps"] = np.array([a[0] for a in adds])
+    out["add_species"] = np.array([a[1] for a in adds])
+    for k, a in enumerate(adds):
+        out["add%d_coords" % k], out["add%d_momenta" % k], out["add%d_weights" % k] = a[2], a[3], a[4]
+    return out
+
+
 def main():
     import ref_driver
     from oracle import fimera as ofim
@@ -146,6 +199,13 @@ def main():
     dst = os.path.join(ROOT, "tests", "golden")
     os.makedirs(dst, exist_ok=True)
     only = sys.argv[1:]
+    if not only or "real_m2_lpa" in only:
+        out = generate_lpa(R, ofim)
+        path = os.path.join(dst, "real_m2_lpa.npz")
+        np.savez_compressed(path, **out)
+        print("%-8s %6.1f kB  adds at steps %s  electrons %d  |EG_fb| %.6e" % (
+            "real_m2_lpa", os.path.getsize(path) / 1e3, sorted(set(out["add_steps"].tolist())),
+            out["s%d_weights" % LPA_NSTEPS].size, np.linalg.norm(out["s%d_EG_fb" % LPA_NSTEPS].ravel())))
     for name, case in CASES.items():
         if only and name not in only:
             continue
