@@ -237,3 +237,65 @@ def test_engine_replays_lpa_window_golden(gfim):
             _check_particles_by_position(z, pre, x, xh, p, w, 2e-11)
             assert eng.count(1) == z[pre + "_ion_weights"].size
     eng.close()
+
+
+# ------------------------------------------------------------------ the reference's Diagnostics on the FEL fixture
+PWR_FCTR = 0.5 * 0.511e6 * 1.6022e-19 / 2.818e-13 * 2.9979e10  # moduls/diagnostics.py:24
+NTHETA = 60  # moduls/diagnostics.py:25
+
+
+def _diagnostics_like_reference(fim, S, eg_fb, left_x):
+    """Diagnostics.nrg_out / pwr_out(..., 'Spot') (diagnostics.py:109-149) written against a fimera backend"""
+    a = S.Args
+    nrg = ((np.abs(eg_fb[:, :, :, :3]) ** 2).sum(-1) * a["EnergyFact"]).sum(-1).sum(-1)
+    nrg = np.r_[nrg[nrg.shape[0] // 2 + 1:], nrg[:nrg.shape[0] // 2 + 1]]
+    dat = fim.fb_vec_out(np.asfortranarray(eg_fb[:, :, :, :3]), left_x, *a["FBoutFull"])
+    pwr = PWR_FCTR * 2 * a["dr"] * ((np.abs(dat) ** 2).sum(-1).sum(-1) * a["RgridFull"][None, :]).sum(-1)
+    return nrg, pwr, fim.intens_profo(dat, NTHETA)
+
+
+def _final_left_x(S, case, nsteps):
+    lx = S.Args["leftX"]
+    for _ in range(nsteps):
+        for sft in _window_shifts(case, S):
+            lx = lx + sft
+    return lx
+
+
+def test_reference_diagnostics_on_oracle(ofim):
+    """the integrated diagnostics of the reference's own Diagnostics class, recorded on the FEL-window fixture, from
+    the replayed state: field energy per kx, power per x, azimuthal spot profile, beam envelopes"""
+    z, case, nsteps = load("env_m1_win")
+    S, run = _ref_run(ofim, z, case)
+    run.make_halfstep(px0=(0.0,))
+    for _ in range(nsteps):
+        run.make_step()
+    nrg, pwr, spot = _diagnostics_like_reference(ofim, S, run.EG_fb, S.Args["leftX"])
+    tol = carrier_tol(S, 1e-12)
+    assert_close(nrg, z["d_nrg"], tol, "nrg_out")
+    assert_close(pwr, z["d_pwr"], tol, "pwr_out")
+    assert_close(spot, z["d_spot"], tol, "pwr_out spot (intens_profo)")
+
+
+@pytest.mark.gpu
+def test_reference_diagnostics_on_engine(gfim):
+    """the same recorded diagnostics from the device: Engine.nrg_out / get_beam_envelops (reductions on the GPU) and
+    fb_vec_out + intens_profo through the drop-in; north_star bar for integrated diagnostics: 1e-6"""
+    from chimera_b200.engine import Engine
+
+    z, case, nsteps = load("env_m1_win")
+    S = SolverSetup(copy.deepcopy(SETUPS[case["setup"]]))
+    u = case["und"]
+    eng = Engine(S, undulator={"a0": u["a0"], "lambda": u["lam"], "X0": u["X0"], "Lx": u["Lx"]})
+    eng.add_species(z["in_coords"], z["in_momenta"], z["in_weights"])
+    eng.upload("EG_fb", z["in_EG_fb"])
+    eng.set_window(case["window"]["Velocity"], staged=case["window"]["Staged"])
+    eng.make_halfstep(px0=(0.0,))
+    eng.step(nsteps)
+    assert_close(np.asarray(eng.nrg_out()), z["d_nrg"], 1e-9, "Engine.nrg_out")
+    env = eng.get_beam_envelops()
+    assert np.abs(env - z["d_env"]).max() <= 1e-6 * np.abs(z["d_env"]).max(), (env, z["d_env"])
+    _, pwr, spot = _diagnostics_like_reference(gfim, S, eng.download("EG_fb"), _final_left_x(S, case, nsteps))
+    assert_close(pwr, z["d_pwr"], 1e-9, "pwr_out through the drop-in")
+    assert_close(spot, z["d_spot"], 1e-9, "spot profile through the drop-in")
+    eng.close()

@@ -135,6 +135,14 @@ def generate(name, case, R, ofim):
     for i in range(1, NSTEPS + 1):
         run.make_step(i)
     snapshot("s", run, out)
+    if case.get("window"):
+        # the reference's own Diagnostics on the final state (moduls/diagnostics.py:109-207): field energy per kx,
+        # power per x with the azimuthal 'Spot' profile (fb_vec_out + intens_profo), beam centroid / rms / emittance
+        D = R.Diagnostics(run, (), out_folder=None)
+        out["d_nrg"] = np.array(D.nrg_out({"Features": ("Return",)})[0])
+        pwr, spot = D.pwr_out({"Features": ("Return", "Spot")})[0]
+        out["d_pwr"], out["d_spot"] = np.array(pwr), np.array(spot)
+        out["d_env"] = np.array(D.get_beam_envelops()[0])
     return out
 
 
