@@ -27,6 +27,9 @@ ap.add_argument("--nx", type=int, default=2048)
 ap.add_argument("--nr", type=int, default=256)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--sort-every", type=int, default=None,
+                help="re-binning cadence in steps (default: the reference's Xchunked[1]+1 = 7, chimera_main.py:310); the "
+                     "co-moving beam keeps its cell order much longer, so production runs can re-bin rarely")
 ap.add_argument("--fused-profile", action="store_true", help="per-stage clock shares of the fused particle kernel (diagnosis)")
 a = ap.parse_args()
 
@@ -52,7 +55,7 @@ from chimera_b200 import _lib  # noqa: E402
 
 _lib.load().chimera_set_device(local)
 S = SolverSetup(cfg)
-eng = Engine(S, group=group)
+eng = Engine(S, group=group, sort_every=a.sort_every)
 eng.use_stream(torch.cuda.current_stream().cuda_stream)
 eng.add_device("undul_analytic", np.array([K0, 1.0, 1.0, float(periods)]))
 # MovingFrame {'TimeStep': dt, 'Steps': 1, 'Velocity': vb, 'Features': ('Staged', 'NoSorting')} (fel-testrun.py:61-63):
@@ -109,7 +112,7 @@ per = {k: v[0] / v[1] for k, v in ph.items() if v[1]}
 out = {"workload": "FEL undulator beam, envelope solver Nx=%d Nr=%d 1 mode, undul_analytic K0=1.95, %.3g macro-particles, "
                    "Xchunked=(16,6), NoPoissonCorrection" % (a.nx, a.nr, n),
        "metric": "particle-steps/s full PIC cycle", "value": kept / (ms * 1e-3), "ms_per_step": ms, "steps": a.steps,
-       "warmup": a.warmup, "n_gpus": world, "particles_per_gpu": n, "particles_after": kept, "phases_ms_per_call": per,
+       "warmup": a.warmup, "sort_every": eng.cfg.sort_every, "n_gpus": world, "particles_per_gpu": n, "particles_after": kept, "phases_ms_per_call": per,
        "phase_calls": {k: v[1] for k, v in ph.items()},
        # envelope cycle, SURVEY 8d basis: push_coords 96 + dep_curr_env 56 + proj_fld_env 128 + push_velocs 96 B
        "particle_cycle_alg_bytes_per_gpu": 376.0 * kept / world, "hbm_gbs_peak": hbm}
@@ -130,7 +133,8 @@ if a.fused_profile:
         ("A_records_histogram", "BC_scan_sort", "D_gather", "E_push", "F_deposit", "G_cell_changers"))}
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fel_bench_n%d.json" % world), "w"), indent=1)
+    tag = "" if a.sort_every is None else "_sort%d" % a.sort_every
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fel_bench_n%d%s.json" % (world, tag)), "w"), indent=1)
     print(json.dumps(out))
 eng.close()
 if world > 1:
