@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main(name, slab, window=0):
     from oracle import fimera as ofim
     from pic_ref import RefRun, RefSpecies
-    from util import SETUPS, TOL, assert_close, carrier_tol, match, plasma, seed_fields
+    from util import SETUPS, TOL, assert_close, carrier_tol, plasma, seed_fields
     from chimera_b200 import sharding
     from chimera_b200.engine import Engine
     from chimera_b200.solver_setup import SolverSetup

@@ -1,6 +1,5 @@
 """CPU: the C-ABI boundary.  libchimera_b200.so loads without a GPU, exports every symbol that
 include/chimera_b200.h declares, and its compute entry points fail loudly (no CPU fallback)."""
-import ctypes
 import os
 import re
 

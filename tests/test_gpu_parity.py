@@ -3,7 +3,7 @@ seeded inputs (1e-12 relative L2 for floating point, exact for integer/index out
 import numpy as np
 import pytest
 
-from util import TOL, assert_close, chunk_sorted, crandn, particles, setup
+from util import assert_close, chunk_sorted, crandn, particles, setup
 
 pytestmark = pytest.mark.gpu
 
