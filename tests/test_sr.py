@@ -263,3 +263,46 @@ def _energy_like(z, key, rad):
     else:
         wgt = 1.0
     return float((((rad[1:] + rad[:-1]) * wgt).sum(-1).sum(-1) * dw).sum())
+
+
+# ---------------------------------------------------------------- physics known answer: undulator resonance
+def _undulator_resonance(f):
+    """One electron through `undul_analytic` with the Boris pusher and the leap-frog position update, its track fed
+    to the far-field SR integral: the transverse momentum amplitude is K and the on-axis spectrum peaks at the
+    undulator resonance  omega_1 = 2 gamma^2 / (lambda_u (1 + K^2/2))  -- a known answer that involves the device
+    field, the push prefactor 2 pi q/m dt (species.py:64,298), the track convention of moduls/SR.py:141-147 and the
+    phase convention of SR.f90:87-100 at once."""
+    K, lam_u, gam, nper, dt = 0.5, 1.0, 20.0, 12, 0.02
+    nt = int((nper + 2) * lam_u / dt)
+    x = np.asfortranarray(np.array([[-1.0 + 1e-9], [0.0], [0.0]]))
+    p = np.asfortranarray(np.array([[np.sqrt(gam ** 2 - 1)], [0.0], [0.0]]))
+    xh = np.zeros_like(x)
+    params = np.array([K, lam_u, 0.0, float(nper)])  # a0, lambda, X0, Lx (devices.f90:174-177)
+    coords = np.zeros((3, nt, 1), order="F")
+    mprv, mnxt = np.zeros_like(coords), np.zeros_like(coords)
+    for it in range(nt):
+        x, xh = f.push_coords(x, p, xh, dt)
+        fld = f.undul_analytic(x, np.zeros((6, 1), order="F"), (it + 1) * dt, params)
+        mprv[:, it, 0] = p[:, 0]
+        p = f.push_velocs(p, fld, -2 * np.pi * dt)
+        mnxt[:, it, 0] = p[:, 0]
+        coords[:, it, 0] = x[:, 0]
+    w_res = 2 * gam ** 2 / (lam_u * (1 + K ** 2 / 2))
+    om = np.linspace(0.3 * w_res, 1.7 * w_res, 281)
+    one, zero = np.array([1.0]), np.array([0.0])
+    s = f.sr_calc_far_tot(np.zeros((om.size, 1, 1), order="F"), coords, mprv, mnxt, np.array([-1.0]), dt, om,
+                          zero, one, zero, one)  # theta = 0, phi = 0
+    return np.abs(mnxt[1:]).max(), K, om[np.argmax(s[:, 0, 0])], w_res, nper
+
+
+def test_undulator_resonance_known_answer(ofim):
+    pt, K, peak, w_res, nper = _undulator_resonance(ofim)
+    assert abs(pt - K) < 2e-3 * K
+    assert abs(peak / w_res - 1.0) < 0.25 / nper  # line width ~ 1/N_periods
+
+
+@pytest.mark.gpu
+def test_gpu_undulator_resonance_known_answer(gfim):
+    pt, K, peak, w_res, nper = _undulator_resonance(gfim)
+    assert abs(pt - K) < 2e-3 * K
+    assert abs(peak / w_res - 1.0) < 0.25 / nper
