@@ -298,3 +298,12 @@ def test_fb_roundtrip_large(ofim, gfim):
     assert_close(rg, ro, what="fb_vec_in large")
     back = gfim.fb_vec_out(rg, a["leftX"], *a["FBout"]) / a["Nx"]
     assert_close(back[:, 1:], V[:, 1:], tol=1e-9, what="DHT+FFT round trip")
+
+
+def test_gaussian_beam_diffraction_on_gpu(gfim):
+    """the physics known answer of tests/test_oracle_kat.py through the CUDA drop-in"""
+    from test_oracle_kat import gaussian_beam_diffraction
+
+    for s, t, got, want in gaussian_beam_diffraction(gfim):
+        assert abs(s - t) <= 0.051
+        assert abs(got / want - 1) < 0.05, (s, got, want)

@@ -203,3 +203,43 @@ def test_device_known_answers(ofim):
     got = ofim.undul_mapped(one, np.zeros((6, 1), order="F"), 0.0, amap, np.array([lam, 0.0, dx]))
     d = 1.2 - 1.0
     assert np.isclose(got[4, 0], (0.75 - d * d) * amap[0, 0] + 0.5 * (0.5 + d) ** 2 * amap[0, 1], rtol=1e-14)
+
+
+def gaussian_beam_diffraction(f):
+    """A focused Gaussian pulse advanced in vacuum by the PSATD push: its peak moves at c and its on-axis amplitude
+    follows a0 / sqrt(1 + (s/xR)^2), xR = pi w0^2 k0 -- the check the reference plots in its demo notebook (doc/
+    fel-lpa-demo.ipynb, cell 45).  Involves the Bessel-zero radial wavenumbers, both DHT matrices, the x-FFT phase
+    convention and the PSATD coefficients at once.  Returns [(distance, measured ratio, theory)]."""
+    from chimera_b200 import synthetic
+    from chimera_b200.solver_setup import SolverSetup
+
+    S = SolverSetup(dict(Grid=(-9.0, 3.0, 4.0, 0.05, 0.1), TimeStep=0.05, MaxAzimuthMode=0, Features=()))
+    a = S.Args
+    w0, k0 = 0.7, 1.0
+    eg = synthetic.laser_seed(S, f, a0=1.0, k0=k0, x0=-5.0, Lx=2.5, LR=w0)
+    x_r = np.pi * w0 ** 2 * k0
+    j = S.zeros_fb(3)
+
+    def on_axis(eg):
+        v = f.fb_vec_out(np.asfortranarray(eg[..., :3]), a["leftX"], *a["FBout"])
+        spec = np.fft.fft(v[:, 1, 0, 2].real)  # envelope = |analytic signal| of the field next to the axis
+        n = spec.size
+        spec[n // 2 + 1:] = 0
+        spec[1:n // 2] *= 2
+        env = np.abs(np.fft.ifft(spec))
+        return env.max(), a["Xgrid"][env.argmax()]
+
+    a0, x0 = on_axis(eg)
+    out = []
+    for step in range(1, 61):
+        eg = f.maxwell_push_wo_spchrg(eg, j, S.PSATD_E, S.PSATD_G)
+        if step % 20 == 0:
+            amp, xp = on_axis(eg)
+            out.append((xp - x0, step * a["dt"], amp / a0, 1 / np.sqrt(1 + ((xp - x0) / x_r) ** 2)))
+    return out
+
+
+def test_gaussian_beam_diffraction(ofim):
+    for s, t, got, want in gaussian_beam_diffraction(ofim):
+        assert abs(s - t) <= 0.051  # the peak moves at c (one grid step of slack)
+        assert abs(got / want - 1) < 0.05, (s, got, want)  # few-cycle pulse: x_R varies over its bandwidth
