@@ -7,9 +7,9 @@ deposition, fancy-index gather, ``einsum``/``matmul`` + ``numpy.fft`` for the tr
 for the spectral calculus -- written from the Fortran sources cited per function.  tests/test_np_ref.py
 requires the two restatements to agree to round-off; a transcription slip in either shows up there.
 
-Only the real ("PIC") solver family is covered (the envelope variants differ by the carrier factor and
-the mode slot range and are covered by the KATs in tests/test_oracle_kat.py).  Array conventions as in
-the reference: Fortran order, grids (Nx, Nr, M[, c]) with radial node 0 the r = -dr/2 ghost.
+Both solver families are covered: the real ("PIC") one and, at the end of the file, the envelope ("KxShift") one
+(grid_deps_env.f90, fb_math_env.f90), plus the devices, the SR integrals and the utils.f90 helpers.  Array
+conventions as in the reference: Fortran order, grids (Nx, Nr, M[, c]) with radial node 0 the r = -dr/2 ghost.
 """
 import numpy as np
 
@@ -442,3 +442,166 @@ def density_2x(x, y, wght, grid, bins_x, bins_y):
         for j in range(5):
             np.add.at(dens, (kx + i, ky + j), w * sx[i] * sy[j])
     return dens / dxg / dyg
+
+
+# ---- envelope ("KxShift") family: f90/grid_deps_env.f90, f90/fb_math_env.f90 -------------------------
+# Mode slots are ordered -nko..nko (slot j <-> mode j - nko); the operators DpS2S / DmS2S carry 2 nko + 3 slots,
+# -nko-1..nko+1 (slot j <-> mode j - nko - 1).  Everything is written per MODE here, not per slot.
+def _env_modes(nm):
+    nko = (nm - 1) // 2
+    return nko, range(-nko, nko + 1)
+
+
+def _carrier(x, kx0, sign):
+    return np.cos(x * kx0) + sign * 1j * np.sin(x * kx0)
+
+
+def _scatter_env(grid, ok, ix, ir, sx, sr, ph, amp):
+    """grid(Nx,Nr,2nko+1) += amp * exp(-i m theta) * Sx * Sr for m = -nko..nko (exp(-i|m|theta) conjugated for m<0)"""
+    nko, modes = _env_modes(grid.shape[2])
+    for m in modes:
+        pm = ph ** abs(m) if m else np.ones_like(ph)
+        v = amp * (np.conj(pm) if m < 0 else pm)
+        for i, wx in ((0, 1.0 - sx), (1, sx)):
+            for k, wr in ((0, 1.0 - sr), (1, sr)):
+                np.add.at(grid[:, :, m + nko], (ix[ok] + i, ir[ok] + k), (v * wx * wr)[ok])
+
+
+def dep_dens_env(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv, kx0):
+    """grid_deps_env.f90:96-162.  Q2: the complex weight w e^{-i kx0 x} enters SQUARED (:145,147)"""
+    ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
+    wc = wghts * _carrier(coord[0], kx0, -1)
+    _scatter_env(dens, ok, ix, ir, sx, sr, ph, wc * wc)
+    _fold_ghost(dens)
+    return dens
+
+
+def dep_curr_env(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv, kx0):
+    """grid_deps_env.f90:18-94.  Q1: only the third component is deposited (:76)"""
+    ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
+    ok = ok & (np.abs(momenta).sum(0) != 0.0)
+    g = np.sqrt(1.0 + (momenta ** 2).sum(0))
+    _scatter_env(curr[..., 2], ok, ix, ir, sx, sr, ph, wghts * _carrier(coord[0], kx0, -1) * momenta[2] / g)
+    for l in range(3):
+        _fold_ghost(curr[..., l])
+    return curr
+
+
+def proj_fld_env(coord, wghts, Fld, Fld_tot, leftX, Rgrid, dx_inv, dr_inv, kx0):
+    """grid_deps_env.f90:164-238: Re[ e^{+i kx0 x} e^{+i m theta} Sx Sr F_m ], phase 1 on the axis (Q4)"""
+    ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
+    r = np.sqrt(coord[1] ** 2 + coord[2] ** 2)
+    ph = np.where(r > 0, np.conj(ph), 1.0)
+    car = _carrier(coord[0], kx0, +1)
+    out = np.array(Fld_tot, dtype=float)
+    nko, modes = _env_modes(Fld.shape[2])
+    idx = np.nonzero(ok)[0]
+    for l in range(6):
+        acc = np.zeros(idx.size)
+        for m in modes:
+            pm = ph[idx] ** abs(m) if m else np.ones(idx.size, dtype=complex)
+            pm = car[idx] * (np.conj(pm) if m < 0 else pm)
+            for i, wx in ((0, 1.0 - sx[idx]), (1, sx[idx])):
+                for k, wr in ((0, 1.0 - sr[idx]), (1, sr[idx])):
+                    acc += (wx * wr * pm * Fld[ix[idx] + i, ir[idx] + k, m + nko, l]).real
+        out[l, idx] += acc
+    return out
+
+
+def eb_correction_env(eb):
+    """grid_deps_env.f90:240-283: 1/pi for every mode; ghost row copied (nko = 0) or negated for ALL modes (Q6)"""
+    eb = np.array(eb) / np.pi
+    eb[:, 0] = eb[:, 1] if eb.shape[2] == 1 else -eb[:, 1]
+    return eb
+
+
+class _EnvOps:
+    """per-mode access: f[m] = field of mode m (zero outside -nko..nko), Dp[m] / Dm[m] for m in -nko-1..nko+1"""
+
+    def __init__(self, Dp, Dm, nm):
+        self.nko = (nm - 1) // 2
+        self.Dp, self.Dm = Dp, Dm
+
+    def dp(self, m):
+        return self.Dp[:, :, m + self.nko + 1]
+
+    def dm(self, m):
+        return self.Dm[:, :, m + self.nko + 1]
+
+
+def fb_grad_env(scl, Dp, Dm, kx):
+    """fb_math_env.f90:18-61"""
+    o = _EnvOps(Dp, Dm, scl.shape[2])
+    nko = o.nko
+    out = np.zeros(scl.shape[:2] + (scl.shape[2], 3), dtype=complex)
+    for m in range(-nko, nko + 1):
+        j = m + nko
+        out[:, :, j, 0] = 1j * kx[:, None] * scl[:, :, j]
+        if m > -nko:
+            g = scl[:, :, j - 1] @ o.dm(m)
+            out[:, :, j, 1] -= g
+            out[:, :, j, 2] += 1j * g
+        if m < nko:
+            g = scl[:, :, j + 1] @ o.dp(m)
+            out[:, :, j, 1] += g
+            out[:, :, j, 2] += 1j * g
+    return out
+
+
+def _div_env(vec, o, kx, m_lo, m_hi):
+    """S[m] for m = m_lo..m_hi (fb_math_env.f90:63-104; :183-206 with the two extra modes)"""
+    nko = o.nko
+    S = np.zeros(vec.shape[:2] + (m_hi - m_lo + 1,), dtype=complex)
+    for m in range(m_lo, m_hi + 1):
+        s = np.zeros(vec.shape[:2], dtype=complex)
+        if -nko <= m <= nko:
+            s += 1j * kx[:, None] * vec[:, :, m + nko, 0]
+        if m > -nko:
+            s -= (vec[:, :, m - 1 + nko, 1] - 1j * vec[:, :, m - 1 + nko, 2]) @ o.dm(m)
+        if m < nko:
+            s += (vec[:, :, m + 1 + nko, 1] + 1j * vec[:, :, m + 1 + nko, 2]) @ o.dp(m)
+        S[:, :, m - m_lo] = s
+    return S
+
+
+def fb_div_env(vec, Dp, Dm, kx):
+    o = _EnvOps(Dp, Dm, vec.shape[2])
+    return _div_env(vec, o, kx, -o.nko, o.nko)
+
+
+def fb_rot_env(vec, Dp, Dm, kx):
+    """fb_math_env.f90:106-162.  Q5: the Dm term of the first component is computed and dropped (:146-151)"""
+    o = _EnvOps(Dp, Dm, vec.shape[2])
+    nko = o.nko
+    out = np.zeros_like(vec)
+    ikx = 1j * kx[:, None]
+    for m in range(-nko, nko + 1):
+        j = m + nko
+        out[:, :, j, 1] = -ikx * vec[:, :, j, 2]
+        out[:, :, j, 2] = ikx * vec[:, :, j, 1]
+        if m < nko:
+            out[:, :, j, 0] -= (1j * vec[:, :, j + 1, 1] - vec[:, :, j + 1, 2]) @ o.dp(m)
+            g = vec[:, :, j + 1, 0] @ o.dp(m)
+            out[:, :, j, 1] += 1j * g
+            out[:, :, j, 2] -= g
+        if m > -nko:
+            g = vec[:, :, j - 1, 0] @ o.dm(m)
+            out[:, :, j, 1] += 1j * g
+            out[:, :, j, 2] += g
+    return out
+
+
+def fb_graddiv_env(vec, Dp, Dm, kx):
+    """fb_math_env.f90:164-233: divergence on modes -nko-1..nko+1, then the gradient with both neighbours always"""
+    o = _EnvOps(Dp, Dm, vec.shape[2])
+    nko = o.nko
+    S = _div_env(vec, o, kx, -nko - 1, nko + 1)  # S[:, :, m + nko + 1]
+    out = np.zeros_like(vec)
+    for m in range(-nko, nko + 1):
+        j = m + nko
+        out[:, :, j, 0] = 1j * kx[:, None] * S[:, :, m + nko + 1]
+        g1 = S[:, :, m - 1 + nko + 1] @ o.dm(m)
+        g2 = S[:, :, m + 1 + nko + 1] @ o.dp(m)
+        out[:, :, j, 1] = -g1 + g2
+        out[:, :, j, 2] = 1j * g1 + 1j * g2
+    return out

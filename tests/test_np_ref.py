@@ -97,3 +97,47 @@ def test_devices(ofim):
         want = getattr(np_ref, name)(x, f, 0.37, *args)
         assert_close(got, want, TOL, name)
         assert np.abs(got - f).max() > 1e-3, name  # the device did something
+
+
+ENV = ["env_m1", "env_m3"]
+
+
+@pytest.mark.parametrize("name", ENV)
+def test_envelope_deposit_and_gather(ofim, name):
+    """the envelope family (grid_deps_env.f90) a second time, in whole-array numpy"""
+    from util import carrier_tol
+
+    S = setup(name)
+    a = S.Args
+    x, p, w = particles(S, 4000, 5, inside_only=True)
+    if name == "env_m1":
+        p[0] += 391.0
+    dp = a["DepProj"]
+    tol = carrier_tol(S, TOL)
+    rho = ofim.dep_dens_env(x, w, S.zeros_sp(), a["leftX"], *dp)
+    assert_close(rho, np_ref.dep_dens_env(x, w, S.zeros_sp(), a["leftX"], *dp), 20 * tol, "dep_dens_env")
+    cur = ofim.dep_curr_env(x, p, w, S.zeros_sp(3), a["leftX"], *dp)
+    assert_close(cur, np_ref.dep_curr_env(x, p, w, S.zeros_sp(3), a["leftX"], *dp), 20 * tol, "dep_curr_env")
+    assert np.abs(cur[..., :2]).max() == 0.0 and np.abs(cur[..., 2]).max() > 0.0  # Q1
+    fld = crandn(np.random.default_rng(3), S.shape_sp + (6,))
+    got = ofim.proj_fld_env(x, w, fld, np.zeros((6, x.shape[1]), order="F"), a["leftX"], *dp)
+    assert_close(got, np_ref.proj_fld_env(x, w, fld, np.zeros((6, x.shape[1])), a["leftX"], *dp), tol, "proj_fld_env")
+    assert_close(ofim.eb_correction_env(fld.copy(order="F")), np_ref.eb_correction_env(fld), TOL, "eb_correction_env")
+
+
+@pytest.mark.parametrize("name", ENV)
+def test_envelope_spectral_calculus(ofim, name):
+    """fb_math_env.f90 in matrix notation, per mode"""
+    S = setup(name)
+    a = S.Args
+    rng = np.random.default_rng(13)
+    Dp, Dm, kx = a["FBDiff"]
+    v, s = crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb)
+    assert_close(ofim.fb_grad_env(S.zeros_fb(3), s, Dp, Dm, kx), np_ref.fb_grad_env(s, Dp, Dm, kx), TOL, "fb_grad_env")
+    assert_close(ofim.fb_div_env(S.zeros_fb(), v, Dp, Dm, kx), np_ref.fb_div_env(v, Dp, Dm, kx), TOL, "fb_div_env")
+    assert_close(ofim.fb_rot_env(S.zeros_fb(3), v, Dp, Dm, kx), np_ref.fb_rot_env(v, Dp, Dm, kx), TOL, "fb_rot_env")
+    assert_close(ofim.fb_graddiv_env(v.copy(order="F"), Dp, Dm, kx), np_ref.fb_graddiv_env(v, Dp, Dm, kx), TOL, "fb_graddiv_env")
+    # the complex-coefficient PSATD push of the envelope solver (maxwell_solvers.f90:62-96)
+    eg, j = crandn(rng, S.shape_fb + (6,)), crandn(rng, S.shape_fb + (3,))
+    got = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, S.PSATD_E, S.PSATD_G)
+    assert_close(got, np_ref.maxwell_push_wo_spchrg(eg, j, S.PSATD_E, S.PSATD_G), TOL, "wo_spchrg (complex coefficients)")
