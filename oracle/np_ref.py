@@ -49,14 +49,16 @@ def _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv):
     return ok, ix, ir, sx, sr, ph
 
 
-def _scatter(grid, ok, ix, ir, sx, sr, ph, amp):
-    """grid(Nx,Nr,M) += amp * exp(-i m theta) * Sx * Sr on the 4 nodes of each particle's cell."""
+def _scatter(grid, ok, ix, ir, sx, sr, ph, amp, keep=None):
+    """grid(Nx,Nr,M) += amp * exp(-i m theta) * Sx * Sr on the 4 nodes of each particle's cell.
+    keep(i): optional per-particle mask of the x node ix + i (the chunk-edge rule of the *_chnk variants)."""
     nm = grid.shape[2]
     for m in range(nm):
         v = amp * ph ** m if m else amp.astype(complex)
         for i, wx in ((0, 1.0 - sx), (1, sx)):
+            sel = ok if keep is None else ok & keep(i)
             for k, wr in ((0, 1.0 - sr), (1, sr)):
-                np.add.at(grid[:, :, m], (ix[ok] + i, ir[ok] + k), (v * wx * wr)[ok])
+                np.add.at(grid[:, :, m], (ix[sel] + i, ir[sel] + k), (v * wx * wr)[sel])
 
 
 def _fold_ghost(grid):
@@ -64,23 +66,61 @@ def _fold_ghost(grid):
     grid[:, 0] = 0.0
 
 
-def dep_dens(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv):
+def dep_dens(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv, keep=None):
     """grid_deps.f90:89-147"""
     ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
-    _scatter(dens, ok, ix, ir, sx, sr, ph, wghts)
+    _scatter(dens, ok, ix, ir, sx, sr, ph, wghts, keep and keep(ix))
     _fold_ghost(dens)
     return dens
 
 
-def dep_curr(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv):
+def dep_curr(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv, keep=None):
     """grid_deps.f90:18-87"""
     ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
     ok = ok & (np.abs(momenta).sum(0) != 0.0)
     g = np.sqrt(1.0 + (momenta ** 2).sum(0))
     for l in range(3):
-        _scatter(curr[..., l], ok, ix, ir, sx, sr, ph, momenta[l] * wghts / g)
+        _scatter(curr[..., l], ok, ix, ir, sx, sr, ph, momenta[l] * wghts / g, keep and keep(ix))
         _fold_ghost(curr[..., l])
     return curr
+
+
+def chunk_rule(ind_in_chunk, guards, nxn):
+    """The x-chunked variants (grid_deps_chnk.f90:38-124, grid_deps_env_chnk.f90) as a node mask on top of the plain
+    deposit: particle ip belongs to chunk c (IndInChunk(c) <= ip < IndInChunk(c+1)) which owns the nodes
+    [c cs, (c+1) cs), cs = Nx/nchnk.  A contribution to local node l = gx - c cs
+      * with 0 < l < cs goes straight to the grid;
+      * with l <= 0 goes to the chunk's `loc_left`, added back only if c cs - guards >= 0 (Q3: lost for chunk 0);
+      * with l >= cs goes to `loc_right`, added back only if (c+1) cs + guards <= Nx - 1.
+    Returns keep(ix) -> (i -> mask of the x node ix + i)."""
+    nchnk = len(ind_in_chunk) - 1
+    cs = nxn // nchnk
+
+    def for_cells(ix):
+        ip = np.arange(ix.size)
+        c = np.searchsorted(np.asarray(ind_in_chunk)[1:], ip, side="right")
+        inside = ip < ind_in_chunk[-1]
+        c = np.minimum(c, nchnk - 1)
+        left = c * cs
+
+        def node(i):
+            l = ix + i - left
+            direct = (l > 0) & (l < cs)
+            to_left = (l <= 0) & (l >= -guards) & (left - guards >= 0)
+            to_right = (l >= cs) & (l <= cs + guards) & (left + cs + guards <= nxn - 1)
+            return inside & (direct | to_left | to_right)
+
+        return node
+
+    return for_cells
+
+
+def dep_dens_chnk(coord, wghts, dens, ind, guards, leftX, Rgrid, dx_inv, dr_inv):
+    return dep_dens(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv, keep=chunk_rule(ind, guards, dens.shape[0]))
+
+
+def dep_curr_chnk(coord, momenta, wghts, curr, ind, guards, leftX, Rgrid, dx_inv, dr_inv):
+    return dep_curr(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv, keep=chunk_rule(ind, guards, curr.shape[0]))
 
 
 def proj_fld(coord, wghts, Fld, Fld_tot, leftX, Rgrid, dx_inv, dr_inv):
@@ -456,32 +496,34 @@ def _carrier(x, kx0, sign):
     return np.cos(x * kx0) + sign * 1j * np.sin(x * kx0)
 
 
-def _scatter_env(grid, ok, ix, ir, sx, sr, ph, amp):
+def _scatter_env(grid, ok, ix, ir, sx, sr, ph, amp, keep=None):
     """grid(Nx,Nr,2nko+1) += amp * exp(-i m theta) * Sx * Sr for m = -nko..nko (exp(-i|m|theta) conjugated for m<0)"""
     nko, modes = _env_modes(grid.shape[2])
     for m in modes:
         pm = ph ** abs(m) if m else np.ones_like(ph)
         v = amp * (np.conj(pm) if m < 0 else pm)
         for i, wx in ((0, 1.0 - sx), (1, sx)):
+            sel = ok if keep is None else ok & keep(i)
             for k, wr in ((0, 1.0 - sr), (1, sr)):
-                np.add.at(grid[:, :, m + nko], (ix[ok] + i, ir[ok] + k), (v * wx * wr)[ok])
+                np.add.at(grid[:, :, m + nko], (ix[sel] + i, ir[sel] + k), (v * wx * wr)[sel])
 
 
-def dep_dens_env(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv, kx0):
+def dep_dens_env(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv, kx0, keep=None):
     """grid_deps_env.f90:96-162.  Q2: the complex weight w e^{-i kx0 x} enters SQUARED (:145,147)"""
     ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
     wc = wghts * _carrier(coord[0], kx0, -1)
-    _scatter_env(dens, ok, ix, ir, sx, sr, ph, wc * wc)
+    _scatter_env(dens, ok, ix, ir, sx, sr, ph, wc * wc, keep and keep(ix))
     _fold_ghost(dens)
     return dens
 
 
-def dep_curr_env(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv, kx0):
+def dep_curr_env(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv, kx0, keep=None):
     """grid_deps_env.f90:18-94.  Q1: only the third component is deposited (:76)"""
     ok, ix, ir, sx, sr, ph = _shape(coord, wghts, leftX, Rgrid, dx_inv, dr_inv)
     ok = ok & (np.abs(momenta).sum(0) != 0.0)
     g = np.sqrt(1.0 + (momenta ** 2).sum(0))
-    _scatter_env(curr[..., 2], ok, ix, ir, sx, sr, ph, wghts * _carrier(coord[0], kx0, -1) * momenta[2] / g)
+    _scatter_env(curr[..., 2], ok, ix, ir, sx, sr, ph, wghts * _carrier(coord[0], kx0, -1) * momenta[2] / g,
+                 keep and keep(ix))
     for l in range(3):
         _fold_ghost(curr[..., l])
     return curr
@@ -605,3 +647,12 @@ def fb_graddiv_env(vec, Dp, Dm, kx):
         out[:, :, j, 1] = -g1 + g2
         out[:, :, j, 2] = 1j * g1 + 1j * g2
     return out
+
+
+def dep_dens_env_chnk(coord, wghts, dens, ind, guards, leftX, Rgrid, dx_inv, dr_inv, kx0):
+    return dep_dens_env(coord, wghts, dens, leftX, Rgrid, dx_inv, dr_inv, kx0, keep=chunk_rule(ind, guards, dens.shape[0]))
+
+
+def dep_curr_env_chnk(coord, momenta, wghts, curr, ind, guards, leftX, Rgrid, dx_inv, dr_inv, kx0):
+    return dep_curr_env(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv, kx0,
+                        keep=chunk_rule(ind, guards, curr.shape[0]))

@@ -141,3 +141,38 @@ def test_envelope_spectral_calculus(ofim, name):
     eg, j = crandn(rng, S.shape_fb + (6,)), crandn(rng, S.shape_fb + (3,))
     got = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, S.PSATD_E, S.PSATD_G)
     assert_close(got, np_ref.maxwell_push_wo_spchrg(eg, j, S.PSATD_E, S.PSATD_G), TOL, "wo_spchrg (complex coefficients)")
+
+
+@pytest.mark.parametrize("name", ["real_m2", "real_m3", "env_m1", "env_m3"])
+@pytest.mark.parametrize("nchnk,guards", [(4, 3), (4, 0), (2, 1)])
+def test_chunked_deposits(ofim, name, nchnk, guards):
+    """the x-chunked variants (grid_deps_chnk.f90, grid_deps_env_chnk.f90) as "plain deposit + node mask": chunk
+    edge handling through loc_left / loc_right incl. what the first and last chunk lose (Q3).  Particles are sorted
+    into chunks and then shaken by up to `guards` cells, so that contributions do cross chunk borders."""
+    from util import carrier_tol, chunk_sorted
+
+    S = setup(name)
+    a = S.Args
+    if a["Nx"] % nchnk:
+        pytest.skip("grid not divisible into %d chunks" % nchnk)
+    x, p, w = particles(S, 5000, 7, inside_only=True)
+    if name == "env_m1":
+        p[0] += 391.0
+    x, p, w, ind = chunk_sorted(S, x, p, w, ofim, nchnk)
+    rng = np.random.default_rng(9)
+    x[0] += a["dx"] * guards * (2 * rng.random(x.shape[1]) - 1) * 0.9  # drift since the last sort, within the guards
+    x[0] = np.clip(x[0], a["leftX"] + 1e-9, a["rightX"] - a["dx"] - 1e-9)
+    x = np.asfortranarray(x)
+    dp = a["DepProj"]
+    env = "_env" if S.env else ""
+    tol = 20 * carrier_tol(S, TOL) if S.env else TOL
+    rho = getattr(ofim, "dep_dens%s_chnk" % env)(x, w, S.zeros_sp(), ind, guards, a["leftX"], *dp)
+    want = getattr(np_ref, "dep_dens%s_chnk" % env)(x, w, S.zeros_sp(), ind, guards, a["leftX"], *dp)
+    assert_close(rho, want, tol, "dep_dens%s_chnk" % env)
+    cur = getattr(ofim, "dep_curr%s_chnk" % env)(x, p, w, S.zeros_sp(3), ind, guards, a["leftX"], *dp)
+    want = getattr(np_ref, "dep_curr%s_chnk" % env)(x, p, w, S.zeros_sp(3), ind, guards, a["leftX"], *dp)
+    assert_close(cur, want, tol, "dep_curr%s_chnk" % env)
+    # and the rule really bites: the chunked result differs from the plain one at the outer edges when guards > 0
+    plain = getattr(ofim, "dep_dens%s" % env)(x, w, S.zeros_sp(), a["leftX"], *dp)
+    if guards > 0:
+        assert np.abs(plain - rho).max() > 0
