@@ -656,3 +656,84 @@ def dep_dens_env_chnk(coord, wghts, dens, ind, guards, leftX, Rgrid, dx_inv, dr_
 def dep_curr_env_chnk(coord, momenta, wghts, curr, ind, guards, leftX, Rgrid, dx_inv, dr_inv, kx0):
     return dep_curr_env(coord, momenta, wghts, curr, leftX, Rgrid, dx_inv, dr_inv, kx0,
                         keep=chunk_rule(ind, guards, curr.shape[0]))
+
+
+# ---- f90/particle_tools.f90: generation, culling, chunking, permutation --------------------------------
+def genparts(Xgrid, Rgrid, RandPackO, PackX, PackR, PackO):
+    """particle_tools.f90:84-128: PPC particles per (x, r) cell at x0 + (x1-x0) PackX, r0 + (r1-r0) PackR on the
+    half-cell-shifted r grid, azimuth PackO * exp(2 pi i RandPackO(cell)); particles with r <= 0 are skipped.
+    Returns coord(4, n) = (x, r sin, r cos, r) in the reference's order (r outer loop, x inner, then the pack)."""
+    dr_2 = 0.5 * (Rgrid[1] - Rgrid[0])
+    rs = Rgrid + dr_2
+    x0, x1 = Xgrid[:-1], Xgrid[1:]
+    r0, r1 = rs[:-1], rs[1:]
+    xx = x0[None, :, None] + (x1 - x0)[None, :, None] * PackX[None, None, :]              # (1, nx-1, ppc)
+    rr = r0[:, None, None] + (r1 - r0)[:, None, None] * PackR[None, None, :]              # (nr-1, 1, ppc)
+    ang = 2.0 * np.pi * RandPackO[:len(x0), :len(r0)].T[:, :, None]
+    oc = PackO[None, None, :] * (np.cos(ang) + 1j * np.sin(ang))                          # (nr-1, nx-1, ppc)
+    xx, rr = np.broadcast_to(xx, oc.shape), np.broadcast_to(rr, oc.shape)
+    keep = rr > 0
+    return np.asfortranarray(np.stack((xx[keep], (rr * oc.imag)[keep], (rr * oc.real)[keep], rr[keep])))
+
+
+def _inside(coord, lims):
+    r2 = coord[1] ** 2 + coord[2] ** 2
+    return (coord[0] >= lims[0]) & (coord[0] <= lims[1]) & (r2 >= lims[2]) & (r2 <= lims[3])
+
+
+def sortpartsout(coord, lims):
+    """particle_tools.f90:130-153: 0-based indices of the particles inside lims = (xmin, xmax, r2min, r2max)"""
+    return np.nonzero(_inside(coord, lims))[0]
+
+
+def chunk_coords_boundaries(coord, lims, Xgrid, nchnk):
+    """particle_tools.f90:155-208: chunk id per particle (-2 outside lims), prefix offsets, number leaving"""
+    n = len(Xgrid)
+    length = (Xgrid[n // nchnk] - Xgrid[0]) if nchnk > 1 else (Xgrid[-1] - Xgrid[0])
+    ich = np.floor((coord[0] - Xgrid[0]) * (1.0 / length)).astype(int)
+    ins = _inside(coord, lims)
+    ids = np.where(ins, ich, -2).astype(np.int8)
+    counts = np.bincount(ich[ins], minlength=nchnk)[:nchnk]
+    return ids, np.concatenate(([0], np.cumsum(counts))).astype(np.int32), int((~ins).sum())
+
+
+def align_data(dat, idx):
+    """particle_tools.f90:270-324 (vec and scl): leading len(idx) entries <- dat[..., idx]"""
+    out = np.array(dat)
+    out[..., :len(idx)] = dat[..., idx]
+    return out
+
+
+# ---- f90/maxwell_solvers.f90: the rest of the elementwise family --------------------------------------
+def maxwell_init_push(EG, J, g_n, C1, C2):
+    """maxwell_solvers.f90:98-129"""
+    out = np.array(EG)
+    out[..., :3] += C1[..., 0:1] * J + C1[..., 1:2] * g_n
+    out[..., 3:] += C2[..., 0:1] * J + C2[..., 1:2] * g_n
+    return out
+
+
+def poiss_corr_stat(J, gdj, g_n, DT, w2_inv):
+    """maxwell_solvers.f90:166-197"""
+    return J + (gdj + DT[:, None, None, None] * g_n) * w2_inv[..., None]
+
+
+def field_drift(EG, kx, beta0, dt):
+    """maxwell_solvers.f90:199-226"""
+    return EG * np.exp(-0.5j * dt * beta0 * kx)[:, None, None, None]
+
+
+# ---- f90/fb_io.f90:230-300 -----------------------------------------------------------------------------
+def fb_filtr(vec, leftX, kx, filtr, modefilt=0):
+    """x-space window on spectral fields: back to x (unnormalised inverse FFT after the phase), multiply the first
+    len(filtr) nodes (mode 0, 'left', the only one the driver uses: solvers.py:619), forward FFT, undo phase and Nx"""
+    nx = vec.shape[0]
+    shift = (np.cos(leftX * kx) + 1j * np.sin(leftX * kx)).reshape((nx,) + (1,) * (vec.ndim - 1))
+    a = np.fft.ifft(vec * shift, axis=0) * nx
+    w = np.ones(nx)
+    if modefilt in (0, 2):
+        w[:len(filtr)] *= filtr
+    if modefilt in (1, 2):  # Aifft(nkx-nxfilt:nkx) has nxfilt+1 elements against filtr's nxfilt: shape bug in the
+        raise NotImplementedError("modes 1, 2 of fb_filtr are ill-formed in the reference (fb_io.f90:279) and unused")
+    a *= w.reshape(shift.shape)
+    return np.fft.fft(a, axis=0) / (nx * shift)

@@ -176,3 +176,58 @@ def test_chunked_deposits(ofim, name, nchnk, guards):
     plain = getattr(ofim, "dep_dens%s" % env)(x, w, S.zeros_sp(), a["leftX"], *dp)
     if guards > 0:
         assert np.abs(plain - rho).max() > 0
+
+
+def test_particle_tools(ofim):
+    """particle_tools.f90: generation, culling, chunk binning and permutation, loop form vs array form"""
+    rng = np.random.default_rng(23)
+    S = setup("real_m2")
+    a = S.Args
+    xg, rg = a["Xgrid"][:20], a["Rgrid"][:9]
+    px, pr, po = np.mgrid[1:2:2j, 1:3:3j, 1:4:4j]
+    packx, packr = ((px - 0.5) / 2).ravel(), ((pr - 0.5) / 3).ravel()
+    packo = np.exp(2j * np.pi * (po - 1) / 4).ravel()
+    rnd = np.asfortranarray(rng.random((xg.size, rg.size)))
+    ppc = packx.size
+    coord = np.zeros((4, (xg.size - 1) * (rg.size - 1) * ppc), order="F")
+    got, n = ofim.genparts(coord, xg, rg, rnd, packx, packr, packo)
+    want = np_ref.genparts(xg, rg, rnd, packx, packr, packo)
+    assert n == want.shape[1]
+    assert_close(got[:, :n], want, TOL, "genparts")
+
+    x, p, w = particles(S, 3000, 5)  # includes particles outside the domain
+    lims = np.asfortranarray([a["leftX"] + 0.3, a["rightX"] - 0.2, 0.0, (0.8 * a["Rgrid"].max()) ** 2])
+    idx, m = ofim.sortpartsout(x, lims)
+    assert np.array_equal(idx[:m], np_ref.sortpartsout(x, lims))
+    for nchnk in (1, 4, 8):
+        ids, ind, out = ofim.chunk_coords_boundaries(x, lims, a["Xgrid"], nchnk)
+        ids2, ind2, out2 = np_ref.chunk_coords_boundaries(x, lims, a["Xgrid"], nchnk)
+        assert np.array_equal(ids, ids2) and np.array_equal(ind, ind2) and out == out2
+    keep = np.nonzero(ids >= 0)[0].astype(np.int64)[::-1].copy()
+    assert np.array_equal(ofim.align_data_vec(x.copy(order="F"), keep), np_ref.align_data(x, keep))
+    assert np.array_equal(ofim.align_data_scl(w.copy(), keep), np_ref.align_data(w, keep))
+
+
+def test_static_kick_family_and_filter(ofim):
+    """maxwell_init_push, poiss_corr_stat, field_drift, omp_* (maxwell_solvers.f90:98-320) and fb_filtr (fb_io.f90:230)"""
+    S = setup("static_m2")
+    a = S.Args
+    rng = np.random.default_rng(29)
+    eg, j, g = crandn(rng, S.shape_fb + (6,)), crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb + (3,))
+    c1, c2 = S.static_coeffs(50.0)
+    assert_close(ofim.maxwell_init_push(eg.copy(order="F"), j, g, c1, c2), np_ref.maxwell_init_push(eg, j, g, c1, c2), TOL,
+                 "maxwell_init_push")
+    beta = 50.0 / np.sqrt(1 + 50.0 ** 2)
+    dtc = -1j * beta * a["kx"]
+    got = ofim.poiss_corr_stat(j.copy(order="F"), eg[..., :3], g, dtc, a["PoissFact"])
+    assert_close(got, np_ref.poiss_corr_stat(j, eg[..., :3], g, dtc, a["PoissFact"]), TOL, "poiss_corr_stat")
+    assert_close(ofim.field_drift(eg.copy(order="F"), a["kx"], beta, a["dt"]), np_ref.field_drift(eg, a["kx"], beta, a["dt"]),
+                 TOL, "field_drift")
+    A = rng.random(S.shape_fb)
+    assert_close(ofim.omp_mult_vec(j.copy(order="F"), A), j * A[..., None], TOL, "omp_mult_vec")
+    assert_close(ofim.omp_mult_scl(j[..., 0].copy(order="F"), A), j[..., 0] * A, TOL, "omp_mult_scl")
+    assert_close(ofim.omp_add_vec(j.copy(order="F"), g), j + g, TOL, "omp_add_vec")
+    assert_close(ofim.omp_add_scl(j[..., 1].copy(order="F"), g[..., 2]), j[..., 1] + g[..., 2], TOL, "omp_add_scl")
+    prof = S.get_damp_profile(6)
+    assert_close(ofim.fb_filtr(j.copy(order="F"), a["leftX"], a["kx"], prof, 0), np_ref.fb_filtr(j, a["leftX"], a["kx"], prof, 0),
+                 TOL, "fb_filtr")
