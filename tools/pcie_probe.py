@@ -27,3 +27,16 @@ t = time.perf_counter()
 lib.chimera_host_register(ctypes.c_void_p(x.ctypes.data), ctypes.c_longlong(x.nbytes)); lib.chimera_host_register(ctypes.c_void_p(y.ctypes.data), ctypes.c_longlong(y.nbytes))
 print("cudaHostRegister 2 x 2.4 GB: %.1f ms" % ((time.perf_counter() - t) * 1e3))
 bw("numpy registered", torch.from_numpy(x), torch.from_numpy(y)); bw("numpy registered (2nd)", torch.from_numpy(x), torch.from_numpy(y))
+# pageable numpy memory: what a per-function drop-in call sees (plain copies) and what csrc/staging.cu makes of it
+# (align_data_scl with the identity permutation = one staged H2D + one staged D2H of the array, plus a tiny kernel)
+import chimera_b200.fimera as gfim
+m = 150_000_000  # 1.2 GB
+z = np.ones(m)
+torch.cuda.synchronize(); t = time.perf_counter(); dev_a[:m].copy_(torch.from_numpy(z)); torch.cuda.synchronize()
+print("pageable plain        h2d   %6.1f GB/s" % (m * 8 / 1e9 / (time.perf_counter() - t)))
+torch.cuda.synchronize(); t = time.perf_counter(); torch.from_numpy(z).copy_(dev_a[:m]); torch.cuda.synchronize()
+print("pageable plain        d2h   %6.1f GB/s" % (m * 8 / 1e9 / (time.perf_counter() - t)))
+idx = np.arange(m, dtype=np.int64)
+gfim.align_data_scl(z[:1000].copy(), idx[:1000])
+t = time.perf_counter(); gfim.align_data_scl(z, idx); dt = time.perf_counter() - t
+print("pageable staged (csrc/staging.cu) h2d 2.4 GB + d2h 1.2 GB in %.1f ms = %.1f GB/s" % (dt * 1e3, 3 * m * 8 / 1e9 / dt))
