@@ -16,8 +16,12 @@ bool Stager::pageable(const void* p) {
 
 int Stager::init() {
   if (ready_) return 0;
+  if (const char* e = getenv("CHIMERA_STAGE_CHUNK_MB")) {
+    const long mb = atol(e);
+    if (mb >= 1 && mb <= 1024) chunk_ = (size_t)mb << 20;
+  }
   for (int i = 0; i < kSlots; ++i) {
-    CHB_CUDA(cudaHostAlloc((void**)&slot_[i], kChunk, cudaHostAllocDefault));
+    CHB_CUDA(cudaHostAlloc((void**)&slot_[i], chunk_, cudaHostAllocDefault));
     CHB_CUDA(cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming));
     busy_[i] = false;
   }
@@ -98,8 +102,8 @@ int Stager::h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t 
   }
   CHB_TRY(init());
   int s = 0;
-  for (size_t off = 0; off < bytes; off += kChunk, s = (s + 1) % kSlots) {
-    const size_t len = std::min(kChunk, bytes - off);
+  for (size_t off = 0; off < bytes; off += chunk_, s = (s + 1) % kSlots) {
+    const size_t len = std::min(chunk_, bytes - off);
     if (busy_[s]) {  // the DMA that last read this slot
       CHB_CUDA(cudaEventSynchronize(ev_[s]));
       busy_[s] = false;
@@ -125,11 +129,11 @@ int Stager::d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t 
       CHB_CUDA(cudaEventSynchronize(ev_[s]));
       busy_[s] = false;
     }
-  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  const size_t nchunks = (bytes + chunk_ - 1) / chunk_;
   size_t issued = 0;
   auto issue = [&](size_t c) -> int {
     const int s = (int)(c % kSlots);
-    const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+    const size_t off = c * chunk_, len = std::min(chunk_, bytes - off);
     CHB_CUDA(cudaMemcpyAsync(slot_[s], (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, st));
     CHB_CUDA(cudaEventRecord(ev_[s], st));
     return 0;
@@ -137,7 +141,7 @@ int Stager::d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t 
   for (; issued < nchunks && issued < (size_t)kSlots; ++issued) CHB_TRY(issue(issued));
   for (size_t c = 0; c < nchunks; ++c) {
     const int s = (int)(c % kSlots);
-    const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+    const size_t off = c * chunk_, len = std::min(chunk_, bytes - off);
     CHB_CUDA(cudaEventSynchronize(ev_[s]));
     parallel_copy((char*)dst_host + off, slot_[s], len);
     if (issued < nchunks) CHB_TRY(issue(issued++));  // the slot just emptied takes the next chunk

@@ -3,7 +3,7 @@
 // The drop-in boundary (include/chimera_b200.h) receives plain numpy-owned pointers: pageable memory.  A
 // cudaMemcpyAsync from/to pageable memory is staged by the driver through one internal buffer on one thread
 // (~10 GB/s measured here, profiles/r01g bench `e2e_per_call`), far below the 55 GB/s the link gives from
-// page-locked memory.  The Stager splits a copy into chunks, moves each chunk between the user buffer and a
+// page-locked memory.  The Stager splits a copy into (cache-sized) chunks, moves each chunk between the user buffer and a
 // ring of page-locked slots with a small pool of host threads, and lets the DMA engine work on the previous
 // slot meanwhile (events guard slot reuse).  Already page-locked buffers (cudaHostRegister / cudaHostAlloc) and
 // small copies bypass it.
@@ -20,7 +20,8 @@ namespace chb {
 
 class Stager {
  public:
-  static constexpr size_t kChunk = size_t(16) << 20;  // bytes per slot
+  static constexpr size_t kChunkDefault = size_t(4) << 20;  // bytes per slot (CHIMERA_STAGE_CHUNK_MB overrides); measured
+                                                            // 2.4 GB up + 1.2 GB down: 4 MB 51.7, 16 MB 40.7, 64 MB 37.9 GB/s
   static constexpr int kSlots = 6;
   static constexpr size_t kMinBytes = size_t(4) << 20;  // below this the plain copy is as fast
 
@@ -37,6 +38,7 @@ class Stager {
   void worker(int id);
 
   bool ready_ = false;
+  size_t chunk_ = kChunkDefault;
   char* slot_[kSlots] = {};
   cudaEvent_t ev_[kSlots] = {};
   bool busy_[kSlots] = {};  // an event has been recorded for the slot and not yet waited for

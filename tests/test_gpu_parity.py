@@ -44,10 +44,10 @@ def test_push_coords(ofim, gfim, n):
 
 @pytest.mark.parametrize("n", [174763, 699051, 2100011, 5000003])
 def test_large_pageable_buffers_are_staged_exactly(ofim, gfim, n):
-    """arrays above 4 MB go through the page-locked staging ring (csrc/staging.cu: 16 MB chunks, 6 slots, host
-    thread pool): sizes just above the threshold, exactly one chunk (3 n 8 B = 16 MiB + 8), several chunks with a
-    ragged tail, and more chunks than slots (slot reuse) -- bit-exact pass-through both ways (align_data_vec is a
-    pure permutation), then parity of a compute call on the same sizes"""
+    """arrays above 4 MB go through the page-locked staging ring (csrc/staging.cu: 4 MB chunks, 6 slots, host
+    thread pool): one chunk plus 8 bytes (3 n 8 B = 4 MiB + 8), four chunks plus 8 bytes, a ragged tail, and many
+    more chunks than slots (slot reuse) -- bit-exact pass-through both ways (align_data_vec is a pure permutation),
+    then parity of a compute call on the same sizes"""
     rng = np.random.default_rng(n)
     dat = np.asfortranarray(rng.standard_normal((3, n)))
     idx = rng.permutation(n).astype(np.int64)
