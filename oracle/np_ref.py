@@ -686,6 +686,11 @@ def sortpartsout(coord, lims):
     return np.nonzero(_inside(coord, lims))[0]
 
 
+def sortoutghosts(coord):
+    """particle_tools.f90:326-341: 0-based indices of the entries that are not exactly zero"""
+    return np.nonzero(np.asarray(coord) != 0.0)[0]
+
+
 def chunk_coords_boundaries(coord, lims, Xgrid, nchnk):
     """particle_tools.f90:155-208: chunk id per particle (-2 outside lims), prefix offsets, number leaving"""
     n = len(Xgrid)

@@ -203,6 +203,10 @@ def test_particle_tools(ofim):
         ids, ind, out = ofim.chunk_coords_boundaries(x, lims, a["Xgrid"], nchnk)
         ids2, ind2, out2 = np_ref.chunk_coords_boundaries(x, lims, a["Xgrid"], nchnk)
         assert np.array_equal(ids, ids2) and np.array_equal(ind, ind2) and out == out2
+    wz = w.copy()
+    wz[::7] = 0.0
+    idx, m = ofim.sortoutghosts(wz)
+    assert np.array_equal(idx[:m], np_ref.sortoutghosts(wz))
     keep = np.nonzero(ids >= 0)[0].astype(np.int64)[::-1].copy()
     assert np.array_equal(ofim.align_data_vec(x.copy(order="F"), keep), np_ref.align_data(x, keep))
     assert np.array_equal(ofim.align_data_scl(w.copy(), keep), np_ref.align_data(w, keep))
