@@ -10,8 +10,14 @@ Multi-GPU (one process per GPU, ``torch.distributed``): particles are sharded ac
 rank deposits into its own J / Rho grids, the grids are summed with an NCCL all-reduce over NVLink and
 the spectral solve is sharded by kx slab (mirror pairs of rows, chimera_b200/sharding.py): every rank
 x-FFTs the summed grids, transforms / corrects / advances only its rows, and the backward-transformed
-slabs are all-gathered before the inverse x-FFT and the gather to the rank's own particles.  There is
+slabs are all-gathered before the inverse x-FFT and the gather to the rank's own particles.  The two
+collectives are pipelined with their neighbours (``Engine.overlap``): the E half of the slab is gathered while
+the B half is computed, the reduction of Rho runs behind the forward transform of J.  There is
 no CPU fallback: without the CUDA library the import of :mod:`chimera_b200._lib` fails.
+
+Also mirrored here: the reference's moving frames (``frame_act`` for windows that act every few steps with
+``AbsorbLayer`` / ``AddPlasma``; ``set_window`` for frames that move every step, 'Staged' or not), per-species
+external-field devices, the 'StaticKick' schedule and the integrated diagnostics of moduls/diagnostics.py.
 """
 from __future__ import annotations
 
