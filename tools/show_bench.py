@@ -1,4 +1,8 @@
+"""Pretty-print the JSON line(s) of bench.py: python tools/show_bench.py <file> (or stdin)."""
+import signal
 import sys, json
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` is fine
 for line in open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin:
     line = line.rstrip()
     if line.startswith('{"metric"') or line.startswith('{"impl"'):
