@@ -66,3 +66,108 @@ def test_product_package_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "liboracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def header_arity():
+    """number of parameters of every `int chimera_<name>(...)` prototype in the header"""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\bint\s+(chimera_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = m.group(2).strip()
+        out[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_shim_passes_as_many_arguments_as_the_header_declares():
+    """static guard against drift between include/chimera_b200.h and the ctypes call sites of f2py_shim.py (ctypes
+    does not check arity): every `call("<name>", ...)` with a literal name and no starred argument is compared"""
+    import ast
+
+    arity = header_arity()
+    src = open(os.path.join(ROOT, "chimera_b200", "f2py_shim.py")).read()
+    checked = 0
+    for node in ast.walk(ast.parse(src)):
+        if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id == "call" and node.args):
+            continue
+        first = node.args[0]
+        if not (isinstance(first, ast.Constant) and isinstance(first.value, str)):
+            continue
+        if any(isinstance(a, ast.Starred) for a in node.args):
+            continue
+        sym = "chimera_" + first.value
+        assert sym in arity, sym
+        assert len(node.args) - 1 == arity[sym], (sym, len(node.args) - 1, arity[sym])
+        checked += 1
+    assert checked >= 15, checked
+
+
+def test_generated_wrappers_pass_as_many_arguments_as_the_header_declares():
+    """the shim functions produced by factories (omp_*, devices, SR, spectral calculus, deposits ...) against a
+    recording stand-in for the library: argument counts as declared in include/chimera_b200.h"""
+    from chimera_b200.f2py_shim import build_module
+    from util import crandn, particles, setup
+
+    seen = {}
+
+    class Fn:
+        def __init__(self, name):
+            self.name, self.restype = name, None
+
+        def __call__(self, *args):
+            seen[self.name] = len(args)
+            return 0
+
+    class Lib:
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return Fn(name)
+
+    f = build_module(Lib(), "chimera")
+    rng = np.random.default_rng(0)
+    for name in ("real_m2", "env_m3"):
+        S = setup(name)
+        a = S.Args
+        env = "_env" if S.env else ""
+        x, p, w = particles(S, 50, 1, inside_only=True)
+        ind = np.array([0, 10, 20, 30, 50], dtype=np.int32)
+        v, sc = crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb)
+        Dp, Dm, kx = a["FBDiff"]
+        getattr(f, "dep_curr" + env)(x, p, w, S.zeros_sp(3), a["leftX"], *a["DepProj"])
+        getattr(f, "dep_dens" + env)(x, w, S.zeros_sp(), a["leftX"], *a["DepProj"])
+        getattr(f, "dep_curr" + env + "_chnk")(x, p, w, S.zeros_sp(3), ind, 3, a["leftX"], *a["DepProj"])
+        getattr(f, "dep_dens" + env + "_chnk")(x, w, S.zeros_sp(), ind, 3, a["leftX"], *a["DepProj"])
+        getattr(f, "proj_fld" + env)(x, w, S.zeros_sp(6), np.zeros((6, 50), order="F"), a["leftX"], *a["DepProj"])
+        getattr(f, "eb_correction" + env)(S.zeros_sp(6))
+        getattr(f, "fb_rot" + env)(S.zeros_fb(3), v, Dp, Dm, kx)
+        getattr(f, "fb_grad" + env)(S.zeros_fb(3), sc, Dp, Dm, kx)
+        getattr(f, "fb_div" + env)(S.zeros_fb(), v, Dp, Dm, kx)
+        getattr(f, "fb_graddiv" + env)(v, Dp, Dm, kx)
+    S = setup("real_m2")
+    a = S.Args
+    v, sc = crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb)
+    f.fb_vec_in(S.zeros_fb(3), S.zeros_sp(3), a["leftX"], *a["FBIn"])
+    f.fb_scl_in(S.zeros_fb(), S.zeros_sp(), a["leftX"], *a["FBIn"])
+    f.fb_vec_out(v, a["leftX"], *a["FBout"])
+    f.fb_scl_out(sc, a["leftX"], *a["FBout"])
+    f.fb_eb_out(S.zeros_sp(6), crandn(rng, S.shape_fb + (6,)), v, a["leftX"], *a["FBout"])
+    f.omp_mult_vec(v, np.ones(S.shape_fb)); f.omp_mult_scl(sc, np.ones(S.shape_fb))
+    f.omp_add_vec(v, v.copy(order="F")); f.omp_add_scl(sc, sc.copy(order="F"))
+    x3, fld = np.zeros((3, 4), order="F"), np.zeros((6, 4), order="F")
+    f.undul_analytic(x3, fld, 0.1, np.ones(4)); f.undul_analytic_taper(x3, fld, 0.1, np.ones(5))
+    f.undul_mapped(x3, fld, 0.1, np.ones((2, 5), order="F"), np.ones(3))
+    f.undul_mapped_tap(x3, fld, 0.1, np.ones((2, 5), order="F"), np.ones(5))
+    f.planewave(x3, fld, 0.1, np.ones(7)); f.gaussbeam(x3, fld, 0.1, 1.0, np.ones(8))
+    tr, om, g2, g3 = np.zeros((3, 6, 2), order="F"), np.ones(4), np.ones(2), np.ones(3)
+    sp = np.zeros((4, 2, 3), order="F")
+    f.sr_calc_far_tot(sp, tr, tr, tr, np.ones(2), 0.1, om, g2, g2, g3, g3)
+    f.sr_calc_far_comp(sp, tr, tr, tr, np.ones(2), 1, 0.1, om, g2, g2, g3, g3)
+    f.sr_calc_near_tot(sp, tr, tr, np.ones(2), 0.1, om, g2, g3, 5.0)
+    f.sr_calc_near_comp(sp, tr, tr, np.ones(2), 2, 0.1, om, g2, g3, 5.0)
+    f.sr_calc_nearcirc_tot(sp, tr, tr, np.ones(2), 0.1, om, g2, g3, g3, 5.0)
+    f.sr_calc_nearcirc_comp(sp, tr, tr, np.ones(2), 3, 0.1, om, g2, g3, g3, 5.0)
+    arity = header_arity()
+    assert len(seen) >= 40, sorted(seen)
+    for sym, n in seen.items():
+        assert n == arity[sym], (sym, n, arity[sym])
