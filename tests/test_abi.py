@@ -171,3 +171,24 @@ def test_generated_wrappers_pass_as_many_arguments_as_the_header_declares():
     assert len(seen) >= 40, sorted(seen)
     for sym, n in seen.items():
         assert n == arity[sym], (sym, n, arity[sym])
+
+
+def test_engine_wrapper_passes_as_many_arguments_as_the_header_declares():
+    """the same static guard for chimera_b200/engine.py (self.lib.chimera_engine_*(...))"""
+    import ast
+
+    arity = header_arity()
+    src = open(os.path.join(ROOT, "chimera_b200", "engine.py")).read()
+    checked = 0
+    for node in ast.walk(ast.parse(src)):
+        if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("chimera_")):
+            continue
+        if any(isinstance(a, ast.Starred) for a in node.args):
+            continue
+        sym = node.func.attr
+        if sym in ("chimera_last_error", "chimera_version"):  # const char* f(void): not an `int` prototype
+            continue
+        assert sym in arity, sym
+        assert len(node.args) == arity[sym], (sym, len(node.args), arity[sym])
+        checked += 1
+    assert checked >= 25, checked
