@@ -192,3 +192,39 @@ def test_engine_wrapper_passes_as_many_arguments_as_the_header_declares():
         assert len(node.args) == arity[sym], (sym, len(node.args), arity[sym])
         checked += 1
     assert checked >= 25, checked
+
+
+def test_engine_config_struct_matches_the_header():
+    """chimera_engine_config (header) and EngineConfig (ctypes) field by field: name, order and C type; the phase
+    enum against the PHASES tuple"""
+    import ctypes
+
+    from chimera_b200.engine import PHASES, EngineConfig
+
+    src = open(HEADER).read()
+    body = re.search(r"typedef struct chimera_engine_config \{(.*?)\} chimera_engine_config;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", " ", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        fields += [(n.strip(), ctype) for n in names.split(",")]
+    cmap = {"int": ctypes.c_int, "double": ctypes.c_double, "chb_i64": ctypes.c_longlong}
+    got = [(n, t) for n, t in EngineConfig._fields_]
+    assert [n for n, _ in got] == [n for n, _ in fields], ([n for n, _ in got], [n for n, _ in fields])
+    for (n, t), (_, ct) in zip(got, fields):
+        assert t is cmap[ct], (n, t, ct)
+    enum = re.search(r"enum chimera_engine_phase \{(.*?)\};", src, flags=re.S).group(1)
+    enum = re.sub(r"/\*.*?\*/", " ", enum, flags=re.S)
+    ids = {m.group(1): int(m.group(2)) for m in re.finditer(r"CHB_([A-Z_]+)\s*=\s*(\d+)", enum)}
+    assert ids.pop("NPHASES") == len(PHASES)
+    names = {"PUSH_COORDS": "push_coords", "SORT": "sort", "DEPOSIT_J": "deposit_J", "DEPOSIT_RHO": "deposit_rho",
+             "DEPOSIT_BG": "deposit_bg", "FB_IN_J": "fb_in_J", "FB_IN_RHO": "fb_in_rho", "POISSON": "poisson",
+             "MAXWELL": "maxwell", "INIT_PUSH": "init_push", "FIELDS_OUT": "fields_out", "GATHER_PUSH": "gather_push",
+             "ADD_BG": "add_bg", "FIELDS_OUT_A": "fields_out_a", "FIELDS_OUT_B": "fields_out_b",
+             "PARTICLES_FUSED": "particles_fused", "STATIC_FIELDS": "static_fields", "WINDOW": "window"}
+    assert set(ids) == set(names)
+    for k, i in ids.items():
+        assert PHASES[i] == names[k], (k, i, PHASES[i])
