@@ -914,6 +914,43 @@ int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nx
   return 0;
 }
 
+// Solver.damp_field on a kx-slab engine.  The x-space window needs every kx row of a column, so the slabs of all ranks
+// are brought together first: the caller all-gathers "EG_fb" into "EG_gath" ([rank][(nx_slab, nkr, nm, 6)], allocated by
+// chimera_engine_damp_prepare together with the full-row scratch "EG_full" and filled with the full "kx_full");
+// this call rebuilds the full rows, applies the same fb_filtr as the unsharded engine and keeps this rank's rows.
+int chimera_engine_damp_prepare(chimera_engine* e) {
+  ENG_CHECK(e);
+  const auto& c = e->cfg;
+  if (!slab(e)) { set_error("damp_prepare: only for kx-slab engines"); return 2; }
+  const size_t full = sizeof(cd) * (size_t)c.nx * c.nkr * c.nm * 6;
+  if (!e->arr.count("EG_gath")) CHB_TRY(alloc_named(e, "EG_gath", full));
+  if (!e->arr.count("EG_full")) CHB_TRY(alloc_named(e, "EG_full", full));
+  if (!e->arr.count("kx_full")) CHB_TRY(alloc_named(e, "kx_full", sizeof(double) * (size_t)c.nx));
+  return 0;
+}
+
+int chimera_engine_damp_field_slab(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode) {
+  ENG_CHECK(e);
+  const auto& c = e->cfg;
+  if (!slab(e)) { set_error("damp_field_slab: only for kx-slab engines"); return 2; }
+  if (!e->arr.count("EG_gath") || !e->arr.count("EG_full") || !e->arr.count("kx_full")) {
+    set_error("damp_field_slab: call chimera_engine_damp_prepare, upload kx_full and all-gather EG_fb into EG_gath first");
+    return 2;
+  }
+  if (!filtr || nxfilt < 1 || nxfilt > c.nx || mode < 0 || mode > 2) { set_error("damp_field: bad filter (%lld points, mode %d)", nxfilt, mode); return 2; }
+  e->scr.reset();
+  double* d_f = e->scr.take_n<double>(nxfilt);
+  if (!d_f) return 6;
+  CHB_CUDA(cudaMemcpyAsync(d_f, filtr, sizeof(double) * nxfilt, cudaMemcpyDefault, e->st));
+  FBCtx fb = fbctx(e);
+  const i64 ncols = c.nkr * c.nm * 6, half = c.nx * c.nkr * c.nm * 3;
+  CHB_TRY(rows_scatter_dev(fb, e->A("EG_full"), e->A("EG_gath"), (const i64*)e->arr["gather_map"].p, c.nx, nxs(e), ncols));
+  CHB_TRY(fb_filtr_dev(fb, e->A("EG_full"), c.leftX, e->D("kx_full"), d_f, mode, c.nx, c.nkr, c.nm, nxfilt));
+  CHB_TRY(fb_filtr_dev(fb, e->A("EG_full") + half, c.leftX, e->D("kx_full"), d_f, mode, c.nx, c.nkr, c.nm, nxfilt));
+  CHB_TRY(rows_take_dev(fb, e->A("EG_fb"), e->A("EG_full"), (const i64*)e->arr["slab_rows"].p, c.nx, nxs(e), ncols));
+  return 0;
+}
+
 // chimera_main.py:286-290 move_frame: Xgrid += shiftX
 int chimera_engine_set_window(chimera_engine* e, double shift_stage1, double shift_stage2) {
   ENG_CHECK(e);

@@ -195,6 +195,18 @@ int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int
   return 0;
 }
 
+// full(i, col) <- gathered[rank][j, col] (map[i] = rank * nxs + j) and slab(j, col) <- full(rows[j], col)
+int rows_scatter_dev(FBCtx& c, cd* full, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols) {
+  put_rows_k<<<grid_for(nkx * ncols, 256), 256, 0, c.st>>>(full, gathered, gather_map, nkx, nxs, ncols, nkx * ncols);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+int rows_take_dev(FBCtx& c, cd* slab, const cd* full, const i64* rows, i64 nkx, i64 nxs, i64 ncols) {
+  take_rows_k<<<grid_for(nxs * ncols, 256), 256, 0, c.st>>>(slab, full, rows, nxs, nkx, nxs * ncols);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 int fb_out_finish_dev(FBCtx& c, cd* out, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols) {
   put_rows_k<<<grid_for(nkx * ncols, 256), 256, 0, c.st>>>(out, gathered, gather_map, nkx, nxs, ncols, nkx * ncols);
   CHB_LAUNCH_CHECK();

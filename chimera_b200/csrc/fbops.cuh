@@ -74,6 +74,9 @@ int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int
                     const double* kx_slab, const PackedOps& Out, i64 nxs, i64 nrn, i64 nm, i64 nkr);
 // rows of the gathered slabs back to natural kx order, inverse x-FFT
 int fb_out_finish_dev(FBCtx& c, cd* out, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols);
+// row exchange between the all-gathered slab layout [rank][(nxs, ncols)], the full (nkx, ncols) array and one slab
+int rows_scatter_dev(FBCtx& c, cd* full, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols);
+int rows_take_dev(FBCtx& c, cd* slab, const cd* full, const i64* rows, i64 nkx, i64 nxs, i64 ncols);
 int fb_grad_dev(FBCtx& c, cd* out, const cd* scl, const PackedOps& Dp, const PackedOps& Dm, const double* kx,
                 const FBMathDims& d);
 int fb_div_dev(FBCtx& c, cd* out, const cd* vec, const PackedOps& Dp, const PackedOps& Dm, const double* kx,

@@ -276,8 +276,23 @@ class Engine:
     def damp_field(self, profile, config="left"):
         """``Solver.damp_field`` (solvers.py:619): absorbing-layer window on E and G in x-space."""
         prof = np.ascontiguousarray(profile, dtype=np.float64)
-        self._check(self.lib.chimera_engine_damp_field(self._h, ctypes.c_void_p(prof.ctypes.data), _i64(prof.shape[0]),
-                                                       {"left": 0, "right": 1, "both": 2}[config]))
+        mode = {"left": 0, "right": 1, "both": 2}[config]
+        if not self.slab:
+            self._check(self.lib.chimera_engine_damp_field(self._h, ctypes.c_void_p(prof.ctypes.data), _i64(prof.shape[0]), mode))
+            return
+        # kx-slab engine: the x-space window needs every kx row of a column -> gather the slabs, filter, keep own rows
+        self.damp_field_gather()
+        self._check(self.lib.chimera_engine_damp_field_slab(self._h, ctypes.c_void_p(prof.ctypes.data), _i64(prof.shape[0]), mode))
+
+    def damp_field_gather(self):
+        """first half of ``damp_field`` on a kx-slab engine: all-gather the ``EG_fb`` slabs into ``EG_gath`` (single-process
+        slab emulations fill ``EG_gath`` themselves and call ``chimera_engine_damp_field_slab`` through ``damp_field``)"""
+        if not getattr(self, "_damp_ready", False):
+            self._check(self.lib.chimera_engine_damp_prepare(self._h))
+            self._upload_raw("kx_full", np.asarray(self.setup.Args["kx"], dtype=np.float64))
+            self._damp_ready = True
+        if self.world > 1:
+            self._dist.all_gather_into_tensor(self.device_tensor("EG_gath"), self.device_tensor("EG_fb"), group=self._group)
 
     def set_window(self, velocity, time_step=None, staged=False):
         """A window that moves EVERY step (``MovingFrames`` entry with ``'Steps': 1``; the FEL runs,

@@ -272,6 +272,11 @@ int chimera_engine_set_time(chimera_engine* e, double t);
  *             device pointers; coords_halfstep = coords; the species grows as needed); call _sort before depositing
  * sort: species.py:351 chunk_and_damp with SimDom = [leftX + left_margin, rightX, 0, upperR^2] */
 int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode);
+/* Solver.damp_field on a kx-slab engine (the x-space window needs every kx row): damp_prepare allocates "EG_gath",
+ * "EG_full" and "kx_full" (upload the full kx); the caller all-gathers the "EG_fb" slabs of all ranks into "EG_gath"
+ * ([rank][(nx_slab, nkr, nm, 6)]); damp_field_slab rebuilds the full rows, applies fb_filtr and keeps this rank's rows */
+int chimera_engine_damp_prepare(chimera_engine* e);
+int chimera_engine_damp_field_slab(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode);
 /* A window that moves EVERY step (MovingFrame 'Steps': 1, e.g. the FEL runs, doc/tests/fel-testrun.py:61-63) inside
  * chimera_engine_step: the grid origin advances by shift_stage1 before push_coords (ChimeraRun.frame_act stage 1,
  * chimera_main.py:83,292-302) and by shift_stage2 between dep_curr and dep_dens (stage 2 of a 'Staged' frame,

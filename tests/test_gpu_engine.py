@@ -243,6 +243,47 @@ def _fields_out_slabs(engines, split):
         e.run("fields_out_b", 1.0)
 
 
+@pytest.mark.parametrize("name,world", [("real_m2", 2), ("real_m2", 4), ("env_m3", 2)])
+def test_damp_field_on_kx_slab_engines(gfim, name, world):
+    """Solver.damp_field (fb_filtr: an x-space window) on engines that hold kx slabs: the slabs are gathered, the full
+    rows filtered and the own rows kept (chimera_engine_damp_field_slab); against the unsharded engine, after a window
+    move so that the phase exp(i kx leftX) is not the initial one.  The all-gather is emulated on one GPU."""
+    import torch
+
+    from chimera_b200 import sharding
+    from chimera_b200.engine import Engine
+
+    S = SolverSetup(copy.deepcopy(SETUPS[name]))
+    eg0 = seed_fields(S, 64)
+    prof = S.get_damp_profile(8)
+    full = Engine(S, slab=False)
+    full.upload("EG_fb", eg0)
+    full.move_window(0.15)
+    full.damp_field(prof)
+    want = full.download("EG_fb")
+    full.close()
+    assert rel_l2(want, eg0) > 1e-3  # the window did something
+    engines = []
+    for r in range(world):
+        e = Engine(S, slab=(r, world))
+        e.upload("EG_fb", eg0)
+        e.move_window(0.15)
+        e.damp_field_gather()  # allocates EG_gath / EG_full, uploads the full kx; no collective in a single process
+        engines.append(e)
+    torch.cuda.synchronize()
+    for e in engines:
+        e.sync()
+    gath = torch.cat([e.device_tensor("EG_fb") for e in engines])
+    for e in engines:
+        e.device_tensor("EG_gath").copy_(gath)
+    torch.cuda.synchronize()
+    for r, e in enumerate(engines):
+        e.damp_field(prof)
+        rows = sharding.kx_slab_rows(S.Args["Nx"], r, world)
+        assert_close(e.download("EG_fb"), want[rows], TOL, "EG_fb slab %d after damp_field" % r)
+        e.close()
+
+
 @pytest.mark.parametrize("name,world,split", [("real_m2", 2, False), ("real_m2", 4, True), ("real_m3", 5, False),
                                               ("env_m3", 2, True), ("real_m3", 5, True)])
 def test_kx_slab_sharded_solve_matches_reference(ofim, gfim, name, world, split):
