@@ -21,7 +21,7 @@ from pic_ref import RefRun, RefSpecies
 
 
 class CpuEngine(Engine):
-    def __init__(self, setup, group=None, slab=None):  # noqa: super().__init__ would load the CUDA library
+    def __init__(self, setup, group=None, slab=None, sort_every=None):  # noqa: super().__init__ would load the CUDA library
         import torch.distributed as dist
 
         self.setup = setup
@@ -33,7 +33,7 @@ class CpuEngine(Engine):
         cfg.poisson_iters = 0 if "NoPoissonCorrection" in feats else 3
         cfg.chunked = int("Xchunked" in a)
         cfg.nchnk, cfg.guards = (int(a["Xchunked"][0]), int(a["Xchunked"][1])) if cfg.chunked else (1, 0)
-        cfg.sort_every = cfg.guards + 1 if cfg.chunked else 0
+        cfg.sort_every = (cfg.guards + 1 if cfg.chunked else 0) if sort_every is None else sort_every
         cfg.nx, cfg.nrn, cfg.nkr, cfg.nm = a["Nx"], a["Nr"], a["Nkr"], a["Mtot"]
         cfg.dt = a["dt"]
         self._dist, self._group, self.group = dist, None, group
@@ -97,6 +97,45 @@ class CpuEngine(Engine):
 
     def sync(self):
         pass
+
+    # ---- moving window: thin wrappers over library calls in the product, restated on the oracle; Engine.frame_act
+    # itself (the multi-rank logic under test) is inherited
+    def damp_field(self, profile, config="left"):
+        import torch
+
+        a, A = self.a, self.arr
+        self._sync_dict()
+        mode = {"left": 0, "right": 1, "both": 2}[config]
+        eg = A["EG_fb"]
+        if self.slab:  # gather the slabs of all ranks, rebuild the full rows (chimera_engine_damp_field_slab)
+            mine = self.device_tensor("EG_fb")
+            gath = torch.zeros(mine.numel() * self.world, dtype=mine.dtype)
+            self._dist.all_gather_into_tensor(gath, mine, group=self._group)
+            full = np.zeros((a["Nx"], a["Nkr"], a["Mtot"], 6), dtype=complex, order="F")
+            n = mine.numel() // 2
+            for r in range(self.world):
+                blk = gath.numpy().view(np.complex128)[r * n:(r + 1) * n].reshape(eg.shape, order="F")
+                full[sharding.kx_slab_rows(a["Nx"], r, self.world)] = blk
+            eg = full
+        for h in (slice(0, 3), slice(3, 6)):
+            eg[..., h] = ofim.fb_filtr(np.asfortranarray(eg[..., h]), self.leftX, a["kx"], np.ascontiguousarray(profile), mode)
+        A["EG_fb"][...] = eg[self.rows] if self.slab else eg
+
+    def move_window(self, shift):
+        self.xgrid = self.xgrid + shift
+        self._sync_dict()
+
+    def append_particles(self, sid, coords, momenta, weights):
+        s = self.r.sp[sid]
+        s.coords = np.asfortranarray(np.concatenate((s.coords, coords), axis=1))
+        s.coords_halfstep = np.asfortranarray(np.concatenate((s.coords_halfstep, coords), axis=1))
+        s.momenta = np.asfortranarray(np.concatenate((s.momenta, momenta), axis=1))
+        s.weights = np.concatenate((s.weights, weights))
+
+    def sort(self, on_halfstep=False, left_margin=0.0, upper_r=None):
+        self._sync_dict()
+        for s in self.r.sp:
+            self.r.chunk_and_damp(s, "cntr" if on_halfstep else "stag", left_margin=left_margin, upper_r=upper_r)
 
     def close(self):
         pass

@@ -110,3 +110,14 @@ def test_engine_schedule_on_two_gloo_ranks(window, overlap):
            os.path.join(HERE, "dist_engine_worker.py"), str(window), str(overlap)]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "OK window" in r.stdout, r.stdout[-4000:]
+
+
+def test_engine_lpa_window_on_two_gloo_ranks():
+    """Engine.frame_act across ranks (damp_field over gathered kx slabs, added particles sharded, window cull at the
+    species' upperR, background and density re-deposited and all-reduced) + Engine.step, replaying the LPA moving-window
+    run recorded from the reference's own driver (tests/golden/real_m2_lpa.npz) on a world_size-2 gloo job"""
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(33500 + os.getpid() % 2000), os.path.join(HERE, "dist_engine_worker.py"), "lpa"]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "OK lpa window" in r.stdout, r.stdout[-4000:]
