@@ -235,3 +235,67 @@ def test_static_kick_family_and_filter(ofim):
     prof = S.get_damp_profile(6)
     assert_close(ofim.fb_filtr(j.copy(order="F"), a["leftX"], a["kx"], prof, 0), np_ref.fb_filtr(j, a["leftX"], a["kx"], prof, 0),
                  TOL, "fb_filtr")
+
+
+def _random_setup(seed):
+    """a small solver dictionary with odd sizes: grids that are not the six fixed test setups"""
+    from chimera_b200.solver_setup import SolverSetup
+
+    rng = np.random.default_rng(seed)
+    nchnk = int(rng.choice([1, 2, 4]))
+    nx = 2 * nchnk * int(rng.integers(3, 7))
+    dx, dr = float(rng.uniform(0.03, 0.2)), float(rng.uniform(0.1, 0.4))
+    nr = int(rng.integers(5, 12))
+    left = float(rng.uniform(-5, 2))
+    env = bool(rng.integers(0, 2))
+    cfg = dict(Grid=(left, left + nx * dx, nr * dr, dx, dr), TimeStep=float(rng.uniform(0.02, 0.1)),
+               MaxAzimuthMode=int(rng.integers(1, 3)), Features=("SpaceCharge",) if (not env and rng.integers(0, 2)) else ())
+    if nchnk > 1:
+        cfg["Xchunked"] = (nchnk, int(rng.integers(0, 3)))
+    if env:
+        cfg["KxShift"] = float(rng.uniform(5, 40))
+    return SolverSetup(cfg)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_grids_both_restatements_agree(ofim, seed):
+    """the two restatements on randomly drawn grid sizes, spacings, mode counts, chunkings and solver families --
+    nothing in either may depend on the shapes of the six fixed setups"""
+    from util import carrier_tol
+
+    S = _random_setup(1000 + seed)
+    a = S.Args
+    env = "_env" if S.env else ""
+    rng = np.random.default_rng(seed)
+    x, p, w = particles(S, 1500, seed, inside_only=True)
+    dp = a["DepProj"]
+    tol = 20 * carrier_tol(S, TOL) if S.env else TOL
+    rho = getattr(ofim, "dep_dens" + env)(x, w, S.zeros_sp(), a["leftX"], *dp)
+    assert_close(rho, getattr(np_ref, "dep_dens" + env)(x, w, S.zeros_sp(), a["leftX"], *dp), tol, "dep_dens" + env)
+    cur = getattr(ofim, "dep_curr" + env)(x, p, w, S.zeros_sp(3), a["leftX"], *dp)
+    assert_close(cur, getattr(np_ref, "dep_curr" + env)(x, p, w, S.zeros_sp(3), a["leftX"], *dp), tol, "dep_curr" + env)
+    fld = crandn(rng, S.shape_sp + (6,))
+    got = getattr(ofim, "proj_fld" + env)(x, w, fld, np.zeros((6, x.shape[1]), order="F"), a["leftX"], *dp)
+    want = getattr(np_ref, "proj_fld" + env)(x, w, fld, np.zeros((6, x.shape[1])), a["leftX"], *dp)
+    assert_close(got, want, carrier_tol(S, TOL), "proj_fld" + env)
+    if "Xchunked" in a:
+        from util import chunk_sorted
+
+        nchnk, guards = a["Xchunked"]
+        xs, ps, ws, ind = chunk_sorted(S, x, p, w, ofim, nchnk)
+        got = getattr(ofim, "dep_dens%s_chnk" % env)(xs, ws, S.zeros_sp(), ind, guards, a["leftX"], *dp)
+        want = getattr(np_ref, "dep_dens%s_chnk" % env)(xs, ws, S.zeros_sp(), ind, guards, a["leftX"], *dp)
+        assert_close(got, want, tol, "dep_dens%s_chnk" % env)
+    Dp, Dm, kx = a["FBDiff"]
+    v, s = crandn(rng, S.shape_fb + (3,)), crandn(rng, S.shape_fb)
+    for name, args, out in (("fb_grad", (s,), S.zeros_fb(3)), ("fb_div", (v,), S.zeros_fb()), ("fb_rot", (v,), S.zeros_fb(3))):
+        got = getattr(ofim, name + env)(out, *args, Dp, Dm, kx)
+        assert_close(got, getattr(np_ref, name + env)(*args, Dp, Dm, kx), TOL, name + env)
+    got = getattr(ofim, "fb_graddiv" + env)(v.copy(order="F"), Dp, Dm, kx)
+    assert_close(got, getattr(np_ref, "fb_graddiv" + env)(v, Dp, Dm, kx), TOL, "fb_graddiv" + env)
+    if not S.env:
+        vec = crandn(rng, S.shape_sp + (3,))
+        kxi, In = a["FBCurrIn"]
+        assert_close(ofim.fb_vec_in(S.zeros_fb(3), vec, a["leftX"], kxi, In), np_ref.fb_in(vec, a["leftX"], kxi, In), TOL, "fb_vec_in")
+        kxo, Out = a["FBout"]
+        assert_close(ofim.fb_vec_out(v, a["leftX"], kxo, Out), np_ref.fb_out(v, a["leftX"], kxo, Out), TOL, "fb_vec_out")
