@@ -258,7 +258,8 @@ class SolverSetup:
                 hit += 1
                 if s_loc <= 0:
                     continue
-                anti *= (1 - np.exp(-((kx / kx0 - 1 - pos) ** 2) / (s_loc * (pos + 1.0) / nx) ** 2))[:, None, None]
+                with np.errstate(divide="ignore", invalid="ignore"):  # the echo at pos = -1 has zero width, as in the reference
+                    anti *= (1 - np.exp(-((kx / kx0 - 1 - pos) ** 2) / (s_loc * (pos + 1.0) / nx) ** 2))[:, None, None]
         return anti * band
 
     # -- convenience ---------------------------------------------------------------------------
