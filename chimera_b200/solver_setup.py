@@ -223,6 +223,51 @@ class SolverSetup:
             cg[..., 4] = (c - 1) / w ** 2 / dt
         return ce, cg
 
+    # -- laser injection (solvers.py:555-603) ----------------------------------------------------
+    def add_gauss_beam(self, fim, laser, EG_fb=None):
+        """``Solver.add_gauss_beam``: a Gaussian pulse ``laser = {'a0','k0','x0','x_foc','Lx','LR'}`` added to ``EG_fb``
+        (a new array when none is given), propagated analytically from its focus to ``x0``.  ``fim`` is the fimera
+        backend that supplies ``fb_scl_in``, ``fb_graddiv[_env]``, ``omp_mult_vec`` and ``omp_add_vec`` (the CUDA
+        drop-in, or the oracle in tests) -- the same calls the reference makes, in the same order."""
+        from scipy.special import j1
+
+        a = self.Args
+        k0, a0 = 2 * np.pi * laser["k0"], 2 * np.pi * laser["a0"]
+        x_focus = laser["x0"] - laser["x_foc"]
+        kx_g, kr_g, w = a["kx_g"], a["kr_g"], a["w"][:, :, :, None]
+        vec_fb = self.zeros_fb(3)
+        if self.env:
+            nko = a["Nko"]
+            e_s0 = a0 * 0.5 * np.pi ** 0.5 * laser["Lx"] * laser["LR"] ** 2 * a["dkx"] / a["lengthR"] ** 2
+            vec_fb[:, :, nko, 2] = (e_s0 / j1(a["lengthR"] * kr_g[:, :, nko]) ** 2 * np.exp(-1j * kx_g * laser["x0"])
+                                    * np.exp(-0.25 * (kx_g - k0) ** 2 * laser["Lx"] ** 2
+                                             - 0.25 * kr_g[:, :, nko] ** 2 * laser["LR"] ** 2))
+            dt_op = -1j * w
+        else:
+            xg, rg = a["Xgrid"], a["Rgrid"]
+            scl = self.zeros_sp()
+            dxx = xg[:, None] - laser["x0"]
+            scl[:, :, 0] = (a0 * np.cos(k0 * dxx) * np.exp(-dxx ** 2 / laser["Lx"] ** 2 - rg[None, :] ** 2 / laser["LR"] ** 2)
+                            * (np.abs(rg[None, :]) < 3.5 * laser["LR"]) * (np.abs(dxx) < 3.5 * laser["Lx"]))
+            scl[:, 0, 0] = 0.0
+            scl_fb = fim.fb_scl_in(self.zeros_fb(), scl, a["leftX"], *a["FBIn"])
+            vec_fb[:, :, :, 2] = scl_fb / a["Nx"]
+            kxg4 = kx_g[:, :, None, None]
+            dt_op = -1j * w * np.sign(kxg4 + (kxg4 == 0))
+        ee = vec_fb.copy(order="F")
+        # div_clean (solvers.py:644-650): E += PoissFact * grad div E
+        gd = (fim.fb_graddiv_env if self.env else fim.fb_graddiv)(vec_fb, *a["FBDiff"])
+        gd = fim.omp_mult_vec(gd, a["PoissFact"])
+        ee = fim.omp_add_vec(ee, gd)
+        gg = dt_op * ee
+        e_new = np.cos(w * x_focus) * ee + np.sin(w * x_focus) / w * gg
+        gg = -w * np.sin(w * x_focus) * ee + np.cos(w * x_focus) * gg
+        shift = np.exp(1j * kx_g[:, :, None, None] * x_focus)
+        out = self.zeros_fb(6) if EG_fb is None else EG_fb
+        out[:, :, :, :3] += e_new * shift
+        out[:, :, :, 3:] += gg * shift
+        return out
+
     # -- static-solution tables (solvers.py:348-358) -------------------------------------------
     def static_coeffs(self, px0):
         a = self.Args

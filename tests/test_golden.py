@@ -299,3 +299,18 @@ def test_reference_diagnostics_on_engine(gfim):
     assert_close(pwr, z["d_pwr"], 1e-9, "pwr_out through the drop-in")
     assert_close(spot, z["d_spot"], 1e-9, "spot profile through the drop-in")
     eng.close()
+
+
+# ------------------------------------------------------------------ laser injection
+@pytest.mark.parametrize("name", ["real_m2", "env_m1", "env_m3"])
+def test_add_gauss_beam_matches_reference_solver(ofim, name):
+    """SolverSetup.add_gauss_beam against the EG_fb the reference's own Solver.add_gauss_beam produced
+    (tools/gen_golden_laser.py): real solver (scalar seed through fb_scl_in, sign(kx) propagator), envelope solver
+    (analytic spectral seed with the Bessel normalisation), divergence cleaning, focus propagation"""
+    z = np.load(os.path.join(GOLDEN, "laser.npz"))
+    S = SolverSetup(copy.deepcopy(SETUPS[name]))
+    laser = dict(zip(("a0", "k0", "x0", "x_foc", "Lx", "LR"), z[name + "_laser"]))
+    got = S.add_gauss_beam(ofim, laser)
+    assert_close(got, z[name + "_EG_fb"], 1e-12, "EG_fb after add_gauss_beam")
+    twice = S.add_gauss_beam(ofim, laser, EG_fb=got.copy(order="F"))
+    assert_close(twice, 2 * z[name + "_EG_fb"], 1e-12, "accumulation into a given EG_fb")
