@@ -207,7 +207,7 @@ class CpuEngine(Engine):
         full = ofim.omp_mult_scl(ofim.fb_scl_in(self.setup.zeros_fb(), self.r.Rho, self.leftX, *a["FBCurrIn"]), a["DepFact"])
         A["Rho_fb"][...] = full[self.rows]
         Dp, Dm, kx = self._calc()
-        A["gradRho_fb_nxt"][...] = np_ref.fb_grad(A["Rho_fb"], Dp, Dm, kx)
+        A["gradRho_fb_nxt"][...] = (np_ref.fb_grad_env if self.cfg.env else np_ref.fb_grad)(A["Rho_fb"], Dp, Dm, kx)
         np_ref.MIRROR_SHIFT = 0
 
     def _ph_init_push(self, arg):
@@ -218,16 +218,23 @@ class CpuEngine(Engine):
         a, A = self.a, self.arr
         Dp, Dm, kx = self._calc()
         j = A["J_fb"]
+        graddiv = np_ref.fb_graddiv_env if self.cfg.env else np_ref.fb_graddiv
         for _ in range(self.cfg.poisson_iters):
-            gd = np_ref.fb_graddiv(j, Dp, Dm, kx)
-            j = np_ref.poiss_corr(j, gd, A["gradRho_fb_prv"], A["gradRho_fb_nxt"], a["dt_inv"], a["PoissFact"][self.rows])
+            gd = graddiv(j, Dp, Dm, kx)
+            if self.cfg.space_charge:
+                j = np_ref.poiss_corr(j, gd, A["gradRho_fb_prv"], A["gradRho_fb_nxt"], a["dt_inv"], a["PoissFact"][self.rows])
+            else:  # solvers.py:322-326: J += PoissFact grad div J
+                j = j + gd * a["PoissFact"][self.rows][..., None]
         A["J_fb"][...] = j
         np_ref.MIRROR_SHIFT = 0
 
     def _ph_maxwell(self, arg):
         A, S = self.arr, self.setup
-        A["EG_fb"][...] = np_ref.maxwell_push_with_spchrg(A["EG_fb"], A["J_fb"], A["gradRho_fb_prv"], A["gradRho_fb_nxt"],
-                                                         S.PSATD_E[self.rows], S.PSATD_G[self.rows])
+        if self.cfg.space_charge:
+            A["EG_fb"][...] = np_ref.maxwell_push_with_spchrg(A["EG_fb"], A["J_fb"], A["gradRho_fb_prv"], A["gradRho_fb_nxt"],
+                                                             S.PSATD_E[self.rows], S.PSATD_G[self.rows])
+        else:
+            A["EG_fb"][...] = np_ref.maxwell_push_wo_spchrg(A["EG_fb"], A["J_fb"], S.PSATD_E[self.rows], S.PSATD_G[self.rows])
 
     def _backward_slab(self, src):
         """backward DHT + phase of the slab rows, no inverse x-FFT (fb_out_slab_dev): (L, Nkr, M, 3) -> (L, Nr, M, 3)"""
@@ -243,7 +250,8 @@ class CpuEngine(Engine):
         part = 1 if arg == 1.0 else (2 if arg == 2.0 else 0)
         if part != 1:
             Dp, Dm, kx = self._calc()
-            A["B_fb"][...] = np_ref.fb_rot(A["EG_fb"][..., 3:], Dp, Dm, kx) * a["PoissFact"][self.rows][..., None]
+            rot = np_ref.fb_rot_env if self.cfg.env else np_ref.fb_rot
+            A["B_fb"][...] = rot(A["EG_fb"][..., 3:], Dp, Dm, kx) * a["PoissFact"][self.rows][..., None]
             np_ref.MIRROR_SHIFT = 0
         if part != 2:
             A["EB_slab"][..., :3] = self._backward_slab(A["EG_fb"][..., :3])
@@ -267,16 +275,21 @@ class CpuEngine(Engine):
                     blk = A["EB_gath"][(h * world + r) * n3:(h * world + r + 1) * n3].reshape(shp3, order="F")
                 full[rr] = blk
             eb = np.fft.ifft(full, axis=0) * nx  # unnormalised backward FFT (Q9)
-            eb[:, :, 0] /= 2 * np.pi  # eb_correction on this half (grid_deps.f90:219-266)
-            eb[:, :, 1:] /= np.pi
-            eb[:, 0, 0] = eb[:, 1, 0]
-            eb[:, 0, 1:] = -eb[:, 1, 1:]
+            if self.cfg.env:  # eb_correction_env on this half (grid_deps_env.f90:240-283)
+                eb /= np.pi
+                eb[:, 0] = eb[:, 1] if a["Mtot"] == 1 else -eb[:, 1]
+            else:             # eb_correction (grid_deps.f90:219-266)
+                eb[:, :, 0] /= 2 * np.pi
+                eb[:, :, 1:] /= np.pi
+                eb[:, 0, 0] = eb[:, 1, 0]
+                eb[:, 0, 1:] = -eb[:, 1, 1:]
             self.r.EB[..., 3 * h:3 * h + 3] = eb
 
     def _ph_gather_push(self, arg):
         a, r = self.a, self.r
         for s in self._moving():
-            s.EB = ofim.proj_fld(s.coords, s.weights, r.EB, np.zeros((6, s.coords.shape[1]), order="F"), self.leftX, *a["DepProj"])
+            proj = ofim.proj_fld_env if self.cfg.env else ofim.proj_fld
+            s.EB = proj(s.coords, s.weights, r.EB, np.zeros((6, s.coords.shape[1]), order="F"), self.leftX, *a["DepProj"])
             s.momenta = ofim.push_velocs(s.momenta, s.EB, s.push_fact * a["dt"] * arg)
 
     def _ph_particles_fused(self, arg):

@@ -98,16 +98,17 @@ def test_kx_slab_spectral_update_matches_full_solve(ofim, two_rank_run):
     assert_close(full[..., 6:], B, 1e-12, "B_fb from slabs")
 
 
-@pytest.mark.parametrize("window,overlap", [(0, 1), (0, 0), (1, 1)])
-def test_engine_schedule_on_two_gloo_ranks(window, overlap):
+@pytest.mark.parametrize("window,overlap,name", [(0, 1, "real_m2"), (0, 0, "real_m2"), (1, 1, "real_m2"), (1, 1, "env_m3")])
+def test_engine_schedule_on_two_gloo_ranks(window, overlap, name):
     """the product's multi-rank host logic (Engine.make_halfstep / Engine.step in chimera_b200/engine.py: fused and
     unfused branches, re-binning cadence, rank-0 background rule, all-reduce of Rho behind fb_in_J, E and B halves of
-    fields out all-gathered separately, per-step 'Staged' window) on a world_size-2 gloo job, the CUDA library
+    fields out all-gathered separately, per-step 'Staged' window; real solver with space charge and still ions, and
+    the envelope solver without) on a world_size-2 gloo job, the CUDA library
     replaced by its CPU stand-in (tests/cpu_engine.py); every rank against the single-process reference sequence"""
     env = dict(os.environ, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(31500 + (os.getpid() + 7 * window + 3 * overlap) % 2000),
-           os.path.join(HERE, "dist_engine_worker.py"), str(window), str(overlap)]
+           "--master-port", str(31500 + (os.getpid() + 7 * window + 3 * overlap + 17 * (name != "real_m2")) % 2000),
+           os.path.join(HERE, "dist_engine_worker.py"), str(window), str(overlap), name]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "OK window" in r.stdout, r.stdout[-4000:]
 
