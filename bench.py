@@ -46,7 +46,6 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused-profile", action="store_true",
                     help="after the timed run: per-stage clock shares of the fused particle kernel (adds barriers; diagnosis)")
-    ap.add_argument("--cpu-nx", type=int, default=256)
     return ap.parse_args()
 
 
@@ -353,7 +352,9 @@ def run_ours(a):
             if world == 1 and not a.no_per_call:
                 out["e2e_per_call"] = run_e2e_per_call(a, torch, S, eng, state)
     if rank == 0 and not a.no_cpu and world == 1:
-        out["cpu_baseline"] = cpu_baseline(a)
+        if a.no_e2e:
+            state = eng.particles(0) + (eng.download("EG_fb"), eng.download("gradRho_fb_nxt"))
+        out["cpu_baseline"] = cpu_baseline(a, S, state, eng.download("BckGrndRho"))
     eng.close()
     if world > 1:
         torch.distributed.barrier()
@@ -442,86 +443,192 @@ def run_e2e_per_call(a, torch, S, eng, state):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_step_model(a, steps, warmup):
-    """Time the reference's algorithm (oracle port, -O3 -ffast-math -fopenmp as the reference Makefile:14)
-    on the host cores on a bounded sample of the workload and scale linearly to the full one:
-      particle kernels on `cpu_particles` of the particles (cost linear in the particle count),
-      spectral update on `cpu_nx` of the Nx kx-rows (every spectral kernel is row-independent;
-      the x-FFT's log factor is ignored, which favours the CPU)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+# CPU arm: the reference's algorithm (oracle port; the Fortran cannot be built here) on the host cores
+CPU_STAGES = {  # BASELINE.md section 3 stage list -> the fimera calls that make it up
+    "push": ("push_coords", "push_velocs"), "gather": ("proj_fld",), "deposit_J": ("dep_curr_chnk",),
+    "deposit_rho": ("dep_dens_chnk",), "rebin": ("chunk_coords_boundaries", "align_data_vec", "align_data_scl"),
+    "dht_fwd_fft": ("fb_vec_in", "fb_scl_in"), "dht_bwd_fft": ("fb_eb_out",),
+    "mode_coupling": ("fb_grad", "fb_graddiv", "fb_rot"), "psatd": ("maxwell_push_with_spchrg",),
+    "poisson": ("poiss_corr",), "elementwise": ("omp_mult_vec", "omp_mult_scl", "omp_add_vec", "eb_correction"),
+}
+
+
+class StageTimer:
+    """fimera proxy that accumulates wall time per entry point (the reference driver's calls, unchanged)"""
+
+    def __init__(self, fim):
+        self._f, self.t = fim, {}
+
+    def __getattr__(self, name):
+        fn = getattr(self._f, name)
+        if not callable(fn):
+            return fn
+
+        def timed(*args, **kw):
+            t0 = time.perf_counter()
+            r = fn(*args, **kw)
+            self.t[name] = self.t.get(name, 0.0) + time.perf_counter() - t0
+            return r
+        return timed
+
+    def stages_ms(self, steps):
+        out = {k: 1e3 * sum(self.t.get(n, 0.0) for n in names) / steps for k, names in CPU_STAGES.items()}
+        return {k: v for k, v in out.items() if v > 0}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def load_cpu_oracle():
+    """the -O3 -ffast-math -fopenmp build (reference Makefile:14 flags) with the team size set HERE: torchrun
+    exports OMP_NUM_THREADS=1 to its workers, which is not what a CPU run of the reference would use"""
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     os.environ.setdefault("OMP_PROC_BIND", "close")
     from oracle.fimera import load
+
+    fast = load(fast=True, native=True)  # -march=native when a compiler is on this host
+    try:
+        cores = int(fast._lib.oracle_set_num_threads(cores))
+    except AttributeError:
+        cores = int(fast._lib.oracle_num_threads())
+    return fast, cores
+
+
+def cpu_chunks(nx, cores):
+    """x-chunks of the CPU run: the chunked deposit runs one thread per chunk (grid_deps_chnk.f90:38-45), so the
+    largest chunk count <= cores that divides Nx keeps every core busy (results do not depend on it)"""
+    c = min(cores, nx // 2)
+    while c > 1 and nx % c:
+        c -= 1
+    return max(c, 1)
+
+
+def cpu_timed_steps(run, timer, n_particles_run, steps, warmup, budget_s):
+    """`warmup` untimed + up to `steps` timed RefRun.make_step calls (the reference's make_step sequence,
+    chimera_main.py:82-92, numpy-side mutations included); the timed count is cut to what fits `budget_s`"""
+    for _ in range(warmup):
+        t0 = time.perf_counter()
+        run.make_step()
+        t_one = time.perf_counter() - t0
+    steps_run = int(max(1, min(steps, budget_s // max(t_one, 1e-3)))) if warmup else steps
+    steps_run = max(steps_run, min(steps, 3))
+    timer.t.clear()
+    per = []
+    for _ in range(steps_run):
+        t0 = time.perf_counter()
+        run.make_step()
+        per.append(time.perf_counter() - t0)
+    t_step = float(np.mean(per))
+    stages = timer.stages_ms(steps_run)
+    stages["python_glue"] = 1e3 * t_step - sum(stages.values())
+    return {"value": n_particles_run / t_step, "ms_per_step": 1e3 * t_step, "steps_run": steps_run, "warmup_run": warmup,
+            "stages_ms": stages, "ms_per_step_each": [1e3 * v for v in per]}
+
+
+def cpu_describe(fast, cores, nchnk, what):
+    return ("%s; every step = RefRun.make_step (the reference's call sequence) on the FULL grid and particle set, no "
+            "extrapolation; g++ -O3 -ffast-math -fopenmp build of oracle/chimera_oracle.cpp (%s), OMP threads=%d, "
+            "deposit chunks=%d (one thread per chunk as grid_deps_chnk.f90:38-45); gfortran/FFTW3 absent so the Fortran "
+            "itself cannot be built; the re-binning step (every 11th, numpy argsort) is timed separately as rebin_s"
+            % (what, "-march=native, built on this host" if fast.build_name == "liboracle_native.so" else "-march=x86-64-v3",
+               cores, nchnk))
+
+
+def cpu_baseline(a, S, state, bck):
+    """cpu_baseline of our arm (N=1): the engine's own state (particles, EG_fb, gradRho, background) downloaded
+    to the host, re-binned into `cores` chunks, then 1 warm-up + 2 timed full steps on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import copy
+
+    from chimera_b200.solver_setup import SolverSetup
+    from pic_ref import RefRun, RefSpecies
+
+    fast, cores = load_cpu_oracle()
+    timer = StageTimer(fast)
+    x, xh, p, w, eg, g = state
+    S2 = copy.copy(S)
+    nchnk = cpu_chunks(a.nx, cores)
+    S2.Args = dict(S.Args, Xchunked=(nchnk, S.Args["Xchunked"][1]))
+    sp = RefSpecies.__new__(RefSpecies)
+    sp.coords, sp.momenta, sp.weights, sp.coords_halfstep = x, p, w, xh
+    sp.push_fact, sp.still, sp.devices, sp.chunks = -2 * np.pi, False, [], None
+    sp.EB = np.zeros((6, 0), order="F")
+    run = RefRun(timer, S2, [sp], sort_every=0)
+    run.Bck, run.EG_fb, run.g_nxt = bck, eg, g
+    t0 = time.perf_counter()
+    run.chunk_and_damp(sp, "stag")
+    rebin_s = time.perf_counter() - t0
+    n = sp.weights.shape[0]
+    r = cpu_timed_steps(run, timer, n, steps=2, warmup=1, budget_s=60)
+    r.update(unit=UNIT, cores=cores, kind="port", rebin_s=rebin_s,
+             sample=cpu_describe(fast, cores, nchnk, "%d particles (all of them) on the %dx%dx%d grid, 1 warm-up + %d timed steps"
+                                 % (n, a.nx, a.nr + 1, a.modes, r["steps_run"])))
+    return r
+
+
+def run_reference(a):
+    """--impl reference: the stated workload in full (whole grid, every particle of the N-GPU job: one species per
+    GPU rank, same seeds as the GPU arm) through the reference's make_step sequence on all host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from concurrent.futures import ThreadPoolExecutor
+
     from chimera_b200 import synthetic
     from chimera_b200.solver_setup import SolverSetup
     from pic_ref import RefRun, RefSpecies
 
-    fast = load(fast=True, native=True)  # -march=native when a compiler is on this host (reference Makefile:14)
-    cores = int(fast._lib.oracle_num_threads())
-    nx_s = min(a.cpu_nx, a.nx)
-    S = SolverSetup(synthetic.lwfa_solver_config(nx=nx_s, nr=a.nr, modes=a.modes, chunks=cores if nx_s % (2 * cores) == 0 else 16))
-    x, p, w = synthetic.plasma_fixed_cell(S.Args, cell=CELL[a.ppc], xp=np)  # the whole sample grid: every chunk thread busy
-    n_s = x.shape[1]
-    run = RefRun(fast, S, [RefSpecies(x, p, w)])
-    run.EG_fb[:] = synthetic.laser_seed(S, fast, x0=S.Args["Xgrid"][nx_s // 2])
-    run.make_halfstep()
-    f = fast
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        s = run.sp[0]
-        run.istep += 1
-        s.coords, s.coords_halfstep = f.push_coords(s.coords, s.momenta, s.coords_halfstep, S.Args["dt"])
-        run.J[:] = 0.0
-        run.J = run._dep("curr", run.J, s, s.coords_halfstep)
-        run.Rho[:] = 0.0
-        run.Rho = run._dep("dens", run.Rho, s, s.coords)
-        t1 = time.perf_counter()
-        aa = S.Args
-        run.J_fb = f.omp_mult_vec(f.fb_vec_in(run.J_fb, run.J, aa["leftX"], *aa["FBCurrIn"]), aa["DepFact"])
-        run.g_prv[:] = run.g_nxt
-        run.Rho_fb = f.omp_mult_scl(f.fb_scl_in(run.Rho_fb, run.Rho, aa["leftX"], *aa["FBCurrIn"]), aa["DepFact"])
-        run.g_nxt = f.fb_grad(run.g_nxt, run.Rho_fb, *aa["FBDiff"])
-        run.update_fields()
-        rot = f.fb_rot(run.B_fb, run.EG_fb[:, :, :, 3:], *aa["FBDiff"])
-        run.B_fb = f.omp_mult_vec(rot, aa["PoissFact"])
-        run.EB = f.eb_correction(f.fb_eb_out(run.EB, run.EG_fb, run.B_fb, aa["leftX"], *aa["FBout"]))
-        t2 = time.perf_counter()
-        s.EB = np.zeros((6, n_s), order="F")
-        s.EB = f.proj_fld(s.coords, s.weights, run.EB, s.EB, aa["leftX"], *aa["DepProj"])
-        s.momenta = f.push_velocs(s.momenta, s.EB, s.push_fact * aa["dt"])
-        t3 = time.perf_counter()
-        if it >= warmup:
-            times.append(((t1 - t0) + (t3 - t2), t2 - t1))
-    tp = float(np.median([t[0] for t in times]))
-    ts = float(np.median([t[1] for t in times]))
-    n_full = n_particles(a)
-    t_full = tp * n_full / n_s + ts * a.nx / nx_s
-    return {
-        "value": n_full / t_full, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": "%d of %d particles (particle kernels, scaled linearly) and %d of %d kx rows (spectral update, scaled linearly); "
-                  "g++ -O3 -ffast-math -fopenmp build of oracle/chimera_oracle.cpp (%s), OMP threads=%d; gfortran/FFTW3 absent so the "
-                  "Fortran itself cannot be built" % (n_s, n_full, nx_s, a.nx, "-march=native, built on this host" if
-                                                       fast.build_name == "liboracle_native.so" else "-march=x86-64-v3", cores),
-        "particle_s_per_step_full": tp * n_full / n_s, "spectral_s_per_step_full": ts * a.nx / nx_s,
-        "ms_per_step_full": t_full * 1e3,
-    }
-
-
-def cpu_baseline(a):
-    return cpu_step_model(a, steps=3, warmup=1)
-
-
-def run_reference(a):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
-    r = cpu_step_model(a, steps=a.steps, warmup=a.warmup)
     world = int(os.environ.get("WORLD_SIZE", a.gpus))
+    fast, cores = load_cpu_oracle()
+    timer = StageTimer(fast)
+    nchnk = cpu_chunks(a.nx, cores)
+    S = SolverSetup(synthetic.lwfa_solver_config(nx=a.nx, nr=a.nr, modes=a.modes, chunks=nchnk))
+    n_gpu = n_particles(a)
+    shares = world
+    try:  # x, x_half, p, w, per-particle EB and the generator's temporaries: ~260 B per particle at the peak
+        import psutil
+
+        avail = psutil.virtual_memory().available
+        while shares > 1 and shares * n_gpu * 260.0 > 0.8 * avail:
+            shares -= 1
+    except Exception:
+        pass
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(shares, 8)) as ex:
+        parts = list(ex.map(lambda r: synthetic.plasma_fixed_cell(S.Args, cell=CELL[a.ppc], seed=20260101 + r, xp=np), range(shares)))
+    species = [RefSpecies(x, p, w) for x, p, w in parts]
+    del parts
+    # still ions coincide with the electrons at t=0: BckGrndRho = -rho_e(0), as build_problem does on the GPU
+    run = RefRun(timer, S, species)
+    for s in species:
+        run.chunk_and_damp(s, "stag")
+    run.Rho[:] = 0.0
+    for s in species:
+        run.Rho = run._dep("dens", run.Rho, s, s.coords)
+    run.Bck = -run.Rho
+    run.EG_fb[:] = synthetic.laser_seed(S, fast)
+    timer.t.clear()
+    t1 = time.perf_counter()
+    run.make_halfstep()
+    rebin_s = sum(timer.t.get(k, 0.0) for k in CPU_STAGES["rebin"])
+    setup_s = (t1 - t0, time.perf_counter() - t1)
+    n_run = sum(s.weights.shape[0] for s in species)
+    r = cpu_timed_steps(run, timer, n_run, steps=a.steps, warmup=max(1, min(a.warmup, 1)), budget_s=150)
+    what = ("%d particles = %d of the %d GPU shares of %d, on the %dx%dx%d grid; %d warm-up + %d timed steps of the %d/%d requested "
+            "(cut to a 150 s budget)" % (n_run, shares, world, n_gpu, a.nx, a.nr + 1, a.modes, r["warmup_run"], r["steps_run"],
+                                         a.warmup, a.steps))
+    r.update(unit=UNIT, cores=cores, kind="port", rebin_s=rebin_s, setup_s=setup_s, sample=cpu_describe(fast, cores, nchnk, what))
     out = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": r["ms_per_step_full"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a)},
-        "cpu_baseline": r, "gpu_launches": 0,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": r["steps_run"],
+        "warmup": r["warmup_run"], "steps_requested": a.steps, "warmup_requested": a.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "particles_total": n_run}, "cpu_baseline": r, "gpu_launches": 0,
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))

@@ -18,6 +18,7 @@
 #include <utility>
 #include <vector>
 #include "common.cuh"
+#include <atomic>
 #include "kernels.cuh"
 
 namespace chb {
@@ -97,7 +98,8 @@ gemm_dmma_k(const __grid_constant__ GemmBatch batch, i64 M, i64 N, i64 K, i64 ld
   const int rows = (int)((M - m0 < BM) ? (M - m0) : BM);  // valid rows of this tile (even)
   const uint32_t row_bytes = (uint32_t)rows * 8u;
 
-  // zero the A stages once: k-rows past K and m-rows past M are never written by the copies
+  // zero the A stages once: m-rows past M are never written by the copies.  k-rows past K of the last k-tile keep
+  // whatever an earlier tile left in the stage (finite data); they meet the zero padding of the packed B tile
   for (int i = tid; i < STAGES * A_STAGE; i += GEMM_THREADS) sA[i] = 0.0;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
@@ -228,10 +230,15 @@ int launch_gemm(cudaStream_t st, const GemmBatch& batch, i64 M, i64 N, i64 K, i6
   if (batch.count <= 0 || M <= 0 || N <= 0) return 0;
   if (batch.count > kGemmMaxBatch) { set_error("gemm batch too large"); return 4; }
   if ((M & 1) || (lda & 1)) { set_error("gemm: M and lda must be even (complex-interleaved rows)"); return 4; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    CHB_CUDA(cudaFuncSetAttribute(gemm_dmma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    attr_set = true;
+  {  // the attribute is per device: remember which devices have it (a process may drive several)
+    static std::atomic<unsigned long long> attr_mask{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_mask.load(std::memory_order_relaxed) & bit)) {
+      CHB_CUDA(cudaFuncSetAttribute(gemm_dmma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+      attr_mask.fetch_or(bit, std::memory_order_relaxed);
+    }
   }
   const int KT = (int)((K + BK - 1) / BK);
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)batch.count);

@@ -157,6 +157,7 @@ class Engine:
             self._upload_raw("slab_rows", self.rows.astype(np.int64))
             self._upload_raw("gather_map", gmap)
         self.nspecies = 0
+        self._px0 = []
         self.istep = 0
         self._pinned = []
         self.fuse = True
@@ -222,8 +223,10 @@ class Engine:
         return torch.as_tensor(_DevView(ptr.value, nb.value, dtype), device="cuda")
 
     # -- particles ---------------------------------------------------------------------------
-    def add_species(self, coords, momenta, weights, charge=-1.0, mass=1.0, still=False, coords_half=None, capacity=0):
-        """Add a species; arrays as in ``Specie.Data`` (species.py:122-126).  Returns its id."""
+    def add_species(self, coords, momenta, weights, charge=-1.0, mass=1.0, still=False, coords_half=None, capacity=0,
+                    px0=0.0):
+        """Add a species; arrays as in ``Specie.Data`` (species.py:122-126); ``px0`` = the species'
+        ``MomentaMeans[0]`` (species.py:60), used by ``make_halfstep``'s static kick.  Returns its id."""
         coords = np.asfortranarray(coords, dtype=float)
         momenta = np.asfortranarray(momenta, dtype=float)
         weights = np.asfortranarray(weights, dtype=float)
@@ -246,6 +249,7 @@ class Engine:
             ctypes.c_void_p(weights_ptr), _i64(n), ctypes.c_double(2 * np.pi * charge / mass), int(bool(still)),
             _i64(0), ctypes.byref(sid)))
         self.nspecies += 1
+        self._px0.append(0.0)
         return sid.value
 
     DEVICE_KINDS = {"undul_analytic": (1, 4), "undul_analytic_taper": (2, 5), "undul_mapped": (3, 3),
@@ -508,9 +512,12 @@ class Engine:
         if self.world > 1:
             self._dist.all_reduce(self.device_tensor("BckGrndRho"), group=self._group)
 
-    def make_halfstep(self, px0=(0.0,), background=False):
+    def make_halfstep(self, px0=None, background=False):
         """``ChimeraRun.make_halfstep`` (chimera_main.py:61-80): bin, deposit, static field of the initial
-        momenta ``px0`` (one entry per species, ``MomentaMeans[0]``), gather, half Boris push."""
+        momenta ``px0`` (one entry per species: ``MomentaMeans[0]``, chimera_main.py:73-75; default: the values given
+        to ``add_species``), gather, half Boris push."""
+        if px0 is None:
+            px0 = tuple(self._px0) or (0.0,)
         self.run("sort", 0.0)
         if background:
             self.deposit_background()
@@ -529,6 +536,10 @@ class Engine:
 
     def step(self, nsteps=1):
         """``nsteps`` x ``ChimeraRun.make_step`` (chimera_main.py:82-92)."""
+        s1, s2 = getattr(self, "_win", (0.0, 0.0))
+        if s1 or s2:  # a frame that moves every step: keep the Python-side window in step with the C side
+            self.cfg.leftX += nsteps * (s1 + s2)
+            self.cfg.rightX += nsteps * (s1 + s2)
         if self.world == 1 and not self.slab:
             self._check(self.lib.chimera_engine_step(self._h, _i64(self.istep + 1), _i64(nsteps)))
             self.istep += nsteps

@@ -1320,4 +1320,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+// bench.py's CPU arm sets the team size itself: torchrun exports OMP_NUM_THREADS=1 to its workers
+int oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 }  // extern "C"
