@@ -75,6 +75,57 @@ def _inout(a, dtype, name, shape):
     return b
 
 
+# Python-visible argument names of the functions produced by the factories below, exactly as f2py names them
+# (tests/golden/fimera.pyf, checked by tests/test_pyf_pin.py) so that keyword calls work as on the reference module.
+# `in` is a Python keyword: the DHT matrix of fb_*_in is `in_` here (f2py accepts it positionally only as well).
+_ARGNAMES = {
+    "dep_curr": "coord momenta wghts curr leftx rgrid dx_inv dr_inv",
+    "dep_curr_chnk": "coord momenta wghts curr indinchunk guards leftx rgrid dx_inv dr_inv",
+    "dep_curr_env": "coord momenta wghts curr leftx rgrid dx_inv dr_inv kx0",
+    "dep_curr_env_chnk": "coord momenta wghts curr indinchunk guards leftx rgrid dx_inv dr_inv kx0",
+    "dep_dens": "coord wghts dens leftx rgrid dx_inv dr_inv",
+    "dep_dens_chnk": "coord wghts dens indinchunk guards leftx rgrid dx_inv dr_inv",
+    "dep_dens_env": "coord wghts dens leftx rgrid dx_inv dr_inv kx0",
+    "dep_dens_env_chnk": "coord wghts dens indinchunk guards leftx rgrid dx_inv dr_inv kx0",
+    "fb_div": "scl_fb_loc vec_fb dps2s dms2s kx",
+    "fb_div_env": "scl_fb_loc vec_fb dps2s dms2s kx",
+    "fb_grad": "vec_fb_loc scl_fb dps2s dms2s kx",
+    "fb_grad_env": "vec_fb_loc scl_fb dps2s dms2s kx",
+    "fb_rot": "vec_fb_loc vec_fb dps2s dms2s kx",
+    "fb_rot_env": "vec_fb_loc vec_fb dps2s dms2s kx",
+    "fb_scl_in": "scl_fb scl leftx kx in_",
+    "fb_scl_out": "scl_fb leftx kx out",
+    "fb_vec_in": "vec_fb vec leftx kx in_",
+    "fb_vec_out": "vec_fb leftx kx out",
+    "gaussbeam": "coord fld time a0 params",
+    "omp_add_scl": "scl_fb a",
+    "omp_add_vec": "vec_fb a",
+    "omp_mult_scl": "scl_fb a",
+    "omp_mult_vec": "vec_fb a",
+    "planewave": "coord fld t params",
+    "proj_fld": "coord wghts fld fld_tot leftx rgrid dx_inv dr_inv",
+    "proj_fld_env": "coord wghts fld fld_tot leftx rgrid dx_inv dr_inv kx0",
+    "sr_calc_far_comp": "spect coords momenta_prv momenta_nxt wghts comp dt omega sinth costh sinph cosph",
+    "sr_calc_far_tot": "spect coords momenta_prv momenta_nxt wghts dt omega sinth costh sinph cosph",
+    "sr_calc_near_comp": "spect coords momenta wghts comp dt omega xgrid ygrid z_scr",
+    "sr_calc_near_tot": "spect coords momenta wghts dt omega xgrid ygrid z_scr",
+    "sr_calc_nearcirc_comp": "spect coords momenta wghts comp dt omega rgrid sinph cosph z_scr",
+    "sr_calc_nearcirc_tot": "spect coords momenta wghts dt omega rgrid sinph cosph z_scr",
+    "undul_analytic_taper": "coord fld t params",
+    "undul_mapped": "coord fld t a0 params",
+    "undul_mapped_tap": "coord fld t a0 params",
+}
+
+
+def _with_signature(f, names):
+    """`f` re-exported under the reference's own parameter names (positional and keyword)"""
+    ns = {"_f": f}
+    exec("def wrapper(%s):\n    return _f(%s)" % (", ".join(names), ", ".join(names)), ns)  # noqa: S102 -- literal table above
+    w = ns["wrapper"]
+    w.__name__, w.__doc__ = f.__name__, f.__doc__
+    return w
+
+
 def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> types.ModuleType:
     """Create a module object exposing the `fimera` API on top of `lib`."""
 
@@ -301,7 +352,7 @@ def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> type
     def _fb_out(name, ncomp):
         tail = (3,) if ncomp == 3 else ()
 
-        def f(inp_fb, leftx, kx, out):
+        def f(inp_fb, leftx, kx, out):  # noqa: names set by _ARGNAMES
             inp_fb = _in(inp_fb, _C16, "vec_fb", (None, None, None) + tail)
             nkx, nkr, nm = inp_fb.shape[:3]
             kx = _in(kx, _F8, "kx", (nkx,))
@@ -586,4 +637,6 @@ def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> type
         return dens
 
     mod.API_NAMES = sorted(k for k, v in vars(mod).items() if callable(v) and not k.startswith("_") and k != "error")
+    for _name, _names in _ARGNAMES.items():
+        setattr(mod, _name, _with_signature(getattr(mod, _name), _names.split()))
     return mod
