@@ -150,11 +150,15 @@ ALG_BYTES = {
     # push_velocs): SURVEY.md section 8d counts that as 408 B/particle-step over the reference-API arrays
     # (96 + 56 + 32 + 128 + 96); fused and resident it only has to move 128 B (R x,p,w  W x,x_half,p)
     "particles_fused": 408.0,
+    # the two halves of a re-binning step: gather + push + push_coords before the sort (proj_fld 128 + push_velocs 96 +
+    # push_coords 96), dep_curr + dep_dens after it (56 + 32)
+    "gather_push_coords": 320.0,
+    "deposit_fused": 88.0,
 }
 FUSED_RESIDENT_BYTES = 128.0
 
 
-TRAFFIC_KERNEL = {"particles_fused": "fused_particles_k", "gather_push": "gather_push_binned_k",
+TRAFFIC_KERNEL = {"particles_fused": "fused_particles_k", "gather_push_coords": "gather_push_coords_k", "gather_push": "gather_push_binned_k",
                   "deposit_J": "deposit_binned_k<0, 1", "deposit_rho": "deposit_binned_k<0, 0", "push_coords": "push_coords_k"}
 
 
@@ -288,6 +292,10 @@ def run_ours(a):
                 by = ALG_BYTES[name] * n_local
                 if name == "particles_fused":
                     by += (96.0 + 2 * 48.0 + 2 * 16.0) * grid_pts  # EB read once, J and Rho read-modify-write
+                if name == "deposit_fused":
+                    by += (2 * 48.0 + 2 * 16.0) * grid_pts
+                if name == "gather_push_coords":
+                    by += 96.0 * grid_pts
                 if name == "deposit_J":
                     by += 2 * 48.0 * grid_pts
                 if name == "deposit_rho":

@@ -568,14 +568,90 @@ int ph_gather_push(chimera_engine* e, double dt_frac) {
   for (auto& s : e->sp) {
     if (s.still || s.np == 0) continue;
     const DeviceSet und = devset(e, s);
-    int rc = launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt * dt_frac, und,
-                                       sortedspec(e, s));
+    int rc = -1;
+    if (e->fuse)  // thread per particle straight from the grid (particles_fused.cu)
+      rc = launch_gather_push_coords(e->st, c.env, s.x, s.xh, s.p, s.w, s.cap, e->A("EB"), g, s.push_fact * c.dt * dt_frac,
+                                     c.dt, und, s.np, 0);
+    if (rc == -1)
+      rc = launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt * dt_frac, und,
+                                     sortedspec(e, s));
     if (rc == -1)
       rc = launch_gather_push_tiled(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
                                     s.push_fact * c.dt * dt_frac, und, s.np);
     CHB_TRY(rc);
   }
   return 0;
+}
+
+// The half of a re-binning step before its sort: gather + push_velocs of step k and push_coords of step k+1 in one
+// streaming kernel (particles_fused.cu), no deposit.  The window stage 1 of step k+1 (chimera_main.py:83) comes after
+// the gather and before anything that looks at the grid position, so it is applied here.
+int ph_gather_push_coords(chimera_engine* e) {
+  auto& c = e->cfg;
+  GridGeom g = geom_ready(e);
+  for (auto& s : e->sp) {
+    if (s.still || s.np == 0) continue;
+    const DeviceSet und = devset(e, s);
+    int rc = launch_gather_push_coords(e->st, c.env, s.x, s.xh, s.p, s.w, s.cap, e->A("EB"), g, s.push_fact * c.dt, c.dt, und,
+                                       s.np, 1);
+    if (rc == -1) {
+      rc = launch_gather_push_binned(e->st, c.env, s.x, s.w, e->A("EB"), s.p, s.cap, g, s.push_fact * c.dt, und, sortedspec(e, s));
+      if (rc == -1)
+        rc = launch_gather_push_tiled(e->st, c.env, soa((const double*)s.x, s.cap), s.w, e->A("EB"), soa(s.p, s.cap), g,
+                                      s.push_fact * c.dt, und, s.np);
+      CHB_TRY(rc);
+      rc = launch_push_coords(e->st, soa(s.x, s.cap), soa((const double*)s.p, s.cap), soa(s.xh, s.cap), c.dt, s.np);
+    }
+    CHB_TRY(rc);
+  }
+  return ph_window(e, 1);
+}
+
+// dep_curr + dep_dens of a step from the stored x_half / x / p in ONE kernel (MODE 2 of the fused kernel): the half
+// of a re-binning step after its sort, and the head of the first step of a step() call.  Applies window stage 2
+// (between dep_curr and dep_dens, chimera_main.py:87) like ph_particles_fused does.
+int ph_deposit_fused(chimera_engine* e, int rho_from_bg) {
+  auto& c = e->cfg;
+  GridGeom g = geom_ready(e);
+  const double lJ = c.leftX, lR = lJ + e->win_s2;
+  GridGeom gJ = g, gR = g;
+  gR.leftX = lR;
+  const bool rho = c.space_charge || c.static_kick;
+  const i64 n = c.nx * c.nrn * c.nm;
+  CHB_CUDA(cudaMemsetAsync(e->A("J"), 0, sizeof(cd) * n * 3, e->st));
+  if (rho) {
+    if (rho_from_bg) CHB_CUDA(cudaMemcpyAsync(e->A("Rho"), e->A("BckGrndRho"), sizeof(cd) * n, cudaMemcpyDeviceToDevice, e->st));
+    else CHB_CUDA(cudaMemsetAsync(e->A("Rho"), 0, sizeof(cd) * n, e->st));
+  }
+  for (auto& s : e->sp) {
+    if (s.still || s.np == 0) continue;
+    const DeviceSet und = devset(e, s);
+    SortedSpec spf = sortedspec(e, s);
+    spf.cta = s.d_cta_f;
+    spf.ncta = s.ncta_f;
+    int rc = -1;
+    if (!c.static_kick)  // 'StaticKick' deposits rho on coords_halfstep (chimera_main.py:186): separate kernels
+      rc = launch_fused_particles(e->st, c.env, c.space_charge, s.x, s.xh, s.p, s.w, s.cap, e->A("EB"), e->A("J"),
+                                  e->A("Rho"), g, chunkspec(e, s), s.push_fact * c.dt, c.dt, und, spf, lJ, lR, 1);
+    if (rc == -1) {
+      for (int curr = 1; curr >= (rho ? 0 : 1); --curr) {
+        cd* grid = curr ? e->A("J") : e->A("Rho");
+        const double* xs = (curr || c.static_kick) ? s.xh : s.x;
+        const GridGeom& gd = curr ? gJ : gR;
+        rc = launch_deposit_binned(e->st, c.env, curr, xs, s.p, s.w, s.cap, grid, gd, chunkspec(e, s), sortedspec(e, s));
+        if (rc == -1)
+          rc = launch_deposit_runs(e->st, c.env, curr, soa(xs, s.cap), soa((const double*)s.p, s.cap), s.w, grid, gd,
+                                   chunkspec(e, s), s.np);
+        CHB_TRY(rc);
+      }
+      rc = 0;
+    }
+    CHB_TRY(rc);
+  }
+  CHB_TRY(launch_ghost_fold(e->st, e->A("J"), c.nx, c.nrn, c.nm * 3));
+  if (rho) CHB_TRY(launch_ghost_fold(e->st, e->A("Rho"), c.nx, c.nrn, c.nm));
+  e->leftX_J = lJ;
+  return ph_window(e, 2);
 }
 
 // gather + push_velocs of step k fused with push_coords + dep_curr + dep_dens of step k+1 (particles_fused.cu);
@@ -681,6 +757,8 @@ int run_phase(chimera_engine* e, int phase, double arg) {
     case CHB_ADD_BG: rc = ph_add_bg(e); break;
     case CHB_STATIC_FIELDS: rc = ph_static_fields(e); break;
     case CHB_WINDOW: rc = ph_window(e, arg == 2.0 ? 2 : 1); break;
+    case CHB_GATHER_PUSH_COORDS: rc = ph_gather_push_coords(e); break;
+    case CHB_DEPOSIT_FUSED: rc = ph_deposit_fused(e, arg != 0.0); break;
     default: set_error("unknown engine phase %d", phase); rc = 2;
   }
   if (e->profile) {
@@ -954,10 +1032,6 @@ int chimera_engine_damp_field_slab(chimera_engine* e, const double* filtr, chb_i
 // chimera_main.py:286-290 move_frame: Xgrid += shiftX
 int chimera_engine_set_window(chimera_engine* e, double shift_stage1, double shift_stage2) {
   ENG_CHECK(e);
-  if (e->cfg.static_kick && (shift_stage1 != 0.0 || shift_stage2 != 0.0)) {
-    set_error("set_window: not available with the 'StaticKick' schedule");
-    return 2;
-  }
   e->win_s1 = shift_stage1;
   e->win_s2 = shift_stage2;
   return 0;
@@ -1169,6 +1243,16 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
     e->dev_time = (double)(istep - 1) * c.dt;  // the pending gather + push closes step istep - 1 (make_device(istep - 1))
     if (gather_pending && !sort_now && e->fuse && !c.static_kick) {
       CHB_TRY(run_phase(e, CHB_PARTICLES_FUSED, 1));
+    } else if (e->fuse) {
+      // re-binning step (the sort sits between push_coords and the deposits) or the first step of the call: one
+      // streaming kernel before the sort, one deposit kernel after it; both apply their window stage
+      if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH_COORDS, 0));
+      else {
+        CHB_TRY(ph_window(e, 1));  // frame_act(istep) (chimera_main.py:83)
+        CHB_TRY(run_phase(e, CHB_PUSH_COORDS, 0));
+      }
+      if (sort_now) CHB_TRY(run_phase(e, CHB_SORT, 1));
+      CHB_TRY(run_phase(e, CHB_DEPOSIT_FUSED, 1));
     } else {
       if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
       const bool win = e->win_s1 != 0.0 || e->win_s2 != 0.0;

@@ -165,7 +165,12 @@ constexpr int kFusedNPB = 512;
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
                            const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
                            const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp,
-                           double leftX_J, double leftX_R);  // node 0 of the J / rho deposit grids (moving window)
+                           double leftX_J, double leftX_R,  // node 0 of the J / rho deposit grids (moving window)
+                           int deposit_only = 0);           // 1: J and rho from the stored x_half / x / p (after a sort)
+// gather + device + Boris push + push_coords in one streaming pass, no deposit (before a re-binning step's sort)
+int launch_gather_push_coords(cudaStream_t st, int env, double* x, double* xh, double* mom, const double* w, i64 cap,
+                              const cd* Fld, const GridGeom& g, double push_dt, double dt, const DeviceSet& und, i64 np,
+                              int coords = 1);  // 0: gather + push only
 void fused_profile_enable(int on);
 void fused_profile_read(unsigned long long out[8]);
 // field gather from a shared-memory tile of the EB grid + undulator + Boris push

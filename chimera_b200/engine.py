@@ -32,7 +32,7 @@ _i64 = ctypes.c_longlong
 PHASES = (
     "push_coords", "sort", "deposit_J", "deposit_rho", "deposit_bg", "fb_in_J", "fb_in_rho", "poisson",
     "maxwell", "init_push", "fields_out", "gather_push", "add_bg", "fields_out_a", "fields_out_b",
-    "particles_fused", "static_fields", "window",
+    "particles_fused", "static_fields", "window", "gather_push_coords", "deposit_fused",
 )
 PHASE_ID = {n: i for i, n in enumerate(PHASES)}
 
@@ -554,8 +554,18 @@ class Engine:
             self.istep += 1
             sort_now = c.sort_every > 0 and self.istep % c.sort_every == 0
             self.set_time((self.istep - 1) * c.dt)  # the pending gather + push closes the previous step
+            bg = 1.0 if self.rank == 0 else 0.0  # the background charge enters the all-reduced density once
             if gather_pending and not sort_now and self.fuse:
-                self.run("particles_fused", 1.0 if self.rank == 0 else 0.0)
+                self.run("particles_fused", bg)
+            elif self.fuse:  # re-binning step / first step of the call: one kernel before the sort, one after
+                if gather_pending:
+                    self.run("gather_push_coords")
+                else:
+                    self.run("window", 1.0)
+                    self.run("push_coords")
+                if sort_now:
+                    self.run("sort", 1.0)
+                self.run("deposit_fused", bg)
             else:
                 if gather_pending:
                     self.run("gather_push", 1.0)
@@ -569,7 +579,7 @@ class Engine:
                 if win:
                     self.run("window", 2.0)
                 if c.space_charge:
-                    self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
+                    self.run("deposit_rho", bg)
             w_j = w_r = None
             if self.world > 1:
                 if self.overlap:

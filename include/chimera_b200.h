@@ -328,7 +328,11 @@ enum chimera_engine_phase {
                              next in one kernel (the per-particle work between two field solves); arg as DEPOSIT_RHO */
   CHB_STATIC_FIELDS = 16, /* chimera_main.py:118-125 update_fields with 'StaticKick' (needs every kx row)        */
   CHB_WINDOW = 17,        /* one stage of a window that moves every step (chimera_main.py:286); arg: 1 | 2       */
-  CHB_NPHASES = 18
+  CHB_GATHER_PUSH_COORDS = 18, /* gather + push of step k and push_coords of step k+1, no deposit (before a sort);
+                                  applies window stage 1                                                          */
+  CHB_DEPOSIT_FUSED = 19, /* dep_curr + dep_dens from the stored x_half / x / p in one kernel (after a sort); arg != 0:
+                             rho starts from BckGrndRho; applies window stage 2                                   */
+  CHB_NPHASES = 20
 };
 int chimera_engine_run(chimera_engine* e, int phase, double arg);
 /* nsteps x make_step on the engine's stream; istep0 = index of the first step (re-binning cadence) */

@@ -304,6 +304,17 @@ class CpuEngine(Engine):
         if self.cfg.space_charge:
             self._ph_deposit_rho(arg)
 
+    def _ph_gather_push_coords(self, arg):  # CHB_GATHER_PUSH_COORDS: before a re-binning step's sort; window stage 1
+        self._ph_gather_push(1.0)
+        self._ph_window(1.0)
+        self._ph_push_coords(0.0)
+
+    def _ph_deposit_fused(self, arg):  # CHB_DEPOSIT_FUSED: after the sort; window stage 2 between J and rho
+        self._ph_deposit_J(0.0)
+        self._ph_window(2.0)
+        if self.cfg.space_charge:
+            self._ph_deposit_rho(arg)
+
 
 def reference_run(setup, species, eg0, nsteps, window=(0.0, 0.0)):
     """the single-process reference sequence the ranks are compared with"""

@@ -224,7 +224,8 @@ def test_engine_config_struct_matches_the_header():
              "DEPOSIT_BG": "deposit_bg", "FB_IN_J": "fb_in_J", "FB_IN_RHO": "fb_in_rho", "POISSON": "poisson",
              "MAXWELL": "maxwell", "INIT_PUSH": "init_push", "FIELDS_OUT": "fields_out", "GATHER_PUSH": "gather_push",
              "ADD_BG": "add_bg", "FIELDS_OUT_A": "fields_out_a", "FIELDS_OUT_B": "fields_out_b",
-             "PARTICLES_FUSED": "particles_fused", "STATIC_FIELDS": "static_fields", "WINDOW": "window"}
+             "PARTICLES_FUSED": "particles_fused", "STATIC_FIELDS": "static_fields", "WINDOW": "window",
+             "GATHER_PUSH_COORDS": "gather_push_coords", "DEPOSIT_FUSED": "deposit_fused"}
     assert set(ids) == set(names)
     for k, i in ids.items():
         assert PHASES[i] == names[k], (k, i, PHASES[i])
