@@ -8,12 +8,12 @@ LIB = os.path.join(HERE, "libchimera_b200.so")
 
 
 def is_stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(os.path.join(HERE, "_npalloc.so")):
         return True
     t = os.path.getmtime(LIB)
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in os.listdir(root):
-            if f.endswith((".cu", ".cuh", ".h", "Makefile")) and os.path.getmtime(os.path.join(root, f)) > t:
+            if f.endswith((".cu", ".cuh", ".h", ".c", "Makefile")) and os.path.getmtime(os.path.join(root, f)) > t:
                 return True
     return False
 

@@ -5,6 +5,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cstdarg>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 #include "../../include/chimera_b200.h"
 #include "fbops.cuh"
@@ -61,13 +62,36 @@ struct Call {
     }
   }
   template <typename T> T* dev(i64 n) { return c.scr.take_n<T>(n); }
+  // Resident mode (chimera_b200/resident.py): the caller's numpy arrays live in CUDA managed memory (numpy data
+  // allocator, NEP 49), so the "host" pointer is a device pointer too -- no staging copy, only a prefetch that is a
+  // no-op once the pages are on the device.  Plain device pointers pass through as well.
+  static int accessible(const void* p) {  // 0: host memory, 1: managed, 2: device
+    if (!p) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return at.type == cudaMemoryTypeManaged ? 1 : (at.type == cudaMemoryTypeDevice ? 2 : 0);
+  }
   template <typename T> T* up(const T* h, i64 n) {
+    if (n > 0) {
+      const int kind = accessible(h);
+      if (kind == 1) {
+        int dev_id = 0;
+        cudaGetDevice(&dev_id);
+        if (cudaMemPrefetchAsync(h, sizeof(T) * (size_t)n, dev_id, c.st) != cudaSuccess) cudaGetLastError();
+      }
+      if (kind) return const_cast<T*>(h);
+    }
     T* d = dev<T>(n);
     if (n > 0) g_h2d_bytes += (long long)(sizeof(T) * (size_t)n);
     if (d && n > 0 && c.stage.h2d(d, h, sizeof(T) * (size_t)n, c.st) != 0) return nullptr;
     return d;
   }
   template <typename T> int down(T* h, const T* d, i64 n) {
+    if ((const void*)h == (const void*)d) return 0;  // computed in place in the caller's managed / device array
+    if (n > 0 && accessible(h)) {
+      CHB_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, c.st));
+      return 0;
+    }
     if (n > 0) CHB_TRY(c.stage.d2h(h, d, sizeof(T) * (size_t)n, c.st));
     if (n > 0) g_d2h_bytes += (long long)(sizeof(T) * (size_t)n);
     return 0;
@@ -337,6 +361,73 @@ int chimera_sync(void) {
   return 0;
 }
 int chimera_kernel_launches(chb_i64* n) { *n = g_launches; return 0; }
+
+// ---- resident mode: numpy's data allocator backed by CUDA managed memory, and the driver's whole-array statements
+// (J[:] = 0, Rho += BckGrndRho, gradRho_prv[:] = gradRho_nxt, chimera_main.py:110-190, solvers.py:318) on the device
+namespace {
+std::mutex g_mm_mu;
+std::unordered_map<const void*, size_t> g_mm;  // managed blocks handed to numpy
+}  // namespace
+void* chimera_managed_alloc(size_t bytes, int zero) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 1;
+  if (cudaMallocManaged(&p, bytes, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (zero) {  // zero on the device: np.zeros arrays of the driver (J, Rho, EB, the spectral state) are used there first
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+    cudaDeviceSynchronize();
+  }
+  std::lock_guard<std::mutex> lk(g_mm_mu);
+  g_mm[p] = bytes;
+  return p;
+}
+int chimera_managed_owns(const void* p, size_t* bytes) {
+  std::lock_guard<std::mutex> lk(g_mm_mu);
+  auto it = g_mm.find(p);
+  if (it == g_mm.end()) return 0;
+  if (bytes) *bytes = it->second;
+  return 1;
+}
+void chimera_managed_free(void* p) {
+  {
+    std::lock_guard<std::mutex> lk(g_mm_mu);
+    g_mm.erase(p);
+  }
+  if (cudaFree(p) != cudaSuccess) cudaGetLastError();  // at interpreter exit the context may be gone already
+}
+void* chimera_managed_realloc(void* p, size_t new_bytes) {
+  size_t old = 0;
+  if (!chimera_managed_owns(p, &old)) return nullptr;
+  void* q = chimera_managed_alloc(new_bytes, 0);
+  if (!q) return nullptr;
+  const size_t n = old < new_bytes ? old : new_bytes;
+  if (n && cudaMemcpy(q, p, n, cudaMemcpyDefault) != cudaSuccess) { cudaGetLastError(); chimera_managed_free(q); return nullptr; }
+  chimera_managed_free(p);
+  return q;
+}
+int chimera_is_device_accessible(const void* p) { return Call::accessible(p); }
+// y[0:n] = value (doubles; a complex array is 2n doubles with value_im in the odd slots)
+int chimera_fill(double* y, chb_i64 n, double value_re, double value_im, int is_complex) {
+  CALL_BEGIN();
+  if (!Call::accessible(y)) { set_error("chimera_fill: not a managed / device array"); return 2; }
+  if (value_re == 0.0 && value_im == 0.0) {
+    CHB_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)n * (is_complex ? 2 : 1), call.c.st));
+    return call.sync();
+  }
+  CHB_TRY(launch_fill(call.c.st, y, n, value_re, value_im, is_complex));
+  return call.sync();
+}
+int chimera_copy(void* dst, const void* src, chb_i64 bytes) {
+  CALL_BEGIN();
+  if (!Call::accessible(dst) || !Call::accessible(src)) { set_error("chimera_copy: not managed / device arrays"); return 2; }
+  CHB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, call.c.st));
+  return call.sync();
+}
+int chimera_add_inplace(double* y, const double* x, chb_i64 n) {  // y += x over n doubles
+  CALL_BEGIN();
+  if (!Call::accessible(y) || !Call::accessible(x)) { set_error("chimera_add_inplace: not managed / device arrays"); return 2; }
+  CHB_TRY(launch_add_f64(call.c.st, y, x, n));
+  return call.sync();
+}
 int chimera_host_traffic(chb_i64* h2d, chb_i64* d2h, int reset) {
   if (h2d) *h2d = g_h2d_bytes;
   if (d2h) *d2h = g_d2h_bytes;

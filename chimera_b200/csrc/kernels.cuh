@@ -237,6 +237,8 @@ struct Unit { int re, im; };  // value = re + i*im, entries in {-1,0,1}
 int launch_combine(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, Unit cb, int mirror, i64 nkx, i64 ncols);
 //   out (+)= ca * a + cb * b   (accumulate when acc != 0)
 int launch_axpby(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, Unit cb, int acc, i64 n);
+int launch_fill(cudaStream_t st, double* y, i64 n, double vr, double vi, int is_complex);  // y[:] = value
+int launch_add_f64(cudaStream_t st, double* y, const double* x, i64 n);                    // y += x
 //   out (+)= i * kx * a   (sign = +-1)
 int launch_ikx(cudaStream_t st, cd* out, const cd* a, const double* kx, double sign, int acc, i64 nkx, i64 ncols);
 //   outm = i a - b, outp = i a + b in one pass

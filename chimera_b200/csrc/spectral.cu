@@ -341,6 +341,28 @@ __global__ void __launch_bounds__(TPB) axpby_k(cd* __restrict__ out, const cd* _
   if (acc) r = cadd(r, out[e]);
   out[e] = r;
 }
+// whole-array statements of the driver on resident arrays: y[:] = value, y += x
+__global__ void __launch_bounds__(TPB) fill_k(double* __restrict__ y, i64 n, double vr, double vi, int is_complex) {
+  const i64 tot = is_complex ? 2 * n : n;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (i64)gridDim.x * blockDim.x)
+    y[i] = (is_complex && (i & 1)) ? vi : vr;
+}
+int launch_fill(cudaStream_t st, double* y, i64 n, double vr, double vi, int is_complex) {
+  if (n <= 0) return 0;
+  fill_k<<<grid_for(n, TPB), TPB, 0, st>>>(y, n, vr, vi, is_complex);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void __launch_bounds__(TPB) add_f64_k(double* __restrict__ y, const double* __restrict__ x, i64 n) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) y[i] += x[i];
+}
+int launch_add_f64(cudaStream_t st, double* y, const double* x, i64 n) {
+  if (n <= 0) return 0;
+  add_f64_k<<<grid_for(n, TPB), TPB, 0, st>>>(y, x, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_axpby(cudaStream_t st, cd* out, const cd* a, Unit ca, const cd* b, Unit cb, int acc, i64 n) {
   if (n <= 0) return 0;
   axpby_k<<<grid_for(n, TPB), TPB, 0, st>>>(out, a, ca, b, cb, acc, n);

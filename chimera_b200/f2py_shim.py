@@ -126,8 +126,14 @@ def _with_signature(f, names):
     return w
 
 
-def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> types.ModuleType:
-    """Create a module object exposing the `fimera` API on top of `lib`."""
+def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera", adopt=None) -> types.ModuleType:
+    """Create a module object exposing the `fimera` API on top of `lib`.  `adopt`: hook applied to every in/out and
+    large out array before the call (chimera_b200.resident.adopt: resident mode of the CUDA drop-in)."""
+    _inout_base = globals()["_inout"]
+
+    def _inout(a, dtype, name, shape):  # noqa: F811 -- shadows the module-level helper for the closures below
+        b = _inout_base(a, dtype, name, shape)
+        return adopt(b) if adopt is not None else b
 
     mod = types.ModuleType(modname)
     mod.error = FimeraError
@@ -359,6 +365,8 @@ def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera") -> type
             out = _in(out, _F8, "out", (nkr, None, nm))
             nrn = out.shape[1] + 1
             res = np.zeros((nkx, nrn, nm) + tail, dtype=_C16, order="F")
+            if adopt is not None:
+                res = adopt(res)
             call(name, res, inp_fb, _dbl(leftx), kx, out, _i64(nkx), _i64(nrn), _i64(nm), _i64(nkr))
             return res
 

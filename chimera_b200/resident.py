@@ -1,0 +1,168 @@
+"""Resident mode of the per-function drop-in: the reference's unmodified Python driver with its arrays living on the GPU.
+
+The reference's driver owns every array as a numpy array, passes them to ~21 ``fimera`` calls per step and mutates
+them in Python in between (``J[:] = 0``, ``Rho += BckGrndRho``, ``gradRho_fb_prv[:] = gradRho_fb_nxt``, ``EB[:] = 0``,
+``vec_fb[:] = J_fb``, ``resize``; reference moduls/chimera_main.py:110-190, species.py:234-256, solvers.py:318).  Copying
+each argument in and out of every call costs 56 GB of PCIe traffic per LWFA step.  Resident mode removes the copies
+without asking anything of the driver:
+
+1. **numpy's data allocator** (NEP 49, ``PyDataMem_SetHandler``) is pointed at CUDA *managed* memory for blocks of
+   1 MB and more (``csrc/npalloc.c`` -> ``chimera_managed_alloc`` of libchimera_b200.so).  Arrays the driver creates with
+   ``np.zeros`` / arithmetic / ``resize`` are then plain numpy arrays that own their data (the driver's ``resize`` calls
+   keep working) and whose pointer is valid on the device: every C-ABI entry point takes it as it is
+   (``csrc/api_host.cu`` ``Call::up``), prefetches it -- a no-op once the pages are on the device -- and computes in place.
+   Whatever the driver does to an array on the host stays correct, with no bookkeeping here: the CUDA driver migrates
+   the touched pages on access.
+2. **The driver's whole-array statements run on the device**: the shim returns :class:`ResidentArray` (an ``ndarray``
+   subclass; views taken from it, e.g. ``EG_fb[:,:,:,3:]``, are ResidentArrays too) whose ``a[:] = scalar``,
+   ``a[:] = other`` and ``a += other`` go to ``chimera_fill`` / ``chimera_copy`` / ``chimera_add_inplace`` when both
+   sides are device-accessible and contiguous, so these statements do not pull the pages back to the host.  Anything
+   else falls through to numpy on the same memory.
+
+``enable()`` switches it on for the process (also: environment ``CHIMERA_B200_RESIDENT=1`` before importing
+``chimera_b200.fimera``); without a CUDA device it raises.  In resident mode use the object a call RETURNS, as the
+reference's driver does (``self.Data[k] = chimera.f(self.Data[k], ...)``): a particle array that is not yet resident
+is replaced by a resident owner on its first in/out call.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_state = {"on": False, "np": None}
+THRESHOLD = 1 << 20
+
+
+def _npalloc():
+    if _state["np"] is None:
+        path = os.path.join(_HERE, "_npalloc.so")
+        if not os.path.exists(path):
+            raise ImportError("%s not found -- run `python -m chimera_b200.build`" % path)
+        h = ctypes.PyDLL(path)
+        h.chb_npalloc_install.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_size_t]
+        h.chb_npalloc_count.restype = ctypes.c_longlong
+        h.chb_npalloc_bytes.restype = ctypes.c_longlong
+        _state["np"] = h
+    return _state["np"]
+
+
+def _fnptr(lib, name):
+    return ctypes.cast(getattr(lib, name), ctypes.c_void_p)
+
+
+def enabled():
+    return _state["on"]
+
+
+def enable(threshold=THRESHOLD):
+    """numpy allocates blocks >= ``threshold`` bytes in CUDA managed memory from now on; the shim returns ResidentArrays"""
+    if _state["on"]:
+        return
+    lib = _lib.load()
+    if _lib.device_count() == 0:
+        raise RuntimeError("chimera_b200 resident mode needs a CUDA device (there is no CPU fallback)")
+    lib.chimera_managed_alloc.restype = ctypes.c_void_p
+    lib.chimera_managed_realloc.restype = ctypes.c_void_p
+    probe = lib.chimera_managed_alloc(ctypes.c_size_t(4096), 1)  # creates the context; fails early without managed memory
+    if not probe:
+        raise RuntimeError("cudaMallocManaged failed: resident mode is not available on this device")
+    lib.chimera_managed_free(ctypes.c_void_p(probe))
+    rc = _npalloc().chb_npalloc_install(_fnptr(lib, "chimera_managed_alloc"), _fnptr(lib, "chimera_managed_realloc"),
+                                        _fnptr(lib, "chimera_managed_free"), _fnptr(lib, "chimera_managed_owns"),
+                                        ctypes.c_size_t(int(threshold)))
+    if rc != 0:
+        raise RuntimeError("could not install the numpy data allocator (rc=%d)" % rc)
+    _state["on"] = True
+
+
+def disable():
+    """back to numpy's own allocator; arrays allocated meanwhile stay valid (each remembers its allocator)"""
+    if _state["on"]:
+        _npalloc().chb_npalloc_uninstall()
+        _state["on"] = False
+
+
+def stats():
+    h = _npalloc()
+    return {"managed_blocks": int(h.chb_npalloc_count()), "managed_bytes": int(h.chb_npalloc_bytes())}
+
+
+def accessible(a) -> bool:
+    """is the array's memory visible to the device (managed or device memory)?"""
+    return bool(a.size) and _lib.load().chimera_is_device_accessible(ctypes.c_void_p(a.ctypes.data)) != 0
+
+
+def _contig(a):
+    return a.flags.f_contiguous or a.flags.c_contiguous
+
+
+def _full(key, ndim):
+    if key is Ellipsis or (isinstance(key, slice) and key == slice(None)):
+        return True
+    if isinstance(key, tuple) and len(key) <= ndim:
+        return all(k is Ellipsis or (isinstance(k, slice) and k == slice(None)) for k in key)
+    return False
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("libchimera_b200: status %d: %s" % (rc, _lib.load().chimera_last_error().decode()))
+
+
+class ResidentArray(np.ndarray):
+    """numpy array in CUDA managed memory whose whole-array statements run on the device (module docstring)"""
+
+    def __setitem__(self, key, value):
+        if _state["on"] and self.size and self.dtype.kind in "fc" and self.dtype.itemsize in (8, 16) and _contig(self) \
+                and _full(key, self.ndim) and accessible(self):
+            lib = _lib.load()
+            if isinstance(value, (int, float, complex, np.number)):
+                v = complex(value)
+                if self.dtype.kind == "c" or v.imag == 0.0:
+                    _check(lib.chimera_fill(ctypes.c_void_p(self.ctypes.data), ctypes.c_longlong(self.size), ctypes.c_double(v.real),
+                                            ctypes.c_double(v.imag), int(self.dtype.kind == "c")))
+                    return
+            elif isinstance(value, np.ndarray) and value.shape == self.shape and value.dtype == self.dtype and \
+                    value.flags.f_contiguous == self.flags.f_contiguous and _contig(value) and accessible(value):
+                _check(lib.chimera_copy(ctypes.c_void_p(self.ctypes.data), ctypes.c_void_p(value.ctypes.data),
+                                        ctypes.c_longlong(self.nbytes)))
+                return
+        super().__setitem__(key, value)
+
+    def __iadd__(self, other):
+        if _state["on"] and isinstance(other, np.ndarray) and other.shape == self.shape and other.dtype == self.dtype and \
+                self.dtype.kind in "fc" and self.dtype.itemsize in (8, 16) and _contig(self) and _contig(other) and \
+                other.flags.f_contiguous == self.flags.f_contiguous and self.size and accessible(self) and accessible(other):
+            n = self.size * (2 if self.dtype.kind == "c" else 1)
+            _check(_lib.load().chimera_add_inplace(ctypes.c_void_p(self.ctypes.data), ctypes.c_void_p(other.ctypes.data),
+                                                   ctypes.c_longlong(n)))
+            return self
+        return super().__iadd__(other)
+
+
+def _particle_like(a):
+    """arrays the driver resizes (species.py:234-254, 394-398): (3|4|6, Np) and (Np,) real arrays"""
+    return a.dtype == np.float64 and (a.ndim == 1 or (a.ndim == 2 and a.shape[0] in (3, 4, 6)))
+
+
+def adopt(a):
+    """what the shim hands back for an in/out or out array in resident mode: the array itself when it already is a
+    ResidentArray; a ResidentArray view of a grid / spectral array (aliasing preserved); a resident OWNER (one device
+    copy, once) of a particle array, which the driver is going to ``resize``"""
+    if not _state["on"] or not isinstance(a, np.ndarray) or isinstance(a, ResidentArray) or a.nbytes < THRESHOLD:
+        return a
+    if _particle_like(a) and a.base is None and a.flags.owndata:
+        if accessible(a):
+            # already managed (allocated after enable()): an owner cannot change class, so move the data once
+            new = ResidentArray(a.shape, dtype=a.dtype, order="F" if a.flags.f_contiguous else "C")
+            _check(_lib.load().chimera_copy(ctypes.c_void_p(new.ctypes.data), ctypes.c_void_p(a.ctypes.data), ctypes.c_longlong(a.nbytes)))
+            return new
+        new = ResidentArray(a.shape, dtype=a.dtype, order="F" if a.flags.f_contiguous else "C")
+        np.ndarray.__setitem__(new, Ellipsis, a)
+        return new
+    return a.view(ResidentArray)

@@ -17,6 +17,7 @@
 #ifndef CHIMERA_B200_H
 #define CHIMERA_B200_H
 #include <stdint.h>
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -29,6 +30,21 @@ int chimera_device_count(int* n);
 int chimera_set_device(int device);          /* default: current CUDA device */
 int chimera_sync(void);
 int chimera_kernel_launches(chb_i64* n);     /* kernels launched by this library so far */
+
+/* ---- resident mode of the per-function drop-in (chimera_b200/resident.py) -------------------------------------
+ * The reference's driver owns every array as a numpy array and mutates them in Python between calls
+ * (moduls/chimera_main.py:110-190, species.py:246-256, solvers.py:318).  With numpy's data allocator (NEP 49) backed
+ * by these functions the arrays live in CUDA managed memory: every entry point above then takes the caller's pointer
+ * as it is (no staging copy; the CUDA driver keeps host accesses coherent), and the driver's whole-array statements
+ * run on the device.  Pointers that are plain host memory keep the staged-copy path. */
+void* chimera_managed_alloc(size_t bytes, int zero);
+void* chimera_managed_realloc(void* p, size_t new_bytes);
+void chimera_managed_free(void* p);
+int chimera_managed_owns(const void* p, size_t* bytes);      /* 1 when p came from chimera_managed_alloc            */
+int chimera_is_device_accessible(const void* p);             /* 0 host, 1 managed, 2 device                          */
+int chimera_fill(double* y, chb_i64 n, double value_re, double value_im, int is_complex); /* y[:] = value          */
+int chimera_copy(void* dst, const void* src, chb_i64 bytes);                              /* dst[:] = src          */
+int chimera_add_inplace(double* y, const double* x, chb_i64 n);                           /* y += x (n doubles)    */
 /* bytes copied host->device / device->host by the host-buffer entry points below since the last reset */
 int chimera_host_traffic(chb_i64* h2d, chb_i64* d2h, int reset);
 
