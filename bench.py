@@ -443,7 +443,8 @@ def run_e2e_per_call(a, torch, S, eng, state, resident):
     sp.coords, sp.momenta, sp.weights, sp.coords_halfstep = x, p, w, xh
     sp.push_fact, sp.still, sp.devices, sp.chunks = -2 * np.pi, False, [], eng.chunks(0)
     sp.EB = np.zeros((6, 0), order="F")
-    run = RefRun(gfim, S, [sp], sort_every=0)
+    timer = StageTimer(gfim)
+    run = RefRun(timer, S, [sp], sort_every=0)
     run.Bck = bck
     run.EG_fb = eg
     run.g_nxt = g
@@ -452,6 +453,7 @@ def run_e2e_per_call(a, torch, S, eng, state, resident):
             run.make_step()
         torch.cuda.synchronize()
         lib.chimera_host_traffic(None, None, 1)
+        timer.t.clear()
         nt = 3 if resident else 1
         t = time.perf_counter()
         for _ in range(nt):
@@ -463,8 +465,10 @@ def run_e2e_per_call(a, torch, S, eng, state, resident):
     finally:
         if resident:
             gfim.resident(False)
+    calls = {k: 1e3 * v / nt for k, v in sorted(timer.t.items(), key=lambda kv: -kv[1])}
+    calls["python_statements"] = dt * 1e3 - sum(calls.values())
     return {"value": sp.coords.shape[1] / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": nt,
-            "h2d_bytes_per_step": int(h2d.value // nt), "d2h_bytes_per_step": int(d2h.value // nt),
+            "h2d_bytes_per_step": int(h2d.value // nt), "d2h_bytes_per_step": int(d2h.value // nt), "calls_ms": calls,
             "path": ("chimera_b200.fimera per-function drop-in, RESIDENT mode: numpy arrays in CUDA managed memory (numpy data "
                      "allocator), no staging copies (the byte counts are what the library still copied: small tables), the "
                      "driver's whole-array statements on the device; every call synchronous") if resident else

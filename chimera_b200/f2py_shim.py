@@ -126,10 +126,16 @@ def _with_signature(f, names):
     return w
 
 
-def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera", adopt=None) -> types.ModuleType:
-    """Create a module object exposing the `fimera` API on top of `lib`.  `adopt`: hook applied to every in/out and
-    large out array before the call (chimera_b200.resident.adopt: resident mode of the CUDA drop-in)."""
-    _inout_base = globals()["_inout"]
+def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera", adopt=None, adopt_input=None) -> types.ModuleType:
+    """Create a module object exposing the `fimera` API on top of `lib`.  `adopt` / `adopt_input`: hooks applied to every
+    in/out (and large out) array and to every intent(in) array before the call (chimera_b200.resident: resident mode of
+    the CUDA drop-in)."""
+    _inout_base, _in_base = globals()["_inout"], globals()["_in"]
+
+    def _in(a, dtype, name, shape):  # noqa: F811 -- shadows the module-level helper for the closures below
+        if adopt_input is not None and isinstance(a, np.ndarray):
+            adopt_input(a)
+        return _in_base(a, dtype, name, shape)
 
     def _inout(a, dtype, name, shape):  # noqa: F811 -- shadows the module-level helper for the closures below
         b = _inout_base(a, dtype, name, shape)

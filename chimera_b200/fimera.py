@@ -15,7 +15,7 @@ import sys
 from . import _lib, resident as _resident
 from .f2py_shim import build_module
 
-_mod = build_module(_lib.load(), "chimera", "chimera_b200.fimera", adopt=_resident.adopt)
+_mod = build_module(_lib.load(), "chimera", "chimera_b200.fimera", adopt=_resident.adopt, adopt_input=_resident.adopt_input)
 _mod.__doc__ = __doc__
 
 

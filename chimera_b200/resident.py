@@ -19,6 +19,14 @@ without asking anything of the driver:
    sides are device-accessible and contiguous, so these statements do not pull the pages back to the host.  Anything
    else falls through to numpy on the same memory.
 
+3. **Arrays the driver only ever passes as inputs** (``gradRho_fb_prv``, ``BckGrndRho``: never returned by a call, so the
+   driver keeps its plain ``np.zeros`` object and ``prv[:] = nxt`` would be a CPU copy that drags both arrays to the
+   host) are upgraded where they are held: the first time such an array is seen as an ``intent(in)`` argument, the
+   entries of the dictionaries that reference it (``solver.Data``, an instance ``__dict__``) are rebound to a
+   ResidentArray *view* of the same memory -- what the driver itself does with every in/out argument
+   (``self.Data[k] = chimera.f(self.Data[k], ...)``).  Particle arrays are left alone (the driver resizes them, a view
+   cannot be resized).  ``upgrade_inputs = False`` switches this off.
+
 ``enable()`` switches it on for the process (also: environment ``CHIMERA_B200_RESIDENT=1`` before importing
 ``chimera_b200.fimera``); without a CUDA device it raises.  In resident mode use the object a call RETURNS, as the
 reference's driver does (``self.Data[k] = chimera.f(self.Data[k], ...)``): a particle array that is not yet resident
@@ -36,6 +44,8 @@ from . import _lib
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _state = {"on": False, "np": None}
 THRESHOLD = 1 << 20
+upgrade_inputs = True
+_seen_inputs = set()
 
 
 def _npalloc():
@@ -166,3 +176,25 @@ def adopt(a):
         np.ndarray.__setitem__(new, Ellipsis, a)
         return new
     return a.view(ResidentArray)
+
+
+def adopt_input(a):
+    """intent(in) array in resident mode: rebind the dictionary entries that hold a plain, device-accessible grid /
+    spectral array to a ResidentArray view of it (module docstring, 3.); once per buffer"""
+    if not _state["on"] or not upgrade_inputs or type(a) is not np.ndarray or a.nbytes < THRESHOLD or _particle_like(a):
+        return a
+    key = (a.ctypes.data, a.nbytes)
+    if key in _seen_inputs:
+        return a
+    _seen_inputs.add(key)
+    if not (_contig(a) and accessible(a)):
+        return a
+    import gc
+
+    view = a.view(ResidentArray)
+    for ref in gc.get_referrers(a):
+        if isinstance(ref, dict):
+            for k, v in list(ref.items()):
+                if v is a:
+                    ref[k] = view
+    return view

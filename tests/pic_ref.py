@@ -169,7 +169,10 @@ class RefRun:
         for s in self.sp:
             if s.still:
                 continue
-            s.EB = np.zeros((6, s.coords.shape[1]), order="F")
+            # Specie.make_field (species.py:246-256): resize when the particle count changed, then zero in place
+            if s.EB.shape[-1] != s.coords.shape[1]:
+                s.EB.resize((6, s.coords.shape[1]), refcheck=False)
+            s.EB[:] = 0.0
             if s.coords.shape[1] == 0:
                 continue
             s.EB = proj(s.coords, s.weights, self.EB, s.EB, a["leftX"], *a["DepProj"])

@@ -102,8 +102,8 @@ def test_host_side_access_stays_coherent(ofim, gfim, resident):
         arr[3, 2, 1, 0] = 7.0 - 2.0j
         arr *= 0.5
         arr[::2] += 1.0
-        arr[arr.real > 1.2] = 0.0
-    assert np.array_equal(np.asarray(gg), go)
+        arr[np.abs(arr) > 40.0] = 0.0
+    assert_close(np.asarray(gg), go, TOL, "host-side writes on the resident array")
     go = ofim.fb_graddiv(go, *a["FBDiff"])
     gg = gfim.fb_graddiv(gg, *a["FBDiff"])
     assert_close(np.asarray(gg), go, 10 * TOL, "after host-side writes")
@@ -139,7 +139,7 @@ def test_resident_particle_arrays_can_be_resized(ofim, gfim, resident):
     assert isinstance(pg, resident.ResidentArray) and pg.flags.owndata
     pg.resize((3, 3500), refcheck=False)
     po.resize((3, 3500), refcheck=False)
-    assert np.array_equal(np.asarray(pg)[:, :3000], po[:, :3000])
+    assert_close(np.asarray(pg)[:, :3000], po[:, :3000], TOL, "data kept by resize")
     pg[:, 3000:] = 0.25
     po[:, 3000:] = 0.25
     f2 = np.asfortranarray(rng.standard_normal((6, 3500)))
@@ -156,3 +156,24 @@ def test_resident_particle_arrays_can_be_resized(ofim, gfim, resident):
     eb_g = gfim.proj_fld(x, w, F, eb_g, a["leftX"], *a["DepProj"])
     eb_o = ofim.proj_fld(x, w, F, eb_o, a["leftX"], *a["DepProj"])
     assert_close(np.asarray(eb_g), eb_o, TOL, "proj_fld into a re-zeroed resident EB")
+
+
+def test_input_only_arrays_are_upgraded_where_they_are_held(ofim, gfim, resident):
+    """gradRho_fb_prv is never returned by a call: the driver keeps its np.zeros object and `prv[:] = nxt`
+    (chimera_main.py:110) would be a CPU copy.  The first call that sees it as intent(in) rebinds the dictionary entry
+    to a ResidentArray view of the same memory."""
+    from util import crandn
+
+    S = setup("real_m2")
+    a = S.Args
+    rng = np.random.default_rng(9)
+    data = {"prv": np.zeros(S.shape_fb + (3,), dtype=complex, order="F"), "nxt": None,
+            "J": crandn(rng, S.shape_fb + (3,)), "v": crandn(rng, S.shape_fb + (3,))}
+    raw = data["prv"]
+    data["nxt"] = gfim.omp_mult_vec(crandn(rng, S.shape_fb + (3,)), a["DepFact"])  # resident (returned by a call)
+    want = ofim.poiss_corr(data["J"].copy(order="F"), data["v"], raw.copy(order="F"), np.asarray(data["nxt"]), a["dt_inv"], a["PoissFact"])
+    got = gfim.poiss_corr(data["J"].copy(order="F"), data["v"], data["prv"], data["nxt"], a["dt_inv"], a["PoissFact"])
+    assert_close(np.asarray(got), want, TOL, "poiss_corr")
+    assert isinstance(data["prv"], resident.ResidentArray) and data["prv"].base is raw  # same memory, upgraded in the dict
+    data["prv"][:] = data["nxt"]  # now a device copy
+    assert np.array_equal(raw, np.asarray(data["nxt"]))
