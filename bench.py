@@ -35,6 +35,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c1a", "c1b", "c2_static", "c2_pic"],
+                    help="c3 = BASELINE configs[2], the LWFA synthetic case the metric is quoted on (default); c1a / c1b = the "
+                         "FEL and LPA stages of configs[0] (the shipped demo), c2_* = the two stages of configs[1] (space-charge "
+                         "drift) at their own small grids, one GPU")
     ap.add_argument("--ppc", type=int, default=48, choices=[16, 48],
                     help="macro-particles per cell: 48 = 1.0e8 particles (the '~1e8' BASELINE.json names), 16 = 3.4e7")
     ap.add_argument("--nx", type=int, default=4096)
@@ -476,13 +480,209 @@ def run_e2e_per_call(a, torch, S, eng, state, resident):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE configs[0] / configs[1]: the shipped demos at their own (small) grids, one GPU
+SMALL_NAMES = {
+    "c1a": "fel-lpa-demo FEL stage (doc/tests/fel-testrun.py): envelope solver Nx=120 Nr=85, 1 mode, analytic undulator, "
+           "'Staged' frame every step",
+    "c1b": "fel-lpa-demo LPA stage (doc/tests/lpa-testrun.py): real solver Nx=528 Nr=65, 2 modes, SpaceCharge + still ions, a0=3 pulse",
+    "c2_static": "space-charge drift demo, 'StaticKick' stage: Nx=304 Nr=301, 2 modes, Gaussian beam px=50, 'Staged' frame every step",
+    "c2_pic": "space-charge drift demo, 'SpaceCharge' stage: Nx=304 Nr=301, 2 modes, Gaussian beam px=50, 'Staged' frame every step",
+}
+
+
+def small_build(a, fim, engine):
+    """(S, species, eg0, case) and, with engine=True, the resident engine after make_halfstep"""
+    import copy
+
+    from chimera_b200 import synthetic
+    from chimera_b200.solver_setup import SolverSetup
+
+    c = synthetic.baseline_case(a.config)
+    S = SolverSetup(copy.deepcopy(c["cfg"]))
+    species = synthetic.baseline_species(S, c)
+    eg0 = S.add_gauss_beam(fim, c["laser"]) if c["laser"] else S.zeros_fb(6)
+    eng = None
+    if engine:
+        from chimera_b200.engine import Engine
+
+        dev = c["device"]
+        eng = Engine(S, undulator=dict(zip(("a0", "lambda", "X0", "Lx"), dev[1])) if dev else None)
+        for sp in species:
+            eng.add_species(sp["coords"], sp["momenta"], sp["weights"], charge=sp["charge"], mass=sp["mass"], still=sp["still"])
+        eng.upload("EG_fb", eg0)
+        if c["window"]:
+            eng.set_window(c["window"][0], staged=c["window"][1])
+        eng.make_halfstep(px0=c["px0"], background=any(sp["still"] for sp in species))
+        eng.sync()
+    return S, species, eg0, c, eng
+
+
+def small_refrun(fim, S, species, eg0, c):
+    """the reference's step sequence (tests/pic_ref.py) on a fimera backend: the per-function drop-in with host
+    numpy buffers (e2e) or the CPU oracle (cpu_baseline)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import copy
+
+    from pic_ref import RefRun, RefSpecies
+
+    S = copy.copy(S)
+    S.Args = copy.deepcopy(S.Args)  # a moving frame shifts the grid in the solver dictionary
+    dev = c["device"]
+    sp = [RefSpecies(s["coords"], s["momenta"], s["weights"], charge=s["charge"], mass=s["mass"], still=s["still"],
+                     device=(getattr(fim, dev[0]), dev[1]) if (dev and not s["still"]) else None) for s in species]
+    run = RefRun(fim, S, sp, background=any(s["still"] for s in species))
+    run.EG_fb[:] = eg0
+    if c["window"]:
+        v, staged = c["window"]
+        dt = S.Args["dt"]
+        run.window = (0.5 * v * dt, 0.5 * v * dt) if staged else (v * dt, 0.0)
+    run.make_halfstep(px0=c["px0"])
+    return run
+
+
+def run_small(a):
+    """one GPU, device-resident engine; `value`: every step timed on its own with the L2 flushed in between (the
+    whole problem fits the 126 MB L2), `l2_warm`: the K steps in one multi-step call, as a simulation runs them"""
+    import torch
+
+    import chimera_b200.fimera as gfim
+    from chimera_b200 import _lib
+
+    torch.cuda.set_device(0)
+    lib = _lib.load()
+    lib.chimera_set_device(0)
+    S, species, eg0, c, eng = small_build(a, gfim, engine=True)
+    # a side stream that torch's events see too (graph capture is not possible on the legacy default stream)
+    side = torch.cuda.Stream()
+    eng.use_stream(side.cuda_stream)
+    torch.cuda.set_stream(side)
+    n = sum(sp["weights"].size for sp in species if not sp["still"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    eng.step(a.warmup)
+    torch.cuda.synchronize()
+    # (1) L2 flushed between steps
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    evs = []
+    l0 = _lib.kernel_launches()
+    for _ in range(a.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.step(1)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    launches = _lib.kernel_launches() - l0
+    ms_cold = sum(e0.elapsed_time(e1) for e0, e1 in evs) / a.steps
+    # (2) the same K steps as one multi-step call (fused across steps, graph replay between re-binnings)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    eng.step(a.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_warm = e0.elapsed_time(e1) / a.steps
+    graphs = eng.graph_info()
+    clocks = sampler.finish()
+    # (3) once more with per-phase events and the contraction profile (graphs off while profiling)
+    eng.profile(True)
+    eng.timings(reset=True)
+    lib.chimera_gemm_profile(1)
+    e0.record()
+    eng.step(a.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_prof = e0.elapsed_time(e1) / a.steps
+    phases = eng.timings(reset=True)
+    eng.profile(False)
+    g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    lib.chimera_gemm_profile_read(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n), 1)
+    lib.chimera_gemm_profile(0)
+    fp64_peak = dgemm_peak_tflops(torch)
+    stages = {k: {"ms_per_call": ms / calls, "share": ms / (ms_prof * a.steps)} for k, (ms, calls) in phases.items()}
+    gemm = {"ms_per_launch": g_ms.value / max(g_n.value, 1), "launches_per_step": g_n.value / a.steps,
+            "share": g_ms.value / (ms_prof * a.steps), "tflops": g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value else 0.0}
+    out = {
+        "metric": METRIC, "value": n / (ms_cold * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_cold, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": SMALL_NAMES[a.config], "particles_total": n, "grid": list(S.shape_sp),
+                   "l2": "L2 flushed between timed steps (256 MB write); every step timed on its own with CUDA events"},
+        "l2_warm": {"value": n / (ms_warm * 1e-3), "ms_per_step": ms_warm, "step_graphs": graphs[0],
+                    "note": "the same K steps as ONE multi-step call (particle work fused across steps, the fused step replayed "
+                            "as a CUDA graph where no window moves every step), no flush"},
+        "gpu_launches": int(launches), "launches_per_step": launches / a.steps, "clocks": clocks,
+        "roofline": {"kernel": "gemm_dmma_k (DHT + mode-coupling contractions)", "bound": "tensor", "achieved": gemm["tflops"],
+                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm["tflops"] / fp64_peak, "traffic": None,
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "share_of_step": gemm["share"]},
+        "stages": stages, "gemm": gemm, "fp64_peak_tflops": fp64_peak,
+        "dht_psatd_ms_per_step": sum(v["ms_per_call"] for k, v in stages.items()
+                                     if k in ("fb_in_J", "fb_in_rho", "poisson", "maxwell", "fields_out", "static_fields")),
+    }
+    eng.close()
+    # end to end: the per-function drop-in with HOST numpy buffers (every call copies in and out), reference sequence
+    if not a.no_e2e:
+        run = small_refrun(gfim, S, species, eg0, c)
+        run.make_step()
+        torch.cuda.synchronize()
+        lib.chimera_host_traffic(None, None, 1)
+        t = time.perf_counter()
+        ne = max(3, min(a.steps, 10))
+        for _ in range(ne):
+            run.make_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t) / ne
+        h2d, d2h = ctypes.c_longlong(), ctypes.c_longlong()
+        lib.chimera_host_traffic(ctypes.byref(h2d), ctypes.byref(d2h), 1)
+        out["e2e"] = {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": ne, "h2d_bytes_per_step": int(h2d.value // ne),
+                      "d2h_bytes_per_step": int(d2h.value // ne),
+                      "path": "chimera_b200.fimera per-function drop-in driven by the reference's make_step sequence: pageable host "
+                              "numpy buffers, every call copies its arguments in and its results out"}
+    if not a.no_cpu:
+        out["cpu_baseline"] = cpu_small(a, S, species, eg0, c, steps=3, warmup=1)
+    print(json.dumps(out))
+
+
+def cpu_small(a, S, species, eg0, c, steps, warmup):
+    fast, cores = load_cpu_oracle()
+    timer = StageTimer(fast)
+    run = small_refrun(timer, S, species, eg0, c)
+    n = sum(sp["weights"].size for sp in species if not sp["still"])
+    r = cpu_timed_steps(run, timer, n, steps=steps, warmup=warmup, budget_s=60)
+    r.update(unit=UNIT, cores=cores, kind="port",
+             sample="the whole workload (%d particles, grid %r), %d warm-up + %d timed RefRun.make_step; g++ -O3 -ffast-math -fopenmp "
+                    "build of oracle/chimera_oracle.cpp, OMP threads=%d, deposit chunks=%d as the configuration says"
+                    % (n, tuple(S.shape_sp), r["warmup_run"], r["steps_run"], cores, S.Args.get("Xchunked", (1, 0))[0]))
+    return r
+
+
+def run_reference_small(a):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    fast, _ = load_cpu_oracle()
+    S, species, eg0, c, _ = small_build(a, fast, engine=False)
+    r = cpu_small(a, S, species, eg0, c, steps=a.steps, warmup=1)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": r["steps_run"],
+        "warmup": r["warmup_run"], "steps_requested": a.steps, "warmup_requested": a.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": SMALL_NAMES[a.config]}, "cpu_baseline": r, "gpu_launches": 0,
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port; the Fortran cannot be built here) on the host cores
-CPU_STAGES = {  # BASELINE.md section 3 stage list -> the fimera calls that make it up
-    "push": ("push_coords", "push_velocs"), "gather": ("proj_fld",), "deposit_J": ("dep_curr_chnk",),
-    "deposit_rho": ("dep_dens_chnk",), "rebin": ("chunk_coords_boundaries", "align_data_vec", "align_data_scl"),
+CPU_STAGES = {  # BASELINE.md section 3 stage list -> the fimera calls that make it up (real and envelope families)
+    "push": ("push_coords", "push_velocs", "undul_analytic"), "gather": ("proj_fld", "proj_fld_env"),
+    "deposit_J": ("dep_curr_chnk", "dep_curr_env_chnk", "dep_curr", "dep_curr_env"),
+    "deposit_rho": ("dep_dens_chnk", "dep_dens_env_chnk", "dep_dens", "dep_dens_env"),
+    "rebin": ("chunk_coords_boundaries", "align_data_vec", "align_data_scl", "sortpartsout"),
     "dht_fwd_fft": ("fb_vec_in", "fb_scl_in"), "dht_bwd_fft": ("fb_eb_out",),
-    "mode_coupling": ("fb_grad", "fb_graddiv", "fb_rot"), "psatd": ("maxwell_push_with_spchrg",),
-    "poisson": ("poiss_corr",), "elementwise": ("omp_mult_vec", "omp_mult_scl", "omp_add_vec", "eb_correction"),
+    "mode_coupling": ("fb_grad", "fb_graddiv", "fb_rot", "fb_grad_env", "fb_graddiv_env", "fb_rot_env"),
+    "psatd": ("maxwell_push_with_spchrg", "maxwell_push_wo_spchrg", "maxwell_init_push", "field_drift"),
+    "poisson": ("poiss_corr", "poiss_corr_stat"),
+    "elementwise": ("omp_mult_vec", "omp_mult_scl", "omp_add_vec", "eb_correction", "eb_correction_env"),
 }
 
 
@@ -669,7 +869,9 @@ def run_reference(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
+    if args.config != "c3":
+        (run_reference_small if args.impl == "reference" else run_small)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

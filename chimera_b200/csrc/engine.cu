@@ -56,6 +56,15 @@ struct chimera_engine {
   int host_id = -1;
   int host_mid_done = 0;
   int fuse = 1;  // use the fused particle kernel inside multi-step calls (chimera_engine_set_fuse)
+  // One fused step (particle kernel + the whole spectral update, ~50 launches) captured as a CUDA graph and replayed
+  // for the steps between two re-binnings: on the demo-size grids a step is a few hundred microseconds and the launch
+  // gaps are a fifth of it.  Two graphs: gradRho_fb_prv / _nxt swap every step (ph_fb_in_rho).
+  struct StepGraph { cudaGraphExec_t exec; const void* nxt; long long launches; };
+  std::vector<StepGraph> graphs;
+  unsigned long long graph_sig = 0;
+  unsigned long long graph_warm_gen = ~0ull;  // scratch generation under which a fused step last ran eagerly
+  int graph_state = 0;  // 1: graphs in use, -1: a capture failed, graphs off for this engine
+  int use_graph = 1;    // chimera_engine_set_graph
   double dev_time = 0.0;  // i_step * TimeStep seen by time-dependent devices in the next gather + push
   // window that moves every step inside chimera_engine_step (chimera_engine_set_window): shift at stage 1 (before
   // push_coords) and at stage 2 (between dep_curr and dep_dens), chimera_main.py:286-302
@@ -834,6 +843,8 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
 int chimera_engine_destroy(chimera_engine* e) {
   if (!e) return 0;
   cudaStreamSynchronize(e->st);
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
   for (auto& kv : e->arr) cudaFree(kv.second.p);
   for (auto& s : e->sp) {
     cudaFree(s.x); cudaFree(s.xh); cudaFree(s.p); cudaFree(s.w);
@@ -1228,6 +1239,103 @@ int chimera_engine_run(chimera_engine* e, int phase, double arg) {
   return run_phase(e, phase, arg);
 }
 
+// ---- CUDA graph of one fused step --------------------------------------------------------------------------------
+static int fused_step_phases(chimera_engine* e) {
+  const auto& c = e->cfg;
+  CHB_TRY(run_phase(e, CHB_PARTICLES_FUSED, 1));
+  CHB_TRY(run_phase(e, CHB_FB_IN_J, 0));
+  if (c.space_charge) CHB_TRY(run_phase(e, CHB_FB_IN_RHO, 0));
+  CHB_TRY(run_phase(e, CHB_POISSON, 0));
+  CHB_TRY(run_phase(e, CHB_MAXWELL, 0));
+  return run_phase(e, CHB_FIELDS_OUT, 0);
+}
+
+static void drop_graphs(chimera_engine* e) {
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
+// Kernel arguments are frozen in a graph: usable only while nothing they depend on changes from step to step -- no
+// window that moves every step (leftX), no time-dependent device list, no per-phase event timing.
+static bool graph_usable(chimera_engine* e) {
+  if (!e->use_graph || e->graph_state < 0 || e->profile || gemm_profile_enabled() || slab(e)) return false;
+  if (e->win_s1 != 0.0 || e->win_s2 != 0.0) return false;
+  for (auto& s : e->sp)
+    if (!s.devs.empty()) return false;
+  return true;
+}
+
+static unsigned long long graph_signature(chimera_engine* e) {
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
+  mix(e->scr.gen);
+  mix((unsigned long long)(e->scr.blocks.empty() ? nullptr : e->scr.blocks[0].p));
+  mix((unsigned long long)e->st);
+  for (auto& s : e->sp) { mix((unsigned long long)s.np); mix((unsigned long long)s.ncta_f); mix((unsigned long long)s.x); }
+  return h;
+}
+
+static int step_graphed(chimera_engine* e) {
+  const unsigned long long sig = graph_signature(e);
+  if (sig != e->graph_sig) {  // particle counts, buffers or the scratch block changed: the recorded arguments are stale
+    drop_graphs(e);
+    e->graph_sig = sig;
+  }
+  if (e->graph_warm_gen != e->scr.gen) {  // one eager step sizes the scratch and creates the FFT plans
+    CHB_TRY(fused_step_phases(e));
+    e->graph_warm_gen = e->scr.gen;
+    return 0;
+  }
+  e->graph_state = 1;
+  const void* nxt = e->cfg.space_charge ? (const void*)e->A("gradRho_fb_nxt") : nullptr;
+  for (auto& g : e->graphs)
+    if (g.nxt == nxt) {
+      CHB_CUDA(cudaGraphLaunch(g.exec, e->st));
+      // the host-side part of the phases
+      if (e->cfg.space_charge) std::swap(e->arr["gradRho_fb_prv"], e->arr["gradRho_fb_nxt"]);
+      e->leftX_J = NAN;
+      g_launches += g.launches;
+      return 0;
+    }
+  const long long l0 = g_launches;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    e->graph_state = -1;
+    return fused_step_phases(e);
+  }
+  const int rc = fused_step_phases(e);  // launches are recorded, nothing runs; the host-side state advances
+  const cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+    cudaGraphDestroy(graph);
+    e->graphs.push_back({exec, nxt, g_launches - l0});
+    CHB_CUDA(cudaGraphLaunch(exec, e->st));
+    return 0;
+  }
+  // capture failed: undo the host-side swap, switch graphs off for this engine and run the step eagerly
+  cudaGetLastError();
+  if (graph) cudaGraphDestroy(graph);
+  if (e->cfg.space_charge && (const void*)e->A("gradRho_fb_nxt") != nxt) std::swap(e->arr["gradRho_fb_prv"], e->arr["gradRho_fb_nxt"]);
+  e->graph_state = -1;
+  return fused_step_phases(e);
+}
+
+int chimera_engine_set_graph(chimera_engine* e, int on) {
+  ENG_CHECK(e);
+  e->use_graph = on ? 1 : 0;
+  if (!on) { drop_graphs(e); e->graph_sig = 0; }
+  else if (e->graph_state < 0) e->graph_state = 0;
+  return 0;
+}
+
+int chimera_engine_graph_info(chimera_engine* e, int* ngraphs, int* state) {
+  ENG_CHECK(e);
+  if (ngraphs) *ngraphs = (int)e->graphs.size();
+  if (state) *state = e->graph_state;
+  return 0;
+}
+
 int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
   ENG_CHECK(e);
   const auto& c = e->cfg;
@@ -1242,6 +1350,10 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
     const bool sort_now = c.sort_every > 0 && istep % c.sort_every == 0;
     e->dev_time = (double)(istep - 1) * c.dt;  // the pending gather + push closes step istep - 1 (make_device(istep - 1))
     if (gather_pending && !sort_now && e->fuse && !c.static_kick) {
+      if (graph_usable(e)) {  // the whole step, spectral update included, as one graph launch
+        CHB_TRY(step_graphed(e));
+        continue;
+      }
       CHB_TRY(run_phase(e, CHB_PARTICLES_FUSED, 1));
     } else if (e->fuse) {
       // re-binning step (the sort sits between push_coords and the deposits) or the first step of the call: one

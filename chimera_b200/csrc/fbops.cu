@@ -12,6 +12,7 @@ int Scratch::reserve(size_t bytes) {
   Block nb{nullptr, round_mb(bytes + 256), 0};
   CHB_CUDA(cudaMalloc((void**)&nb.p, nb.cap));
   blocks.push_back(nb);
+  ++gen;
   return 0;
 }
 void* Scratch::take(size_t bytes) {
@@ -36,6 +37,7 @@ void* Scratch::take(size_t bytes) {
         return nullptr;
       }
       blocks.push_back(nb);
+      ++gen;
     }
   }
   return nullptr;
@@ -45,6 +47,7 @@ void Scratch::reset() {
     size_t tot = 0;
     for (auto& b : blocks) { tot += b.cap; cudaFree(b.p); }
     blocks.clear();
+    ++gen;
     Block nb{nullptr, round_mb(tot), 0};
     if (cudaMalloc((void**)&nb.p, nb.cap) == cudaSuccess) blocks.push_back(nb);
   }

@@ -18,6 +18,7 @@ struct Scratch {
   struct Block { char* p; size_t cap, used; };
   std::vector<Block> blocks;
   size_t high = 0;
+  unsigned long long gen = 0;          // bumped whenever a block is allocated or freed (captured graphs hold its addresses)
   int reserve(size_t bytes);            // make sure one block of at least `bytes` exists
   void* take(size_t bytes);             // 256-byte aligned; nullptr only if cudaMalloc fails
   template <typename T> T* take_n(i64 n) { return (T*)take(sizeof(T) * (size_t)(n > 0 ? n : 1)); }

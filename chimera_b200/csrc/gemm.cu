@@ -7,7 +7,9 @@
 //
 // sm_100a mapping.  tcgen05 has no f64 kind, so FP64 tensor work is mma.sync m8n8k4 (SASS DMMA).
 //   * CTA tile 128 x 64 x 16, 8 warps as 4(M) x 2(N), warp tile 32 x 32 = 16 DMMA per k4 step,
-//     accumulators in registers (64 per lane).
+//     accumulators in registers (64 per lane).  A 64 x 64 x 16 variant (warp tile 16 x 32) serves the launches whose
+//     128-row grid would not fill the GPU twice over: the demo-size grids (Nx = 120 .. 528) and the 512-row kx slabs
+//     of an 8-GPU run.
 //   * A (the data) is staged by the TMA engine: one cp.async.bulk (UBLKCP) per k-row of the tile
 //     into rows padded to 132 doubles, which makes the per-lane A-fragment reads (8 rows x 4 k)
 //     bank-conflict free; completion is tracked with an mbarrier per stage (expect_tx).
@@ -24,12 +26,14 @@
 namespace chb {
 
 namespace {
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3;
-constexpr int SA = BM + 4;                       // padded row stride of the A tile (doubles)
-constexpr int A_STAGE = BK * SA;                 // doubles
+constexpr int BN = 64, BK = 16, STAGES = 3;
 constexpr int B_STAGE = BK * BN;                 // doubles
 constexpr int GEMM_THREADS = 256;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + STAGES * sizeof(uint64_t);
+template <int BM> struct Tile {
+  static constexpr int SA = BM + 4;              // padded row stride of the A tile (doubles)
+  static constexpr int A_STAGE = BK * SA;        // doubles
+  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + STAGES * sizeof(uint64_t);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -80,8 +84,11 @@ __global__ void __launch_bounds__(256) gemm_pack_b_k(double* __restrict__ Bp, co
   Bp[e] = (k < K && n < N) ? B[k + ldb * n] : 0.0;
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+template <int BM>
+__global__ void __launch_bounds__(GEMM_THREADS, BM == 128 ? 2 : 4)
 gemm_dmma_k(const __grid_constant__ GemmBatch batch, i64 M, i64 N, i64 K, i64 lda, i64 ldc, int KT) {
+  constexpr int SA = Tile<BM>::SA, A_STAGE = Tile<BM>::A_STAGE;
+  constexpr int WM = BM / 4, MF = WM / 8;  // warp tile rows, 8-row fragments per warp
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sA = reinterpret_cast<double*>(smem_raw);
   double* sB = sA + STAGES * A_STAGE;
@@ -123,26 +130,26 @@ gemm_dmma_k(const __grid_constant__ GemmBatch batch, i64 M, i64 N, i64 K, i64 ld
   if (warp == 0)
     for (int kt = 0; kt < STAGES && kt < KT; ++kt) issue(kt);
 
-  double acc[4][4][2];
+  double acc[MF][4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MF; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int kt = 0; kt < KT; ++kt) {
     const int s = kt % STAGES;
     mbar_wait(&full[s], (uint32_t)((kt / STAGES) & 1));
-    const double* a_s = sA + s * A_STAGE + wm * 32 + g;
+    const double* a_s = sA + s * A_STAGE + wm * WM + g;
     const double* b_s = sB + s * B_STAGE + wn * 4 * 32 + lane;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      double a[4], b[4];
+      double a[MF], b[4];
 #pragma unroll
-      for (int mf = 0; mf < 4; ++mf) a[mf] = a_s[(4 * ks + t) * SA + 8 * mf];
+      for (int mf = 0; mf < MF; ++mf) a[mf] = a_s[(4 * ks + t) * SA + 8 * mf];
 #pragma unroll
       for (int nf = 0; nf < 4; ++nf) b[nf] = b_s[(ks * 8 + nf) * 32];
 #pragma unroll
-      for (int mf = 0; mf < 4; ++mf)
+      for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
         for (int nf = 0; nf < 4; ++nf) dmma(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
     }
@@ -153,8 +160,8 @@ gemm_dmma_k(const __grid_constant__ GemmBatch batch, i64 M, i64 N, i64 K, i64 ld
   // epilogue: lane (g,t) owns C[8mf+g][8nf+2t..2t+1]
   const double alpha = pr.alpha, beta = pr.beta;
 #pragma unroll
-  for (int mf = 0; mf < 4; ++mf) {
-    const i64 row = m0 + wm * 32 + 8 * mf + g;
+  for (int mf = 0; mf < MF; ++mf) {
+    const i64 row = m0 + wm * WM + 8 * mf + g;
     if (row >= M) continue;
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf)
@@ -218,6 +225,7 @@ void gemm_profile_enable(int on) {
   g_prof.drain();
   g_prof.on = on;
 }
+int gemm_profile_enabled() { return g_prof.on; }
 void gemm_profile_read(double* ms, double* flops, long long* launches, int reset) {
   g_prof.drain();
   if (ms) *ms = g_prof.ms;
@@ -230,24 +238,30 @@ int launch_gemm(cudaStream_t st, const GemmBatch& batch, i64 M, i64 N, i64 K, i6
   if (batch.count <= 0 || M <= 0 || N <= 0) return 0;
   if (batch.count > kGemmMaxBatch) { set_error("gemm batch too large"); return 4; }
   if ((M & 1) || (lda & 1)) { set_error("gemm: M and lda must be even (complex-interleaved rows)"); return 4; }
+  // 64-row tiles when the 128-row grid is short of two full waves of its 2 CTAs per SM (148 SMs)
+  const i64 ctas128 = ((M + 127) / 128) * ((N + BN - 1) / BN) * batch.count;
+  const bool small = ctas128 < 4 * 148;
   {  // the attribute is per device: remember which devices have it (a process may drive several)
     static std::atomic<unsigned long long> attr_mask{0};
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_mask.load(std::memory_order_relaxed) & bit)) {
-      CHB_CUDA(cudaFuncSetAttribute(gemm_dmma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+      CHB_CUDA(cudaFuncSetAttribute(gemm_dmma_k<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<128>::SMEM));
+      CHB_CUDA(cudaFuncSetAttribute(gemm_dmma_k<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<64>::SMEM));
       attr_mask.fetch_or(bit, std::memory_order_relaxed);
     }
   }
   const int KT = (int)((K + BK - 1) / BK);
-  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)batch.count);
+  const int bm = small ? 64 : 128;
+  dim3 grid((unsigned)((M + bm - 1) / bm), (unsigned)((N + BN - 1) / BN), (unsigned)batch.count);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     e0 = g_prof.get(); e1 = g_prof.get();
     cudaEventRecord(e0, st);
   }
-  gemm_dmma_k<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(batch, M, N, K, lda, ldc, KT);
+  if (small) gemm_dmma_k<64><<<grid, GEMM_THREADS, Tile<64>::SMEM, st>>>(batch, M, N, K, lda, ldc, KT);
+  else gemm_dmma_k<128><<<grid, GEMM_THREADS, Tile<128>::SMEM, st>>>(batch, M, N, K, lda, ldc, KT);
   if (g_prof.on) {
     cudaEventRecord(e1, st);
     g_prof.pending.push_back({e0, e1});

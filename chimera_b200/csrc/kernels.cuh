@@ -208,6 +208,7 @@ i64 gemm_packed_size(i64 K, i64 N);  // doubles
 int launch_gemm_pack_b(cudaStream_t st, double* Bp, const double* B, i64 K, i64 N, i64 ldb);
 int launch_gemm(cudaStream_t st, const GemmBatch& batch, i64 M, i64 N, i64 K, i64 lda, i64 ldc);
 void gemm_profile_enable(int on);
+int gemm_profile_enabled();
 void gemm_profile_read(double* ms, double* flops, long long* launches, int reset);
 
 // ---- spectral.cu : elementwise kernels of the Fourier-Bessel PSATD update

@@ -454,6 +454,16 @@ class Engine:
         self.fuse = bool(on)
         self._check(self.lib.chimera_engine_set_fuse(self._h, int(self.fuse)))
 
+    def set_graph(self, on=True):
+        """Replay the fused step as a CUDA graph between two re-binnings (default on; single GPU, no per-step window)."""
+        self._check(self.lib.chimera_engine_set_graph(self._h, int(bool(on))))
+
+    def graph_info(self):
+        """(number of cached step graphs, state: 1 = in use, 0 = not warmed up, -1 = capture failed, graphs off)"""
+        n, st = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self.lib.chimera_engine_graph_info(self._h, ctypes.byref(n), ctypes.byref(st)))
+        return n.value, st.value
+
     def use_stream(self, cuda_stream_ptr):
         self._check(self.lib.chimera_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
 

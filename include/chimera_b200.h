@@ -356,6 +356,10 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps);
 int chimera_engine_sync(chimera_engine* e);
 /* multi-step calls fuse the particle work between two field solves into one kernel (default on) */
 int chimera_engine_set_fuse(chimera_engine* e, int on);
+/* replay the fused step (particle kernel + spectral update) as a CUDA graph between two re-binnings (default on; used when
+   no window moves every step and no device field depends on time) */
+int chimera_engine_set_graph(chimera_engine* e, int on);
+int chimera_engine_graph_info(chimera_engine* e, int* ngraphs, int* state); /* cached graphs; state 1 warm, -1 capture failed */
 /* One make_step (chimera_main.py:82-92) with the PIC state in HOST buffers, the reference's calling model:
  * coords/momenta (3,np) Fortran-ordered in-out, coords_half (3,np) out, weights (np) in (rewritten in the
  * new particle order on re-binning steps), EG_fb (nx,nkr,nm,6) and gradRho_fb_nxt (nx,nkr,nm,3) complex

@@ -544,3 +544,38 @@ def test_engine_static_kick_schedule(ofim, gfim):
     eng.step(6)
     compare_state(ref, eng, 50 * TOL, names=("J", "Rho", "EG_fb", "EB"))
     eng.close()
+
+
+@pytest.mark.parametrize("name,ions", [("real_m2", True), ("real_m3", False), ("env_m3", False)])
+def test_step_graph_replay_matches_eager_steps(ofim, gfim, name, ions):
+    """the fused step replayed as a CUDA graph between two re-binnings (csrc/engine.cu step_graphed) against the same
+    engine stepping eagerly: 25 steps cross two re-binnings (graphs re-used after each) and both gradRho parities"""
+    from chimera_b200.engine import Engine
+
+    S = SolverSetup(copy.deepcopy(SETUPS[name]))
+    x, p, w = plasma(S, 2, 2, 81)
+    eg0 = seed_fields(S, 82, 0.1)
+    engines = []
+    for graph in (True, False):
+        e = Engine(S, sort_every=9)
+        e.set_graph(graph)
+        e.add_species(x, p, w)
+        if ions:
+            xi, pi_, wi = plasma(S, 2, 2, 88)
+            e.add_species(xi, 0 * pi_, -wi, charge=1.0, mass=1886.0, still=True)
+        e.upload("EG_fb", eg0)
+        e.make_halfstep(background=ions)
+        e.step(25)
+        engines.append(e)
+    eng, eager = engines
+    n, state = eng.graph_info()
+    assert state == 1 and n == (2 if eng.cfg.space_charge else 1), (n, state)
+    assert eager.graph_info()[0] == 0
+    for nm in ("EG_fb", "EB", "J"):
+        assert_close(eng.download(nm), eager.download(nm), 100 * TOL, nm)
+    xa, _, pa, wa = eng.particles(0)
+    xb, _, pb, wb = eager.particles(0)
+    perm = match(wb, wa)
+    assert_close(pa[:, perm], pb, 100 * TOL, "momenta")
+    eng.close()
+    eager.close()
