@@ -65,6 +65,7 @@ struct chimera_engine {
   unsigned long long graph_warm_gen = ~0ull;  // scratch generation under which a fused step last ran eagerly
   int graph_state = 0;  // 1: graphs in use, -1: a capture failed, graphs off for this engine
   int use_graph = 1;    // chimera_engine_set_graph
+  std::vector<double> static_px;  // mean momentum per species for the next static_fields phase (multi-rank runs)
   double dev_time = 0.0;  // i_step * TimeStep seen by time-dependent devices in the next gather + push
   // window that moves every step inside chimera_engine_step (chimera_engine_set_window): shift at stage 1 (before
   // push_coords) and at stage 2 (between dep_curr and dep_dens), chimera_main.py:286-302
@@ -480,33 +481,42 @@ int ph_maxwell(chimera_engine* e) {
 // quasi-static field of each species' charge and current moving with its mean momentum
 int ph_static_fields(chimera_engine* e) {
   const auto& c = e->cfg;
-  if (slab(e)) { set_error("StaticKick schedule is not available on a kx-slab engine"); return 2; }
   if (!e->arr.count("w")) { set_error("StaticKick schedule: engine was created without static_kick"); return 2; }
-  const i64 P = c.nx * c.nkr * c.nm;
+  const i64 nxl = nxs(e);  // kx rows held here: all of them, or this rank's slab (every operation below is per kx row)
+  const i64 P = nxl * c.nkr * c.nm;
   FBCtx fb = fbctx(e);
   CHB_CUDA(cudaMemsetAsync(e->A("EG_fb"), 0, sizeof(cd) * P * 6, e->st));
-  for (auto& s : e->sp) {
-    if (s.np == 0) continue;
-    // PXmean = sum(px w) / sum(w) (chimera_main.py:121-122): reduced on the device, 16 doubles to the host
-    double* d_m = e->scr.take_n<double>(16);
-    if (!d_m) return 6;
-    double m[16];
-    CHB_TRY(launch_beam_moments(e->st, s.xh, s.p, s.w, s.cap, s.np, d_m));
-    CHB_CUDA(cudaMemcpyAsync(m, d_m, sizeof(m), cudaMemcpyDeviceToHost, e->st));
-    CHB_CUDA(cudaStreamSynchronize(e->st));
-    const double px = m[5] / m[0];
+  for (size_t is = 0; is < e->sp.size(); ++is) {
+    auto& s = e->sp[is];
+    double px;
+    if (is < e->static_px.size()) {
+      // given from outside (chimera_engine_set_static_px): across ranks the 16 moments are all-reduced first
+      px = e->static_px[is];
+      if (std::isnan(px)) continue;  // the species is empty on every rank
+    } else {
+      if (s.np == 0) continue;
+      // PXmean = sum(px w) / sum(w) (chimera_main.py:121-122): reduced on the device, 16 doubles to the host
+      double* d_m = e->scr.take_n<double>(16);
+      if (!d_m) return 6;
+      double m[16];
+      CHB_TRY(launch_beam_moments(e->st, s.xh, s.p, s.w, s.cap, s.np, d_m));
+      CHB_CUDA(cudaMemcpyAsync(m, d_m, sizeof(m), cudaMemcpyDeviceToHost, e->st));
+      CHB_CUDA(cudaStreamSynchronize(e->st));
+      px = m[5] / m[0];
+    }
     const double beta0 = px / sqrt(1.0 + px * px);
     if (c.poisson_iters > 0) {  // solvers.py:360-383 poiss_corr_stat (one pass, unless NoPoissonCorrection)
-      cd* DT = e->scr.take_n<cd>(c.nx);
+      cd* DT = e->scr.take_n<cd>(nxl);
       if (!DT) return 6;
-      CHB_TRY(launch_dt_stat(e->st, DT, e->D("kx"), beta0, c.nx));
+      CHB_TRY(launch_dt_stat(e->st, DT, e->D("kx"), beta0, nxl));
       CHB_TRY(fb_graddiv_dev(fb, e->A("vec_fb"), e->A("J_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e)));
-      CHB_TRY(launch_poiss_corr_stat(e->st, e->A("J_fb"), e->A("vec_fb"), e->A("gradRho_fb_nxt"), DT, e->D("PoissFact"), c.nx, P));
+      CHB_TRY(launch_poiss_corr_stat(e->st, e->A("J_fb"), e->A("vec_fb"), e->A("gradRho_fb_nxt"), DT, e->D("PoissFact"), nxl, P));
     }
     CHB_TRY(launch_maxwell_static_push(e->st, e->A("EG_fb"), e->A("J_fb"), e->A("gradRho_fb_nxt"), e->D("w"), e->D("kx"),
-                                       beta0, c.nx, P));
-    CHB_TRY(launch_field_drift(e->st, e->A("EG_fb"), e->D("kx"), beta0, c.dt, c.nx, c.nkr * c.nm * 6));
+                                       beta0, nxl, P));
+    CHB_TRY(launch_field_drift(e->st, e->A("EG_fb"), e->D("kx"), beta0, c.dt, nxl, c.nkr * c.nm * 6));
   }
+  e->static_px.clear();
   return 0;
 }
 
@@ -1326,6 +1336,14 @@ int chimera_engine_set_graph(chimera_engine* e, int on) {
   e->use_graph = on ? 1 : 0;
   if (!on) { drop_graphs(e); e->graph_sig = 0; }
   else if (e->graph_state < 0) e->graph_state = 0;
+  return 0;
+}
+
+// 'StaticKick' across ranks: PXmean of every species (chimera_main.py:121-122) from the all-reduced beam moments, used
+// by the next CHB_STATIC_FIELDS phase instead of the local reduction (NaN: species empty everywhere)
+int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n) {
+  ENG_CHECK(e);
+  e->static_px.assign(px, px + (n > 0 ? n : 0));
   return 0;
 }
 

@@ -186,7 +186,7 @@ class Engine:
         except Exception:
             pass
 
-    _KX_FIRST = ("kx", "kx_base", "DepFact", "PoissFact", "PSATD_E", "PSATD_G", "CPSATD1", "CPSATD2", "EG_fb", "J_fb",
+    _KX_FIRST = ("w", "kx", "kx_base", "DepFact", "PoissFact", "PSATD_E", "PSATD_G", "CPSATD1", "CPSATD2", "EG_fb", "J_fb",
                  "B_fb", "Rho_fb", "gradRho_fb_prv", "gradRho_fb_nxt", "vec_fb")
 
     def _upload_raw(self, name, arr):
@@ -296,7 +296,7 @@ class Engine:
             self._upload_raw("kx_full", np.asarray(self.setup.Args["kx"], dtype=np.float64))
             self._damp_ready = True
         if self.world > 1:
-            self._dist.all_gather_into_tensor(self.device_tensor("EG_gath"), self.device_tensor("EG_fb"), group=self._group)
+            self._all_gather_into(self.device_tensor("EG_gath"), self.device_tensor("EG_fb"))
 
     def set_window(self, velocity, time_step=None, staged=False):
         """A window that moves EVERY step (``MovingFrames`` entry with ``'Steps': 1``; the FEL runs,
@@ -477,7 +477,7 @@ class Engine:
         runs behind it"""
         w_j = self._dist.all_reduce(self.device_tensor("J"), group=self._group, async_op=True)
         w_r = None
-        if self.cfg.space_charge:
+        if self.cfg.space_charge or self.cfg.static_kick:
             w_r = self._dist.all_reduce(self.device_tensor("Rho"), group=self._group, async_op=True)
         return w_j, w_r
 
@@ -497,16 +497,24 @@ class Engine:
         slab, gath = self.device_tensor("EB_slab"), self.device_tensor("EB_gath")
         hs, hg = slab.numel() // 2, gath.numel() // 2
         self.run("fields_out_a", 1.0)
-        w_e = self._dist.all_gather_into_tensor(gath[:hg], slab[:hs], group=self._group, async_op=True)
+        w_e = self._all_gather_into(gath[:hg], slab[:hs], async_op=True)
         self.run("fields_out_a", 2.0)
-        w_b = self._dist.all_gather_into_tensor(gath[hg:], slab[hs:], group=self._group, async_op=True)
+        w_b = self._all_gather_into(gath[hg:], slab[hs:], async_op=True)
         w_e.wait()
         self.run("fields_out_b", 1.0)
         w_b.wait()
         self.run("fields_out_b", 2.0)
 
+    def _all_gather_into(self, out, inp, async_op=False):
+        """``all_gather_into_tensor``; on a backend without it (gloo: two ranks sharing one GPU in the tests) the list form"""
+        try:
+            return self._dist.all_gather_into_tensor(out, inp, group=self._group, async_op=async_op)
+        except (RuntimeError, NotImplementedError):
+            parts = list(out.view(self.world, -1).unbind(0))
+            return self._dist.all_gather(parts, inp.reshape(-1), group=self._group, async_op=async_op)
+
     def _allgather_eb(self):
-        self._dist.all_gather_into_tensor(self.device_tensor("EB_gath"), self.device_tensor("EB_slab"), group=self._group)
+        self._all_gather_into(self.device_tensor("EB_gath"), self.device_tensor("EB_slab"))
 
     def _deposit_and_reduce(self):
         self.run("deposit_J")
@@ -515,6 +523,17 @@ class Engine:
             self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
         if self.world > 1:
             self._allreduce_grids()
+
+    def _static_fields(self):
+        """``update_fields`` under 'StaticKick' (chimera_main.py:118-125) across ranks / on kx slabs: the mean momentum of
+        every species from its all-reduced moments, then the quasi-static field on this engine's kx rows"""
+        px = []
+        for sid in range(self.nspecies):
+            m = self.beam_moments(sid)
+            px.append(m[5] / m[0] if m[0] != 0.0 else float("nan"))
+        arr = (ctypes.c_double * len(px))(*px)
+        self._check(self.lib.chimera_engine_set_static_px(self._h, arr, len(px)))
+        self.run("static_fields")
 
     def deposit_background(self):
         """``ChimeraRun.dep_bg`` (chimera_main.py:220-248): still species -> BckGrndRho."""
@@ -554,8 +573,6 @@ class Engine:
             self._check(self.lib.chimera_engine_step(self._h, _i64(self.istep + 1), _i64(nsteps)))
             self.istep += nsteps
             return
-        if self.cfg.static_kick:
-            raise NotImplementedError("'StaticKick' schedule: single GPU, unsharded spectral solve only")
         # same schedule as chimera_engine_step (csrc/engine.cu): inside a multi-step call the particle work between
         # two field solves (gather + push of step k, push_coords + deposits of step k+1) is one fused kernel
         c = self.cfg
@@ -565,8 +582,8 @@ class Engine:
             sort_now = c.sort_every > 0 and self.istep % c.sort_every == 0
             self.set_time((self.istep - 1) * c.dt)  # the pending gather + push closes the previous step
             bg = 1.0 if self.rank == 0 else 0.0  # the background charge enters the all-reduced density once
-            if gather_pending and not sort_now and self.fuse:
-                self.run("particles_fused", bg)
+            if gather_pending and not sort_now and self.fuse and not c.static_kick:
+                self.run("particles_fused", bg)  # ('StaticKick' deposits rho on coords_halfstep: not the fused kernel's layout)
             elif self.fuse:  # re-binning step / first step of the call: one kernel before the sort, one after
                 if gather_pending:
                     self.run("gather_push_coords")
@@ -588,7 +605,7 @@ class Engine:
                 self.run("deposit_J")
                 if win:
                     self.run("window", 2.0)
-                if c.space_charge:
+                if c.space_charge or c.static_kick:
                     self.run("deposit_rho", bg)
             w_j = w_r = None
             if self.world > 1:
@@ -600,10 +617,13 @@ class Engine:
             self.run("fb_in_J")
             if w_r is not None:
                 w_r.wait()
-            if c.space_charge:
+            if c.space_charge or c.static_kick:
                 self.run("fb_in_rho")
-            self.run("poisson")
-            self.run("maxwell")
+            if c.static_kick:
+                self._static_fields()
+            else:
+                self.run("poisson")
+                self.run("maxwell")
             self._fields_out()
             gather_pending = True
         if gather_pending:

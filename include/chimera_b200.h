@@ -358,6 +358,7 @@ int chimera_engine_sync(chimera_engine* e);
 int chimera_engine_set_fuse(chimera_engine* e, int on);
 /* replay the fused step (particle kernel + spectral update) as a CUDA graph between two re-binnings (default on; used when
    no window moves every step and no device field depends on time) */
+int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n); /* 'StaticKick' across ranks: PXmean per species */
 int chimera_engine_set_graph(chimera_engine* e, int on);
 int chimera_engine_graph_info(chimera_engine* e, int* ngraphs, int* state); /* cached graphs; state 1 warm, -1 capture failed */
 /* One make_step (chimera_main.py:82-92) with the PIC state in HOST buffers, the reference's calling model:
