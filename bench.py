@@ -341,6 +341,19 @@ def run_ours(a):
                                          if k in ("fb_in_J", "fb_in_rho", "poisson", "maxwell", "fields_out", "fields_out_a", "fields_out_b")),
             "fp64_peak_tflops": fp64_peak,
         }
+    if world > 1:
+        # the collectives on their own: a short extra pass in which each one runs synchronously between two events
+        # (in the timed region above they overlap with the kernels; these are their stand-alone times)
+        eng.comm_profile = True
+        eng.comm_timings(reset=True)
+        eng.step(3)
+        comm = eng.comm_timings(reset=True)
+        eng.comm_profile = False
+        if rank == 0:
+            out["collectives"] = {k: {"ms_per_call": ms / n, "calls_per_step": n / 3.0} for k, (ms, n) in comm.items()}
+            out["collectives"]["dataflow"] = ("column blocks: reduce-scatter J/Rho -> x-FFT of the own block -> all-to-all to kx slabs; "
+                                              "slab -> all-to-all -> inverse x-FFT of the own block -> all-gather EB") if eng.colflow else \
+                                             "all-reduce J/Rho, x-FFT of everything on every rank, all-gather of the EB slabs"
     if a.fused_profile and rank == 0:
         lib.chimera_fused_profile(1)
         eng.profile(True)

@@ -22,7 +22,8 @@ extern long long g_h2d_bytes, g_d2h_bytes;  // api_host.cu: host<->device traffi
 
 struct NamedArray {
   void* p = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;  // the array proper (what upload / download move)
+  size_t alloc = 0;  // allocated: J, Rho, EB, EB_slab carry spare columns for the column-block dataflow
 };
 
 struct Species {
@@ -47,8 +48,11 @@ struct Species {
 
 using namespace chb;
 
+constexpr size_t kColPad = 64;  // spare columns of J / Rho / EB (column blocks of up to 64 ranks)
+
 struct chimera_engine {
   chimera_engine_config cfg;
+  int col_world = 0;  // > 0: column-block dataflow set up for this many ranks (chimera_engine_set_colflow)
   cudaStream_t st = nullptr;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of chimera_engine_step_host
   std::vector<cudaEvent_t> host_evs;
@@ -202,11 +206,12 @@ namespace {
 #define ENG_CHECK(e) \
   if (!(e)) { set_error("null engine handle"); return 2; }
 
-int alloc_named(chimera_engine* e, const char* name, size_t bytes, bool zero = true) {
+int alloc_named(chimera_engine* e, const char* name, size_t bytes, bool zero = true, size_t spare = 0) {
   NamedArray a;
   a.bytes = bytes;
-  CHB_CUDA(cudaMalloc(&a.p, bytes ? bytes : 16));
-  if (zero) CHB_CUDA(cudaMemsetAsync(a.p, 0, bytes ? bytes : 16, e->st));
+  a.alloc = bytes + spare;
+  CHB_CUDA(cudaMalloc(&a.p, a.alloc ? a.alloc : 16));
+  if (zero) CHB_CUDA(cudaMemsetAsync(a.p, 0, a.alloc ? a.alloc : 16, e->st));
   e->arr[name] = a;
   return 0;
 }
@@ -527,6 +532,54 @@ int ph_init_push(chimera_engine* e) {
                                   e->A("CPSATD2"), P);
 }
 
+// ---- column-block dataflow of the multi-rank solve ------------------------------------------
+// J (Nx, Nr, M, 3) is a column-major [Nx x C] matrix (x fastest).  Instead of all-reducing it and x-transforming all of it
+// on every rank: reduce-scatter by column block -> x-FFT of the own block -> all-to-all (column block -> kx slab) -> DHT on
+// the slab.  Backward: slab -> all-to-all (kx slab -> column block) -> inverse x-FFT of the own block -> all-gather of
+// the blocks, which land in EB in their natural order.  C is padded to a multiple of the rank count (kColPad).
+static i64 col_block(const chimera_engine* e, i64 ncols) { return (ncols + e->col_world - 1) / e->col_world; }
+
+// which: 0 = J (3 components), 1 = Rho.  In: "<X>_blk" (reduce-scatter output).  Out: "<X>_send".
+int ph_col_fwd(chimera_engine* e, int which) {
+  const auto& c = e->cfg;
+  if (!e->col_world) { set_error("column dataflow is not set up (chimera_engine_set_colflow)"); return 2; }
+  FBCtx fb = fbctx(e);
+  const i64 cb = col_block(e, c.nrn * c.nm * (which ? 1 : 3));
+  return col_fwd_dev(fb, e->A(which ? "Rho_send" : "J_send"), e->A(which ? "Rho_blk" : "J_blk"),
+                     (const i64*)e->arr["gather_map"].p, c.nx, nxs(e), cb);
+}
+
+// forward DHT of the slab that came in through the all-to-all ("J_in" / "Rho_in": (nx_slab, padded columns))
+int ph_fb_in_col(chimera_engine* e, int which) {
+  const auto& c = e->cfg;
+  FBCtx fb = fbctx(e);
+  if (!which) {
+    const double lx = std::isnan(e->leftX_J) ? c.leftX : e->leftX_J;
+    e->leftX_J = NAN;
+    return fb_in_slab_post_dev(fb, e->A("J_fb"), e->A("J_in"), lx, e->D("kx_base"), e->pInCurr, e->D("DepFact"), nxs(e), c.nrn,
+                               c.nm, c.nkr, 3);
+  }
+  std::swap(e->arr["gradRho_fb_prv"], e->arr["gradRho_fb_nxt"]);  // gradRho_fb_prv[:] = gradRho_fb_nxt
+  CHB_TRY(fb_in_slab_post_dev(fb, e->A("Rho_fb"), e->A("Rho_in"), c.leftX, e->D("kx_base"), e->pInCurr, e->D("DepFact"), nxs(e),
+                              c.nrn, c.nm, c.nkr, 1));
+  return fb_grad_dev(fb, e->A("gradRho_fb_nxt"), e->A("Rho_fb"), e->pDp, e->pDm, e->D("kx"), mdims(e));
+}
+
+// backward: "EB_recv" ((rank, column, row) blocks from the all-to-all) -> "EB_blk": rows put in place, inverse x-FFT
+int ph_col_bwd(chimera_engine* e) {
+  const auto& c = e->cfg;
+  if (!e->col_world) { set_error("column dataflow is not set up (chimera_engine_set_colflow)"); return 2; }
+  FBCtx fb = fbctx(e);
+  return fb_out_finish_dev(fb, e->A("EB_blk"), e->A("EB_recv"), (const i64*)e->arr["gather_map"].p, c.nx, nxs(e),
+                           col_block(e, c.nrn * c.nm * 6));
+}
+
+// after the all-gather of the blocks into EB: normalisation and ghost row (eb_correction, grid_deps.f90:219)
+int ph_eb_finish(chimera_engine* e) {
+  const auto& c = e->cfg;
+  return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
+}
+
 // fields out, first half: B from G, backward DHT (+ phase).  Unsharded: also the inverse x-FFT and the
 // normalisation, i.e. the whole of G2B_FBRot + fb_fld_out (solvers.py:536, 450).  kx-slab mode: stops at
 // "EB_slab"; the caller all-gathers the slabs into "EB_gath" and runs the second half.
@@ -778,6 +831,10 @@ int run_phase(chimera_engine* e, int phase, double arg) {
     case CHB_WINDOW: rc = ph_window(e, arg == 2.0 ? 2 : 1); break;
     case CHB_GATHER_PUSH_COORDS: rc = ph_gather_push_coords(e); break;
     case CHB_DEPOSIT_FUSED: rc = ph_deposit_fused(e, arg != 0.0); break;
+    case CHB_COL_FWD: rc = ph_col_fwd(e, arg != 0.0); break;
+    case CHB_FB_IN_COL: rc = ph_fb_in_col(e, arg != 0.0); break;
+    case CHB_COL_BWD: rc = ph_col_bwd(e); break;
+    case CHB_EB_FINISH: rc = ph_eb_finish(e); break;
     default: set_error("unknown engine phase %d", phase); rc = 2;
   }
   if (e->profile) {
@@ -819,6 +876,7 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
   const int nd = (int)(c.env ? c.nm + 2 : c.nm + 1);
   const int ncoef = c.space_charge ? 5 : 3;
   struct { const char* n; size_t b; } spec[] = {
+      // (J, Rho and EB get kColPad spare columns below: the column-block dataflow splits them into `world` equal blocks)
       {"J", Pg * 3 * C}, {"Rho", Pg * C}, {"BckGrndRho", Pg * C}, {"EB", Pg * 6 * C},
       {"EG_fb", Pf * 6 * C}, {"J_fb", Pf * 3 * C}, {"B_fb", Pf * 3 * C}, {"Rho_fb", Pf * C},
       {"gradRho_fb_prv", Pf * 3 * C}, {"gradRho_fb_nxt", Pf * 3 * C}, {"vec_fb", Pf * 3 * C},
@@ -830,7 +888,9 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
       {"PSATD_G", (c.coef_complex ? C : sizeof(double)) * Pf * ncoef},
       {"CPSATD1", Pf * 2 * C}, {"CPSATD2", Pf * 2 * C}, {"Rgrid", sizeof(double) * c.nrn}};
   for (auto& s : spec) {
-    int rc = alloc_named(e, s.n, s.b);
+    const std::string nm(s.n);
+    const bool padded = nm == "J" || nm == "Rho" || nm == "EB";
+    int rc = alloc_named(e, s.n, s.b, true, padded ? kColPad * (size_t)c.nx * C : 0);
     if (rc) { chimera_engine_destroy(e); return rc; }
   }
   if (c.static_kick) {
@@ -842,7 +902,7 @@ int chimera_engine_create(const chimera_engine_config* cfg, chimera_engine** out
         {"slab_rows", sizeof(i64) * nxf}, {"gather_map", sizeof(i64) * (size_t)c.nx},
         {"EB_slab", nxf * c.nrn * c.nm * 6 * C}, {"EB_gath", Pg * 6 * C}};
     for (auto& s : extra) {
-      int rc = alloc_named(e, s.n, s.b);
+      int rc = alloc_named(e, s.n, s.b, true, std::string(s.n) == "EB_slab" ? kColPad * nxf * C : 0);
       if (rc) { chimera_engine_destroy(e); return rc; }
     }
   }
@@ -908,7 +968,7 @@ int chimera_engine_array(chimera_engine* e, const char* name, void** dev_ptr, ch
   NamedArray* a;
   CHB_TRY(find_array(e, name, &a));
   *dev_ptr = a->p;
-  *nbytes = (chb_i64)a->bytes;
+  *nbytes = (chb_i64)a->alloc;  // with the spare columns: the caller views what it needs
   return 0;
 }
 
@@ -1344,6 +1404,24 @@ int chimera_engine_set_graph(chimera_engine* e, int on) {
 int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n) {
   ENG_CHECK(e);
   e->static_px.assign(px, px + (n > 0 ? n : 0));
+  return 0;
+}
+
+// buffers of the column-block dataflow for `world` ranks (kx-slab engines only)
+int chimera_engine_set_colflow(chimera_engine* e, int world) {
+  ENG_CHECK(e);
+  const auto& c = e->cfg;
+  if (!slab(e)) { set_error("column dataflow: kx-slab engines only"); return 2; }
+  if (world < 2 || (size_t)world > kColPad || nxs(e) * world != c.nx) { set_error("column dataflow: bad rank count %d", world); return 2; }
+  e->col_world = world;
+  const size_t C = sizeof(cd), nx = (size_t)c.nx, L = (size_t)nxs(e);
+  const size_t cj = (size_t)col_block(e, c.nrn * c.nm * 3), cr = (size_t)col_block(e, c.nrn * c.nm), ce = (size_t)col_block(e, c.nrn * c.nm * 6);
+  struct { const char* n; size_t b; } spec[] = {
+      {"J_blk", nx * cj * C}, {"J_send", nx * cj * C}, {"J_in", L * cj * world * C},
+      {"Rho_blk", nx * cr * C}, {"Rho_send", nx * cr * C}, {"Rho_in", L * cr * world * C},
+      {"EB_recv", nx * ce * C}, {"EB_blk", nx * ce * C}};
+  for (auto& s : spec)
+    if (!e->arr.count(s.n)) CHB_TRY(alloc_named(e, s.n, s.b));
   return 0;
 }
 

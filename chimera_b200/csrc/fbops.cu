@@ -182,6 +182,42 @@ int fb_in_slab_dev(FBCtx& c, cd* out_fb, const cd* in, double leftX, const doubl
   return 0;
 }
 
+// the second half of fb_in_slab_dev on a slab that is already x-transformed (column-block dataflow: the x-FFT ran on
+// this rank's column block and the rows came in through the all-to-all)
+int fb_in_slab_post_dev(FBCtx& c, cd* out_fb, const cd* slab, double leftX, const double* kx_slab, const PackedOps& In,
+                        const double* fact_slab, i64 nxs, i64 nrn, i64 nm, i64 nkr, int ncomp) {
+  const i64 nr = nrn - 1;
+  Batcher gb(c.st, 2 * nxs, nkr, nr, 2 * nxs, 2 * nxs);
+  for (int l = 0; l < ncomp; ++l)
+    for (i64 m = 0; m < nm; ++m)
+      gb.add(slab + nxs * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nxs * nkr * (m + nm * l), 1.0, 0.0);
+  CHB_TRY(gb.flush());
+  CHB_TRY(launch_rowscale_phase(c.st, out_fb, kx_slab, leftX, -1.0, 1.0, fact_slab, nxs, nkr * nm * ncomp, nkr * nm));
+  return 0;
+}
+
+namespace {
+// send[(r * ncols + col) * nxs + j] = blk[i + nkx * col] with map[i] = r * nxs + j: the rows of every rank's kx slab,
+// contiguous per destination rank
+__global__ void __launch_bounds__(256) pack_cols_k(cd* __restrict__ send, const cd* __restrict__ blk,
+                                                   const i64* __restrict__ map, i64 nkx, i64 nxs, i64 ncols, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const i64 col = e / nkx, i = e - col * nkx;
+  const i64 m = __ldg(map + i), r = m / nxs, j = m - r * nxs;
+  send[(r * ncols + col) * nxs + j] = blk[e];
+}
+}  // namespace
+
+// column-block dataflow, forward: x-FFT of this rank's column block (nkx, ncols) in place, then the rows sorted by
+// destination rank for the all-to-all
+int col_fwd_dev(FBCtx& c, cd* send, cd* blk, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols) {
+  CHB_TRY(c.fft->exec(c.st, blk, nkx, ncols, CUFFT_FORWARD));
+  pack_cols_k<<<grid_for(nkx * ncols, 256), 256, 0, c.st>>>(send, blk, gather_map, nkx, nxs, ncols, nkx * ncols);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int ncomp_each, double leftX,
                     const double* kx_slab, const PackedOps& Out, i64 nxs, i64 nrn, i64 nm, i64 nkr) {
   const i64 nr = nrn - 1;

@@ -75,6 +75,12 @@ int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int
                     const double* kx_slab, const PackedOps& Out, i64 nxs, i64 nrn, i64 nm, i64 nkr);
 // rows of the gathered slabs back to natural kx order, inverse x-FFT
 int fb_out_finish_dev(FBCtx& c, cd* out, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols);
+// column-block dataflow of the multi-rank solve (engine.cu "colflow"): forward, x-FFT of a column block + rows sorted by
+// destination rank; the DHT half of fb_in_slab_dev on a slab that arrived x-transformed.  Backward: fb_out_finish_dev
+// on the received (rank, column, row) blocks is exactly the unpack + inverse x-FFT of a column block.
+int col_fwd_dev(FBCtx& c, cd* send, cd* blk, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols);
+int fb_in_slab_post_dev(FBCtx& c, cd* out_fb, const cd* slab, double leftX, const double* kx_slab, const PackedOps& In,
+                        const double* fact_slab, i64 nxs, i64 nrn, i64 nm, i64 nkr, int ncomp);
 // row exchange between the all-gathered slab layout [rank][(nxs, ncols)], the full (nkx, ncols) array and one slab
 int rows_scatter_dev(FBCtx& c, cd* full, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols);
 int rows_take_dev(FBCtx& c, cd* slab, const cd* full, const i64* rows, i64 nkx, i64 nxs, i64 ncols);

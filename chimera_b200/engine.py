@@ -33,6 +33,7 @@ PHASES = (
     "push_coords", "sort", "deposit_J", "deposit_rho", "deposit_bg", "fb_in_J", "fb_in_rho", "poisson",
     "maxwell", "init_push", "fields_out", "gather_push", "add_bg", "fields_out_a", "fields_out_b",
     "particles_fused", "static_fields", "window", "gather_push_coords", "deposit_fused",
+    "col_fwd", "fb_in_col", "col_bwd", "eb_finish",
 )
 PHASE_ID = {n: i for i, n in enumerate(PHASES)}
 
@@ -89,6 +90,9 @@ class Engine:
         rows of every spectral array.  Default: on under a process group whenever ``Nx`` is divisible by
         ``2*world``.  ``(rank, world)`` selects a slab without a process group (tests drive the exchange).
     """
+
+    colflow = False       # column-block dataflow of the multi-rank solve in use (_setup_colflow)
+    comm_profile = False  # time every collective on its own (comm_timings)
 
     def __init__(self, setup, chunked=None, sort_every=None, poisson_iters=None, undulator=None, group=None, slab=None):
         self.lib = _lib.load()
@@ -167,6 +171,10 @@ class Engine:
 
             # run on torch's current stream so that the NCCL collectives are ordered with the kernels
             self.use_stream(torch.cuda.current_stream().cuda_stream)
+        self.colflow = False
+        self._comm_events = []
+        if group is not None:
+            self._setup_colflow()
 
     # -- plumbing ----------------------------------------------------------------------------
     def _check(self, rc):
@@ -214,13 +222,19 @@ class Engine:
         self._check(self.lib.chimera_engine_download(self._h, name.encode(), ctypes.c_void_p(out.ctypes.data), _i64(out.nbytes)))
         return out
 
-    def device_tensor(self, name, dtype=np.float64):
-        """torch view (no copy) of a named engine array, e.g. for ``torch.distributed.all_reduce``."""
+    def device_tensor(self, name, dtype=np.float64, raw=False):
+        """torch view (no copy) of a named engine array, e.g. for ``torch.distributed.all_reduce``.  J, Rho, EB and EB_slab
+        are allocated with spare columns for the column-block dataflow: the view covers the array proper unless ``raw``."""
         import torch
 
         ptr, nb = ctypes.c_void_p(), _i64()
         self._check(self.lib.chimera_engine_array(self._h, name.encode(), ctypes.byref(ptr), ctypes.byref(nb)))
-        return torch.as_tensor(_DevView(ptr.value, nb.value, dtype), device="cuda")
+        t = torch.as_tensor(_DevView(ptr.value, nb.value, dtype), device="cuda")
+        if not raw and name in ("J", "Rho", "EB", "EB_slab"):
+            c = self.cfg
+            shape = self.shape_of(name) if name != "EB_slab" else (c.nx_slab, c.nrn, c.nm, 6)
+            t = t[:int(np.prod(shape)) * 16 // np.dtype(dtype).itemsize]
+        return t
 
     # -- particles ---------------------------------------------------------------------------
     def add_species(self, coords, momenta, weights, charge=-1.0, mass=1.0, still=False, coords_half=None, capacity=0,
@@ -470,7 +484,7 @@ class Engine:
     def _allreduce_grids(self):
         names = ("J", "Rho") if (self.cfg.space_charge or self.cfg.static_kick) else ("J",)
         for n in names:
-            self._dist.all_reduce(self.device_tensor(n), group=self._group)
+            self._comm("all_reduce_" + n, lambda a, n=n: self._dist.all_reduce(self.device_tensor(n), group=self._group))
 
     def _allreduce_grids_async(self):
         """J then Rho on the collective stream; returns the two handles: fb_in_J only needs J, so the reduction of Rho
@@ -489,12 +503,25 @@ class Engine:
         if not self.slab:
             self.run("fields_out")
             return
+        if self.world > 1 and self.colflow:
+            c = self.cfg
+            self.run("fields_out_a")
+            h = self._comm("all_to_all_EB", lambda a: self._all_to_all(self.device_tensor("EB_recv")[:2 * c.nx * self._cb["EB"]],
+                                                                      self._cview("EB_slab", c.nx_slab, "EB"), a))
+            h.wait()
+            self.run("col_bwd")
+            h = self._comm("all_gather_EB", lambda a: self._all_gather_into(self._cview("EB", c.nx, "EB"),
+                                                                         self.device_tensor("EB_blk")[:2 * c.nx * self._cb["EB"]], a))
+            if h is not None:
+                h.wait()
+            self.run("eb_finish")
+            return
         if self.world == 1 or not self.overlap:
             self.run("fields_out_a")
             self._allgather_eb()
             self.run("fields_out_b")
             return
-        slab, gath = self.device_tensor("EB_slab"), self.device_tensor("EB_gath")
+        slab, gath = self._eb_slab(), self.device_tensor("EB_gath")
         hs, hg = slab.numel() // 2, gath.numel() // 2
         self.run("fields_out_a", 1.0)
         w_e = self._all_gather_into(gath[:hg], slab[:hs], async_op=True)
@@ -514,15 +541,131 @@ class Engine:
             return self._dist.all_gather(parts, inp.reshape(-1), group=self._group, async_op=async_op)
 
     def _allgather_eb(self):
-        self._all_gather_into(self.device_tensor("EB_gath"), self.device_tensor("EB_slab"))
+        self._all_gather_into(self.device_tensor("EB_gath"), self._eb_slab())
 
-    def _deposit_and_reduce(self):
+    def _eb_slab(self):
+        """the backward-transformed slab (nx_slab, Nr, M, 6) without the spare columns of its allocation"""
+        c = self.cfg
+        return self.device_tensor("EB_slab")
+
+    def _deposit_only(self):
         self.run("deposit_J")
         if self.cfg.space_charge or self.cfg.static_kick:
             # the background charge enters the sum once (rank 0), chimera_main.py:189-190
             self.run("deposit_rho", 1.0 if self.rank == 0 else 0.0)
+
+    def _deposit_and_reduce(self):
+        self._deposit_only()
         if self.world > 1:
             self._allreduce_grids()
+
+    # -- collectives (with the fall-backs the gloo test transport needs) -------------------------------------------
+    class _Done:
+        def wait(self):
+            return True
+
+    def _comm(self, name, fn):
+        """run a collective; with ``comm_profile`` on, synchronously between two CUDA events (its own time, no overlap)"""
+        if not getattr(self, "comm_profile", False):
+            return fn(self.overlap)
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h = fn(False)
+        if h is not None:
+            h.wait()
+        e1.record()
+        self._comm_events.append((name, e0, e1))
+        return self._Done()
+
+    def comm_timings(self, reset=True):
+        """{collective: (ms, calls)} measured while ``comm_profile`` was on"""
+        import torch
+
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._comm_events:
+            ms, n = out.get(name, (0.0, 0))
+            out[name] = (ms + e0.elapsed_time(e1), n + 1)
+        if reset:
+            self._comm_events = []
+        return out
+
+    def _reduce_scatter(self, out, inp, async_op):
+        try:
+            return self._dist.reduce_scatter_tensor(out, inp, group=self._group, async_op=async_op) or self._Done()
+        except (RuntimeError, NotImplementedError):  # gloo: all-reduce, keep the own block
+            self._dist.all_reduce(inp, group=self._group)
+            out.copy_(inp.view(self.world, -1)[self.rank])
+            return self._Done()
+
+    def _all_to_all(self, out, inp, async_op):
+        try:
+            return self._dist.all_to_all_single(out, inp, group=self._group, async_op=async_op) or self._Done()
+        except (RuntimeError, NotImplementedError):  # gloo on CUDA tensors: gather everything, keep what is addressed here
+            import torch
+
+            tmp = torch.empty(self.world * inp.numel(), dtype=inp.dtype, device=inp.device)
+            self._all_gather_into(tmp, inp)
+            out.view(self.world, -1).copy_(tmp.view(self.world, self.world, -1)[:, self.rank])
+            return self._Done()
+
+    def _setup_colflow(self):
+        """column-block dataflow of the multi-rank solve (csrc/engine.cu): reduce-scatter of J / Rho by
+        column block, x-FFT of the own block, all-to-all to kx slabs; backward the other way round and an all-gather of
+        the column blocks of EB.  Needs kx slabs over all the ranks of the group."""
+        self.colflow = False
+        self._comm_events = []
+        if not (self.slab and self.world > 1 and self.slab_world == self.world and self.slab_rank == self.rank):
+            return
+        if not hasattr(self.lib, "chimera_engine_set_colflow") or self.world > 64:
+            return
+        self._check(self.lib.chimera_engine_set_colflow(self._h, self.world))
+        c, w = self.cfg, self.world
+        self._cb = {k: -(-(c.nrn * c.nm * n) // w) for k, n in (("J", 3), ("Rho", 1), ("EB", 6))}
+        self.colflow = True
+
+    def _cview(self, name, rows, key):
+        """the first rows x (column block x world) complex entries of a named array, as doubles"""
+        return self.device_tensor(name, raw=True)[:2 * rows * self._cb[key] * self.world]
+
+    def _reduce_and_transform(self):
+        """sum the deposited grids over the ranks and take them to Fourier-Bessel space on this engine's kx rows
+        (``fb_curr_in`` / ``fb_dens_in`` + ``FBGradDens``, solvers.py:407-448)"""
+        c = self.cfg
+        rho = bool(c.space_charge or c.static_kick)
+        if self.world == 1 or not self.colflow:
+            w_r = None
+            if self.world > 1:
+                if self.overlap:
+                    w_j, w_r = self._allreduce_grids_async()
+                    w_j.wait()
+                else:
+                    self._allreduce_grids()
+            self.run("fb_in_J")
+            if w_r is not None:
+                w_r.wait()
+            if rho:
+                self.run("fb_in_rho")
+            return
+        nx, L, W = c.nx, c.nx_slab, self.world
+        blk = lambda name, key: self.device_tensor(name)[:2 * nx * self._cb[key]]  # noqa: E731
+        h_j = self._comm("reduce_scatter_J", lambda a: self._reduce_scatter(blk("J_blk", "J"), self._cview("J", nx, "J"), a))
+        h_r = self._comm("reduce_scatter_Rho", lambda a: self._reduce_scatter(blk("Rho_blk", "Rho"), self._cview("Rho", nx, "Rho"), a)) if rho else None
+        h_j.wait()
+        self.run("col_fwd", 0.0)
+        a_j = self._comm("all_to_all_J", lambda a: self._all_to_all(self._cview("J_in", L, "J"), blk("J_send", "J"), a))
+        a_r = None
+        if rho:
+            h_r.wait()
+            self.run("col_fwd", 1.0)
+            a_r = self._comm("all_to_all_Rho", lambda a: self._all_to_all(self._cview("Rho_in", L, "Rho"), blk("Rho_send", "Rho"), a))
+        a_j.wait()
+        self.run("fb_in_col", 0.0)
+        if rho:
+            a_r.wait()
+            self.run("fb_in_col", 1.0)
 
     def _static_fields(self):
         """``update_fields`` under 'StaticKick' (chimera_main.py:118-125) across ranks / on kx slabs: the mean momentum of
@@ -550,10 +693,9 @@ class Engine:
         self.run("sort", 0.0)
         if background:
             self.deposit_background()
-        self._deposit_and_reduce()
-        self.run("fb_in_J")
+        self._deposit_only()
+        self._reduce_and_transform()
         if self.cfg.space_charge or self.cfg.static_kick:
-            self.run("fb_in_rho")
             for p in px0:  # solvers.py:333-358, one static kick per species
                 c1, c2 = self.setup.static_coeffs(p)
                 self.upload("CPSATD1", c1)
@@ -607,18 +749,7 @@ class Engine:
                     self.run("window", 2.0)
                 if c.space_charge or c.static_kick:
                     self.run("deposit_rho", bg)
-            w_j = w_r = None
-            if self.world > 1:
-                if self.overlap:
-                    w_j, w_r = self._allreduce_grids_async()
-                    w_j.wait()
-                else:
-                    self._allreduce_grids()
-            self.run("fb_in_J")
-            if w_r is not None:
-                w_r.wait()
-            if c.space_charge or c.static_kick:
-                self.run("fb_in_rho")
+            self._reduce_and_transform()
             if c.static_kick:
                 self._static_fields()
             else:

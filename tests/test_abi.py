@@ -228,7 +228,8 @@ def test_engine_config_struct_matches_the_header():
              "MAXWELL": "maxwell", "INIT_PUSH": "init_push", "FIELDS_OUT": "fields_out", "GATHER_PUSH": "gather_push",
              "ADD_BG": "add_bg", "FIELDS_OUT_A": "fields_out_a", "FIELDS_OUT_B": "fields_out_b",
              "PARTICLES_FUSED": "particles_fused", "STATIC_FIELDS": "static_fields", "WINDOW": "window",
-             "GATHER_PUSH_COORDS": "gather_push_coords", "DEPOSIT_FUSED": "deposit_fused"}
+             "GATHER_PUSH_COORDS": "gather_push_coords", "DEPOSIT_FUSED": "deposit_fused", "COL_FWD": "col_fwd",
+             "FB_IN_COL": "fb_in_col", "COL_BWD": "col_bwd", "EB_FINISH": "eb_finish"}
     assert set(ids) == set(names)
     for k, i in ids.items():
         assert PHASES[i] == names[k], (k, i, PHASES[i])
