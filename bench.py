@@ -330,8 +330,10 @@ def run_ours(a):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "particles_total": n_total, "particles_after": n_now,
-                       "parallelism": ("particles sharded x%d, J/Rho all-reduced (NCCL), spectral solve sharded by kx slab (%d rows per GPU), "
-                                       "EB slabs all-gathered" % (world, eng.cfg.nx_slab)) if eng.slab else
+                       "parallelism": ("particles sharded x%d; spectral solve sharded by kx slab (%d rows per GPU); %s (NCCL)"
+                                       % (world, eng.cfg.nx_slab, "J/Rho reduce-scattered by column block, x-FFT per block, all-to-all "
+                                          "to the slabs and back, EB column blocks all-gathered" if eng.colflow else
+                                          "J/Rho all-reduced, EB slabs all-gathered")) if eng.slab else
                                       ("particles sharded x%d, grids all-reduced (NCCL), spectral solve replicated" % world),
                        "l2": "inputs larger than L2 (particle arrays %.1f GB, grids %.2f GB)"
                              % (n_local * 80 / 1e9, grid_pts * 16 * 10 / 1e9)},

@@ -53,6 +53,7 @@ constexpr size_t kColPad = 64;  // spare columns of J / Rho / EB (column blocks 
 struct chimera_engine {
   chimera_engine_config cfg;
   int col_world = 0;  // > 0: column-block dataflow set up for this many ranks (chimera_engine_set_colflow)
+  int col_rank = 0;   // this rank's column block
   cudaStream_t st = nullptr;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of chimera_engine_step_host
   std::vector<cudaEvent_t> host_evs;
@@ -570,14 +571,17 @@ int ph_col_bwd(chimera_engine* e) {
   const auto& c = e->cfg;
   if (!e->col_world) { set_error("column dataflow is not set up (chimera_engine_set_colflow)"); return 2; }
   FBCtx fb = fbctx(e);
-  return fb_out_finish_dev(fb, e->A("EB_blk"), e->A("EB_recv"), (const i64*)e->arr["gather_map"].p, c.nx, nxs(e),
-                           col_block(e, c.nrn * c.nm * 6));
+  const i64 cb = col_block(e, c.nrn * c.nm * 6);
+  return col_bwd_dev(fb, e->A("EB_blk"), e->A("EB_recv"), (const i64*)e->arr["gather_map"].p, c.nx, nxs(e), cb,
+                     e->col_rank * cb, c.nrn, c.nm, c.env);
 }
 
-// after the all-gather of the blocks into EB: normalisation and ghost row (eb_correction, grid_deps.f90:219)
+// after the all-gather of the blocks into EB: the ghost rows of eb_correction (grid_deps.f90:248-265; the normalisation
+// went into col_bwd)
 int ph_eb_finish(chimera_engine* e) {
   const auto& c = e->cfg;
-  return launch_eb_correction(e->st, e->A("EB"), c.nx, c.nrn, c.nm, c.env);
+  FBCtx fb = fbctx(e);
+  return eb_ghost_dev(fb, e->A("EB"), c.nx, c.nrn, c.nm, c.env, 6);
 }
 
 // fields out, first half: B from G, backward DHT (+ phase).  Unsharded: also the inverse x-FFT and the
@@ -1408,8 +1412,10 @@ int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n) {
 }
 
 // buffers of the column-block dataflow for `world` ranks (kx-slab engines only)
-int chimera_engine_set_colflow(chimera_engine* e, int world) {
+int chimera_engine_set_colflow(chimera_engine* e, int rank, int world) {
   ENG_CHECK(e);
+  if (rank < 0 || rank >= world) { set_error("column dataflow: bad rank %d of %d", rank, world); return 2; }
+  e->col_rank = rank;
   const auto& c = e->cfg;
   if (!slab(e)) { set_error("column dataflow: kx-slab engines only"); return 2; }
   if (world < 2 || (size_t)world > kColPad || nxs(e) * world != c.nx) { set_error("column dataflow: bad rank count %d", world); return 2; }

@@ -246,6 +246,50 @@ int rows_take_dev(FBCtx& c, cd* slab, const cd* full, const i64* rows, i64 nkx, 
   return 0;
 }
 
+namespace {
+// put_rows_k for one column block of EB with the normalisation of eb_correction (grid_deps.f90:219-266: 1/2pi for mode 0
+// of the real solver, 1/pi otherwise) folded in: the factor is per column and commutes with the x-FFT that follows
+__global__ void __launch_bounds__(256) put_rows_norm_k(cd* __restrict__ out, const cd* __restrict__ gath,
+                                                       const i64* __restrict__ map, i64 nkx, i64 nxs, i64 ncols, i64 col0,
+                                                       i64 nrn, i64 nm, int env, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const i64 col = e / nkx, i = e - col * nkx;
+  const i64 m = __ldg(map + i), r = m / nxs, j = m - r * nxs;
+  const int slot = (int)(((col0 + col) / nrn) % nm);
+  const double pi_inv = 1.0 / 3.14159265358979323846;
+  const double f = (!env && slot == 0) ? 0.5 * pi_inv : pi_inv;
+  const cd v = __ldg(gath + r * nxs * ncols + j + nxs * col);
+  out[e] = cmake(f * v.x, f * v.y);
+}
+// ghost row of every (mode, component) plane from row 1 (copy, or negate: Q6)
+__global__ void __launch_bounds__(256) eb_ghost_k(cd* __restrict__ eb, i64 nxn, i64 nrn, i64 nm, int env, i64 n) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const i64 q = e / nxn, ix = e - q * nxn;
+  const int slot = (int)(q % nm);
+  const bool negate = env ? (nm > 1) : (slot > 0);
+  cd* pl = eb + nxn * nrn * q;
+  const cd v = pl[ix + nxn];
+  pl[ix] = negate ? cmake(-v.x, -v.y) : v;
+}
+}  // namespace
+
+// column-block dataflow, backward: received (rank, column, row) blocks -> rows in place, normalised, inverse x-FFT
+int col_bwd_dev(FBCtx& c, cd* blk, const cd* recv, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols, i64 col0, i64 nrn,
+                i64 nm, int env) {
+  put_rows_norm_k<<<grid_for(nkx * ncols, 256), 256, 0, c.st>>>(blk, recv, gather_map, nkx, nxs, ncols, col0, nrn, nm, env,
+                                                                nkx * ncols);
+  CHB_LAUNCH_CHECK();
+  return c.fft->exec(c.st, blk, nkx, ncols, CUFFT_INVERSE);
+}
+int eb_ghost_dev(FBCtx& c, cd* eb, i64 nxn, i64 nrn, i64 nm, int env, int ncomp) {
+  const i64 n = nxn * nm * ncomp;
+  eb_ghost_k<<<grid_for(n, 256), 256, 0, c.st>>>(eb, nxn, nrn, nm, env, n);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 int fb_out_finish_dev(FBCtx& c, cd* out, const cd* gathered, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols) {
   put_rows_k<<<grid_for(nkx * ncols, 256), 256, 0, c.st>>>(out, gathered, gather_map, nkx, nxs, ncols, nkx * ncols);
   CHB_LAUNCH_CHECK();

@@ -79,6 +79,9 @@ int fb_out_finish_dev(FBCtx& c, cd* out, const cd* gathered, const i64* gather_m
 // destination rank; the DHT half of fb_in_slab_dev on a slab that arrived x-transformed.  Backward: fb_out_finish_dev
 // on the received (rank, column, row) blocks is exactly the unpack + inverse x-FFT of a column block.
 int col_fwd_dev(FBCtx& c, cd* send, cd* blk, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols);
+int col_bwd_dev(FBCtx& c, cd* blk, const cd* recv, const i64* gather_map, i64 nkx, i64 nxs, i64 ncols, i64 col0, i64 nrn,
+                i64 nm, int env);  // col0: first column of the block; eb_correction's normalisation folded in
+int eb_ghost_dev(FBCtx& c, cd* eb, i64 nxn, i64 nrn, i64 nm, int env, int ncomp);  // ghost rows of eb_correction
 int fb_in_slab_post_dev(FBCtx& c, cd* out_fb, const cd* slab, double leftX, const double* kx_slab, const PackedOps& In,
                         const double* fact_slab, i64 nxs, i64 nrn, i64 nm, i64 nkr, int ncomp);
 // row exchange between the all-gathered slab layout [rank][(nxs, ncols)], the full (nkx, ncols) array and one slab

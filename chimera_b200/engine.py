@@ -621,7 +621,7 @@ class Engine:
             return
         if not hasattr(self.lib, "chimera_engine_set_colflow") or self.world > 64:
             return
-        self._check(self.lib.chimera_engine_set_colflow(self._h, self.world))
+        self._check(self.lib.chimera_engine_set_colflow(self._h, self.rank, self.world))
         c, w = self.cfg, self.world
         self._cb = {k: -(-(c.nrn * c.nm * n) // w) for k, n in (("J", 3), ("Rho", 1), ("EB", 6))}
         self.colflow = True

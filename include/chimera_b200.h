@@ -351,8 +351,8 @@ enum chimera_engine_phase {
   /* column-block dataflow of the multi-rank solve (chimera_engine_set_colflow) */
   CHB_COL_FWD = 20,       /* x-FFT of the reduce-scattered column block + rows sorted by destination rank; arg 0 J, 1 Rho */
   CHB_FB_IN_COL = 21,     /* forward DHT of the slab received through the all-to-all (+ fb_grad for Rho); arg 0 J, 1 Rho  */
-  CHB_COL_BWD = 22,       /* received (rank, column, row) blocks -> own column block of EB, inverse x-FFT                  */
-  CHB_EB_FINISH = 23,     /* eb_correction on the all-gathered EB                                                         */
+  CHB_COL_BWD = 22,       /* received (rank, column, row) blocks -> own column block of EB, normalised, inverse x-FFT      */
+  CHB_EB_FINISH = 23,     /* ghost rows of eb_correction on the all-gathered EB                                           */
   CHB_NPHASES = 24
 };
 int chimera_engine_run(chimera_engine* e, int phase, double arg);
@@ -364,7 +364,7 @@ int chimera_engine_set_fuse(chimera_engine* e, int on);
 /* replay the fused step (particle kernel + spectral update) as a CUDA graph between two re-binnings (default on; used when
    no window moves every step and no device field depends on time) */
 int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n); /* 'StaticKick' across ranks: PXmean per species */
-int chimera_engine_set_colflow(chimera_engine* e, int world); /* allocate the column-block dataflow buffers (kx-slab engines) */
+int chimera_engine_set_colflow(chimera_engine* e, int rank, int world); /* column-block dataflow buffers (kx-slab engines) */
 int chimera_engine_set_graph(chimera_engine* e, int on);
 int chimera_engine_graph_info(chimera_engine* e, int* ngraphs, int* state); /* cached graphs; state 1 warm, -1 capture failed */
 /* One make_step (chimera_main.py:82-92) with the PIC state in HOST buffers, the reference's calling model:
