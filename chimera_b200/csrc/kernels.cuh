@@ -161,7 +161,10 @@ int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const d
                               i64 cap, const GridGeom& g, double dt, const DeviceSet& und, const SortedSpec& sp);
 // particles_fused.cu: gather + device + Boris push + position update + J / rho deposit in one kernel.
 // `sp.cta` must be the CTA table for kFusedNPB particles per CTA.  push_dt = 2 pi q/m dt, dt = time step.
-constexpr int kFusedNPB = 512;
+#ifndef CHB_FNPB
+#define CHB_FNPB 512
+#endif
+constexpr int kFusedNPB = CHB_FNPB;  // particles per CTA of the fused kernel (tuning builds override it)
 int launch_fused_particles(cudaStream_t st, int env, int space_charge, double* x, double* xh, double* mom,
                            const double* w, i64 cap, const cd* Fld, cd* J, cd* Rho, const GridGeom& g,
                            const ChunkSpec& ch, double push_dt, double dt, const DeviceSet& und, const SortedSpec& sp,

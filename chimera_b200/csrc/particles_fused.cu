@@ -44,6 +44,9 @@ namespace {
 #ifndef CHB_FDSPLIT
 #define CHB_FDSPLIT 2
 #endif
+#ifndef CHB_FSPLIT
+#define CHB_FSPLIT 2
+#endif
 #ifndef CHB_FSYNC
 #define CHB_FSYNC 0
 #endif
@@ -55,6 +58,7 @@ namespace {
 #endif
 constexpr int FNPB = kFusedNPB, FT = CHB_FT, FRUN = CHB_FRUN;
 constexpr int FDSPLIT = CHB_FDSPLIT;
+constexpr int FSPLIT = CHB_FSPLIT;  // lanes that share a (segment, unit) in the deposit stage: 2 or 4
 constexpr int FBX = 40, FBR = 16, FBINS = FBX * FBR;
 constexpr int FPPT = (FNPB + FT - 1) / FT;
 constexpr int FMAXTASK = FNPB / FRUN + (FBINS < FNPB ? FBINS : FNPB);
@@ -444,11 +448,11 @@ fused_pass_k(double* __restrict__ x, double* __restrict__ xh, double* __restrict
   // Each (segment, unit) is shared by a lane pair: lane h takes the particles q = h, h + 2, ... of the run; the
   // halves are exchanged with one shuffle per accumulator (lane 0 ends up with the sums of the left x node pair,
   // lane 1 with the right pair) and each lane issues its half of the red.global.adds.
-  const int nwork = ntask * NU * 2;
+  const int nwork = ntask * NU * FSPLIT;
 #pragma unroll 1
   for (int t = tid; t < ((nwork + 31) & ~31); t += FT) {
     const bool valid = t < nwork;
-    const int h = t & 1, tu = valid ? (t >> 1) : 0;
+    const int hs = t % FSPLIT, h = hs & 1, tu = valid ? (t / FSPLIT) : 0;
     const int task = tu / NU, u = tu - task * NU;
     const bool isJ = u < NCJ;
     const int tw = tasks[task];
@@ -465,7 +469,7 @@ fused_pass_k(double* __restrict__ x, double* __restrict__ xh, double* __restrict
         for (int m = 0; m < NM; ++m) a[i][k][m] = cmake(0.0, 0.0);
     int any = 0;
 #pragma unroll 2
-    for (int q = h; q < n; q += 2) {
+    for (int q = hs; q < n; q += FSPLIT) {
       const int li = order[start + q];
       if (!(fast[li] & bit)) continue;
       any = 1;
@@ -494,6 +498,18 @@ fused_pass_k(double* __restrict__ x, double* __restrict__ xh, double* __restrict
         }
       }
     }
+    if (FSPLIT == 4) {  // lanes hs and hs ^ 2 first pool their partial sums
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            a[i][k][m].x += __shfl_xor_sync(0xffffffffu, a[i][k][m].x, 2);
+            if (ENV || m > 0) a[i][k][m].y += __shfl_xor_sync(0xffffffffu, a[i][k][m].y, 2);
+          }
+      any |= __shfl_xor_sync(0xffffffffu, any, 2);
+    }
     // lane h keeps x node h: send the other node's partial sums to the partner, add what it sends
     cd mine[2][NM];
 #pragma unroll
@@ -505,7 +521,7 @@ fused_pass_k(double* __restrict__ x, double* __restrict__ xh, double* __restrict
         mine[k][m].y = (!ENV && m == 0) ? 0.0 : keep.y + __shfl_xor_sync(0xffffffffu, give.y, 1);
       }
     any |= __shfl_xor_sync(0xffffffffu, any, 1);
-    if (!valid || !any) continue;
+    if (!valid || !any || hs >= 2) continue;
     const int kr = key / FBX, kx = key - kr * FBX;
     const i64 gx = (i64)ix0 + kx + h, gr = (i64)ir0 + kr;
     if (gx < klo || gx > khi) continue;
@@ -900,11 +916,11 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
   // Each (segment, unit) is shared by a lane pair: lane h takes the particles q = h, h + 2, ... of the run; the
   // halves are exchanged with one shuffle per accumulator (lane 0 ends up with the sums of the left x node pair,
   // lane 1 with the right pair) and each lane issues its half of the red.global.adds.
-  const int nwork = ntask * NU * 2;
+  const int nwork = ntask * NU * FSPLIT;
 #pragma unroll 1
   for (int t = tid; t < ((nwork + 31) & ~31); t += FT) {
     const bool valid = t < nwork;
-    const int h = t & 1, tu = valid ? (t >> 1) : 0;
+    const int hs = t % FSPLIT, h = hs & 1, tu = valid ? (t / FSPLIT) : 0;
     const int task = tu / NU, u = tu - task * NU;
     const bool isJ = u < NCJ;
     const int tw = tasks[task];
@@ -921,7 +937,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         for (int m = 0; m < NM; ++m) a[i][k][m] = cmake(0.0, 0.0);
     int any = 0;
 #pragma unroll 2
-    for (int q = h; q < n; q += 2) {
+    for (int q = hs; q < n; q += FSPLIT) {
       const int li = order[start + q];
       if (!(fast[li] & bit)) continue;
       any = 1;
@@ -950,6 +966,18 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         }
       }
     }
+    if (FSPLIT == 4) {  // lanes hs and hs ^ 2 first pool their partial sums
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            a[i][k][m].x += __shfl_xor_sync(0xffffffffu, a[i][k][m].x, 2);
+            if (ENV || m > 0) a[i][k][m].y += __shfl_xor_sync(0xffffffffu, a[i][k][m].y, 2);
+          }
+      any |= __shfl_xor_sync(0xffffffffu, any, 2);
+    }
     // lane h keeps x node h: send the other node's partial sums to the partner, add what it sends
     cd mine[2][NM];
 #pragma unroll
@@ -961,7 +989,7 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
         mine[k][m].y = (!ENV && m == 0) ? 0.0 : keep.y + __shfl_xor_sync(0xffffffffu, give.y, 1);
       }
     any |= __shfl_xor_sync(0xffffffffu, any, 1);
-    if (!valid || !any) continue;
+    if (!valid || !any || hs >= 2) continue;
     const int kr = key / FBX, kx = key - kr * FBX;
     const i64 gx = (i64)ix0 + kx + h, gr = (i64)ir0 + kr;
     if (gx < klo || gx > khi) continue;
