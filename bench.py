@@ -319,6 +319,7 @@ def run_ours(a):
             roof = {"kernel": "gemm_dmma_k (DHT + mode-coupling contractions)", "bound": "tensor",
                     "achieved": gemm["tflops"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm["tflops"] / fp64_peak,
                     "traffic": ncu_traffic("gemm_dmma_k"), "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor; MEASURED_PEAKS.json has no FP64 figure)",
+                    "frac_of_nominal_40_tflops": gemm["tflops"] / 40.0,
                     "share_of_step": gemm["share"]}
         else:
             s = stages[top]

@@ -118,7 +118,9 @@ def _r4(x):
     return float(np.float32(x))
 
 
-def _sum(x):
+def _sum(x, dim=None):
+    if dim is not None:  # SUM(array, DIM=d): the other axes are kept; element order along d as in memory
+        return np.add.reduce(np.asarray(x), axis=int(dim) - 1)
     # sequential left-to-right like a Fortran loop (numpy's pairwise sum only differs for > 8 elements)
     x = np.asarray(x).ravel(order="F")
     acc = x[0] * 0
@@ -171,7 +173,7 @@ INTRINSICS = {
     "cosh": "np.cosh", "dcosh": "np.cosh", "sinh": "np.sinh", "dsinh": "np.sinh", "log": "np.log", "dlog": "np.log",
     "floor": "_floor", "int": "_int", "nint": "_nint", "dble": "np.real", "real": "np.real", "aimag": "np.imag",
     "dimag": "np.imag", "conjg": "np.conj", "dconjg": "np.conj", "cmplx": "_cmplx", "dcmplx": "_cmplx", "sum": "_sum",
-    "mod": "np.fmod", "min": "min", "max": "max", "sign": "_sign", "fftw_plan_dft_1d": "_fftw_plan",
+    "mod": "np.fmod", "min": "min", "max": "max", "maxval": "np.max", "minval": "np.min", "sign": "_sign", "fftw_plan_dft_1d": "_fftw_plan",
 }
 
 # ------------------------------------------------------------------------------------------------ lexer / parser
@@ -337,7 +339,12 @@ class Parser:
         if self.peek()[1] in (")", None):
             return args
         while True:
-            args.append(self.section_or_expr())
+            if self.peek()[0] == "name" and self.peek(1)[1] == "=" :  # keyword argument (SUM(x, DIM=1))
+                kw = self.eat()[1]
+                self.eat("=")
+                args.append("%s=%s" % (kw, self.expr()))
+            else:
+                args.append(self.section_or_expr())
             if self.peek()[1] == ",":
                 self.eat(",")
                 continue

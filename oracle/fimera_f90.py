@@ -17,7 +17,7 @@ from .f90py import F90Module
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("CHIMERA_REF", "/root/reference")
 FILES = ["fb_io", "fb_math", "fb_math_env", "grid_deps", "grid_deps_env", "grid_deps_chnk", "grid_deps_env_chnk",
-         "maxwell_solvers", "particle_tools", "devices"]
+         "maxwell_solvers", "particle_tools", "devices", "utils", "SR"]
 
 
 def _intent(v):

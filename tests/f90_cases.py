@@ -92,6 +92,26 @@ def cases(ofim):
     xd, fd, dev = device_cases(np.random.default_rng(16), n=300)
     for name, args in dev:
         yield "device:" + name, name, (xd, fd, 0.3, *args)
+    # utils.f90 diagnostics helpers and SR.f90 (NEXT rows 3 and 4)
+    r = np.random.default_rng(55)
+    for nm in (1, 3):
+        fld = np.asfortranarray(r.standard_normal((17, 9, nm, 3)) + 1j * r.standard_normal((17, 9, nm, 3)))
+        yield "intens_profo_m%d" % nm, "intens_profo", (fld, 12)
+    yield "density_2x", "density_2x", (r.uniform(-1.2, 1.2, 900), r.uniform(-0.7, 2.4, 900), r.random(900),
+                                       np.array([-1.0, 1.0, -0.5, 2.0]), 20, 13)
+    from test_sr import far_grid, near_args, tracks
+
+    x, mp, mn, w, dt = tracks(40, 3, 43)
+    g = far_grid(7, 2, 3)
+    s0 = np.asfortranarray(r.random((7, 2, 3)))
+    yield "sr_far_tot", "sr_calc_far_tot", (s0, x, mp, mn, w, dt, *g)
+    yield "sr_far_comp2", "sr_calc_far_comp", (s0, x, mp, mn, w, 2, dt, *g)
+    for circ in (False, True):
+        na = near_args(circ, 6, 3, 2)
+        s1 = np.asfortranarray(r.random((6, 3, 2)))
+        tag = "nearcirc" if circ else "near"
+        yield "sr_%s_tot" % tag, "sr_calc_%s_tot" % tag, (s1, x, mn, w, dt, *na)
+        yield "sr_%s_comp3" % tag, "sr_calc_%s_comp" % tag, (s1, x, mn, w, 3, dt, *na)
 
 
 def flatten(out):

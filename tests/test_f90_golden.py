@@ -167,3 +167,39 @@ def test_fixtures_are_what_the_reference_fortran_gives_today():
         res = getattr(F, fn)(*[a.copy(order="F") if isinstance(a, np.ndarray) else a for a in args])
         for k, arr in enumerate(flatten(res)):
             assert np.array_equal(f90_cases.fingerprint(arr), KERNELS["%s|%d" % (cid, k)]), cid
+
+
+# ---- the WHOLE reference stack: its unmodified Python driver on top of its own Fortran ------------------------------
+@pytest.mark.skipif(not os.path.isdir("/root/reference/f90"), reason="needs the reference checkout (build container)")
+@pytest.mark.parametrize("name", ["real_m2", "real_m3", "env_m1", "env_m3", "static_m2", "env_m1_win"])
+def test_reference_driver_on_its_own_fortran_reproduces_the_fixtures(name):
+    """tests/golden/<name>.npz were recorded by running the reference's ChimeraRun / Solver / Specie on the C++ oracle
+    (tools/gen_golden.py).  Here the same unmodified driver runs on the reference's OWN Fortran (oracle/f90py.py): every
+    recorded state (after make_halfstep and after 4 make_step: grids, spectral fields, particles, and for the windowed FEL
+    case the reference's Diagnostics) must come out the same, so those fixtures are outputs of the reference itself."""
+    import gen_golden
+    import ref_driver
+    from oracle import fimera_f90
+
+    F = fimera_f90.load()
+    R = ref_driver.install(F)
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = gen_golden.generate(name, gen_golden.CASES[name], R, F)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    S = setup(gen_golden.CASES[name]["setup"])
+    tol = carrier_tol(S, 1e-12)
+    checked = 0
+    for k in gold.files:
+        if not k.startswith(("h_", "s_", "d_", "tab_")) or gold[k].dtype.kind not in "fc":
+            continue
+        a, b = np.asarray(out[k]), gold[k]
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        den = np.linalg.norm(b.ravel())
+        err = np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0)
+        t = 20 * tol if (S.env and k.endswith("_J")) else tol
+        assert err <= t, "%s/%s: the reference on its own Fortran differs from the fixture by %.3e" % (name, k, err)
+        checked += 1
+    assert checked >= 8, checked
