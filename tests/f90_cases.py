@@ -27,6 +27,9 @@ def cases(ofim):
     x, p, w = particles(S, 400, 5)
     dom = np.asfortranarray([a["leftX"] + 0.5, a["rightX"] - 0.3, 0.0, (0.8 * a["Rgrid"].max()) ** 2])
     yield "sortpartsout", "sortpartsout", (x, dom)
+    wz = w.copy()
+    wz[::7] = 0.0
+    yield "sortoutghosts", "sortoutghosts", (wz,)
     dom = np.asfortranarray([a["leftX"], a["rightX"], 0.0, a["Rgrid"].max() ** 2])
     for nchnk in (1, 4):
         yield "chunk_coords_boundaries_%d" % nchnk, "chunk_coords_boundaries", (x, dom, a["Xgrid"], nchnk)

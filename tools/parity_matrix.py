@@ -52,6 +52,10 @@ def main():
     import ctypes
 
     lib = ctypes.CDLL(os.path.join(ROOT, "chimera_b200", "libchimera_b200.so"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import f90_cases
+
+    f90_funcs = {fn for _, fn, _ in f90_cases.cases(ofim)}
     for name in ofim.API_NAMES:
         # tests spell the variants literally or build them as base + "_env" / "_chnk" (tests/test_gpu_parity.py:126-250,
         # tests/test_np_ref.py, tests/pic_ref.py:79): accept the base name next to a suffix expression as well
@@ -68,21 +72,27 @@ def main():
         # the step-level tests reach most kernels through the sequence in tests/pic_ref.py
         via_seq = bool(pat.search(tests.get("pic_ref.py", ""))) or name.startswith(("dep_curr", "dep_dens"))
         gpu_t = [f for f in gpu_files if pat.search(tests[f]) and "pytest.mark.gpu" in tests[f] or (f.startswith("test_gpu") and pat.search(tests[f]))]
-        rows.append("| `%s` | %s | %s | %s | %s | %s | %s |" % (
-            name, REF.get(name, "?"),
+        # executed reference Fortran: the vectors of tests/golden/f90_kernels.npz are keyed "<case>|<k>", the case table
+        # (tests/f90_cases.py) names the fimera function of every case
+        f90 = "yes" if name in f90_funcs else "—"
+        rows.append("| `%s` | %s | %s | %s | %s | %s | %s | %s |" % (
+            name, REF.get(name, "?"), f90,
             "yes" if ("oracle_%s" % name) in cpp else "NO",
             ("`%s`" % npname if not npname.startswith("(") else npname) if has_np else "—",
             "yes" if ("chimera_%s(" % name) in hdr and hasattr(lib, "chimera_%s" % name) else "NO",
             ", ".join(sorted(set(t.replace("test_", "").replace(".py", "") for t in cpu_t))) or "—",
             (", ".join(sorted(set(t.replace("test_", "").replace(".py", "") for t in gpu_t))) or "—") + (" + step sequence" if via_seq else "")))
     out = ["# PARITY — coverage per `fimera` entry point", "",
-           "Generated by `tools/parity_matrix.py` from the sources. Columns: reference subroutine; C++ oracle restatement",
+           "Generated by `tools/parity_matrix.py` from the sources. Columns: reference subroutine; whether golden vectors from",
+           "the reference's OWN Fortran exist for it (executed by `oracle/f90py.py`, `tests/golden/f90_kernels.npz`, checked",
+           "against the oracle and the CUDA library by `tests/test_f90_golden.py`); C++ oracle restatement",
            "(`oracle/*.cpp`); independent numpy restatement (`oracle/np_ref.py`); CUDA entry point (`include/chimera_b200.h` +",
            "`chimera_b200/csrc`); CPU tests that exercise it (oracle vs numpy, known answers, golden fixtures, shim); GPU tests",
            "(CUDA vs oracle / fixtures). \"step sequence\": also reached by every engine / drop-in step test through",
            "`tests/pic_ref.py`, the restatement of `ChimeraRun.make_halfstep/make_step/frame_act` that the golden fixtures",
            "recorded from the reference's own driver pin.", "",
-           "| entry point | reference | C++ oracle | numpy restatement | CUDA | CPU tests | GPU tests |", "|---|---|---|---|---|---|---|"]
+           "| entry point | reference | executed Fortran vectors | C++ oracle | numpy restatement | CUDA | CPU tests | GPU tests |",
+           "|---|---|---|---|---|---|---|---|"]
     out += rows
     out += ["", "%d entry points; the reference's Python uses 50 of them (SURVEY.md section 8b)." % len(rows), ""]
     open(os.path.join(ROOT, "PARITY.md"), "w").write("\n".join(out))
