@@ -637,24 +637,47 @@ def run_small(a):
                                      if k in ("fb_in_J", "fb_in_rho", "poisson", "maxwell", "fields_out", "static_fields")),
     }
     eng.close()
-    # end to end: the per-function drop-in with HOST numpy buffers (every call copies in and out), reference sequence
+    # end to end: the per-function drop-in driven by the reference's make_step sequence -- with HOST numpy buffers (every
+    # call copies its arguments in and its results out: `e2e`), and in resident mode (`e2e_resident`: the driver's numpy
+    # arrays in CUDA managed memory, no copies)
     if not a.no_e2e:
-        run = small_refrun(gfim, S, species, eg0, c)
-        run.make_step()
-        torch.cuda.synchronize()
-        lib.chimera_host_traffic(None, None, 1)
-        t = time.perf_counter()
-        ne = max(3, min(a.steps, 10))
-        for _ in range(ne):
-            run.make_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t) / ne
-        h2d, d2h = ctypes.c_longlong(), ctypes.c_longlong()
-        lib.chimera_host_traffic(ctypes.byref(h2d), ctypes.byref(d2h), 1)
-        out["e2e"] = {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": ne, "h2d_bytes_per_step": int(h2d.value // ne),
-                      "d2h_bytes_per_step": int(d2h.value // ne),
-                      "path": "chimera_b200.fimera per-function drop-in driven by the reference's make_step sequence: pageable host "
-                              "numpy buffers, every call copies its arguments in and its results out"}
+        import copy
+
+        def drive(resident):
+            Sx = S
+            if resident:
+                gfim.resident(True)
+                Sx = copy.deepcopy(S)  # tables built after the switch, as a driver that imports the drop-in first gets them
+            try:
+                timer = StageTimer(gfim)
+                sp2 = [dict(sp, **{k: np.array(sp[k], order="F") for k in ("coords", "momenta", "weights")}) for sp in species]
+                run = small_refrun(timer, Sx, sp2, np.array(eg0, order="F"), c)
+                for _ in range(2):
+                    run.make_step()
+                torch.cuda.synchronize()
+                lib.chimera_host_traffic(None, None, 1)
+                timer.t.clear()
+                t = time.perf_counter()
+                ne = max(3, min(a.steps, 10))
+                for _ in range(ne):
+                    run.make_step()
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t) / ne
+                h2d, d2h = ctypes.c_longlong(), ctypes.c_longlong()
+                lib.chimera_host_traffic(ctypes.byref(h2d), ctypes.byref(d2h), 1)
+            finally:
+                if resident:
+                    gfim.resident(False)
+            calls = {k: 1e3 * v / ne for k, v in sorted(timer.t.items(), key=lambda kv: -kv[1])}
+            calls["python_statements"] = dt * 1e3 - sum(calls.values())
+            return {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": ne, "h2d_bytes_per_step": int(h2d.value // ne),
+                    "d2h_bytes_per_step": int(d2h.value // ne), "calls_ms": calls,
+                    "path": "chimera_b200.fimera per-function drop-in driven by the reference's make_step sequence, " +
+                            ("RESIDENT mode: numpy arrays in CUDA managed memory, no staging copies" if resident else
+                             "pageable host numpy buffers, every call copies its arguments in and its results out")}
+
+        out["e2e"] = drive(False)
+        out["e2e_resident"] = drive(True)
     if not a.no_cpu:
         out["cpu_baseline"] = cpu_small(a, S, species, eg0, c, steps=3, warmup=1)
     print(json.dumps(out))

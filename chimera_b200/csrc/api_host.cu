@@ -366,37 +366,83 @@ int chimera_kernel_launches(chb_i64* n) { *n = g_launches; return 0; }
 // (J[:] = 0, Rho += BckGrndRho, gradRho_prv[:] = gradRho_nxt, chimera_main.py:110-190, solvers.py:318) on the device
 namespace {
 std::mutex g_mm_mu;
-std::unordered_map<const void*, size_t> g_mm;  // managed blocks handed to numpy
+struct MBlock { size_t bytes, cap; };                        // what numpy asked for, what was allocated
+std::unordered_map<const void*, MBlock> g_mm;                 // managed blocks handed to numpy
+std::unordered_map<size_t, std::vector<void*>> g_mm_free;     // freed blocks by capacity: numpy temporaries come in
+size_t g_mm_cached = 0;                                       // repeating sizes, and cudaMallocManaged / cudaFree cost
+constexpr size_t kMMCacheMax = size_t(8) << 30;               // milliseconds each (cudaFree also synchronises the device)
+constexpr size_t kMMGran = size_t(2) << 20;
 }  // namespace
 void* chimera_managed_alloc(size_t bytes, int zero) {
-  void* p = nullptr;
   if (bytes == 0) bytes = 1;
-  if (cudaMallocManaged(&p, bytes, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const size_t cap = (bytes + kMMGran - 1) / kMMGran * kMMGran;
+  void* p = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mm_mu);
+    auto it = g_mm_free.find(cap);
+    if (it != g_mm_free.end() && !it->second.empty()) {
+      p = it->second.back();
+      it->second.pop_back();
+      g_mm_cached -= cap;
+    }
+  }
+  if (!p && cudaMallocManaged(&p, cap, cudaMemAttachGlobal) != cudaSuccess) {
+    cudaGetLastError();
+    chimera_managed_trim();  // give the cached blocks back and try once more
+    if (cudaMallocManaged(&p, cap, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
   if (zero) {  // zero on the device: np.zeros arrays of the driver (J, Rho, EB, the spectral state) are used there first
     if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
     cudaDeviceSynchronize();
   }
   std::lock_guard<std::mutex> lk(g_mm_mu);
-  g_mm[p] = bytes;
+  g_mm[p] = MBlock{bytes, cap};
   return p;
 }
 int chimera_managed_owns(const void* p, size_t* bytes) {
   std::lock_guard<std::mutex> lk(g_mm_mu);
   auto it = g_mm.find(p);
   if (it == g_mm.end()) return 0;
-  if (bytes) *bytes = it->second;
+  if (bytes) *bytes = it->second.bytes;
   return 1;
 }
 void chimera_managed_free(void* p) {
+  size_t cap = 0;
   {
     std::lock_guard<std::mutex> lk(g_mm_mu);
-    g_mm.erase(p);
+    auto it = g_mm.find(p);
+    if (it != g_mm.end()) { cap = it->second.cap; g_mm.erase(it); }
+    if (cap && g_mm_cached + cap <= kMMCacheMax) {
+      g_mm_free[cap].push_back(p);
+      g_mm_cached += cap;
+      return;
+    }
   }
   if (cudaFree(p) != cudaSuccess) cudaGetLastError();  // at interpreter exit the context may be gone already
 }
+void chimera_managed_trim(void) {
+  std::unordered_map<size_t, std::vector<void*>> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_mm_mu);
+    drop.swap(g_mm_free);
+    g_mm_cached = 0;
+  }
+  for (auto& kv : drop)
+    for (void* q : kv.second)
+      if (cudaFree(q) != cudaSuccess) cudaGetLastError();
+}
 void* chimera_managed_realloc(void* p, size_t new_bytes) {
   size_t old = 0;
-  if (!chimera_managed_owns(p, &old)) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mm_mu);
+    auto it = g_mm.find(p);
+    if (it == g_mm.end()) return nullptr;
+    old = it->second.bytes;
+    if (new_bytes <= it->second.cap) {  // fits the block: nothing moves
+      it->second.bytes = new_bytes ? new_bytes : 1;
+      return p;
+    }
+  }
   void* q = chimera_managed_alloc(new_bytes, 0);
   if (!q) return nullptr;
   const size_t n = old < new_bytes ? old : new_bytes;

@@ -27,6 +27,14 @@ without asking anything of the driver:
    (``self.Data[k] = chimera.f(self.Data[k], ...)``).  Particle arrays are left alone (the driver resizes them, a view
    cannot be resized).  ``upgrade_inputs = False`` switches this off.
 
+4. **Other numpy expressions on resident arrays** (the driver's ``(momenta[0] * weights).sum() / weights.sum()`` under
+   'StaticKick', chimera_main.py:121-122; the reductions of moduls/diagnostics.py) would pull their operands to the host
+   page by page.  ``ResidentArray.__array_ufunc__`` runs the common element-wise ufuncs and the add / max / min
+   reductions on the device instead -- through torch, on the very same memory (``__cuda_array_interface__``; strided
+   views such as ``momenta[0]`` included) -- when an operand is large; everything else, and everything small, is numpy on
+   the host as before.  Results are new numpy arrays (managed memory) or scalars.  ``offload_ufuncs = False`` switches
+   it off.
+
 ``enable()`` switches it on for the process (also: environment ``CHIMERA_B200_RESIDENT=1`` before importing
 ``chimera_b200.fimera``); without a CUDA device it raises.  In resident mode use the object a call RETURNS, as the
 reference's driver does (``self.Data[k] = chimera.f(self.Data[k], ...)``): a particle array that is not yet resident
@@ -45,7 +53,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _state = {"on": False, "np": None}
 THRESHOLD = 1 << 20
 upgrade_inputs = True
+offload_ufuncs = True
 _seen_inputs = set()
+_torch = {"mod": None, "map": None}
 
 
 def _npalloc():
@@ -95,6 +105,7 @@ def disable():
     if _state["on"]:
         _npalloc().chb_npalloc_uninstall()
         _state["on"] = False
+        _lib.load().chimera_managed_trim()  # freed blocks are cached for reuse while the mode is on
 
 
 def stats():
@@ -124,8 +135,100 @@ def _check(rc):
         raise RuntimeError("libchimera_b200: status %d: %s" % (rc, _lib.load().chimera_last_error().decode()))
 
 
+class _CudaView:
+    """``__cuda_array_interface__`` of a numpy array in managed / device memory (shape, strides, dtype as they are)"""
+
+    def __init__(self, a):
+        self.__cuda_array_interface__ = {"shape": a.shape, "typestr": a.dtype.str, "data": (a.ctypes.data, False), "version": 2,
+                                         "strides": a.strides if a.size else None}
+
+
+def _torch_ops():
+    if _torch["map"] is None:
+        import torch
+
+        _torch["mod"] = torch
+        _torch["map"] = {np.add: torch.add, np.subtract: torch.sub, np.multiply: torch.mul, np.true_divide: torch.div,
+                         np.negative: torch.neg, np.absolute: torch.abs, np.conjugate: torch.conj_physical,
+                         np.square: torch.square, np.sqrt: torch.sqrt, np.exp: torch.exp, np.maximum: torch.maximum,
+                         np.minimum: torch.minimum}
+    return _torch["mod"], _torch["map"]
+
+
+def _offload(ufunc, method, inputs, out, kwargs):
+    """the ufunc on the device through torch, or NotImplemented"""
+    if method not in ("__call__", "reduce") or not any(isinstance(x, np.ndarray) and x.nbytes >= THRESHOLD for x in inputs):
+        return NotImplemented
+    for x in inputs:
+        if isinstance(x, np.ndarray):
+            if x.dtype.kind not in "fc" or x.dtype.itemsize not in (8, 16) or (x.nbytes >= 4096 and not accessible(x)):
+                return NotImplemented
+        elif not isinstance(x, (int, float, complex, np.number)):
+            return NotImplemented
+    try:
+        torch, ops = _torch_ops()
+    except Exception:
+        return NotImplemented
+    as_t = lambda x: torch.as_tensor(_CudaView(x), device="cuda") if isinstance(x, np.ndarray) and x.nbytes >= 4096 else (  # noqa: E731
+        torch.as_tensor(np.asarray(x), device="cuda") if isinstance(x, np.ndarray) else x)
+    if method == "__call__":
+        op = ops.get(ufunc)
+        if op is None or set(kwargs) - {"casting", "order", "subok"}:
+            return NotImplemented
+        if ufunc is np.absolute and any(isinstance(x, np.ndarray) and x.dtype.kind == "c" for x in inputs):
+            rdtype = np.dtype("float64")
+        else:
+            rdtype = np.result_type(*[x.dtype if isinstance(x, np.ndarray) else x for x in inputs])
+        shape = np.broadcast_shapes(*[x.shape for x in inputs if isinstance(x, np.ndarray)])
+        if out is not None:
+            res = out[0]
+            if not (isinstance(res, np.ndarray) and res.shape == shape and res.dtype == rdtype and accessible(res)):
+                return NotImplemented
+        else:
+            forder = all(x.flags.f_contiguous for x in inputs if isinstance(x, np.ndarray) and x.ndim > 1)
+            res = np.empty(shape, dtype=rdtype, order="F" if forder else "C").view(ResidentArray)
+            if res.nbytes >= 4096 and not accessible(res):
+                return NotImplemented
+        op(*[as_t(x) for x in inputs], out=as_t(res))
+        torch.cuda.current_stream().synchronize()
+        return res
+    # reductions: sum / max / min over all axes or the given ones
+    red = {np.add: "sum", np.maximum: "amax", np.minimum: "amin"}.get(ufunc)
+    if red is None or out is not None or set(kwargs) - {"axis", "keepdims", "dtype"} or kwargs.get("dtype") is not None:
+        return NotImplemented
+    (x,) = inputs
+    t, axis = as_t(x), kwargs.get("axis", 0)
+    dims = tuple(range(x.ndim)) if axis is None else (axis if isinstance(axis, tuple) else (axis,))
+    if red != "sum" and x.dtype.kind == "c":
+        return NotImplemented
+    r = getattr(torch, red)(t, dim=dims, keepdim=bool(kwargs.get("keepdims", False)))
+    if r.ndim == 0:
+        return x.dtype.type(r.item())
+    res = np.empty(tuple(r.shape), dtype=x.dtype, order="F").view(ResidentArray)
+    if res.nbytes >= 4096 and accessible(res):
+        as_t(res).copy_(r)
+        torch.cuda.current_stream().synchronize()
+        return res
+    res[...] = r.cpu().numpy()
+    return res
+
+
 class ResidentArray(np.ndarray):
     """numpy array in CUDA managed memory whose whole-array statements run on the device (module docstring)"""
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        if _state["on"] and offload_ufuncs:
+            r = _offload(ufunc, method, inputs, out, kwargs)
+            if r is not NotImplemented:
+                return r
+        # numpy on the host, on the same memory (the CUDA driver migrates what is touched)
+        args = [np.asarray(x) if isinstance(x, ResidentArray) else x for x in inputs]
+        if out is not None:
+            kwargs["out"] = tuple(np.asarray(o) if isinstance(o, ResidentArray) else o for o in out)
+        r = getattr(ufunc, method)(*args, **kwargs)
+        if out is not None:
+            return out[0] if len(out) == 1 else out
+        return r.view(ResidentArray) if isinstance(r, np.ndarray) and r.nbytes >= THRESHOLD else r
 
     def __setitem__(self, key, value):
         if _state["on"] and self.size and self.dtype.kind in "fc" and self.dtype.itemsize in (8, 16) and _contig(self) \

@@ -177,3 +177,37 @@ def test_input_only_arrays_are_upgraded_where_they_are_held(ofim, gfim, resident
     assert isinstance(data["prv"], resident.ResidentArray) and data["prv"].base is raw  # same memory, upgraded in the dict
     data["prv"][:] = data["nxt"]  # now a device copy
     assert np.array_equal(raw, np.asarray(data["nxt"]))
+
+
+def test_numpy_expressions_on_resident_arrays_run_on_the_device(ofim, gfim, resident):
+    """chimera_main.py:121-122 (PXmean of the 'StaticKick' schedule) and the reductions of moduls/diagnostics.py on
+    arrays a call returned: common ufuncs and add / max / min reductions go through torch on the same managed memory
+    (strided views included); the results are what numpy gives on host copies"""
+    S = setup("real_m2")
+    a = S.Args
+    x, p, w = particles(S, 40000, 17, inside_only=True)
+    rng = np.random.default_rng(18)
+    f = np.asfortranarray(rng.standard_normal((6, 40000)))
+    pg = gfim.push_velocs(p.copy(order="F"), f, 0.3)
+    wg = np.array(w).view(resident.ResidentArray)  # the driver's weights: managed, made resident by any call that returns it
+    ph, wh = np.array(np.asarray(pg)), np.array(w)  # host copies
+    got = (pg[0] * wg).sum() / wg.sum()
+    want = (ph[0] * wh).sum() / wh.sum()
+    assert abs(got / want - 1) < 1e-13
+    assert isinstance(pg[0] * wg, resident.ResidentArray)
+    from util import crandn
+
+    EG = gfim.field_drift(crandn(rng, S.shape_fb + (6,)), a["kx"], 0.5, a["TimeStep"])
+    EGh = np.array(np.asarray(EG))
+    ef = np.array(a["EnergyFact"]).view(resident.ResidentArray)
+    got = ((np.abs(EG[:, :, :, :3]) ** 2).sum(-1) * ef).sum(-1).sum(-1)      # Diagnostics.nrg_out, diagnostics.py:109-124
+    want = ((np.abs(EGh[:, :, :, :3]) ** 2).sum(-1) * a["EnergyFact"]).sum(-1).sum(-1)
+    assert_close(np.asarray(got), want, 1e-13, "nrg_out expression")
+    assert abs(np.abs(EG).max() - np.abs(EGh).max()) == 0.0
+    z = EG * 2.0 - EG
+    assert_close(np.asarray(z), EGh, 1e-15, "element-wise chain")
+    EG *= 0.5   # in place, out= path
+    assert_close(np.asarray(EG), 0.5 * EGh, 1e-15, "in-place multiply")
+    # unsupported pieces fall back to numpy on the same memory
+    assert np.allclose(np.sin(np.asarray(pg[1, :10])), np.sin(ph[1, :10]))
+    assert np.array_equal(np.asarray(np.floor(pg)), np.floor(ph))
