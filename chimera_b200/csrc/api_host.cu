@@ -137,6 +137,35 @@ static int deposit_host(int env, int curr, const double* coord, const double* mo
     ch = ChunkSpec{1, d_ind, (int)nchnk, guards, nxn / nchnk};
   }
   GridGeom g = make_geom(Rgrid, d_r, leftX, dx_inv, dr_inv, kx0, nxn, nrn, nm);
+  // Chunk-sorted particles of the driver keep the cell order they were generated in (genparts + a stable argsort), so
+  // the CTA-binned deposit of the resident engine applies: particle planes in scratch, CTA table from the chunk table.
+  // Whatever does not sit in a CTA's cell window takes the per-particle path inside that kernel, so any order is
+  // correct; small calls and mode counts without an instantiation use the direct kernel.
+  if (ind && np >= (i64)1 << 16 && Call::accessible(ind) != 2) {
+    double* xs = call.dev<double>(3 * np); NEED(xs);
+    CHB_TRY(launch_planes_from_aos(call.c.st, xs, d_x, 3, np, np));
+    double* ps = nullptr;
+    if (curr) {
+      ps = call.dev<double>(3 * np); NEED(ps);
+      CHB_TRY(launch_planes_from_aos(call.c.st, ps, d_p, 3, np, np));
+    }
+    std::vector<int> cta((size_t)nchnk + 1, 0);
+    for (i64 c = 0; c < nchnk; ++c) {
+      const int n = ind[c + 1] - ind[c];
+      cta[c + 1] = cta[c] + (n > 0 ? (n + kDepNPB - 1) / kDepNPB : 0);
+    }
+    int* d_cta = call.dev<int>(nchnk + 1); NEED(d_cta);
+    CHB_CUDA(cudaMemcpyAsync(d_cta, cta.data(), sizeof(int) * (size_t)(nchnk + 1), cudaMemcpyHostToDevice, call.c.st));
+    CHB_CUDA(cudaStreamSynchronize(call.c.st));  // `cta` leaves scope
+    SortedSpec sp{ch.ind, d_cta, (int)nchnk, cta[nchnk], nxn / nchnk, 0};
+    const int rc = launch_deposit_binned(call.c.st, env, curr, xs, ps, d_w, np, d_g, g, ch, sp);
+    if (rc != -1) {
+      CHB_TRY(rc);
+      CHB_TRY(launch_ghost_fold(call.c.st, d_g, nxn, nrn, nm * (curr ? 3 : 1)));
+      CHB_TRY(call.down(grid, (double*)d_g, 2 * ng));
+      return call.sync();
+    }
+  }
   CHB_TRY(launch_deposit_direct(call.c.st, env, curr, aos((const double*)d_x, 3), aos((const double*)d_p, 3), d_w, d_g,
                                 g, ch, np, true));
   CHB_TRY(call.down(grid, (double*)d_g, 2 * ng));

@@ -136,6 +136,7 @@ int launch_gather(cudaStream_t st, int env, CPView x, const double* w, const cd*
 int launch_gather_push(cudaStream_t st, int env, CPView x, const double* w, const cd* Fld, PView mom,
                        const GridGeom& g, double dt, const DeviceSet& und, i64 np);
 int launch_devices(cudaStream_t st, CPView x, PView fld, const DeviceSet& und, i64 np);
+int launch_planes_from_aos(cudaStream_t st, double* dst, const double* src, int ncomp, i64 cap, i64 np);
 int launch_deposit_direct(cudaStream_t st, int env, int curr, CPView x, CPView mom, const double* w, cd* grid,
                           const GridGeom& g, const ChunkSpec& ch, i64 np, bool fold);
 int launch_ghost_fold(cudaStream_t st, cd* grid, i64 nxn, i64 nrn, i64 nplanes);

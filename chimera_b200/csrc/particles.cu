@@ -191,6 +191,22 @@ int launch_ghost_fold(cudaStream_t st, cd* grid, i64 nxn, i64 nrn, i64 nplanes) 
   return 0;
 }
 
+// (ncomp, np) Fortran-ordered array (component fastest) -> ncomp planes of `cap` doubles: the layout the binned
+// kernels read (used by the per-function entry points, whose arguments are the reference's (3, Np) arrays)
+__global__ void __launch_bounds__(256) planes_from_aos_k(double* __restrict__ dst, const double* __restrict__ src, int ncomp,
+                                                         i64 cap, i64 np) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= np * ncomp) return;
+  const i64 ip = e / ncomp;
+  dst[(e - ip * ncomp) * cap + ip] = src[e];
+}
+int launch_planes_from_aos(cudaStream_t st, double* dst, const double* src, int ncomp, i64 cap, i64 np) {
+  if (np <= 0) return 0;
+  planes_from_aos_k<<<grid_for(np * ncomp, 256), 256, 0, st>>>(dst, src, ncomp, cap, np);
+  CHB_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_deposit_direct(cudaStream_t st, int env, int curr, CPView x, CPView mom, const double* w, cd* grid,
                           const GridGeom& g, const ChunkSpec& ch, i64 np, bool fold) {
   if (g.nm > 2 * kMaxModes) { set_error("too many azimuthal modes (%lld)", g.nm); return 3; }
