@@ -241,6 +241,7 @@ def run_ours(a):
     S, eng, n_local = build_problem(a, torch, rank, world, group)
 
     def barrier():
+        eng.sync()  # completes the gather + push a step call leaves pending (chimera_engine_set_lazy_tail)
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
@@ -259,6 +260,7 @@ def run_ours(a):
     barrier()
     e0.record()
     eng.step(a.steps)
+    eng.sync()  # K complete steps inside the timed region: the last step's gather + push included
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -575,8 +577,9 @@ def run_small(a):
     n = sum(sp["weights"].size for sp in species if not sp["still"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     eng.step(a.warmup)
-    torch.cuda.synchronize()
-    # (1) L2 flushed between steps
+    eng.sync()
+    # (1) L2 flushed between steps; one-step calls (a step's closing gather + push runs inside the next call's fused
+    # kernel, the last one in the sync that is timed after the loop)
     sampler = ClockSampler(0)
     sampler.start()
     time.sleep(0.3)
@@ -589,6 +592,11 @@ def run_small(a):
         eng.step(1)
         e1.record()
         evs.append((e0, e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.sync()
+    e1.record()
+    evs.append((e0, e1))
     torch.cuda.synchronize()
     launches = _lib.kernel_launches() - l0
     ms_cold = sum(e0.elapsed_time(e1) for e0, e1 in evs) / a.steps
@@ -597,6 +605,7 @@ def run_small(a):
     torch.cuda.synchronize()
     e0.record()
     eng.step(a.steps)
+    eng.sync()
     e1.record()
     torch.cuda.synchronize()
     ms_warm = e0.elapsed_time(e1) / a.steps
@@ -608,6 +617,7 @@ def run_small(a):
     lib.chimera_gemm_profile(1)
     e0.record()
     eng.step(a.steps)
+    eng.sync()
     e1.record()
     torch.cuda.synchronize()
     ms_prof = e0.elapsed_time(e1) / a.steps

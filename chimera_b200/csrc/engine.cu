@@ -72,6 +72,12 @@ struct chimera_engine {
   int use_graph = 1;    // chimera_engine_set_graph
   std::vector<double> static_px;  // mean momentum per species for the next static_fields phase (multi-rank runs)
   double dev_time = 0.0;  // i_step * TimeStep seen by time-dependent devices in the next gather + push
+  // the gather + push that closes the last step of a chimera_engine_step call is left pending, so that the next call
+  // can run it inside its first fused kernel; every other entry point that reads or changes engine state completes it
+  // first (ENG_ENTER)
+  bool tail_pending = false;
+  double tail_time = 0.0;  // dev_time of the pending gather + push
+  int lazy_tail = 1;       // chimera_engine_set_lazy_tail
   // window that moves every step inside chimera_engine_step (chimera_engine_set_window): shift at stage 1 (before
   // push_coords) and at stage 2 (between dep_curr and dep_dens), chimera_main.py:286-302
   double win_s1 = 0.0, win_s2 = 0.0;
@@ -206,6 +212,11 @@ namespace {
 
 #define ENG_CHECK(e) \
   if (!(e)) { set_error("null engine handle"); return 2; }
+// entry points that observe or change the state a pending gather + push would touch complete it first
+#define ENG_ENTER(e) \
+  ENG_CHECK(e);      \
+  if ((e)->tail_pending) CHB_TRY(flush_tail(e));
+int flush_tail(chimera_engine* e);
 
 int alloc_named(chimera_engine* e, const char* name, size_t bytes, bool zero = true, size_t spare = 0) {
   NamedArray a;
@@ -852,6 +863,14 @@ int run_phase(chimera_engine* e, int phase, double arg) {
   return rc;
 }
 
+// the gather + push_velocs that closes the last step of the previous chimera_engine_step call
+int flush_tail(chimera_engine* e) {
+  if (!e->tail_pending) return 0;
+  e->tail_pending = false;
+  e->dev_time = e->tail_time;
+  return run_phase(e, CHB_GATHER_PUSH, 1.0);
+}
+
 }  // namespace
 
 extern "C" {
@@ -946,7 +965,7 @@ static int find_array(chimera_engine* e, const char* name, NamedArray** a) {
 }
 
 int chimera_engine_upload(chimera_engine* e, const char* name, const void* src, chb_i64 nbytes) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   NamedArray* a;
   CHB_TRY(find_array(e, name, &a));
   if ((size_t)nbytes != a->bytes) { set_error("upload '%s': %lld bytes given, %zu expected", name, nbytes, a->bytes); return 2; }
@@ -958,7 +977,7 @@ int chimera_engine_upload(chimera_engine* e, const char* name, const void* src, 
 }
 
 int chimera_engine_download(chimera_engine* e, const char* name, void* dst, chb_i64 nbytes) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   NamedArray* a;
   CHB_TRY(find_array(e, name, &a));
   if ((size_t)nbytes != a->bytes) { set_error("download '%s': %lld bytes given, %zu expected", name, nbytes, a->bytes); return 2; }
@@ -968,7 +987,7 @@ int chimera_engine_download(chimera_engine* e, const char* name, void* dst, chb_
 }
 
 int chimera_engine_array(chimera_engine* e, const char* name, void** dev_ptr, chb_i64* nbytes) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   NamedArray* a;
   CHB_TRY(find_array(e, name, &a));
   *dev_ptr = a->p;
@@ -979,7 +998,7 @@ int chimera_engine_array(chimera_engine* e, const char* name, void** dev_ptr, ch
 int chimera_engine_add_species(chimera_engine* e, const double* coords, const double* coords_half, const double* momenta,
                                const double* weights, chb_i64 np, double push_fact, int still, chb_i64 capacity,
                                int* id) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (np < 0) { set_error("add_species: np < 0"); return 2; }
   Species s;
   s.np = np;
@@ -1027,7 +1046,7 @@ int chimera_engine_add_species(chimera_engine* e, const double* coords, const do
 
 int chimera_engine_add_device(chimera_engine* e, int id, int kind, double a0, const double* params, int nparams,
                               const double* map, chb_i64 nx) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < -1 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   static const int need[7] = {0, 4, 5, 3, 5, 7, 8};
   if (kind < DEV_UNDUL_ANALYTIC || kind > DEV_GAUSSBEAM) { set_error("add_device: unknown device kind %d", kind); return 2; }
@@ -1052,7 +1071,7 @@ int chimera_engine_add_device(chimera_engine* e, int id, int kind, double a0, co
 }
 
 int chimera_engine_set_time(chimera_engine* e, double t) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   e->dev_time = t;
   return 0;
 }
@@ -1062,7 +1081,7 @@ int chimera_engine_set_time(chimera_engine* e, double t) {
 // ------------------------------------------------------------------------------------------
 // solvers.py:619-633 damp_field(config, damp_b = False): x-space window on E and G
 int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   const auto& c = e->cfg;
   if (slab(e)) { set_error("damp_field needs every kx row (x-FFT): not available on a kx-slab engine"); return 2; }
   if (!filtr || nxfilt < 1 || nxfilt > c.nx || mode < 0 || mode > 2) { set_error("damp_field: bad filter (%lld points, mode %d)", nxfilt, mode); return 2; }
@@ -1082,7 +1101,7 @@ int chimera_engine_damp_field(chimera_engine* e, const double* filtr, chb_i64 nx
 // chimera_engine_damp_prepare together with the full-row scratch "EG_full" and filled with the full "kx_full");
 // this call rebuilds the full rows, applies the same fb_filtr as the unsharded engine and keeps this rank's rows.
 int chimera_engine_damp_prepare(chimera_engine* e) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   const auto& c = e->cfg;
   if (!slab(e)) { set_error("damp_prepare: only for kx-slab engines"); return 2; }
   const size_t full = sizeof(cd) * (size_t)c.nx * c.nkr * c.nm * 6;
@@ -1093,7 +1112,7 @@ int chimera_engine_damp_prepare(chimera_engine* e) {
 }
 
 int chimera_engine_damp_field_slab(chimera_engine* e, const double* filtr, chb_i64 nxfilt, int mode) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   const auto& c = e->cfg;
   if (!slab(e)) { set_error("damp_field_slab: only for kx-slab engines"); return 2; }
   if (!e->arr.count("EG_gath") || !e->arr.count("EG_full") || !e->arr.count("kx_full")) {
@@ -1116,14 +1135,14 @@ int chimera_engine_damp_field_slab(chimera_engine* e, const double* filtr, chb_i
 
 // chimera_main.py:286-290 move_frame: Xgrid += shiftX
 int chimera_engine_set_window(chimera_engine* e, double shift_stage1, double shift_stage2) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   e->win_s1 = shift_stage1;
   e->win_s2 = shift_stage2;
   return 0;
 }
 
 int chimera_engine_move_window(chimera_engine* e, double shiftX) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   e->cfg.leftX += shiftX;
   e->cfg.rightX += shiftX;
   return 0;
@@ -1157,7 +1176,7 @@ static int species_reserve(chimera_engine* e, Species& s, i64 need) {
 // is no longer binned afterwards: a re-binning (chimera_engine_sort) must follow before the next deposit.
 int chimera_engine_append_particles(chimera_engine* e, int id, const double* coords, const double* momenta,
                                     const double* weights, chb_i64 n) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   if (n < 0) { set_error("append_particles: n < 0"); return 2; }
   if (n == 0) return 0;
@@ -1189,13 +1208,13 @@ int chimera_engine_append_particles(chimera_engine* e, int id, const double* coo
 // species.py:351-398 chunk_and_damp with an explicit absorbing layer: particles left of leftX + left_margin, right
 // of rightX or beyond the radial limit are dropped, the rest re-binned (on coords_halfstep when on_halfstep != 0)
 int chimera_engine_sort(chimera_engine* e, int on_halfstep, double left_margin) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   return ph_sort(e, on_halfstep, left_margin);
 }
 // the same with the radial limit of the call given explicitly: a window's damp_plasma culls at the SPECIES' upperR
 // (species.py:92,376: its r grid has one node less than the solver's), not at the solver's like the per-step re-binning
 int chimera_engine_sort_window(chimera_engine* e, int on_halfstep, double left_margin, double upper_r2) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   return ph_sort(e, on_halfstep, left_margin, upper_r2);
 }
 
@@ -1205,7 +1224,7 @@ int chimera_engine_sort_window(chimera_engine* e, int on_halfstep, double left_m
 // diagnostics.py:109-124 nrg_out before its roll: out[kx] = sum_{kr,m} EnergyFact * sum_{c<3} |EG_fb[..,c]|^2.
 // energy_fact (nx, nkr, nm) float64, host or device, is kept in HBM after the first call (pass NULL later).
 int chimera_engine_field_energy(chimera_engine* e, const double* energy_fact, double* out) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   const auto& c = e->cfg;
   const i64 nkx = nxs(e), ncols = c.nkr * c.nm;
   if (!out) { set_error("field_energy: null output"); return 2; }
@@ -1224,7 +1243,7 @@ int chimera_engine_field_energy(chimera_engine* e, const double* energy_fact, do
 
 // diagnostics.py:174-207 get_beam_envelops: the sums it is built from, on coords_halfstep and momenta
 int chimera_engine_beam_moments(chimera_engine* e, int id, double* out16) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   Species& s = e->sp[id];
   e->scr.reset();
@@ -1237,7 +1256,7 @@ int chimera_engine_beam_moments(chimera_engine* e, int id, double* out16) {
 }
 
 int chimera_engine_spectrum(chimera_engine* e, int id, int quantity, double lo, double hi, chb_i64 nbins, double* hist) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   if (nbins < 1 || nbins > 4096 || !(hi > lo) || quantity < 0 || quantity > 1) { set_error("spectrum: bad binning"); return 2; }
   Species& s = e->sp[id];
@@ -1252,7 +1271,7 @@ int chimera_engine_spectrum(chimera_engine* e, int id, int quantity, double lo, 
 
 // out[ix] = A[ix, ir, m, l] of a complex grid array (e.g. "EB", ir = 0: the on-axis wake field)
 int chimera_engine_lineout(chimera_engine* e, const char* name, chb_i64 ir, chb_i64 m, chb_i64 l, double* out) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   NamedArray* a;
   CHB_TRY(find_array(e, name, &a));
   const auto& c = e->cfg;
@@ -1274,7 +1293,7 @@ int chimera_engine_lineout(chimera_engine* e, const char* name, chb_i64 ir, chb_
 }
 
 int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   *np = e->sp[id].np;
   return 0;
@@ -1282,7 +1301,7 @@ int chimera_engine_species_count(chimera_engine* e, int id, chb_i64* np) {
 
 int chimera_engine_get_species(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
                                double* weights) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   Species& s = e->sp[id];
   if (s.np == 0) return 0;
@@ -1301,7 +1320,7 @@ int chimera_engine_get_species(chimera_engine* e, int id, double* coords, double
 }
 
 int chimera_engine_get_chunks(chimera_engine* e, int id, int* ind) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   const int nchnk = e->cfg.chunked ? e->cfg.nchnk : 1;
   for (int c = 0; c <= nchnk; ++c) ind[c] = e->sp[id].h_ind[c];
@@ -1309,7 +1328,7 @@ int chimera_engine_get_chunks(chimera_engine* e, int id, int* ind) {
 }
 
 int chimera_engine_run(chimera_engine* e, int phase, double arg) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   return run_phase(e, phase, arg);
 }
 
@@ -1406,14 +1425,14 @@ int chimera_engine_set_graph(chimera_engine* e, int on) {
 // 'StaticKick' across ranks: PXmean of every species (chimera_main.py:121-122) from the all-reduced beam moments, used
 // by the next CHB_STATIC_FIELDS phase instead of the local reduction (NaN: species empty everywhere)
 int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   e->static_px.assign(px, px + (n > 0 ? n : 0));
   return 0;
 }
 
 // buffers of the column-block dataflow for `world` ranks (kx-slab engines only)
 int chimera_engine_set_colflow(chimera_engine* e, int rank, int world) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (rank < 0 || rank >= world) { set_error("column dataflow: bad rank %d of %d", rank, world); return 2; }
   e->col_rank = rank;
   const auto& c = e->cfg;
@@ -1446,11 +1465,17 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
   // of step k+1 -- is independent per particle, so inside a multi-step call it runs as ONE kernel
   // (CHB_PARTICLES_FUSED); the first step's head, the last step's tail and re-binning steps (the sort sits
   // between push_coords and the deposits, chimera_main.py:82-86) use the separate phases.
-  bool gather_pending = false;
+  // The tail of the call's last step stays pending (tail_pending) and becomes part of the next call's first fused
+  // kernel: a caller that steps one at a time (diagnostics every step) runs the same kernels as one long call.
+  if (nsteps <= 0) return 0;
+  bool gather_pending = e->tail_pending;
+  e->tail_pending = false;
   for (i64 k = 0; k < nsteps; ++k) {
     const i64 istep = istep0 + k;
     const bool sort_now = c.sort_every > 0 && istep % c.sort_every == 0;
-    e->dev_time = (double)(istep - 1) * c.dt;  // the pending gather + push closes step istep - 1 (make_device(istep - 1))
+    // the pending gather + push closes the step before (make_device(istep - 1)); carried over from an earlier call it
+    // keeps the time of that call's last step
+    e->dev_time = (k == 0 && gather_pending) ? e->tail_time : (double)(istep - 1) * c.dt;
     if (gather_pending && !sort_now && e->fuse && !c.static_kick) {
       if (graph_usable(e)) {  // the whole step, spectral update included, as one graph launch
         CHB_TRY(step_graphed(e));
@@ -1489,7 +1514,17 @@ int chimera_engine_step(chimera_engine* e, chb_i64 istep0, chb_i64 nsteps) {
     gather_pending = true;
   }
   e->dev_time = (double)(istep0 + nsteps - 1) * c.dt;
-  if (gather_pending) CHB_TRY(run_phase(e, CHB_GATHER_PUSH, 1.0));
+  if (e->lazy_tail && e->fuse) {
+    e->tail_pending = true;
+    e->tail_time = e->dev_time;
+    return 0;
+  }
+  return run_phase(e, CHB_GATHER_PUSH, 1.0);
+}
+
+int chimera_engine_set_lazy_tail(chimera_engine* e, int on) {
+  ENG_ENTER(e);
+  e->lazy_tail = on ? 1 : 0;
   return 0;
 }
 
@@ -1514,7 +1549,7 @@ static int host_mark(chimera_engine* e, cudaStream_t on, cudaStream_t waiter) {
 int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, double* coords_half, double* momenta,
                                    double* weights, chb_i64 np, double* EG_fb, double* gradRho_fb_nxt, chb_i64 istep,
                                    int rebin) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (id < 0 || id >= (int)e->sp.size()) { set_error("bad species id %d", id); return 2; }
   Species& s = e->sp[id];
   if (s.still) { set_error("step_host: species %d is still", id); return 2; }
@@ -1600,7 +1635,7 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
 
 // kx-slab mode only: field update on this rank's slab and the first half of fields out (-> "EB_slab")
 int chimera_engine_step_host_mid(chimera_engine* e) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (e->host_id < 0) { set_error("step_host_mid without step_host_begin"); return 2; }
   const auto& c = e->cfg;
   auto mark = [&](cudaStream_t on, cudaStream_t waiter) -> int { return host_mark(e, on, waiter); };
@@ -1631,7 +1666,7 @@ int chimera_engine_step_host_mid(chimera_engine* e) {
 // second half: (the caller may all-reduce J / Rho on the engine stream in between) transforms, Poisson
 // correction, PSATD advance, fields out, gather + push, copies out; synchronises everything
 int chimera_engine_step_host_end(chimera_engine* e, chb_i64* np_out) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   if (e->host_id < 0) { set_error("step_host_end without step_host_begin"); return 2; }
   Species& s = e->sp[e->host_id];
   const auto& c = e->cfg;
@@ -1728,13 +1763,13 @@ int chimera_engine_step_host(chimera_engine* e, int id, double* coords, double* 
 }
 
 int chimera_engine_set_fuse(chimera_engine* e, int on) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   e->fuse = on ? 1 : 0;
   return 0;
 }
 
 int chimera_engine_set_rho_from_bg(chimera_engine* e, int from_bg) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   e->host_rho_from_bg = from_bg ? 1.0 : 0.0;
   return 0;
 }
@@ -1749,13 +1784,13 @@ int chimera_host_unregister(void* ptr) {
 }
 
 int chimera_engine_sync(chimera_engine* e) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   CHB_CUDA(cudaStreamSynchronize(e->st));
   return 0;
 }
 
 int chimera_engine_set_stream(chimera_engine* e, void* cuda_stream) {
-  ENG_CHECK(e);
+  ENG_ENTER(e);
   CHB_CUDA(cudaStreamSynchronize(e->st));
   if (e->own_stream) cudaStreamDestroy(e->st);
   e->st = (cudaStream_t)cuda_stream;

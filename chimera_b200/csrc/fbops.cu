@@ -58,7 +58,8 @@ void Scratch::destroy() {
   blocks.clear();
 }
 
-int FFTCache::exec(cudaStream_t st, cd* data, i64 n, i64 batch, int dir) {
+int FFTCache::exec(cudaStream_t st, cd* data, i64 n, i64 batch, int dir) { return exec(st, data, data, n, batch, dir); }
+int FFTCache::exec(cudaStream_t st, cd* in, cd* out, i64 n, i64 batch, int dir) {
   if (n <= 0 || batch <= 0) return 0;
   auto key = std::make_pair(n, batch);
   auto it = plans.find(key);
@@ -70,7 +71,7 @@ int FFTCache::exec(cudaStream_t st, cd* data, i64 n, i64 batch, int dir) {
     it = plans.emplace(key, h).first;
   }
   cufftResult r = cufftSetStream(it->second, st);
-  if (r == CUFFT_SUCCESS) r = cufftExecZ2Z(it->second, (cufftDoubleComplex*)data, (cufftDoubleComplex*)data, dir);
+  if (r == CUFFT_SUCCESS) r = cufftExecZ2Z(it->second, (cufftDoubleComplex*)in, (cufftDoubleComplex*)out, dir);
   if (r != CUFFT_SUCCESS) { set_error("cufftExecZ2Z failed: %d", (int)r); return 7; }
   return 0;
 }
@@ -99,10 +100,12 @@ struct Batcher {
   GemmBatch b;
   int rc = 0;
   Batcher(cudaStream_t s, i64 M_, i64 N_, i64 K_, i64 lda_, i64 ldc_) : st(s), M(M_), N(N_), K(K_), lda(lda_), ldc(ldc_) { b.count = 0; }
-  void add(const cd* A, const double* Bp, cd* C, double alpha, double beta) {
+  // every C of the batch leaves the kernel row-scaled by exp(i sign leftX kx) (and by the `fact` given to add)
+  void phase(const double* kx, double leftX, double sign) { b.phase_kx = kx; b.phase_leftX = leftX; b.phase_sign = sign; }
+  void add(const cd* A, const double* Bp, cd* C, double alpha, double beta, const double* fact = nullptr) {
     if (rc) return;
     if (b.count == kGemmMaxBatch) flush();
-    b.p[b.count++] = GemmProblem{(const double*)A, Bp, (double*)C, alpha, beta};
+    b.p[b.count++] = GemmProblem{(const double*)A, Bp, (double*)C, alpha, beta, fact};
   }
   int flush() {
     if (!rc && b.count) rc = launch_gemm(st, b, M, N, K, lda, ldc);
@@ -115,14 +118,20 @@ struct Batcher {
 // ------------------------------------------------------------------------------------------
 int fb_in_dev(FBCtx& c, cd* out_fb, const cd* in, double leftX, const double* kx, const PackedOps& In,
               const double* fact, i64 nkx, i64 nrn, i64 nm, i64 nkr, int ncomp) {
-  const i64 nr = nrn - 1;
+  // x-FFT first (out of place, into scratch), then the Hankel contraction with shiftX_inv and the quadrature factor
+  // (fb_io.f90:52-57) in its epilogue: the two transforms act on different axes, and this order leaves no separate
+  // pass over the spectral array
+  const i64 nr = nrn - 1, ncols = nrn * nm * ncomp;
+  cd* xf = c.scr->take_n<cd>(nkx * ncols);
+  if (!xf) return 6;
+  CHB_TRY(c.fft->exec(c.st, const_cast<cd*>(in), xf, nkx, ncols, CUFFT_FORWARD));
   Batcher gb(c.st, 2 * nkx, nkr, nr, 2 * nkx, 2 * nkx);
+  gb.phase(kx, leftX, -1.0);
   for (int l = 0; l < ncomp; ++l)
     for (i64 m = 0; m < nm; ++m)
-      gb.add(in + nkx * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nkx * nkr * (m + nm * l), 1.0, 0.0);
+      gb.add(xf + nkx * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nkx * nkr * (m + nm * l), 1.0, 0.0,
+             fact ? fact + nkx * nkr * m : nullptr);
   CHB_TRY(gb.flush());
-  CHB_TRY(c.fft->exec(c.st, out_fb, nkx, nkr * nm * ncomp, CUFFT_FORWARD));
-  CHB_TRY(launch_rowscale_phase(c.st, out_fb, kx, leftX, -1.0, 1.0, fact, nkx, nkr * nm * ncomp, nkr * nm));
   return 0;
 }
 
@@ -133,13 +142,13 @@ int fb_out_dev(FBCtx& c, cd* out, const cd* const* srcs, int nsrc, int ncomp_eac
   // the contractions overwrite radial nodes 1..nr of every plane; only the ghost node 0 is left to zero (fb_io.f90:203)
   CHB_CUDA(cudaMemset2DAsync(out, sizeof(cd) * nkx * nrn, 0, sizeof(cd) * nkx, (size_t)(nm * ncomp), c.st));
   Batcher gb(c.st, 2 * nkx, nr, nkr, 2 * nkx, 2 * nkx);
+  gb.phase(kx, leftX, +1.0);  // shiftX (fb_io.f90:216-222) in the epilogue; the ghost node stays zero either way
   for (int j = 0; j < nsrc; ++j)
     for (int l = 0; l < ncomp_each; ++l)
       for (i64 m = 0; m < nm; ++m)
         gb.add(srcs[j] + nkx * nkr * (m + nm * l), Out.slot[m],
                out + nkx * (1 + nrn * (m + nm * (l + ncomp_each * j))), 1.0, 0.0);
   CHB_TRY(gb.flush());
-  CHB_TRY(launch_rowscale_phase(c.st, out, kx, leftX, +1.0, 1.0, nullptr, nkx, nrn * nm * ncomp, 1));
   CHB_TRY(c.fft->exec(c.st, out, nkx, nrn * nm * ncomp, CUFFT_INVERSE));
   return 0;
 }
@@ -174,11 +183,12 @@ int fb_in_slab_dev(FBCtx& c, cd* out_fb, const cd* in, double leftX, const doubl
   take_rows_k<<<grid_for(nxs * ncols, 256), 256, 0, c.st>>>(slab, full, rows, nxs, nkx, nxs * ncols);
   CHB_LAUNCH_CHECK();
   Batcher gb(c.st, 2 * nxs, nkr, nr, 2 * nxs, 2 * nxs);
+  gb.phase(kx_slab, leftX, -1.0);  // shiftX_inv and the quadrature factor (fb_io.f90:52-57) in the epilogue
   for (int l = 0; l < ncomp; ++l)
     for (i64 m = 0; m < nm; ++m)
-      gb.add(slab + nxs * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nxs * nkr * (m + nm * l), 1.0, 0.0);
+      gb.add(slab + nxs * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nxs * nkr * (m + nm * l), 1.0, 0.0,
+             fact_slab ? fact_slab + nxs * nkr * m : nullptr);
   CHB_TRY(gb.flush());
-  CHB_TRY(launch_rowscale_phase(c.st, out_fb, kx_slab, leftX, -1.0, 1.0, fact_slab, nxs, nkr * nm * ncomp, nkr * nm));
   return 0;
 }
 
@@ -188,11 +198,12 @@ int fb_in_slab_post_dev(FBCtx& c, cd* out_fb, const cd* slab, double leftX, cons
                         const double* fact_slab, i64 nxs, i64 nrn, i64 nm, i64 nkr, int ncomp) {
   const i64 nr = nrn - 1;
   Batcher gb(c.st, 2 * nxs, nkr, nr, 2 * nxs, 2 * nxs);
+  gb.phase(kx_slab, leftX, -1.0);  // shiftX_inv and the quadrature factor (fb_io.f90:52-57) in the epilogue
   for (int l = 0; l < ncomp; ++l)
     for (i64 m = 0; m < nm; ++m)
-      gb.add(slab + nxs * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nxs * nkr * (m + nm * l), 1.0, 0.0);
+      gb.add(slab + nxs * (1 + nrn * (m + nm * l)), In.slot[m], out_fb + nxs * nkr * (m + nm * l), 1.0, 0.0,
+             fact_slab ? fact_slab + nxs * nkr * m : nullptr);
   CHB_TRY(gb.flush());
-  CHB_TRY(launch_rowscale_phase(c.st, out_fb, kx_slab, leftX, -1.0, 1.0, fact_slab, nxs, nkr * nm * ncomp, nkr * nm));
   return 0;
 }
 
@@ -224,13 +235,13 @@ int fb_out_slab_dev(FBCtx& c, cd* out_slab, const cd* const* srcs, int nsrc, int
   const int ncomp = nsrc * ncomp_each;
   CHB_CUDA(cudaMemset2DAsync(out_slab, sizeof(cd) * nxs * nrn, 0, sizeof(cd) * nxs, (size_t)(nm * ncomp), c.st));
   Batcher gb(c.st, 2 * nxs, nr, nkr, 2 * nxs, 2 * nxs);
+  gb.phase(kx_slab, leftX, +1.0);
   for (int j = 0; j < nsrc; ++j)
     for (int l = 0; l < ncomp_each; ++l)
       for (i64 m = 0; m < nm; ++m)
         gb.add(srcs[j] + nxs * nkr * (m + nm * l), Out.slot[m],
                out_slab + nxs * (1 + nrn * (m + nm * (l + ncomp_each * j))), 1.0, 0.0);
   CHB_TRY(gb.flush());
-  CHB_TRY(launch_rowscale_phase(c.st, out_slab, kx_slab, leftX, +1.0, 1.0, nullptr, nxs, nrn * nm * ncomp, 1));
   return 0;
 }
 

@@ -29,6 +29,7 @@ struct Scratch {
 struct FFTCache {
   std::map<std::pair<i64, i64>, cufftHandle> plans;
   int exec(cudaStream_t st, cd* data, i64 n, i64 batch, int dir);  // in place, dir = CUFFT_FORWARD / CUFFT_INVERSE
+  int exec(cudaStream_t st, cd* in, cd* out, i64 n, i64 batch, int dir);  // out of place (`in` is not written)
   void destroy();
 };
 

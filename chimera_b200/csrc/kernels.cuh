@@ -202,11 +202,17 @@ struct GemmProblem {
   const double* Bp;  // packed operator
   double* C;         // ldc in doubles
   double alpha, beta;
+  const double* fact;  // optional real factor per complex element of C, (M/2 x N) column-major (epilogue, with the phase)
 };
 constexpr int kGemmMaxBatch = 48;
 struct GemmBatch {
   GemmProblem p[kGemmMaxBatch];
   int count;
+  // optional epilogue of every problem of the batch (beta must be 0): complex row i of C times
+  // exp(i * phase_sign * phase_leftX * phase_kx[i]), then times fact -- the shiftX / shiftX_inv row scale of
+  // fb_io.f90:52-57, :216-222 that otherwise costs a pass over C (launch_rowscale_phase)
+  const double* phase_kx = nullptr;
+  double phase_leftX = 0.0, phase_sign = 1.0;
 };
 i64 gemm_packed_size(i64 K, i64 N);  // doubles
 int launch_gemm_pack_b(cudaStream_t st, double* Bp, const double* B, i64 K, i64 N, i64 ldb);

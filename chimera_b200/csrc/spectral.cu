@@ -30,17 +30,24 @@ __global__ void __launch_bounds__(TPB) rowscale_phase_k(cd* __restrict__ a, cons
   const cd ph = cmake(scale * cs, scale * sign * sn);
   const i64 c0 = (i64)blockIdx.y * cols_per_block;
   const i64 c1 = (c0 + cols_per_block < ncols) ? c0 + cols_per_block : ncols;
-  for (i64 c = c0; c < c1; ++c) {
-    cd v = cmul(a[i + nkx * c], ph);
-    if (fact) v = cscale(__ldg(fact + i + nkx * (c % fact_cols)), v);
-    a[i + nkx * c] = v;
+  for (i64 c = c0; c < c1; c += 4) {  // 4 independent loads in flight per thread
+    cd v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c + k < c1) {
+        v[k] = cmul(a[i + nkx * (c + k)], ph);
+        if (fact) v[k] = cscale(__ldg(fact + i + nkx * ((c + k) % fact_cols)), v[k]);
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c + k < c1) a[i + nkx * (c + k)] = v[k];
   }
 }
 
 int launch_rowscale_phase(cudaStream_t st, cd* a, const double* kx, double leftX, double sign, double scale,
                           const double* fact, i64 nkx, i64 ncols, i64 fact_cols) {
   if (nkx <= 0 || ncols <= 0) return 0;
-  const i64 cpb = 16;
+  const i64 cpb = (nkx * ncols < (i64)1 << 22) ? 4 : 16;  // short grids: more CTAs, one group of loads per thread
   dim3 grid(grid_for(nkx, TPB), (unsigned)((ncols + cpb - 1) / cpb));
   rowscale_phase_k<<<grid, TPB, 0, st>>>(a, kx, leftX, sign, scale, fact, nkx, ncols, fact_cols ? fact_cols : 1, cpb);
   CHB_LAUNCH_CHECK();
@@ -63,24 +70,33 @@ int launch_rowscale_cplx(cudaStream_t st, cd* a, const cd* s, i64 nkx, i64 ncols
 
 // eb_correction (grid_deps.f90:219-266) / eb_correction_env (grid_deps_env.f90:240-283):
 // normalise by 1/2pi (m=0, real) or 1/pi, then fill the ghost row from row 1 (copy or negate).
+// One thread per (ix, 8 rows): the rows of a thread are independent loads in flight together, and the grid has
+// nrn/8 times more CTAs than a thread-per-column walk (which ran a 300-deep dependent chain on 24 CTAs at Nr = 301).
+constexpr int kEbRows = 8;
 __global__ void __launch_bounds__(TPB) eb_correction_k(cd* __restrict__ eb, i64 nxn, i64 nrn, i64 nm, int env) {
   const i64 ix = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (ix >= nxn) return;
   const i64 q = blockIdx.y;  // plane = slot + nm*l
+  const i64 r0 = 1 + (i64)blockIdx.z * kEbRows;
   const int slot = (int)(q % nm);
   const double pi_inv = 1.0 / 3.14159265358979323846;
   const double f = (!env && slot == 0) ? 0.5 * pi_inv : pi_inv;
   const bool negate = env ? (nm > 1) : (slot > 0);  // Q6
-  cd* pl = eb + nxn * nrn * q;
-  for (i64 ir = 1; ir < nrn; ++ir) {
-    cd v = cscale(f, pl[ix + nxn * ir]);
-    pl[ix + nxn * ir] = v;
-    if (ir == 1) pl[ix] = negate ? cneg(v) : v;
-  }
+  cd* pl = eb + nxn * nrn * q + ix;
+  cd v[kEbRows];
+#pragma unroll
+  for (int k = 0; k < kEbRows; ++k)
+    if (r0 + k < nrn) v[k] = cscale(f, pl[nxn * (r0 + k)]);
+#pragma unroll
+  for (int k = 0; k < kEbRows; ++k)
+    if (r0 + k < nrn) pl[nxn * (r0 + k)] = v[k];
+  if (r0 == 1 && nrn > 1) pl[0] = negate ? cneg(v[0]) : v[0];
 }
 int launch_eb_correction(cudaStream_t st, cd* eb, i64 nxn, i64 nrn, i64 nm, int env, int ncomp) {
-  if (nxn <= 0) return 0;
-  dim3 grid(grid_for(nxn, TPB), (unsigned)(nm * ncomp));
+  if (nxn <= 0 || nrn <= 0) return 0;
+  const i64 nrb = nrn > 1 ? (nrn - 1 + kEbRows - 1) / kEbRows : 1;
+  if (nrb > 65535) { set_error("eb_correction: Nr too large"); return 4; }
+  dim3 grid(grid_for(nxn, TPB), (unsigned)(nm * ncomp), (unsigned)nrb);
   eb_correction_k<<<grid, TPB, 0, st>>>(eb, nxn, nrn, nm, env);
   CHB_LAUNCH_CHECK();
   return 0;
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(TPB) field_drift_k(cd* __restrict__ EG, const 
 }
 int launch_field_drift(cudaStream_t st, cd* EG, const double* kx, double beta0, double dt, i64 nkx, i64 ncols) {
   if (nkx <= 0 || ncols <= 0) return 0;
-  const i64 cpb = 16;
+  const i64 cpb = (nkx * ncols < (i64)1 << 22) ? 4 : 16;  // short grids: more CTAs, one group of loads per thread
   dim3 grid(grid_for(nkx, TPB), (unsigned)((ncols + cpb - 1) / cpb));
   field_drift_k<<<grid, TPB, 0, st>>>(EG, kx, -0.5 * dt * beta0, nkx, ncols, cpb);
   CHB_LAUNCH_CHECK();

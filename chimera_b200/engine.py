@@ -472,6 +472,11 @@ class Engine:
         """Replay the fused step as a CUDA graph between two re-binnings (default on; single GPU, no per-step window)."""
         self._check(self.lib.chimera_engine_set_graph(self._h, int(bool(on))))
 
+    def set_lazy_tail(self, on=True):
+        """``step`` leaves the gather + push that closes its last step pending so that the next ``step`` call runs it
+        inside its first fused kernel (default on); any other call on the engine completes it first."""
+        self._check(self.lib.chimera_engine_set_lazy_tail(self._h, int(bool(on))))
+
     def graph_info(self):
         """(number of cached step graphs, state: 1 = in use, 0 = not warmed up, -1 = capture failed, graphs off)"""
         n, st = ctypes.c_int(0), ctypes.c_int(0)

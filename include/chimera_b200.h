@@ -364,10 +364,16 @@ int chimera_engine_sync(chimera_engine* e);
 int chimera_engine_set_fuse(chimera_engine* e, int on);
 /* replay the fused step (particle kernel + spectral update) as a CUDA graph between two re-binnings (default on; used when
    no window moves every step and no device field depends on time) */
-int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n); /* 'StaticKick' across ranks: PXmean per species */
-int chimera_engine_set_colflow(chimera_engine* e, int rank, int world); /* column-block dataflow buffers (kx-slab engines) */
 int chimera_engine_set_graph(chimera_engine* e, int on);
 int chimera_engine_graph_info(chimera_engine* e, int* ngraphs, int* state); /* cached graphs; state 1 warm, -1 capture failed */
+/* chimera_engine_step leaves the gather + push_velocs that closes its last step pending, and the next chimera_engine_step
+   runs it inside its first fused kernel (a loop of one-step calls then runs the kernels of one long call).  Every other
+   engine entry point that reads or changes state (download, array, sync, run, diagnostics, ...) completes it first, so
+   the deferral is not observable through the API; device pointers from chimera_engine_array are current after
+   chimera_engine_sync.  Default on; 0 completes every call eagerly. */
+int chimera_engine_set_lazy_tail(chimera_engine* e, int on);
+int chimera_engine_set_static_px(chimera_engine* e, const double* px, int n); /* 'StaticKick' across ranks: PXmean per species */
+int chimera_engine_set_colflow(chimera_engine* e, int rank, int world); /* column-block dataflow buffers (kx-slab engines) */
 /* One make_step (chimera_main.py:82-92) with the PIC state in HOST buffers, the reference's calling model:
  * coords/momenta (3,np) Fortran-ordered in-out, coords_half (3,np) out, weights (np) in (rewritten in the
  * new particle order on re-binning steps), EG_fb (nx,nkr,nm,6) and gradRho_fb_nxt (nx,nkr,nm,3) complex

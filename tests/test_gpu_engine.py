@@ -579,3 +579,55 @@ def test_step_graph_replay_matches_eager_steps(ofim, gfim, name, ions):
     assert_close(pa[:, perm], pb, 100 * TOL, "momenta")
     eng.close()
     eager.close()
+
+
+@pytest.mark.parametrize("name,ions,und", [("real_m2", True, False), ("env_m1", False, True), ("static_m2", False, False)])
+def test_one_step_calls_run_the_kernels_of_one_long_call(ofim, gfim, name, ions, und):
+    """chimera_engine_step leaves the closing gather + push pending and the next call fuses it (csrc/engine.cu
+    tail_pending): 14 one-step calls (with reads of the state in between, which must see completed momenta) against one
+    14-step call on an engine that completes every call eagerly.  Crosses a re-binning; the time-dependent device of the
+    envelope case checks the time the carried gather + push is evaluated at."""
+    from chimera_b200.engine import Engine
+
+    S = SolverSetup(copy.deepcopy(SETUPS[name]))
+    x, p, w = plasma(S, 2, 2, 91)
+    static = name.startswith("static")
+    if static:
+        p[0] += 50.0
+    eg0 = seed_fields(S, 92, 0.1)
+    engines = []
+    for lazy in (True, False):
+        e = Engine(S, sort_every=9)
+        e.set_lazy_tail(lazy)
+        e.set_graph(False)
+        sid = e.add_species(x, p, w)
+        if und:
+            e.add_device("planewave", [0.3, 1.0, S.Args["leftX"], 40.0, 2.0, 0.1, 0.2], sid=sid)
+        if ions:
+            xi, pi_, wi = plasma(S, 2, 2, 98)
+            e.add_species(xi, 0 * pi_, -wi, charge=1.0, mass=1886.0, still=True)
+        if not static:
+            e.upload("EG_fb", eg0)
+        e.make_halfstep(**({"px0": (50.0,)} if static else {"background": ions}))
+        engines.append(e)
+    lazy, eager = engines
+    seen = []
+    for k in range(14):
+        lazy.step(1)
+        if k in (3, 10):  # a read in the middle completes the pending work: same momenta as the eager engine then
+            seen.append(lazy.particles(0)[2].copy())
+    eager.step(4)
+    ref4 = eager.particles(0)[2].copy()
+    eager.step(10)
+    assert_close(seen[0], ref4, 100 * TOL, "momenta after 4 steps")
+    for nm in ("EG_fb", "EB", "J"):
+        # the envelope deposit sums terms that carry exp(-i kx0 x): a cancelling sum (compare_state), and the fused and
+        # the separate kernels add them in different orders
+        assert_close(lazy.download(nm), eager.download(nm), (20 if S.env and nm == "J" else 1) * 100 * TOL, nm)
+    xa, _, pa, wa = lazy.particles(0)
+    xb, _, pb, wb = eager.particles(0)
+    perm = match(wb, wa)
+    assert_close(pa[:, perm], pb, 100 * TOL, "momenta")
+    assert_close(xa[:, perm], xb, 100 * TOL, "coords")
+    lazy.close()
+    eager.close()

@@ -132,11 +132,12 @@ def test_deposit_plain(ofim, gfim, name, n):
 
 @pytest.mark.parametrize("name", ["real_m2", "env_m1", "env_m3"])
 @pytest.mark.parametrize("guards", [0, 3])
-def test_deposit_chunked(ofim, gfim, name, guards):
+@pytest.mark.parametrize("n", [20000, 150000])  # 150000: above the size where api_host.cu takes the CTA-binned kernel
+def test_deposit_chunked(ofim, gfim, name, guards, n):
     S = setup(name)
     a = S.Args
     nchnk = 4
-    x, p, w = particles(S, 20000, 10, inside_only=True)
+    x, p, w = particles(S, n, 10, inside_only=True)
     x, p, w, chunks = chunk_sorted(S, x, p, w, ofim, nchnk)
     # let particles drift up to `guards` cells after the sort, as between two sorts of the driver
     x[0] += a["dx"] * guards * (np.random.default_rng(11).random(x.shape[1]) - 0.5) * 1.9
