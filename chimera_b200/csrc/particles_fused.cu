@@ -59,7 +59,13 @@ namespace {
 constexpr int FNPB = kFusedNPB, FT = CHB_FT, FRUN = CHB_FRUN;
 constexpr int FDSPLIT = CHB_FDSPLIT;
 constexpr int FSPLIT = CHB_FSPLIT;  // lanes that share a (segment, unit) in the deposit stage: 2 or 4
-constexpr int FBX = 40, FBR = 16, FBINS = FBX * FBR;
+#ifndef CHB_FBX
+#define CHB_FBX 40
+#endif
+#ifndef CHB_FBR
+#define CHB_FBR 16
+#endif
+constexpr int FBX = CHB_FBX, FBR = CHB_FBR, FBINS = FBX * FBR;
 constexpr int FPPT = (FNPB + FT - 1) / FT;
 constexpr int FMAXTASK = FNPB / FRUN + (FBINS < FNPB ? FBINS : FNPB);
 constexpr int FITEMS = (FBINS + FT - 1) / FT;

@@ -141,6 +141,27 @@ def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera", adopt=N
         b = _inout_base(a, dtype, name, shape)
         return adopt(b) if adopt is not None else b
 
+    # The real solver without space charge keeps REAL PSATD tables that f2py casts to complex on every
+    # maxwell_push_wo_spchrg call (maxwell_solvers.f90:67-68): two table-sized allocations + copies per step.  The cast
+    # is kept per source array (identity, buffer, shape and a few probe values: the driver rebuilds the tables as new
+    # arrays when the time step changes, it does not edit them in place).
+    _casts = {}
+
+    def _cast_once(a, name, shape):
+        if not isinstance(a, np.ndarray) or a.dtype == _C16 or a.size == 0:
+            return _in(a, _C16, name, shape)
+        flat = a.reshape(-1, order="A")
+        probe = (float(flat[0]), float(flat[flat.size // 2]), float(flat[-1]))
+        key = (name, id(a), a.ctypes.data, a.shape, a.dtype.str)
+        hit = _casts.get(key)
+        if hit is not None and hit[0] == probe:
+            return hit[1]
+        out = _in(a, _C16, name, shape)
+        for k in [k for k in _casts if k[0] == name]:
+            del _casts[k]
+        _casts[key] = (probe, out)
+        return out
+
     mod = types.ModuleType(modname)
     mod.error = FimeraError
     mod.__doc__ = "fimera-compatible API backed by %s_* entry points of %s" % (prefix, getattr(lib, "_name", lib))
@@ -473,8 +494,8 @@ def build_module(lib: ctypes.CDLL, prefix: str, modname: str = "fimera", adopt=N
     def maxwell_push_wo_spchrg(eg_fb, j_fb, c1, c2):
         eg, nkx, nkr, nm = _spec3(eg_fb, "eg_fb", (6,))
         j = _in(j_fb, _C16, "j_fb", (nkx, nkr, nm, 3))
-        c1 = _in(c1, _C16, "c1", (nkx, nkr, nm, 3))  # real tables are cast, maxwell_solvers.f90:67
-        c2 = _in(c2, _C16, "c2", (nkx, nkr, nm, 3))
+        c1 = _cast_once(c1, "c1", (nkx, nkr, nm, 3))  # real tables are cast, maxwell_solvers.f90:67
+        c2 = _cast_once(c2, "c2", (nkx, nkr, nm, 3))
         call("maxwell_push_wo_spchrg", eg, j, c1, c2, _i64(nkx), _i64(nkr), _i64(nm))
         return eg
 

@@ -76,6 +76,18 @@ def test_real_psatd_tables_are_cast_to_complex(ofim):
     a = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, S.PSATD_E, S.PSATD_G)
     b = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, S.PSATD_E.astype(complex), S.PSATD_G.astype(complex))
     assert np.array_equal(a, b)
+    # the cast is kept per table: a second call gives the same result, a rebuilt table (new array, e.g. after a change
+    # of the time step) and an edit of the same array are both seen
+    a2 = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, S.PSATD_E, S.PSATD_G)
+    assert np.array_equal(a2, a)
+    E2 = np.asfortranarray(S.PSATD_E * 0.5)
+    c = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, E2, S.PSATD_G)
+    d = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, E2.astype(complex), S.PSATD_G.astype(complex))
+    assert np.array_equal(c, d) and not np.array_equal(c, a)
+    E2 *= 3.0
+    e = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, E2, S.PSATD_G)
+    f = ofim.maxwell_push_wo_spchrg(eg.copy(order="F"), j, E2.astype(complex), S.PSATD_G.astype(complex))
+    assert np.array_equal(e, f)
 
 
 def test_both_backends_expose_the_same_api(ofim):
