@@ -1556,7 +1556,9 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
   if (e->cfg.static_kick) { set_error("step_host: no 'StaticKick' schedule; use chimera_engine_step"); return 2; }
   if (e->win_s1 != 0.0 || e->win_s2 != 0.0) { set_error("step_host: no per-step window; use chimera_engine_step"); return 2; }
   if (np < 0 || np > s.cap) { set_error("step_host: np=%lld exceeds the species capacity %lld", np, s.cap); return 2; }
-  if (!coords || !coords_half || !momenta || !weights) { set_error("step_host: null particle buffer"); return 2; }
+  // coords_half may be NULL: the centred positions are used inside the step only (deposit, re-binning) and a caller that
+  // lets the engine do both has no use for them on the host -- 24 B per particle less on the device->host link
+  if (!coords || !momenta || !weights) { set_error("step_host: null particle buffer"); return 2; }
   const auto& c = e->cfg;
   CHB_TRY(ensure_ops(e));
   if (!e->s_h2d) {
@@ -1589,12 +1591,15 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
     if (!sort_now) {
       soa_to_aos_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.x2 + 3 * a, s.x + a, 3, s.cap, n);
       CHB_LAUNCH_CHECK();
-      soa_to_aos_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.xh2 + 3 * a, s.xh + a, 3, s.cap, n);
-      CHB_LAUNCH_CHECK();
+      if (coords_half) {
+        soa_to_aos_k<<<grid_for(3 * n, 256), 256, 0, e->st>>>(s.xh2 + 3 * a, s.xh + a, 3, s.cap, n);
+        CHB_LAUNCH_CHECK();
+      }
       CHB_TRY(mark(e->st, e->s_d2h));
       CHB_CUDA(cudaMemcpyAsync(coords + 3 * a, s.x2 + 3 * a, D * 3 * n, cudaMemcpyDeviceToHost, e->s_d2h));
-      CHB_CUDA(cudaMemcpyAsync(coords_half + 3 * a, s.xh2 + 3 * a, D * 3 * n, cudaMemcpyDeviceToHost, e->s_d2h));
-      g_d2h_bytes += (long long)(D * 6 * n);
+      if (coords_half)
+        CHB_CUDA(cudaMemcpyAsync(coords_half + 3 * a, s.xh2 + 3 * a, D * 3 * n, cudaMemcpyDeviceToHost, e->s_d2h));
+      g_d2h_bytes += (long long)(D * (coords_half ? 6 : 3) * n);
     }
   }
   // spectral state of the solver: needed from the density transform on
@@ -1615,13 +1620,15 @@ int chimera_engine_step_host_begin(chimera_engine* e, int id, double* coords, do
     if (m > 0) {
       soa_to_aos_k<<<grid_for(3 * m, 256), 256, 0, e->st>>>(s.x2, s.x, 3, s.cap, m);
       CHB_LAUNCH_CHECK();
-      soa_to_aos_k<<<grid_for(3 * m, 256), 256, 0, e->st>>>(s.xh2, s.xh, 3, s.cap, m);
-      CHB_LAUNCH_CHECK();
+      if (coords_half) {
+        soa_to_aos_k<<<grid_for(3 * m, 256), 256, 0, e->st>>>(s.xh2, s.xh, 3, s.cap, m);
+        CHB_LAUNCH_CHECK();
+      }
       CHB_TRY(mark(e->st, e->s_d2h));
       CHB_CUDA(cudaMemcpyAsync(coords, s.x2, D * 3 * m, cudaMemcpyDeviceToHost, e->s_d2h));
-      CHB_CUDA(cudaMemcpyAsync(coords_half, s.xh2, D * 3 * m, cudaMemcpyDeviceToHost, e->s_d2h));
+      if (coords_half) CHB_CUDA(cudaMemcpyAsync(coords_half, s.xh2, D * 3 * m, cudaMemcpyDeviceToHost, e->s_d2h));
       CHB_CUDA(cudaMemcpyAsync(weights, s.w, D * m, cudaMemcpyDeviceToHost, e->s_d2h));
-      g_d2h_bytes += (long long)(D * 7 * m);
+      g_d2h_bytes += (long long)(D * (coords_half ? 7 : 4) * m);
     }
   }
   CHB_TRY(run_phase(e, CHB_DEPOSIT_J, 0));

@@ -771,7 +771,8 @@ class Engine:
         """One ``ChimeraRun.make_step`` (chimera_main.py:82-92) on HOST arrays, the reference's calling model.
 
         ``coords``/``momenta`` (3,Np) and ``weights`` (Np,) are the species' numpy arrays (Fortran order,
-        float64), updated in place; ``coords_half`` (3,Np) receives the centred positions; ``EG_fb`` and
+        float64), updated in place; ``coords_half`` (3,Np) receives the centred positions (``None``: not copied back --
+        they are only used inside the step, for the deposit and the re-binning the engine does itself); ``EG_fb`` and
         ``gradRho_fb_nxt`` are the solver's spectral state, updated in place (``None``: keep the
         engine-resident copy).  Host<->device copies are pipelined with the kernels inside the call
         (csrc/engine.cu ``chimera_engine_step_host``); page-lock the arrays once with :meth:`pin` for full
@@ -779,6 +780,8 @@ class Engine:
         n = coords.shape[1]
         for name, arr, shp in (("coords", coords, (3, n)), ("coords_half", coords_half, (3, n)),
                                ("momenta", momenta, (3, n)), ("weights", weights, (n,))):
+            if arr is None and name == "coords_half":
+                continue
             if arr.dtype != np.float64 or not arr.flags.f_contiguous or arr.shape != shp or not arr.flags.writeable:
                 raise ValueError("step_host: %s must be a writeable Fortran-ordered float64 array of shape %r" % (name, shp))
         for name, arr in (("EG_fb", EG_fb), ("gradRho_fb_nxt", gradRho_fb_nxt)):

@@ -380,6 +380,8 @@ int chimera_engine_set_colflow(chimera_engine* e, int rank, int world); /* colum
  * in-out (either may be NULL: the engine-resident copy is used and nothing is copied).  Operators, tables,
  * BckGrndRho and still species stay resident.  Copies run on two extra streams and overlap the kernels;
  * pass page-locked buffers (chimera_host_register) for full PCIe speed.  The call is synchronous.
+ * coords_half may be NULL: the centred positions are then not copied back (a caller that leaves deposit and re-binning
+ * to the engine never reads them; saves 24 B per particle on the device->host link).
  * rebin != 0 forces a re-binning in this step (required after the caller reordered or added particles);
  * *np_out = particles kept (re-binning culls the ones that left the domain). */
 int chimera_engine_step_host(chimera_engine* e, int species, double* coords, double* coords_half, double* momenta,

@@ -177,10 +177,12 @@ def test_engine_dropin_sequence_matches(ofim, gfim):
     assert_close(runs[1].sp[0].momenta[:, perm], runs[0].sp[0].momenta, TOL, "momenta")
 
 
-@pytest.mark.parametrize("name,ions", [("real_m2", True), ("real_m3", False), ("env_m1", False)])
-def test_engine_step_host_matches_reference_sequence(ofim, gfim, name, ions):
+@pytest.mark.parametrize("name,ions,want_half", [("real_m2", True, True), ("real_m3", False, True), ("env_m1", False, True),
+                                                 ("real_m2", True, False)])
+def test_engine_step_host_matches_reference_sequence(ofim, gfim, name, ions, want_half):
     """chimera_engine_step_host: the whole PIC state crosses PCIe every step (host numpy arrays in and
-    out, copies pipelined with the kernels); 5 steps include a re-binning step for Xchunked=(4,3)."""
+    out, copies pipelined with the kernels); 5 steps include a re-binning step for Xchunked=(4,3).
+    want_half = False: coords_halfstep not requested back (NULL), everything else unchanged."""
     und = dict(a0=0.3, **{"lambda": 1.3}, X0=-1.0, Lx=9.0) if name == "env_m1" else None
     S, ref, eng = build_pair(ofim, name, 51, still_ions=ions, undulator=und)
     ref.make_halfstep()
@@ -192,14 +194,17 @@ def test_engine_step_host_matches_reference_sequence(ofim, gfim, name, ions):
     n = x.shape[1]
     for _ in range(5):
         ref.make_step()
-        n = eng.step_host(x[:, :n], xh[:, :n], p[:, :n], w[:n], eg, g)  # leading columns stay Fortran-contiguous
+        n = eng.step_host(x[:, :n], xh[:, :n] if want_half else None, p[:, :n], w[:n], eg, g)  # leading columns stay Fortran-contiguous
     tol = carrier_tol(S, 5 * TOL)
     s = ref.sp[0]
     assert n == s.weights.shape[0]
     perm = match(s.weights, w[:n])
     assert_close(p[:, :n][:, perm], s.momenta, tol, "momenta")
     assert_close(x[:, :n][:, perm], s.coords, tol, "coords")
-    assert_close(xh[:, :n][:, perm], s.coords_halfstep, tol, "coords_halfstep")
+    if want_half:
+        assert_close(xh[:, :n][:, perm], s.coords_halfstep, tol, "coords_halfstep")
+    else:  # still on the device
+        assert_close(eng.particles(0)[1][:, perm], s.coords_halfstep, tol, "coords_halfstep (engine)")
     assert_close(eg, ref.EG_fb, tol, "EG_fb")
     if g is not None:
         assert_close(g, ref.g_nxt, tol, "gradRho_fb_nxt")
