@@ -183,6 +183,25 @@ static int gather_host(int env, const double* coord, const double* wghts, const 
   double* d_o = call.up(Fld_tot, 6 * np); NEED(d_o);
   double* d_r = call.up(Rgrid, nrn); NEED(d_r);
   GridGeom g = make_geom(Rgrid, d_r, leftX, dx_inv, dr_inv, kx0, nxn, nrn, nm);
+  // Large calls: the CTA-binned gather on particle planes in scratch (one "chunk" holding everything).  The driver's
+  // particles keep the cell order they were generated / chunk-sorted in, so consecutive particles share cells; whatever
+  // falls outside a CTA's cell window takes the per-particle path inside the kernel, so any order is correct.
+  if (np >= (i64)1 << 16) {
+    double* xs = call.dev<double>(3 * np); NEED(xs);
+    CHB_TRY(launch_planes_from_aos(call.c.st, xs, d_x, 3, np, np));
+    const int ncta = (int)((np + kDepNPB - 1) / kDepNPB);
+    const int tab[4] = {0, (int)np, 0, ncta};  // IndInChunk(0:1), CTA prefix(0:1)
+    int* d_tab = call.dev<int>(4); NEED(d_tab);
+    CHB_CUDA(cudaMemcpyAsync(d_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, call.c.st));
+    CHB_CUDA(cudaStreamSynchronize(call.c.st));  // `tab` leaves scope
+    SortedSpec sp{d_tab, d_tab + 2, 1, ncta, nxn, 0};
+    const int rc = launch_gather_binned_out(call.c.st, env, xs, d_w, d_f, d_o, np, g, sp);
+    if (rc != -1) {
+      CHB_TRY(rc);
+      CHB_TRY(call.down(Fld_tot, d_o, 6 * np));
+      return call.sync();
+    }
+  }
   CHB_TRY(launch_gather(call.c.st, env, aos((const double*)d_x, 3), d_w, d_f, aos(d_o, 6), g, np));
   CHB_TRY(call.down(Fld_tot, d_o, 6 * np));
   return call.sync();

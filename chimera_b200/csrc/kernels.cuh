@@ -160,6 +160,8 @@ int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, c
                           i64 cap, cd* grid, const GridGeom& g, const ChunkSpec& ch, const SortedSpec& sp);
 int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* mom,
                               i64 cap, const GridGeom& g, double dt, const DeviceSet& und, const SortedSpec& sp);
+int launch_gather_binned_out(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* fld_tot,
+                             i64 cap, const GridGeom& g, const SortedSpec& sp);
 // particles_fused.cu: gather + device + Boris push + position update + J / rho deposit in one kernel.
 // `sp.cta` must be the CTA table for kFusedNPB particles per CTA.  push_dt = 2 pi q/m dt, dt = time step.
 #ifndef CHB_FNPB

@@ -676,7 +676,10 @@ struct GatLayout {
                                  2 * sizeof(unsigned short) * kDepNPB;
 };
 
-template <int ENV, int NM>
+// OUT = 0: the gathered field goes into the Boris push (`mom` = momentum planes).  OUT = 1: it is added to the
+// reference's per-particle array Fld_tot(6, np) (`mom` = that array, component fastest): proj_fld on its own, for the
+// per-function entry points.
+template <int ENV, int NM, int OUT>
 __global__ void __launch_bounds__(GB_THREADS, 2)
 gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w, const cd* __restrict__ Fld,
                      double* __restrict__ mom, i64 cap, GridGeom g, double dt_2, DeviceSet und, SortedSpec sp) {
@@ -808,6 +811,13 @@ gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w,
     double F[6];
 #pragma unroll
     for (int l = 0; l < 6; ++l) F[l] = fbuf[l * kDepNPB + li];
+    if (OUT) {
+      if (skey[li] != 0xFFFFu || F[0] != 0.0 || F[1] != 0.0 || F[2] != 0.0 || F[3] != 0.0 || F[4] != 0.0 || F[5] != 0.0) {
+#pragma unroll
+        for (int l = 0; l < 6; ++l) mom[6 * ip + l] += F[l];
+      }
+      continue;
+    }
     if (und.n) apply_devices(und, __ldg(x + ip), __ldg(x + cap + ip), __ldg(x + 2 * cap + ip), F);
     double px = mom[ip], py = mom[cap + ip], pz = mom[2 * cap + ip];
     boris(px, py, pz, F[0], F[1], F[2], F[3], F[4], F[5], dt_2);
@@ -815,7 +825,7 @@ gather_push_binned_k(const double* __restrict__ x, const double* __restrict__ w,
   }
 }
 
-template <int ENV>
+template <int ENV, int OUT>
 int launch_gather_binned_nm(cudaStream_t st, const double* x, const double* w, const cd* Fld, double* mom, i64 cap,
                             const GridGeom& g, double dt_2, const DeviceSet& und, const SortedSpec& sp) {
   const size_t smem = GatLayout<ENV>::smem;
@@ -823,11 +833,11 @@ int launch_gather_binned_nm(cudaStream_t st, const double* x, const double* w, c
   case NMV: {                                                                                                     \
     static bool attr = false;                                                                                     \
     if (!attr) {                                                                                                  \
-      CHB_CUDA(cudaFuncSetAttribute(gather_push_binned_k<ENV, NMV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+      CHB_CUDA(cudaFuncSetAttribute(gather_push_binned_k<ENV, NMV, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)smem));                                                                  \
       attr = true;                                                                                                \
     }                                                                                                             \
-    gather_push_binned_k<ENV, NMV><<<sp.ncta, GB_THREADS, smem, st>>>(x, w, Fld, mom, cap, g, dt_2, und, sp);     \
+    gather_push_binned_k<ENV, NMV, OUT><<<sp.ncta, GB_THREADS, smem, st>>>(x, w, Fld, mom, cap, g, dt_2, und, sp); \
   } break;
   switch ((int)g.nm) {
     CHB_GB(1)
@@ -847,8 +857,19 @@ int launch_gather_push_binned(cudaStream_t st, int env, const double* x, const d
                               i64 cap, const GridGeom& g, double dt, const DeviceSet& und, const SortedSpec& sp) {
   if (sp.ncta <= 0) return 0;
   if (env && (g.nm % 2) != 1) { set_error("envelope gather needs an odd number of mode slots"); return 2; }
-  return env ? launch_gather_binned_nm<1>(st, x, w, Fld, mom, cap, g, 0.5 * dt, und, sp)
-             : launch_gather_binned_nm<0>(st, x, w, Fld, mom, cap, g, 0.5 * dt, und, sp);
+  return env ? launch_gather_binned_nm<1, 0>(st, x, w, Fld, mom, cap, g, 0.5 * dt, und, sp)
+             : launch_gather_binned_nm<0, 0>(st, x, w, Fld, mom, cap, g, 0.5 * dt, und, sp);
+}
+
+// proj_fld alone on binned particles: Fld_tot(6, np) += gathered field (-1: no instantiation for this mode count)
+int launch_gather_binned_out(cudaStream_t st, int env, const double* x, const double* w, const cd* Fld, double* fld_tot,
+                             i64 cap, const GridGeom& g, const SortedSpec& sp) {
+  if (sp.ncta <= 0) return 0;
+  if (env && (g.nm % 2) != 1) { set_error("envelope gather needs an odd number of mode slots"); return 2; }
+  DeviceSet none;
+  memset(&none, 0, sizeof(none));
+  return env ? launch_gather_binned_nm<1, 1>(st, x, w, Fld, fld_tot, cap, g, 0.0, none, sp)
+             : launch_gather_binned_nm<0, 1>(st, x, w, Fld, fld_tot, cap, g, 0.0, none, sp);
 }
 
 int launch_deposit_binned(cudaStream_t st, int env, int curr, const double* x, const double* mom, const double* w,

@@ -151,7 +151,7 @@ def test_deposit_chunked(ofim, gfim, name, guards, n):
 
 
 @pytest.mark.parametrize("name", ALL)
-@pytest.mark.parametrize("n", [0, 64, 30011])
+@pytest.mark.parametrize("n", [0, 64, 30011, 150001])  # 150001: above the size where api_host.cu takes the CTA-binned kernel
 def test_proj_fld(ofim, gfim, name, n):
     S = setup(name)
     a = S.Args
