@@ -4,6 +4,8 @@
 // operation without the per-call copies is the engine's job (engine.cu).
 #include <cub/device/device_scan.cuh>
 #include <cstdarg>
+#include <cstring>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -49,6 +51,9 @@ struct HostCtx {
 };
 static HostCtx g_ctx;
 
+// resident mode (below): does the managed range [p, p + bytes) need a prefetch to the device before a kernel uses it?
+bool managed_needs_prefetch(const void* p, size_t bytes);
+
 // RAII scope of one host call: staging helpers + final sync + scratch reset
 struct Call {
   HostCtx& c;
@@ -74,7 +79,7 @@ struct Call {
   template <typename T> T* up(const T* h, i64 n) {
     if (n > 0) {
       const int kind = accessible(h);
-      if (kind == 1) {
+      if (kind == 1 && managed_needs_prefetch(h, sizeof(T) * (size_t)n)) {
         int dev_id = 0;
         cudaGetDevice(&dev_id);
         if (cudaMemPrefetchAsync(h, sizeof(T) * (size_t)n, dev_id, c.st) != cudaSuccess) cudaGetLastError();
@@ -151,6 +156,10 @@ static int deposit_host(int env, int curr, const double* coord, const double* mo
     }
     std::vector<int> cta((size_t)nchnk + 1, 0);
     for (i64 c = 0; c < nchnk; ++c) {
+      if (ind[c] < 0 || ind[c + 1] < ind[c] || ind[c + 1] > np) {  // the reference would read out of bounds
+        set_error("deposit: IndInChunk is not a prefix table within 0..np (entry %lld)", (long long)c);
+        return 2;
+      }
       const int n = ind[c + 1] - ind[c];
       cta[c + 1] = cta[c] + (n > 0 ? (n + kDepNPB - 1) / kDepNPB : 0);
     }
@@ -414,8 +423,8 @@ int chimera_kernel_launches(chb_i64* n) { *n = g_launches; return 0; }
 // (J[:] = 0, Rho += BckGrndRho, gradRho_prv[:] = gradRho_nxt, chimera_main.py:110-190, solvers.py:318) on the device
 namespace {
 std::mutex g_mm_mu;
-struct MBlock { size_t bytes, cap; };                        // what numpy asked for, what was allocated
-std::unordered_map<const void*, MBlock> g_mm;                 // managed blocks handed to numpy
+struct MBlock { size_t bytes, cap; bool on_dev; };            // what numpy asked for, what was allocated, see below
+std::map<const void*, MBlock> g_mm;                           // managed blocks handed to numpy, by base address
 std::unordered_map<size_t, std::vector<void*>> g_mm_free;     // freed blocks by capacity: numpy temporaries come in
 size_t g_mm_cached = 0;                                       // repeating sizes, and cudaMallocManaged / cudaFree cost
 constexpr size_t kMMCacheMax = size_t(8) << 30;               // milliseconds each (cudaFree also synchronises the device)
@@ -444,8 +453,45 @@ void* chimera_managed_alloc(size_t bytes, int zero) {
     cudaDeviceSynchronize();
   }
   std::lock_guard<std::mutex> lk(g_mm_mu);
-  g_mm[p] = MBlock{bytes, cap};
+  g_mm[p] = MBlock{bytes, cap, zero != 0};  // zeroed on the device: the pages are there
   return p;
+}
+
+extern "C++" {
+namespace chb {
+// cudaMemPrefetchAsync on a range that already lives on the device is not free: ~1 ms per GB of range walked, 30 ms of
+// the 70 ms per-call LWFA step.  So a block is prefetched when it is first seen after its (re)allocation -- numpy arrays
+// the driver built on the CPU, e.g. the re-ordered particle arrays of a re-binning step -- and when the Python layer
+// reports a host-side write (chimera_managed_touched); otherwise it is taken to be where the last call left it.  A range
+// the host touched behind our back is still correct (managed memory is coherent), it comes back through page faults.
+// CHIMERA_B200_PREFETCH=always restores the prefetch per call, =never drops it.
+bool managed_needs_prefetch(const void* p, size_t bytes) {
+  static const int policy = [] {
+    const char* e = getenv("CHIMERA_B200_PREFETCH");
+    return !e ? 1 : (!strcmp(e, "always") ? 2 : (!strcmp(e, "never") ? 0 : 1));
+  }();
+  if (policy != 1) return policy == 2;
+  std::lock_guard<std::mutex> lk(g_mm_mu);
+  auto it = g_mm.upper_bound(p);
+  if (it == g_mm.begin()) return true;  // not one of our blocks (someone else's managed memory)
+  --it;
+  const char* base = (const char*)it->first;
+  if ((const char*)p + bytes > base + it->second.cap) return true;
+  if (it->second.on_dev) return false;
+  // a partial range (a slice of the array) is prefetched without changing the block's state
+  if ((const char*)p == base && bytes >= it->second.bytes) it->second.on_dev = true;
+  return true;
+}
+}  // namespace chb
+}  // extern "C++"
+
+// host-side write to a managed array reported by the Python layer (chimera_b200/resident.py): prefetch it next time
+void chimera_managed_touched(const void* p) {
+  std::lock_guard<std::mutex> lk(g_mm_mu);
+  auto it = g_mm.upper_bound(p);
+  if (it == g_mm.begin()) return;
+  --it;
+  if ((const char*)p < (const char*)it->first + it->second.cap) it->second.on_dev = false;
 }
 int chimera_managed_owns(const void* p, size_t* bytes) {
   std::lock_guard<std::mutex> lk(g_mm_mu);
@@ -488,6 +534,7 @@ void* chimera_managed_realloc(void* p, size_t new_bytes) {
     old = it->second.bytes;
     if (new_bytes <= it->second.cap) {  // fits the block: nothing moves
       it->second.bytes = new_bytes ? new_bytes : 1;
+      it->second.on_dev = false;  // the driver fills the new tail on the host
       return p;
     }
   }

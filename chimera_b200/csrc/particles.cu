@@ -23,9 +23,44 @@ __global__ void __launch_bounds__(256) push_velocs_k(PView mom, CPView fld, doub
   mom.at(2, ip) = pz;
 }
 
+// The reference's (ncomp, Np) arrays (component fastest) through shared memory: a CTA moves the contiguous block of its
+// 256 particles with coalesced accesses and each thread picks its components there -- a thread-per-particle walk of the
+// array touches every 32-byte sector with three (six) separate instructions.
+constexpr int kAosT = 256;
+template <int NC>
+__device__ __forceinline__ void aos_block_load(double* s, const double* g, i64 first, int n) {
+  for (int i = threadIdx.x; i < NC * n; i += kAosT) s[i] = g[NC * first + i];  // plain loads: some of these arrays are in/out
+}
+template <int NC>
+__device__ __forceinline__ void aos_block_store(double* __restrict__ g, const double* s, i64 first, int n) {
+  for (int i = threadIdx.x; i < NC * n; i += kAosT) g[NC * first + i] = s[i];
+}
+
+__global__ void __launch_bounds__(kAosT) push_velocs_aos_k(double* __restrict__ mom, const double* __restrict__ fld,
+                                                           double dt_2, i64 np) {
+  __shared__ double sp[3 * kAosT], sf[6 * kAosT];
+  const i64 first = (i64)blockIdx.x * kAosT;
+  const int n = (int)(np - first < kAosT ? np - first : kAosT), t = threadIdx.x;
+  aos_block_load<3>(sp, mom, first, n);
+  aos_block_load<6>(sf, fld, first, n);
+  __syncthreads();
+  if (t < n) {
+    double px = sp[3 * t], py = sp[3 * t + 1], pz = sp[3 * t + 2];
+    boris(px, py, pz, sf[6 * t], sf[6 * t + 1], sf[6 * t + 2], sf[6 * t + 3], sf[6 * t + 4], sf[6 * t + 5], dt_2);
+    sp[3 * t] = px; sp[3 * t + 1] = py; sp[3 * t + 2] = pz;
+  }
+  __syncthreads();
+  aos_block_store<3>(mom, sp, first, n);
+}
+
+static inline bool is_aos(const double* p, i64 cs, i64 ps, int ncomp) { return p && cs == 1 && ps == ncomp; }
+
 int launch_push_velocs(cudaStream_t st, PView mom, CPView fld, double dt, i64 np) {
   if (np <= 0) return 0;
-  push_velocs_k<<<grid_for(np, 256), 256, 0, st>>>(mom, fld, 0.5 * dt, np);
+  if (is_aos(mom.p, mom.cs, mom.ps, 3) && is_aos(fld.p, fld.cs, fld.ps, 6))
+    push_velocs_aos_k<<<grid_for(np, kAosT), kAosT, 0, st>>>(mom.p, fld.p, 0.5 * dt, np);
+  else
+    push_velocs_k<<<grid_for(np, 256), 256, 0, st>>>(mom, fld, 0.5 * dt, np);
   CHB_LAUNCH_CHECK();
   return 0;
 }
@@ -53,9 +88,37 @@ __global__ void __launch_bounds__(256) push_coords_k(PView x, CPView mom, PView 
   }
 }
 
+__global__ void __launch_bounds__(kAosT) push_coords_aos_k(double* __restrict__ x, const double* __restrict__ mom,
+                                                           double* __restrict__ xc, double dt, i64 np) {
+  __shared__ double sx[3 * kAosT], sp[3 * kAosT], sc[3 * kAosT];
+  const i64 first = (i64)blockIdx.x * kAosT;
+  const int n = (int)(np - first < kAosT ? np - first : kAosT), t = threadIdx.x;
+  aos_block_load<3>(sx, x, first, n);
+  aos_block_load<3>(sp, mom, first, n);
+  __syncthreads();
+  if (t < n) {  // the arithmetic of push_coords_k, operation for operation
+    const double p[3] = {sp[3 * t], sp[3 * t + 1], sp[3 * t + 2]};
+    const double p2 = __dadd_rn(__dadd_rn(__dmul_rn(p[0], p[0]), __dmul_rn(p[1], p[1])), __dmul_rn(p[2], p[2]));
+    const double dt_gp = __ddiv_rn(dt, __dsqrt_rn(__dadd_rn(1.0, p2)));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double x0 = sx[3 * t + c];
+      const double x1 = __dadd_rn(x0, __dmul_rn(p[c], dt_gp));
+      sx[3 * t + c] = x1;
+      sc[3 * t + c] = __dmul_rn(0.5, __dadd_rn(x0, x1));
+    }
+  }
+  __syncthreads();
+  aos_block_store<3>(x, sx, first, n);
+  aos_block_store<3>(xc, sc, first, n);
+}
+
 int launch_push_coords(cudaStream_t st, PView x, CPView mom, PView xc, double dt, i64 np) {
   if (np <= 0) return 0;
-  push_coords_k<<<grid_for(np, 256), 256, 0, st>>>(x, mom, xc, dt, np);
+  if (is_aos(x.p, x.cs, x.ps, 3) && is_aos(mom.p, mom.cs, mom.ps, 3) && is_aos(xc.p, xc.cs, xc.ps, 3) && x.p != xc.p)
+    push_coords_aos_k<<<grid_for(np, kAosT), kAosT, 0, st>>>(x.p, mom.p, xc.p, dt, np);
+  else
+    push_coords_k<<<grid_for(np, 256), 256, 0, st>>>(x, mom, xc, dt, np);
   CHB_LAUNCH_CHECK();
   return 0;
 }

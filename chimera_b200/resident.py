@@ -86,6 +86,7 @@ def enable(threshold=THRESHOLD):
     lib = _lib.load()
     if _lib.device_count() == 0:
         raise RuntimeError("chimera_b200 resident mode needs a CUDA device (there is no CPU fallback)")
+    lib.chimera_managed_touched.restype = None
     lib.chimera_managed_alloc.restype = ctypes.c_void_p
     lib.chimera_managed_realloc.restype = ctypes.c_void_p
     probe = lib.chimera_managed_alloc(ctypes.c_size_t(4096), 1)  # creates the context; fails early without managed memory
@@ -213,6 +214,17 @@ def _offload(ufunc, method, inputs, out, kwargs):
     return res
 
 
+def _host_touch(*arrays):
+    """the host is about to read or write these arrays: the library prefetches a managed block only once per
+    (re)allocation (csrc/api_host.cu managed_needs_prefetch), so tell it which blocks went back to the host"""
+    if not _state["on"]:
+        return
+    lib = _lib.load()
+    for a in arrays:
+        if isinstance(a, np.ndarray) and a.nbytes >= THRESHOLD:
+            lib.chimera_managed_touched(ctypes.c_void_p(a.ctypes.data))
+
+
 class ResidentArray(np.ndarray):
     """numpy array in CUDA managed memory whose whole-array statements run on the device (module docstring)"""
 
@@ -222,6 +234,9 @@ class ResidentArray(np.ndarray):
             if r is not NotImplemented:
                 return r
         # numpy on the host, on the same memory (the CUDA driver migrates what is touched)
+        _host_touch(*inputs)
+        if out is not None:
+            _host_touch(*out)
         args = [np.asarray(x) if isinstance(x, ResidentArray) else x for x in inputs]
         if out is not None:
             kwargs["out"] = tuple(np.asarray(o) if isinstance(o, ResidentArray) else o for o in out)
@@ -245,6 +260,7 @@ class ResidentArray(np.ndarray):
                 _check(lib.chimera_copy(ctypes.c_void_p(self.ctypes.data), ctypes.c_void_p(value.ctypes.data),
                                         ctypes.c_longlong(self.nbytes)))
                 return
+        _host_touch(self, value)
         super().__setitem__(key, value)
 
     def __iadd__(self, other):
@@ -255,6 +271,7 @@ class ResidentArray(np.ndarray):
             _check(_lib.load().chimera_add_inplace(ctypes.c_void_p(self.ctypes.data), ctypes.c_void_p(other.ctypes.data),
                                                    ctypes.c_longlong(n)))
             return self
+        _host_touch(self, other)
         return super().__iadd__(other)
 
 

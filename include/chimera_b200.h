@@ -41,6 +41,10 @@ void* chimera_managed_alloc(size_t bytes, int zero);
 void* chimera_managed_realloc(void* p, size_t new_bytes);
 void chimera_managed_free(void* p);                          /* the block goes to a size-bucketed cache (<= 8 GB)       */
 void chimera_managed_trim(void);                             /* release the cached blocks                               */
+void chimera_managed_touched(const void* p);                 /* the host wrote into the block holding p: prefetch it to
+                                                                the device at its next use (blocks are otherwise
+                                                                prefetched once per (re)allocation;
+                                                                CHIMERA_B200_PREFETCH=always|first|never)               */
 int chimera_managed_owns(const void* p, size_t* bytes);      /* 1 when p came from chimera_managed_alloc            */
 int chimera_is_device_accessible(const void* p);             /* 0 host, 1 managed, 2 device                          */
 int chimera_fill(double* y, chb_i64 n, double value_re, double value_im, int is_complex); /* y[:] = value          */

@@ -44,7 +44,7 @@ def test_shim_covers_every_per_function_entry_point():
     skip = ("last_error", "version", "device_count", "set_device", "sync", "kernel_launches", "host_traffic", "bench_gemm",
             "gemm_profile", "gemm_profile_read", "fused_profile", "fused_profile_read", "host_register", "host_unregister",
             # resident mode (chimera_b200/resident.py binds these, they are not fimera functions)
-            "managed_alloc", "managed_realloc", "managed_free", "managed_owns", "managed_trim", "is_device_accessible", "fill", "copy",
+            "managed_alloc", "managed_realloc", "managed_free", "managed_owns", "managed_trim", "managed_touched", "is_device_accessible", "fill", "copy",
             "add_inplace")
     for sym in declared_symbols():
         name = sym[len("chimera_"):]
