@@ -423,7 +423,7 @@ int chimera_kernel_launches(chb_i64* n) { *n = g_launches; return 0; }
 // (J[:] = 0, Rho += BckGrndRho, gradRho_prv[:] = gradRho_nxt, chimera_main.py:110-190, solvers.py:318) on the device
 namespace {
 std::mutex g_mm_mu;
-struct MBlock { size_t bytes, cap; bool on_dev; };            // what numpy asked for, what was allocated, see below
+struct MBlock { size_t bytes, cap; bool on_dev; unsigned uses; };  // what numpy asked for, what was allocated, see below
 std::map<const void*, MBlock> g_mm;                           // managed blocks handed to numpy, by base address
 std::unordered_map<size_t, std::vector<void*>> g_mm_free;     // freed blocks by capacity: numpy temporaries come in
 size_t g_mm_cached = 0;                                       // repeating sizes, and cudaMallocManaged / cudaFree cost
@@ -453,18 +453,21 @@ void* chimera_managed_alloc(size_t bytes, int zero) {
     cudaDeviceSynchronize();
   }
   std::lock_guard<std::mutex> lk(g_mm_mu);
-  g_mm[p] = MBlock{bytes, cap, zero != 0};  // zeroed on the device: the pages are there
+  g_mm[p] = MBlock{bytes, cap, false, 0};  // np.zeros + a fill on the host is a common pattern: first use prefetches
   return p;
 }
 
 extern "C++" {
 namespace chb {
-// cudaMemPrefetchAsync on a range that already lives on the device is not free: ~1 ms per GB of range walked, 30 ms of
-// the 70 ms per-call LWFA step.  So a block is prefetched when it is first seen after its (re)allocation -- numpy arrays
-// the driver built on the CPU, e.g. the re-ordered particle arrays of a re-binning step -- and when the Python layer
-// reports a host-side write (chimera_managed_touched); otherwise it is taken to be where the last call left it.  A range
-// the host touched behind our back is still correct (managed memory is coherent), it comes back through page faults.
-// CHIMERA_B200_PREFETCH=always restores the prefetch per call, =never drops it.
+// cudaMemPrefetchAsync on a range that already lives on the device is not free: ~50 us per call plus ~1 ms per GB of
+// range walked -- 30 ms of the 70 ms per-call LWFA step, a quarter of the demo-size steps.  So a block is prefetched when
+// it is first seen after its (re)allocation -- numpy arrays the driver built on the CPU: the re-ordered particle arrays of
+// a re-binning step, tables made with np.zeros + a fill --, when the Python layer reports a host-side access
+// (chimera_managed_touched), and at every 16th use (bounds what an unreported host access can cost: such a range is still
+// correct, managed memory is coherent, but it comes in through page faults -- measured 12 MB in 50 ms); otherwise it is
+// taken to be where the last call left it.  Blocks under 4 MB are prefetched at every call as before.
+// CHIMERA_B200_PREFETCH=always | never overrides.
+constexpr size_t kPrefetchAlwaysBelow = size_t(4) << 20;
 bool managed_needs_prefetch(const void* p, size_t bytes) {
   static const int policy = [] {
     const char* e = getenv("CHIMERA_B200_PREFETCH");
@@ -476,8 +479,8 @@ bool managed_needs_prefetch(const void* p, size_t bytes) {
   if (it == g_mm.begin()) return true;  // not one of our blocks (someone else's managed memory)
   --it;
   const char* base = (const char*)it->first;
-  if ((const char*)p + bytes > base + it->second.cap) return true;
-  if (it->second.on_dev) return false;
+  if ((const char*)p + bytes > base + it->second.cap || it->second.cap < kPrefetchAlwaysBelow) return true;
+  if (it->second.on_dev) return (++it->second.uses & 15u) == 0;
   // a partial range (a slice of the array) is prefetched without changing the block's state
   if ((const char*)p == base && bytes >= it->second.bytes) it->second.on_dev = true;
   return true;
@@ -535,6 +538,7 @@ void* chimera_managed_realloc(void* p, size_t new_bytes) {
     if (new_bytes <= it->second.cap) {  // fits the block: nothing moves
       it->second.bytes = new_bytes ? new_bytes : 1;
       it->second.on_dev = false;  // the driver fills the new tail on the host
+      it->second.uses = 0;
       return p;
     }
   }
