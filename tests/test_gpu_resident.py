@@ -211,3 +211,29 @@ def test_numpy_expressions_on_resident_arrays_run_on_the_device(ofim, gfim, resi
     # unsupported pieces fall back to numpy on the same memory
     assert np.allclose(np.sin(np.asarray(pg[1, :10])), np.sin(ph[1, :10]))
     assert np.array_equal(np.asarray(np.floor(pg)), np.floor(ph))
+
+
+def test_blocks_prefetched_once_stay_correct_under_unreported_host_writes(ofim, gfim, resident):
+    """Managed blocks of 4 MB and more are prefetched at their first use after allocation, after host accesses the
+    ResidentArray layer sees and at every 16th use, not at every call (csrc/api_host.cu managed_needs_prefetch).  What the
+    host does to such an array behind the library's back -- here through plain ndarray views, which no hook sees -- must
+    still be what the next call computes with (managed memory is coherent): 20 calls cross the 16th-use rule."""
+    rng = np.random.default_rng(5)
+    n = 400000  # (3, n) float64 = 9.6 MB: above the always-prefetch size
+    x = np.zeros((3, n), order="F")  # np.zeros + a fill on the host: the static-kick tables' pattern
+    x[:] = rng.standard_normal((3, n))
+    p = np.asfortranarray(rng.standard_normal((3, n)))
+    xc = np.zeros((3, n), order="F")
+    assert resident.accessible(x) and resident.accessible(p)
+    xo, po = np.array(x, order="F"), np.array(p, order="F")  # the oracle's copies (ordinary host arrays either way)
+    dt = 0.05
+    for k in range(20):
+        x, xc = gfim.push_coords(x, p, xc, dt)
+        xo, xco = ofim.push_coords(xo, po, np.zeros((3, n), order="F"), dt)
+        assert_close(np.asarray(x), xo, TOL, "coords after call %d" % k)  # a stale page would be an O(1) error
+        assert_close(np.asarray(xc), xco, TOL, "coords_halfstep after call %d" % k)
+        if k % 3 == 0:  # an unreported host write into both inputs
+            np.asarray(p)[:, k::7] *= -0.5
+            po[:, k::7] *= -0.5
+            np.asarray(x)[1, ::5] += 0.25
+            xo[1, ::5] += 0.25
