@@ -53,6 +53,9 @@ namespace {
 #ifndef CHB_FMINB
 #define CHB_FMINB 3
 #endif
+#ifndef CHB_FPREFETCH
+#define CHB_FPREFETCH 0
+#endif
 #ifndef CHB_GPC_MINB
 #define CHB_GPC_MINB 3
 #endif
@@ -638,6 +641,17 @@ fused_particles_k(double* __restrict__ x, double* __restrict__ xh, double* __res
     const i64 ip = cr.first + (in ? li : 0);
     xa[j] = __ldg(x + ip); ya[j] = __ldg(x + cap + ip); za[j] = __ldg(x + 2 * cap + ip);
     wa[j] = in ? __ldg(w + ip) : 0.0;
+#if CHB_FPREFETCH
+    // the momenta are first needed in stage (E): start their way from DRAM now
+#if CHB_FPREFETCH == 2
+#define CHB_PF "prefetch.global.L1 [%0];"
+#else
+#define CHB_PF "prefetch.global.L2 [%0];"
+#endif
+    asm volatile(CHB_PF ::"l"(mom + ip));
+    asm volatile(CHB_PF ::"l"(mom + cap + ip));
+    asm volatile(CHB_PF ::"l"(mom + 2 * cap + ip));
+#endif
   }
   for (int i = tid; i < FBINS; i += FT) bins[i] = 0;
   if (tid == 0) {
